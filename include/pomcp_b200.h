@@ -1,0 +1,234 @@
+/*
+ * pomcp_b200.h — C ABI of libpomcp_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of JuliaPOMDP/POMCP.jl.
+ * Every entry point names the reference interface it replaces (file:line is
+ * relative to the POMCP.jl source tree).  All functions are extern "C", take
+ * plain pointers and sizes, return an int32 status (pomcp_status) and never
+ * throw.  Host buffers are caller-owned and are copied in/out before the call
+ * returns; no device pointer ever crosses this boundary.
+ *
+ * One handle = one CUDA device + one stream + one search tree.  Calls on one
+ * handle must be serialised by the caller; different handles are independent
+ * (root-parallel search uses one handle per GPU / per process).
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * POMCP_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef POMCP_B200_H
+#define POMCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POMCP_B200_ABI_VERSION 1
+#define POMCP_MAX_ROCKS 16
+#define POMCP_MAX_ACTIONS 32
+
+/* Status codes <-> reference exceptions (src/exceptions.jl:1-26,
+ * src/particle_filter.jl:94-101, src/solver.jl:56-58,62). */
+typedef enum pomcp_status {
+  POMCP_OK = 0,
+  POMCP_ERR_ALL_SAMPLES_TERMINAL = 1, /* AllSamplesTerminal, src/solver.jl:56-58 */
+  POMCP_ERR_PARTICLE_DEPLETION = 2,   /* particle_depletion_error(), src/particle_filter.jl:94-101 */
+  POMCP_ERR_POOL_EXHAUSTED = 3,       /* device node pool / particle log full (no reference counterpart) */
+  POMCP_ERR_UNSUPPORTED = 4,          /* arbitrary Julia callbacks cannot run on device */
+  POMCP_ERR_INVALID_ARG = 5,          /* incl. discount == 1 (UndefVarError in src/solver.jl:97-102) */
+  POMCP_ERR_CUDA = 6,
+  POMCP_ERR_NCCL = 7,
+  POMCP_ERR_NAN_VALUE = 8             /* @assert !isnan(best_V), src/solver.jl:62 */
+} pomcp_status;
+
+/* Problems whose generative model is compiled into the library
+ * (replaces the POMDPs.jl callbacks generate_sor / isterminal / discount /
+ * actions used at src/solver.jl:82-83,126 and src/actions.jl:30-31). */
+typedef enum pomcp_problem_id {
+  POMCP_TIGER = 0,       /* S=u32{0 tiger-right,1 tiger-left}, A={0 listen,1 open-left,2 open-right}, O={0,1} */
+  POMCP_BABY = 1,        /* S=u32 hungry, A={0 wait,1 feed}, O={0 quiet,1 crying} */
+  POMCP_ROCKSAMPLE = 2,  /* S=u32 packed, A={0 N,1 E,2 S,3 W,4 sample,5+i check_i}, O={0 good,1 bad,2 none} */
+  POMCP_LIGHTDARK1D = 3  /* S={int64 status,double y}, A={0:-1,1:0(stop),2:+1}, O=double */
+} pomcp_problem_id;
+
+/* RockSample packed state: bits 0-3 x, 4-7 y, 8-23 rock goodness, bit 31 terminal. */
+#define POMCP_RS_TERMINAL 0x80000000u
+
+typedef struct pomcp_lightdark_state {
+  int64_t status; /* < 0 terminal (notebooks/Minimal_Example.ipynb:50-77) */
+  double y;
+} pomcp_lightdark_state;
+
+typedef struct pomcp_problem {
+  int32_t problem_id;
+  int32_t _pad0;
+  double discount;
+  /* Tiger */
+  double tiger_r_listen, tiger_r_findtiger, tiger_r_escapetiger, tiger_p_listen_correctly;
+  /* Baby */
+  double baby_r_feed, baby_r_hungry, baby_p_become_hungry, baby_p_cry_when_hungry,
+      baby_p_cry_when_not_hungry;
+  /* RockSample(n,k) */
+  int32_t rs_n, rs_k;
+  int32_t rs_rock_x[POMCP_MAX_ROCKS], rs_rock_y[POMCP_MAX_ROCKS];
+  int32_t rs_start_x, rs_start_y;
+  double rs_half_eff_dist, rs_r_good, rs_r_bad, rs_r_exit;
+  /* LightDark1D (notebooks/Minimal_Example.ipynb:68-146) */
+  double ld_correct_r, ld_incorrect_r, ld_init_mean, ld_init_std;
+} pomcp_problem;
+
+/* estimate_value kinds (src/rollout.jl:8-69). */
+typedef enum pomcp_estimator {
+  POMCP_EST_RANDOM_ROLLOUT = 0, /* RolloutEstimator(RandomSolver()), src/constructor.jl:14 */
+  POMCP_EST_CONSTANT = 1        /* estimate_value(n::Number,...), src/rollout.jl:10 */
+} pomcp_estimator;
+
+/* node_belief_updater kinds (src/solver.jl:135-139). */
+typedef enum pomcp_belief_mode {
+  POMCP_BELIEF_UNWEIGHTED = 0, /* DeadReinvigorator: states pushed at visited nodes, src/solver.jl:146-148 */
+  POMCP_BELIEF_EXTERNAL = 1    /* belief maintained outside the tree (e.g. SIR filter): nothing stored */
+} pomcp_belief_mode;
+
+typedef enum pomcp_search_mode {
+  POMCP_MODE_EXACT = 0,  /* strictly sequential simulations, incremental-mean backup: bit-parity mode */
+  POMCP_MODE_BATCHED = 1 /* waves of simulations in flight, atomics on the node pool: throughput mode */
+} pomcp_search_mode;
+
+/* Mirrors the POMCPSolver fields (src/POMCP.jl:137-152) with the defaults of
+ * the keyword constructor (src/constructor.jl:8-18); the trailing block holds
+ * the device-side knobs that have no reference counterpart. */
+typedef struct pomcp_solver_params {
+  double eps;           /* 0.01 */
+  int64_t max_depth;    /* typemax(Int) */
+  double c;             /* 1.0 */
+  int64_t tree_queries; /* 100 */
+  uint64_t seed;        /* replaces rng::AbstractRNG */
+  double init_V;        /* 0.0 (numeric form only, src/tree.jl:34) */
+  int64_t init_N;       /* 0   (numeric form only, src/tree.jl:43) */
+  int32_t num_sparse_actions; /* must be <= 0: full action space, src/actions.jl:30-31 */
+  int32_t estimator;          /* pomcp_estimator */
+  double estimator_value;     /* for POMCP_EST_CONSTANT */
+  int32_t belief_mode;        /* pomcp_belief_mode */
+  int32_t search_mode;        /* pomcp_search_mode */
+  /* ---- device knobs ---- */
+  int64_t max_nodes;     /* belief-node pool capacity (0 = derive from tree_queries) */
+  int64_t max_log;       /* particle-log capacity in entries (0 = derive) */
+  int32_t wave_min;      /* batched: smallest wave (0 = default 32) */
+  int32_t wave_max;      /* batched: largest wave (0 = default 32768) */
+  int32_t wave_ramp_div; /* batched: wave = clamp(visits_so_far / div) (0 = default 8) */
+  int32_t rank;          /* root-parallel rank, mixed into the Philox key */
+} pomcp_solver_params;
+
+typedef struct pomcp_counters {
+  int64_t simulations;    /* queries that ran a simulation */
+  int64_t terminal_skips; /* queries consumed by a terminal root sample, src/solver.jl:49 */
+  int64_t rollouts;       /* leaf evaluations */
+  int64_t rollout_steps;  /* generative steps inside rollouts */
+  int64_t tree_steps;     /* generative steps inside the tree */
+  int64_t nodes;          /* belief nodes allocated in the pool */
+  int64_t log_entries;    /* (node,state) particle-log entries */
+  int64_t max_depth_seen;
+  int64_t waves;          /* batched-mode waves launched by the last search */
+  int64_t kernel_launches;/* kernels launched by this handle since creation */
+} pomcp_counters;
+
+typedef struct pomcp_handle pomcp_handle;
+
+int32_t pomcp_abi_version(void);
+const char* pomcp_status_string(int32_t status);
+/* Last error text for a handle (NULL handle: last creation error). */
+const char* pomcp_last_error(const pomcp_handle* h);
+
+void pomcp_default_solver_params(pomcp_solver_params* out); /* src/constructor.jl:8-18 */
+void pomcp_default_problem(int32_t problem_id, pomcp_problem* out);
+int32_t pomcp_num_actions(const pomcp_problem* p);
+int32_t pomcp_state_bytes(const pomcp_problem* p);
+
+/* solve(solver, pomdp) -> planner: src/solver.jl:5-14,30-32.  Allocates the
+ * node pool, path buffers and particle arrays on `device`. */
+int32_t pomcp_create(const pomcp_problem* problem, const pomcp_solver_params* params, int32_t device,
+                     pomcp_handle** out);
+int32_t pomcp_destroy(pomcp_handle* h);
+
+/* initialize_belief(up, b) -> RootNode(0, b, {}): src/updater.jl:45-47,
+ * src/solver.jl:278-281.  Fresh root over a particle collection ... */
+int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t n);
+/* ... or over the problem's initial state distribution. */
+int32_t pomcp_set_belief_initial(pomcp_handle* h);
+/* Copy the root belief's particles out (ParticleCollection of the root node). */
+int32_t pomcp_get_belief_particles(pomcp_handle* h, void* out, int64_t cap, int64_t* n);
+
+/* action(planner, belief) -> search(): src/solver.jl:16-23,41-71.  Runs
+ * tree_queries simulations from the current root and returns the arg-max-V
+ * root action together with the root children statistics.  tree_queries < 0
+ * uses the value given at creation. */
+int32_t pomcp_search(pomcp_handle* h, int64_t tree_queries, int32_t* action_out, int64_t* root_N_out,
+                     double* root_V_out, int32_t n_actions);
+
+/* Replay hook for bit-parity tests: the search consumes `uniforms` in call
+ * order instead of Philox draws and `rollout_returns` instead of running
+ * rollouts (exact mode only). */
+int32_t pomcp_search_replay(pomcp_handle* h, int64_t tree_queries, const double* uniforms, int64_t n_uniforms,
+                            const double* rollout_returns, int64_t n_returns, int32_t* action_out,
+                            int64_t* root_N_out, double* root_V_out, int32_t n_actions,
+                            int64_t* uniforms_used, int64_t* returns_used);
+
+/* update(::RootUpdater{<:ParticleReinvigorator}, b_old, a, o): src/updater.jl:13-27.
+ * Re-roots the tree at child (a,o); POMCP_ERR_PARTICLE_DEPLETION if absent or empty.
+ * obs_bits: the observation index, or the IEEE bits of a continuous observation. */
+int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits);
+
+/* update(::SIRParticleFilter, b::ParticleCollection, a, o) (call site test/runtests.jl:57):
+ * propagate, weight by the observation density, systematic resample to n_out
+ * particles; the result becomes a fresh root belief (no tree reuse, src/solver.jl:278-281). */
+int32_t pomcp_pf_update_sir(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint64_t seed, int64_t n_out);
+
+/* Parity hooks on the individual kernels. */
+/* Systematic (low-variance) resampling of given weights.  mode 0: fixed-point
+ * parallel kernels (production); mode 1: sequential fp64 chain on one thread
+ * (verification of the upstream running-sum semantics). */
+int32_t pomcp_resample_systematic(pomcp_handle* h, const double* weights, int64_t n, double r, int64_t n_out,
+                                  int32_t mode, int64_t* idx_out);
+/* Random-policy rollouts from given start states: one thread per trajectory. */
+int32_t pomcp_rollout_batch(pomcp_handle* h, const void* states, int64_t n, int32_t steps, uint64_t seed,
+                            double* returns_out, int32_t* steps_out);
+/* Per-particle SIR weights w_i = pdf(observation(a, s'_i), o) and propagated states. */
+int32_t pomcp_pf_weights(pomcp_handle* h, const void* states, int64_t n, int32_t a, uint64_t obs_bits,
+                         uint64_t seed, double* weights_out, void* next_states_out);
+
+/* Tree inspection (replaces poking at BeliefNode fields; src/tree.jl:7-26). */
+int32_t pomcp_get_root_stats(pomcp_handle* h, int64_t* root_N, int64_t* act_N, double* act_V, int32_t n_actions);
+/* Children statistics of the belief node reached from the root by the given
+ * (action, observation) history; *node_N = -1 if the node does not exist. */
+int32_t pomcp_get_node_stats(pomcp_handle* h, const int32_t* actions, const uint64_t* obs_bits, int32_t depth,
+                             int64_t* node_N, int64_t* n_particles, int64_t* act_N, double* act_V,
+                             int32_t n_actions);
+/* Whole-tree dump in allocation order (for structural invariants). */
+int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap_nodes, int64_t* n_nodes, int64_t* node_N,
+                        int64_t* act_N, double* act_V, int32_t* child /* [node][action][obs], -1 none; NULL ok */);
+int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out);
+int32_t pomcp_reset_counters(pomcp_handle* h);
+
+/* Root-parallel multi-GPU search: one tree per rank, root statistics merged by
+ * one NCCL all-reduce before the arg-max of src/solver.jl:60-70. */
+int32_t pomcp_nccl_unique_id(void* id_out_128_bytes);
+int32_t pomcp_comm_init(pomcp_handle* h, const void* nccl_unique_id_128_bytes, int32_t rank, int32_t nranks);
+int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t tree_queries, int32_t* action_out,
+                                  int64_t* root_N_out, double* root_V_out, int32_t n_actions);
+
+/* Device-timer access for the bench harness: elapsed milliseconds spent in the
+ * named phase by the last call (CUDA events on the handle's stream). */
+typedef enum pomcp_phase { POMCP_PHASE_SEARCH = 0, POMCP_PHASE_ROLLOUT = 1, POMCP_PHASE_PF = 2,
+                           POMCP_PHASE_REROOT = 3, POMCP_PHASE_COUNT = 4 } pomcp_phase;
+int32_t pomcp_last_phase_ms(pomcp_handle* h, int32_t phase, double* ms_out, int64_t* launches_out);
+/* Device-resident variants used by the bench's kernel-only timing: run on
+ * whatever belief is already in HBM and leave results there. */
+int32_t pomcp_search_async(pomcp_handle* h, int64_t tree_queries);
+int32_t pomcp_sync(pomcp_handle* h);
+int32_t pomcp_flush_l2(pomcp_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POMCP_B200_H */

@@ -1,0 +1,532 @@
+"""Host-side mirror of the POMCP.jl plugin surface over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference
+(src/POMCP.jl:20-67 exports): POMCPSolver (src/constructor.jl:8-31), solve /
+action (src/solver.jl:16-34), updater / initialize_belief / update
+(src/updater.jl:13-47), the NoDecision / AllSamplesTerminal exceptions and
+default_action dispatch (src/exceptions.jl:1-26), the particle-depletion
+ErrorException (src/particle_filter.jl:94-101) and the SIR particle filter the
+reference's tests plug in (test/runtests.jl:57).  All compute goes through
+libpomcp_b200.so; nothing here evaluates the algorithm on the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as abi
+from ._lib import lib
+from .problems import POMDP, obs_bits
+
+__all__ = [
+    "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "RandomSolver", "DefaultReinvigoratorStub",
+    "DeadReinvigorator", "ParticleReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
+    "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
+    "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
+    "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
+]
+
+
+# ---------------------------------------------------------------- exceptions
+class POMCPError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__(f"{abi.STATUS_NAMES.get(status, status)}: {msg}")
+
+
+class NoDecision(Exception):
+    """abstract NoDecision <: Exception (src/exceptions.jl:1-7)."""
+
+
+class AllSamplesTerminal(NoDecision):
+    """src/exceptions.jl:9-18."""
+
+    def __init__(self, belief=None):
+        self.belief = belief
+        super().__init__("POMCP failed to choose an action because all states sampled from the belief were "
+                         "terminal.\n\nTo specify an action for this case, use the default_action solver parameter.")
+
+
+class ParticleDepletion(RuntimeError):
+    """ErrorException of particle_depletion_error() (src/particle_filter.jl:94-101)."""
+
+    def __init__(self):
+        super().__init__(
+            "POMCP.jl: Particle Depletion! To fix this, you have three options:\n"
+            "      1) use more tree_queries (will only work for very small problems)\n"
+            "      2) implement a ParticleReinvigorator with reinvigorate!() and handle_unseen_observation()\n"
+            "      3) implement a more advanced updater for the agent (POMCP can use any\n"
+            "         belief/state distribution that supports rand())")
+
+
+class PoolExhausted(POMCPError):
+    pass
+
+
+def _check(rc, h=None, belief=None):
+    if rc == abi.OK:
+        return
+    if rc == abi.ERR_ALL_SAMPLES_TERMINAL:
+        raise AllSamplesTerminal(belief)
+    if rc == abi.ERR_PARTICLE_DEPLETION:
+        raise ParticleDepletion()
+    msg = lib().pomcp_last_error(h)
+    msg = msg.decode() if msg else ""
+    if rc == abi.ERR_POOL_EXHAUSTED:
+        raise PoolExhausted(rc, msg)
+    if rc == abi.ERR_INVALID_ARG:
+        raise ValueError(f"pomcp_b200: invalid argument: {msg}")
+    if rc == abi.ERR_UNSUPPORTED:
+        raise NotImplementedError(f"pomcp_b200: unsupported on device: {msg}")
+    if rc == abi.ERR_NAN_VALUE:
+        raise AssertionError("!isnan(best_V)")
+    raise POMCPError(rc, msg)
+
+
+# ---------------------------------------------------------------- solver pieces
+class ExceptionRethrow:
+    """src/exceptions.jl:21."""
+
+
+class RandomSolver:
+    """POMDPToolbox.RandomSolver: uniform-random rollout policy (src/constructor.jl:14)."""
+
+
+class RolloutEstimator:
+    """MCTS.RolloutEstimator(solver_or_policy) (src/rollout.jl:43-46)."""
+
+    def __init__(self, solver=None):
+        self.solver = solver if solver is not None else RandomSolver()
+
+
+class ParticleReinvigorator:
+    """abstract ParticleReinvigorator (src/particle_filter.jl:37).  Subclasses run on the HOST:
+    handle_unseen_observation(old_node, a, o) -> state array (src/particle_filter.jl:60-73),
+    reinvigorate(particles, old_node, a, o) -> state array or None (src/particle_filter.jl:46-58)."""
+
+    def reinvigorate(self, particles, old_node, a, o):
+        raise NotImplementedError(f"POMCP.jl reinvigorate! not implemented for reinvigorator {type(self)}")
+
+    def handle_unseen_observation(self, old_node, a, o):
+        raise NotImplementedError(
+            f"POMCP.jl: handle_unseen_observation not implemented for reinvigorator {type(self)}")
+
+
+class DeadReinvigorator(ParticleReinvigorator):
+    """Default: no domain knowledge (src/particle_filter.jl:78,85-92)."""
+
+    def reinvigorate(self, particles, old_node, a, o):
+        if len(particles) == 0:
+            raise ParticleDepletion()
+        return None
+
+    def handle_unseen_observation(self, old_node, a, o):
+        raise ParticleDepletion()
+
+
+class DefaultReinvigoratorStub:
+    """src/particle_filter.jl:83; replaced by DeadReinvigorator in solve() (src/solver.jl:6-10)."""
+
+
+class POMCPSolver:
+    """Keyword constructor with the reference defaults (src/constructor.jl:8-18; fields documented
+    at src/POMCP.jl:75-136).  `rng` is an integer seed (Philox key) instead of an AbstractRNG.
+    Device-only keywords: search_mode ("batched"|"exact"), wave_min, wave_max, wave_ramp_div,
+    max_nodes, max_log, device, rank."""
+
+    def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0,
+                 node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
+                 default_action=None, search_mode="batched", wave_min=0, wave_max=0, wave_ramp_div=0, max_nodes=0,
+                 max_log=0, device=0, rank=0):
+        self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
+        self.rng = rng
+        self.node_belief_updater = node_belief_updater if node_belief_updater is not None \
+            else DefaultReinvigoratorStub()
+        self.estimate_value = estimate_value if estimate_value is not None else RolloutEstimator(RandomSolver())
+        self.init_V, self.init_N, self.num_sparse_actions = init_V, init_N, num_sparse_actions
+        self.default_action = default_action if default_action is not None else ExceptionRethrow()
+        self.search_mode = search_mode
+        self.wave_min, self.wave_max, self.wave_ramp_div = wave_min, wave_max, wave_ramp_div
+        self.max_nodes, self.max_log, self.device, self.rank = max_nodes, max_log, device, rank
+
+    def c_params(self, belief_mode):
+        sp = abi.SolverParams()
+        lib().pomcp_default_solver_params(C.byref(sp))
+        sp.eps, sp.max_depth, sp.c, sp.tree_queries = self.eps, min(int(self.max_depth), 2 ** 63 - 1), self.c, \
+            self.tree_queries
+        sp.seed = int(self.rng) & (2 ** 64 - 1)
+        if callable(self.init_V) or callable(self.init_N):
+            raise NotImplementedError("init_V/init_N callbacks cannot run on device (src/tree.jl:35,44)")
+        sp.init_V, sp.init_N = float(self.init_V), int(self.init_N)
+        sp.num_sparse_actions = int(self.num_sparse_actions)
+        ev = self.estimate_value
+        if isinstance(ev, RolloutEstimator) and isinstance(ev.solver, RandomSolver):
+            sp.estimator = abi.EST_RANDOM_ROLLOUT
+        elif isinstance(ev, (int, float)):
+            sp.estimator, sp.estimator_value = abi.EST_CONSTANT, float(ev)  # src/rollout.jl:10
+        else:
+            raise NotImplementedError(
+                "estimate_value: only RolloutEstimator(RandomSolver()) and numeric estimates run on device "
+                "(FORollout/FOValue/function estimators are arbitrary host callbacks, src/rollout.jl:9,24-39)")
+        sp.belief_mode = belief_mode
+        sp.search_mode = {"exact": abi.MODE_EXACT, "batched": abi.MODE_BATCHED}[self.search_mode]
+        sp.max_nodes, sp.max_log = int(self.max_nodes), int(self.max_log)
+        sp.wave_min, sp.wave_max, sp.wave_ramp_div = self.wave_min, self.wave_max, self.wave_ramp_div
+        sp.rank = self.rank
+        return sp
+
+
+# ---------------------------------------------------------------- beliefs
+class ParticleCollection:
+    """ParticleFilters.ParticleCollection: unweighted particle belief (src/particle_filter.jl:1-18)."""
+
+    def __init__(self, particles):
+        self.particles = np.ascontiguousarray(particles)
+
+    def __len__(self):
+        return len(self.particles)
+
+
+class InitialStateDistribution:
+    """initial_state_distribution(pomdp): sampled on device by the model's own rule."""
+
+    def __init__(self, pomdp):
+        self.pomdp = pomdp
+
+
+def initial_state_distribution(pomdp):
+    return InitialStateDistribution(pomdp)
+
+
+class BeliefNode:
+    """Handle to a belief node of the device tree (src/tree.jl:14-26).  It is both the belief and
+    the search root (src/updater.jl:20-26); only the planner's current root is addressable."""
+
+    def __init__(self, planner, generation, B=None):
+        self.planner, self.generation, self.B = planner, generation, B
+
+    def _live(self):
+        if self.generation != self.planner._generation:
+            raise ValueError("stale BeliefNode: the planner's tree has been re-rooted since")
+
+    @property
+    def N(self):
+        self._live()
+        return self.planner.root_stats()[0]
+
+    @property
+    def children(self):
+        """{action: (N, V)} of the root's ActNodes."""
+        self._live()
+        _, N, V = self.planner.root_stats()
+        return {a: (int(N[a]), float(V[a])) for a in range(len(N))}
+
+    def particles(self):
+        self._live()
+        return self.planner.belief_particles()
+
+
+class RootNode(BeliefNode):
+    pass
+
+
+# ---------------------------------------------------------------- planner
+class POMCPPlanner:
+    """POMCPPlanner (src/POMCP.jl:260-268): owns the opaque device handle."""
+
+    def __init__(self, solver, pomdp, belief_mode=abi.BELIEF_UNWEIGHTED):
+        if not isinstance(pomdp, POMDP):
+            raise NotImplementedError("only the built-in problem models run on device")
+        self.solver, self.problem = solver, pomdp
+        nbu = solver.node_belief_updater
+        if isinstance(nbu, DefaultReinvigoratorStub):
+            nbu = DeadReinvigorator()  # src/solver.jl:6-10
+        if not isinstance(nbu, ParticleReinvigorator):
+            raise NotImplementedError("node_belief_updater: only ParticleReinvigorators are supported on device")
+        self.node_belief_updater = nbu
+        self._p = pomdp.c_struct()
+        self._sp = solver.c_params(belief_mode)
+        self.nA = pomdp.n_actions
+        h = C.c_void_p()
+        rc = lib().pomcp_create(C.byref(self._p), C.byref(self._sp), int(solver.device), C.byref(h))
+        if rc != abi.OK:
+            _check(rc, None)
+        self._h = h
+        self._generation = 0
+        self._tree_ref = None  # src/POMCP.jl:266-267
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pomcp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- thin wrappers over the C ABI
+    def set_belief_particles(self, states):
+        states = np.ascontiguousarray(states, dtype=self.problem.state_dtype)
+        _check(lib().pomcp_set_belief_particles(self._h, states.ctypes.data_as(C.c_void_p), len(states)), self._h)
+        self._generation += 1
+
+    def set_belief_initial(self):
+        _check(lib().pomcp_set_belief_initial(self._h), self._h)
+        self._generation += 1
+
+    def belief_particles(self):
+        n = C.c_int64(0)
+        _check(lib().pomcp_get_belief_particles(self._h, None, 0, C.byref(n)), self._h)
+        out = np.zeros(n.value, dtype=self.problem.state_dtype)
+        if n.value:
+            _check(lib().pomcp_get_belief_particles(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)),
+                   self._h)
+        return out
+
+    def search(self, tree_queries=-1, belief=None):
+        a = C.c_int32(-1)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        rc = lib().pomcp_search(self._h, tree_queries, C.byref(a), N.ctypes.data_as(C.c_void_p),
+                                V.ctypes.data_as(C.c_void_p), self.nA)
+        _check(rc, self._h, belief)
+        return a.value, N, V
+
+    def search_replay(self, tree_queries, uniforms, returns):
+        a = C.c_int32(-1)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        returns = np.ascontiguousarray(returns, dtype=np.float64)
+        uu, ru = C.c_int64(0), C.c_int64(0)
+        rc = lib().pomcp_search_replay(self._h, tree_queries, uniforms.ctypes.data_as(C.c_void_p), len(uniforms),
+                                       returns.ctypes.data_as(C.c_void_p), len(returns), C.byref(a),
+                                       N.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p), self.nA,
+                                       C.byref(uu), C.byref(ru))
+        _check(rc, self._h)
+        return a.value, N, V, uu.value, ru.value
+
+    def search_rootparallel(self, tree_queries=-1):
+        a = C.c_int32(-1)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        rc = lib().pomcp_search_rootparallel(self._h, tree_queries, C.byref(a), N.ctypes.data_as(C.c_void_p),
+                                             V.ctypes.data_as(C.c_void_p), self.nA)
+        _check(rc, self._h)
+        return a.value, N, V
+
+    def update_unweighted(self, a, o):
+        rc = lib().pomcp_update_unweighted(self._h, int(a), obs_bits(o))
+        _check(rc, self._h)
+        self._generation += 1
+
+    def pf_update_sir(self, a, o, seed, n_out):
+        _check(lib().pomcp_pf_update_sir(self._h, int(a), obs_bits(o), int(seed), int(n_out)), self._h)
+        self._generation += 1
+
+    def root_stats(self):
+        rn = C.c_int64(0)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        _check(lib().pomcp_get_root_stats(self._h, C.byref(rn), N.ctypes.data_as(C.c_void_p),
+                                          V.ctypes.data_as(C.c_void_p), self.nA), self._h)
+        return rn.value, N, V
+
+    def node_stats(self, history):
+        acts = np.array([h[0] for h in history], dtype=np.int32)
+        obs = np.array([obs_bits(h[1]) for h in history], dtype=np.uint64)
+        nN, npart = C.c_int64(0), C.c_int64(0)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        _check(lib().pomcp_get_node_stats(self._h, acts.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
+                                          len(history), C.byref(nN), C.byref(npart), N.ctypes.data_as(C.c_void_p),
+                                          V.ctypes.data_as(C.c_void_p), self.nA), self._h)
+        return nN.value, npart.value, N, V
+
+    def dump_tree(self):
+        n = C.c_int64(0)
+        _check(lib().pomcp_dump_tree(self._h, 0, C.byref(n), None, None, None, None), self._h)
+        nn = n.value
+        nO = getattr(self.problem, "n_observations", 0)
+        node_N = np.zeros(nn, dtype=np.int64)
+        act_N = np.zeros((nn, self.nA), dtype=np.int64)
+        act_V = np.zeros((nn, self.nA), dtype=np.float64)
+        child = np.full((nn, self.nA, max(nO, 1)), -1, dtype=np.int32) if nO else None
+        _check(lib().pomcp_dump_tree(self._h, nn, C.byref(n), node_N.ctypes.data_as(C.c_void_p),
+                                     act_N.ctypes.data_as(C.c_void_p), act_V.ctypes.data_as(C.c_void_p),
+                                     None if child is None else child.ctypes.data_as(C.c_void_p)), self._h)
+        return node_N, act_N, act_V, child
+
+    def counters(self):
+        c = abi.Counters()
+        _check(lib().pomcp_get_counters(self._h, C.byref(c)), self._h)
+        return c.as_dict()
+
+    def reset_counters(self):
+        _check(lib().pomcp_reset_counters(self._h), self._h)
+
+    def phase_ms(self, phase):
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        _check(lib().pomcp_last_phase_ms(self._h, phase, C.byref(ms), C.byref(n)), self._h)
+        return ms.value, n.value
+
+    def rollout_batch(self, states, steps, seed):
+        states = np.ascontiguousarray(states, dtype=self.problem.state_dtype)
+        ret = np.zeros(len(states), dtype=np.float64)
+        ns = np.zeros(len(states), dtype=np.int32)
+        _check(lib().pomcp_rollout_batch(self._h, states.ctypes.data_as(C.c_void_p), len(states), int(steps),
+                                         int(seed), ret.ctypes.data_as(C.c_void_p), ns.ctypes.data_as(C.c_void_p)),
+               self._h)
+        return ret, ns
+
+    def pf_weights(self, states, a, o, seed):
+        states = np.ascontiguousarray(states, dtype=self.problem.state_dtype)
+        w = np.zeros(len(states), dtype=np.float64)
+        nxt = np.zeros(len(states), dtype=self.problem.state_dtype)
+        _check(lib().pomcp_pf_weights(self._h, states.ctypes.data_as(C.c_void_p), len(states), int(a), obs_bits(o),
+                                      int(seed), w.ctypes.data_as(C.c_void_p), nxt.ctypes.data_as(C.c_void_p)),
+               self._h)
+        return w, nxt
+
+    def resample_systematic(self, weights, r, n_out, mode=0):
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        idx = np.zeros(n_out, dtype=np.int64)
+        rc = lib().pomcp_resample_systematic(self._h, weights.ctypes.data_as(C.c_void_p), len(weights), float(r),
+                                             int(n_out), int(mode), idx.ctypes.data_as(C.c_void_p))
+        _check(rc, self._h)
+        return idx
+
+    def comm_init(self, unique_id: bytes, rank, nranks):
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(lib().pomcp_comm_init(self._h, buf, rank, nranks), self._h)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().pomcp_nccl_unique_id(buf))
+    return buf.raw
+
+
+# ---------------------------------------------------------------- POMDPs.jl verbs
+def solve(solver, pomdp, belief_mode=abi.BELIEF_UNWEIGHTED):
+    """solve(solver, pomdp) -> POMCPPlanner (src/solver.jl:30-32)."""
+    return POMCPPlanner(solver, pomdp, belief_mode)
+
+
+def default_action(spec, belief, ex):
+    """src/exceptions.jl:23-26."""
+    if isinstance(spec, ExceptionRethrow):
+        raise ex
+    if isinstance(spec, POMCPPlanner):
+        return action(spec, belief)
+    if callable(spec):
+        return spec(belief, ex)
+    return spec
+
+
+def _make_node(planner, belief):
+    """make_node (src/solver.jl:276-281): a BeliefNode is searched in place, anything else gets
+    a fresh RootNode."""
+    if isinstance(belief, BeliefNode):
+        if belief.planner is not planner:
+            raise ValueError("BeliefNode belongs to another planner")
+        belief._live()
+        return belief
+    if isinstance(belief, ParticleCollection):
+        planner.set_belief_particles(belief.particles)
+    elif isinstance(belief, InitialStateDistribution):
+        planner.set_belief_initial()
+    elif isinstance(belief, np.ndarray):
+        planner.set_belief_particles(belief)
+    else:
+        raise NotImplementedError("belief must be a BeliefNode, ParticleCollection or initial_state_distribution "
+                                  "(arbitrary rand(rng, b) callbacks cannot run on device)")
+    return RootNode(planner, planner._generation, belief)
+
+
+def action(policy, belief):
+    """action(policy, belief) (src/solver.jl:16-23)."""
+    try:
+        node = _make_node(policy, belief)
+        policy._tree_ref = node
+        a, _, _ = policy.search(policy.solver.tree_queries, belief)
+        return a
+    except (NoDecision, ParticleDepletion, AssertionError, PoolExhausted) as ex:
+        return default_action(policy.solver.default_action, belief, ex)
+
+
+class RootUpdater:
+    """RootUpdater (src/updater.jl:8-10)."""
+
+    def __init__(self, planner):
+        self.planner = planner
+        self.node_belief_updater = planner.node_belief_updater
+
+
+def updater(policy):
+    """updater(policy::POMCPPlanner) (src/updater.jl:41)."""
+    return RootUpdater(policy)
+
+
+def initialize_belief(up, b):
+    """initialize_belief(up::RootUpdater, b) = RootNode(0, b, {}) (src/updater.jl:45-47)."""
+    if isinstance(up, SIRParticleFilter):
+        return up.initialize_belief(b)
+    if isinstance(b, BeliefNode):
+        return b
+    return _make_node(up.planner, b)
+
+
+def update(up, b_old, a, o):
+    """update(updater, b_old, a, o) (src/updater.jl:13-27 for RootUpdater; SIR filter otherwise)."""
+    if isinstance(up, SIRParticleFilter):
+        return up.update(b_old, a, o)
+    pl = up.planner
+    if not isinstance(b_old, BeliefNode):
+        raise TypeError("RootUpdater.update needs the BeliefNode returned by initialize_belief/update")
+    b_old._live()
+    try:
+        pl.update_unweighted(a, o)
+    except ParticleDepletion:
+        r = up.node_belief_updater
+        if isinstance(r, DeadReinvigorator):
+            raise
+        new_particles = r.handle_unseen_observation(b_old, a, o)  # src/updater.jl:14-18 (host hook)
+        pl.set_belief_particles(new_particles)
+        return BeliefNode(pl, pl._generation)
+    node = BeliefNode(pl, pl._generation)
+    r = up.node_belief_updater
+    if not isinstance(r, DeadReinvigorator):
+        extra = r.reinvigorate(node.particles(), b_old, a, o)  # src/updater.jl:21-23 (host hook)
+        if extra is not None and len(extra):
+            raise NotImplementedError("adding particles to a re-rooted device node is not supported yet")
+    return node
+
+
+class SIRParticleFilter:
+    """ParticleFilters.SIRParticleFilter(model, n) (test/runtests.jl:57): propagate, weight,
+    systematic resample on the device.  Beliefs are ParticleCollections, so the planner builds a
+    fresh root every step (src/solver.jl:278-281)."""
+
+    def __init__(self, planner, n, rng=0):
+        self.planner, self.n, self.seed, self._step = planner, int(n), int(rng), 0
+
+    def initialize_belief(self, b):
+        if isinstance(b, InitialStateDistribution):
+            raise NotImplementedError("draw the initial particles on the host and pass a ParticleCollection")
+        return b if isinstance(b, ParticleCollection) else ParticleCollection(b)
+
+    def update(self, b, a, o, on_device=False):
+        pl = self.planner
+        if not on_device:
+            pl.set_belief_particles(b.particles)
+        self._step += 1
+        pl.pf_update_sir(a, o, (self.seed * 0x9E3779B97F4A7C15 + self._step) & (2 ** 64 - 1), self.n)
+        return ParticleCollection(pl.belief_particles())
+
+
+def root_parallel_action(policy):
+    """Root-parallel decision: every rank searches its own tree, root N / N*V are merged by one
+    NCCL all-reduce inside pomcp_search_rootparallel (needs comm_init on every rank)."""
+    return policy.search_rootparallel(policy.solver.tree_queries)[0]
