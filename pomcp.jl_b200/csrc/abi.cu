@@ -1,0 +1,1055 @@
+// libpomcp_b200.so — host side of the C ABI declared in include/pomcp_b200.h.
+// One handle = one device + one stream + one tree.  All kernels are in
+// tree.cuh (search) and pf.cuh (particle filter); this file owns memory, launch schedules,
+// status mapping and the NCCL root merge.  There is no CPU fallback anywhere.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pomcp_b200.h"
+#include "pf.cuh"
+#include "tree.cuh"
+
+using namespace pomcp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct PhaseTimer {
+  std::vector<cudaEvent_t> ev;  // pairs
+  int used = 0;
+  long long launches = 0;
+  void reset() { used = 0; launches = 0; }
+  cudaEvent_t next() {
+    if (used == (int)ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  double total_ms() {
+    double t = 0;
+    for (int i = 0; i + 1 < used; i += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) t += ms;
+    }
+    return t;
+  }
+  void destroy() {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+// ---- NCCL through dlopen: the library itself has no link-time NCCL dependency
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(nccl_uid*) = nullptr;
+  int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(nccl_comm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+    GetUniqueId = (int (*)(nccl_uid*))dlsym(lib, "ncclGetUniqueId");
+    CommInitRank = (int (*)(nccl_comm*, int, nccl_uid, int))dlsym(lib, "ncclCommInitRank");
+    AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    CommDestroy = (int (*)(nccl_comm))dlsym(lib, "ncclCommDestroy");
+    GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+}  // namespace
+
+struct pomcp_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  pomcp_problem prob{};
+  pomcp_solver_params sp{};
+  DevModel dm{};
+  double* d_eta = nullptr;
+  int nA = 0, nO = 0, state_bytes = 4, levels = 0;
+  bool hashed = false, exact = false, unweighted = true;
+  double log_ratio = 0;
+  double* d_gpow = nullptr;
+  Pool pool{};
+  size_t ht_entries = 0;
+  WaveBuf wb{};
+  int wave_cap = 0, wave_min = 32, wave_max = 32768, ramp_div = 8;
+  void* d_bel[2] = {nullptr, nullptr};
+  size_t bel_cap[2] = {0, 0};
+  int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles
+  long long n_bel = 0;
+  uint32_t root = 0, epoch = 0;
+  long long root_visits = 0;
+  unsigned long long nodes_used = 1, log_used = 0;
+  SearchResult* d_res = nullptr;
+  SearchResult* h_res = nullptr;
+  DevCtr* h_ctr = nullptr;
+  PfCtl* d_pfctl = nullptr;
+  PfCtl* h_pfctl = nullptr;
+  NodeStats* d_ns = nullptr;
+  NodeStats* h_ns = nullptr;
+  unsigned long long* d_cum = nullptr;
+  size_t cum_cap = 0;
+  unsigned long long* d_scan_status = nullptr;  // [0] = ticket, [1..] = tile status
+  size_t scan_cap = 0;
+  void* d_tmp = nullptr;
+  size_t tmp_cap = 0;
+  void* d_tmp2 = nullptr;
+  size_t tmp2_cap = 0;
+  float4* d_flush = nullptr;
+  size_t flush_n = 0;
+  PhaseTimer timers[POMCP_PHASE_COUNT];
+  pomcp_counters host_ctr{};
+  long long launches = 0, last_waves = 0;
+  bool pending = false;
+  nccl_comm comm = nullptr;
+  int nranks = 1;
+  std::string err;
+};
+
+namespace {
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                  \
+      return POMCP_ERR_CUDA;                                                                         \
+    }                                                                                                \
+  } while (0)
+
+#define DISPATCH_PID(pid, ...)                                                       \
+  switch (pid) {                                                                     \
+    case POMCP_TIGER: { constexpr int PID = POMCP_TIGER; __VA_ARGS__; } break;       \
+    case POMCP_BABY: { constexpr int PID = POMCP_BABY; __VA_ARGS__; } break;         \
+    case POMCP_ROCKSAMPLE: { constexpr int PID = POMCP_ROCKSAMPLE; __VA_ARGS__; } break; \
+    default: { constexpr int PID = POMCP_LIGHTDARK1D; __VA_ARGS__; } break;          \
+  }
+
+int fail(pomcp_handle* h, int st, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return st;
+}
+
+int model_dims(const pomcp_problem* p, int& nA, int& nO, int& sb) {
+  switch (p->problem_id) {
+    case POMCP_TIGER: nA = 3; nO = 2; sb = 4; return POMCP_OK;
+    case POMCP_BABY: nA = 2; nO = 2; sb = 4; return POMCP_OK;
+    case POMCP_ROCKSAMPLE:
+      if (p->rs_n < 1 || p->rs_n > 15 || p->rs_k < 0 || p->rs_k > POMCP_MAX_ROCKS) return POMCP_ERR_INVALID_ARG;
+      nA = 5 + p->rs_k; nO = 3; sb = 4; return POMCP_OK;
+    case POMCP_LIGHTDARK1D: nA = 3; nO = 0; sb = 16; return POMCP_OK;
+  }
+  return POMCP_ERR_INVALID_ARG;
+}
+
+template <class T>
+int dev_alloc(pomcp_handle* h, T** p, size_t n) {
+  CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+  return POMCP_OK;
+}
+
+int ensure_bytes(pomcp_handle* h, void** p, size_t* cap, size_t need) {
+  if (need <= *cap) return POMCP_OK;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr;
+  size_t nc = std::max<size_t>(need, 256);
+  CK(cudaMalloc(p, nc));
+  *cap = nc;
+  return POMCP_OK;
+}
+
+int launch_check(pomcp_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    h->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return POMCP_ERR_CUDA;
+  }
+  h->launches++;
+  return POMCP_OK;
+}
+
+int pool_fill(pomcp_handle* h, unsigned long long n_nodes) {
+  if (n_nodes == 0) return POMCP_OK;
+  unsigned long long work = n_nodes * (unsigned long long)h->nA * (unsigned long long)std::max(h->nO, 1);
+  int blocks = (int)std::min<unsigned long long>((work + 255) / 256, 148ull * 16);
+  k_pool_fill<<<blocks, 256, 0, h->stream>>>(h->pool, h->nA, h->nO, n_nodes, (uint32_t)h->sp.init_N, h->sp.init_V,
+                                             h->exact ? 1 : 0);
+  return launch_check(h, "k_pool_fill");
+}
+
+// RootNode(0, b, {}) (src/solver.jl:278-281): wipe what the previous tree used, root = node 0
+int fresh_root(pomcp_handle* h) {
+  int rc = pool_fill(h, std::min<unsigned long long>(h->nodes_used, h->pool.max_nodes));
+  if (rc) return rc;
+  if (h->hashed) CK(cudaMemsetAsync(h->pool.ht, 0, h->ht_entries * sizeof(uint32_t), h->stream));
+  DevCtr z{};
+  z.node_count = 1;
+  // keep cumulative counters: only the allocation cursors restart
+  CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->h_ctr->node_count = 1;
+  h->h_ctr->log_count = 0;
+  h->h_ctr->pool_overflow = h->h_ctr->log_overflow = h->h_ctr->replay_overflow = 0;
+  CK(cudaMemcpyAsync(h->pool.ctr, h->h_ctr, sizeof(DevCtr), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->root = 0;
+  h->root_visits = 0;
+  h->nodes_used = 1;
+  h->log_used = 0;
+  return POMCP_OK;
+}
+
+SearchCfg make_cfg(pomcp_handle* h) {
+  SearchCfg c{};
+  c.c = h->sp.c;
+  c.init_V = h->sp.init_V;
+  c.init_N = h->sp.init_N;
+  c.log_ratio = h->log_ratio;
+  c.est_value = h->sp.estimator_value;
+  c.max_depth = h->sp.max_depth;
+  c.gpow = h->d_gpow;
+  c.levels = h->levels;
+  c.belief_unweighted = h->unweighted ? 1 : 0;
+  c.estimator = h->sp.estimator;
+  c.key0 = (uint32_t)h->sp.seed;
+  c.key1 = (uint32_t)(h->sp.seed >> 32);
+  c.rank = (uint32_t)h->sp.rank;
+  c.epoch = h->epoch;
+  c.bel = (h->bel_kind == 2) ? h->d_bel[h->bel_cur] : nullptr;
+  c.n_bel = h->n_bel;
+  c.root = h->root;
+  return c;
+}
+
+int reset_search_flags(pomcp_handle* h) {
+  // any_nonterminal / overflow flags are per search
+  size_t off = offsetof(DevCtr, pool_overflow);
+  CK(cudaMemsetAsync((char*)h->pool.ctr + off, 0, sizeof(DevCtr) - off, h->stream));
+  return POMCP_OK;
+}
+
+int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long n_uni, const double* d_rets,
+                   long long n_rets) {
+  if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
+  if (Q < 0) Q = h->sp.tree_queries;
+  if (Q >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "tree_queries must be < 2^32");
+  int rc = reset_search_flags(h);
+  if (rc) return rc;
+  SearchCfg cfg = make_cfg(h);
+  const bool replay = d_uni != nullptr;
+  cfg.uni = d_uni; cfg.n_uni = n_uni; cfg.rets = d_rets; cfg.n_rets = n_rets;
+  PhaseTimer& ts = h->timers[POMCP_PHASE_SEARCH];
+  PhaseTimer& tr = h->timers[POMCP_PHASE_ROLLOUT];
+  ts.reset(); tr.reset();
+  h->last_waves = 0;
+  CK(cudaEventRecord(ts.next(), h->stream));
+  if (h->exact || replay) {
+    if (!h->exact) return fail(h, POMCP_ERR_INVALID_ARG, "replay needs search_mode = exact");
+    DISPATCH_PID(h->prob.problem_id, {
+      if (replay) k_search_exact<PID, true><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, Q, h->d_res);
+      else k_search_exact<PID, false><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, Q, h->d_res);
+    });
+    rc = launch_check(h, "k_search_exact");
+    if (rc) return rc;
+    ts.launches++;
+    h->root_visits += Q;
+  } else {
+    long long q = 0;
+    while (q < Q) {
+      long long B = h->root_visits / h->ramp_div;
+      B = std::max<long long>(B, h->wave_min);
+      B = std::min<long long>(B, h->wave_max);
+      B = std::min<long long>(B, Q - q);
+      int wave = (int)B;
+      DISPATCH_PID(h->prob.problem_id, {
+        k_descend<PID><<<(wave * 32 + 127) / 128, 128, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, wave, (uint32_t)q);
+      });
+      rc = launch_check(h, "k_descend");
+      if (rc) return rc;
+      CK(cudaEventRecord(tr.next(), h->stream));
+      DISPATCH_PID(h->prob.problem_id, {
+        k_finish<PID><<<(wave + 255) / 256, 256, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, wave, (uint32_t)q);
+      });
+      rc = launch_check(h, "k_finish");
+      if (rc) return rc;
+      CK(cudaEventRecord(tr.next(), h->stream));
+      tr.launches++;
+      ts.launches += 2;
+      q += B;
+      h->root_visits += B;
+      h->last_waves++;
+    }
+  }
+  k_root_result<<<1, 32, 0, h->stream>>>(h->pool, h->nA, h->root, h->exact ? 1 : 0, h->sp.init_V, h->d_res);
+  rc = launch_check(h, "k_root_result");
+  if (rc) return rc;
+  ts.launches++;
+  CK(cudaEventRecord(ts.next(), h->stream));
+  h->epoch++;
+  h->pending = true;
+  return POMCP_OK;
+}
+
+// wait for the stream, pull result + counters back
+int finish_search(pomcp_handle* h) {
+  CK(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(SearchResult), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->pending = false;
+  h->nodes_used = std::max<unsigned long long>(h->h_ctr->node_count, 1);
+  h->log_used = std::min<unsigned long long>(h->h_ctr->log_count, h->pool.log_cap);
+  h->root_visits = h->h_res->root_N;
+  if (h->h_res->status == POMCP_ERR_POOL_EXHAUSTED)
+    h->err = "node pool or particle log exhausted (raise max_nodes / max_log)";
+  return h->h_res->status;
+}
+
+void copy_out(pomcp_handle* h, int32_t* action_out, int64_t* N, double* V, int32_t nA) {
+  if (action_out) *action_out = h->h_res->action;
+  for (int a = 0; a < h->nA && a < nA; ++a) {
+    if (N) N[a] = h->h_res->N[a];
+    if (V) V[a] = h->h_res->V[a];
+  }
+}
+
+template <int PID>
+ModelSrc<PID> make_src(pomcp_handle* h, const void* states, int a, uint64_t obs, uint64_t seed) {
+  ModelSrc<PID> s;
+  s.states = (const typename ModelT<PID>::State*)states;
+  s.m = h->dm;
+  s.a = a;
+  s.obs = obs;
+  s.k0 = (uint32_t)seed;
+  s.k1 = (uint32_t)(seed >> 32);
+  return s;
+}
+
+int ensure_scan(pomcp_handle* h, long long n) {
+  size_t tiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2;
+  int rc = ensure_bytes(h, (void**)&h->d_scan_status, &h->scan_cap, tiles * sizeof(unsigned long long));
+  if (rc) return rc;
+  CK(cudaMemsetAsync(h->d_scan_status, 0, tiles * sizeof(unsigned long long), h->stream));
+  return POMCP_OK;
+}
+
+// K6 -> K7 -> K8 on an arbitrary weight source
+template <class Src, class Out>
+int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long long n_out, Out* d_out) {
+  int rc = ensure_bytes(h, (void**)&h->d_cum, &h->cum_cap, (size_t)n * sizeof(unsigned long long));
+  if (rc) return rc;
+  rc = ensure_scan(h, n);
+  if (rc) return rc;
+  PfCtl z{};
+  z.first_alive = ~0ull;
+  *h->h_pfctl = z;
+  CK(cudaMemcpyAsync(h->d_pfctl, h->h_pfctl, sizeof(PfCtl), cudaMemcpyHostToDevice, h->stream));
+  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_pf_max<Src><<<blocks, 256, 0, h->stream>>>(src, n, h->d_pfctl);
+  rc = launch_check(h, "k_pf_max");
+  if (rc) return rc;
+  int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  k_pf_scan<Src><<<tiles, SCAN_THREADS, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, h->d_scan_status + 1,
+                                                        h->d_scan_status);
+  rc = launch_check(h, "k_pf_scan");
+  if (rc) return rc;
+  k_pf_finalize<<<1, 32, 0, h->stream>>>(h->d_cum, n, h->d_pfctl);
+  rc = launch_check(h, "k_pf_finalize");
+  if (rc) return rc;
+  k_pf_emit<Src, Out><<<(int)((n + 255) / 256), 256, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, ru, n_out, d_out);
+  rc = launch_check(h, "k_pf_emit");
+  if (rc) return rc;
+  h->timers[POMCP_PHASE_PF].launches += 4;
+  return POMCP_OK;
+}
+
+}  // namespace
+
+// ===================================================================== C ABI
+extern "C" {
+
+int32_t pomcp_abi_version(void) { return POMCP_B200_ABI_VERSION; }
+
+const char* pomcp_status_string(int32_t s) {
+  switch (s) {
+    case POMCP_OK: return "OK";
+    case POMCP_ERR_ALL_SAMPLES_TERMINAL: return "ALL_SAMPLES_TERMINAL";
+    case POMCP_ERR_PARTICLE_DEPLETION: return "PARTICLE_DEPLETION";
+    case POMCP_ERR_POOL_EXHAUSTED: return "POOL_EXHAUSTED";
+    case POMCP_ERR_UNSUPPORTED: return "UNSUPPORTED";
+    case POMCP_ERR_INVALID_ARG: return "INVALID_ARG";
+    case POMCP_ERR_CUDA: return "CUDA_ERROR";
+    case POMCP_ERR_NCCL: return "NCCL_ERROR";
+    case POMCP_ERR_NAN_VALUE: return "NAN_VALUE";
+  }
+  return "UNKNOWN";
+}
+
+const char* pomcp_last_error(const pomcp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void pomcp_default_solver_params(pomcp_solver_params* o) {  // src/constructor.jl:8-18
+  std::memset(o, 0, sizeof(*o));
+  o->eps = 0.01;
+  o->max_depth = INT64_MAX;
+  o->c = 1.0;
+  o->tree_queries = 100;
+  o->seed = 0;
+  o->init_V = 0.0;
+  o->init_N = 0;
+  o->num_sparse_actions = 0;
+  o->estimator = POMCP_EST_RANDOM_ROLLOUT;
+  o->belief_mode = POMCP_BELIEF_UNWEIGHTED;
+  o->search_mode = POMCP_MODE_BATCHED;
+}
+
+void pomcp_default_problem(int32_t pid, pomcp_problem* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->problem_id = pid;
+  p->tiger_r_listen = -1; p->tiger_r_findtiger = -100; p->tiger_r_escapetiger = 10; p->tiger_p_listen_correctly = 0.85;
+  p->baby_r_feed = -5; p->baby_r_hungry = -10; p->baby_p_become_hungry = 0.1; p->baby_p_cry_when_hungry = 0.8;
+  p->baby_p_cry_when_not_hungry = 0.1;
+  p->rs_n = 7; p->rs_k = 0; p->rs_start_x = 0; p->rs_start_y = 3; p->rs_half_eff_dist = 20;
+  p->rs_r_good = 10; p->rs_r_bad = -10; p->rs_r_exit = 10;
+  p->ld_correct_r = 10; p->ld_incorrect_r = -10; p->ld_init_mean = 2; p->ld_init_std = 3;
+  p->discount = (pid == POMCP_TIGER || pid == POMCP_ROCKSAMPLE) ? 0.95 : 0.9;
+}
+
+int32_t pomcp_num_actions(const pomcp_problem* p) {
+  int nA, nO, sb;
+  return model_dims(p, nA, nO, sb) == POMCP_OK ? nA : -1;
+}
+int32_t pomcp_state_bytes(const pomcp_problem* p) {
+  int nA, nO, sb;
+  return model_dims(p, nA, nO, sb) == POMCP_OK ? sb : -1;
+}
+
+int32_t pomcp_destroy(pomcp_handle* h) {
+  if (!h) return POMCP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  void* ptrs[] = {h->d_eta, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
+                  h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
+                  h->pool.log_state, h->pool.ctr, h->wb.path_slot, h->wb.path_node, h->wb.path_r, h->wb.path_state,
+                  h->wb.leaf_state, h->wb.leaf_info, h->d_bel[0], h->d_bel[1], h->d_res, h->d_pfctl, h->d_ns,
+                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->h_res) cudaFreeHost(h->h_res);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  if (h->h_pfctl) cudaFreeHost(h->h_pfctl);
+  if (h->h_ns) cudaFreeHost(h->h_ns);
+  for (auto& t : h->timers) t.destroy();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return POMCP_OK;
+}
+
+int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int32_t device, pomcp_handle** out) {
+  if (!p || !sp || !out) return fail(nullptr, POMCP_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  int nA, nO, sb;
+  if (model_dims(p, nA, nO, sb) != POMCP_OK) return fail(nullptr, POMCP_ERR_INVALID_ARG, "bad problem descriptor");
+  if (!(p->discount > 0.0) || !(p->discount < 1.0))
+    return fail(nullptr, POMCP_ERR_INVALID_ARG, "discount must be in (0,1) (gamma == 1 is broken upstream, src/solver.jl:97-102)");
+  if (!(sp->eps > 0.0) || !(sp->eps < 1.0)) return fail(nullptr, POMCP_ERR_INVALID_ARG, "eps must be in (0,1)");
+  if (sp->num_sparse_actions > 0)
+    return fail(nullptr, POMCP_ERR_UNSUPPORTED, "num_sparse_actions > 0 (random action sub-sampling) is not supported");
+  if (sp->estimator != POMCP_EST_RANDOM_ROLLOUT && sp->estimator != POMCP_EST_CONSTANT)
+    return fail(nullptr, POMCP_ERR_UNSUPPORTED, "estimator");
+  if (sp->init_N < 0 || sp->max_depth < 0) return fail(nullptr, POMCP_ERR_INVALID_ARG, "init_N/max_depth < 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, POMCP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(nullptr, POMCP_ERR_INVALID_ARG, "bad device index");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, POMCP_ERR_CUDA, "device is not sm_100 class (library is built for sm_100a only)");
+
+  pomcp_handle* h = new pomcp_handle();
+  auto bail = [&](int st) {
+    g_create_error = h->err;
+    pomcp_destroy(h);
+    return st;
+  };
+#define CKC(expr) do { int rc__ = (expr); if (rc__) return bail(rc__); } while (0)
+#define CKU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e__); return bail(POMCP_ERR_CUDA); } } while (0)
+  h->device = device;
+  h->prob = *p;
+  h->sp = *sp;
+  h->nA = nA; h->nO = nO; h->state_bytes = sb;
+  h->hashed = (nO == 0);
+  h->exact = sp->search_mode == POMCP_MODE_EXACT;
+  h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
+  CKU(cudaSetDevice(device));
+  CKU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+  // horizon tables: gamma^depth < eps cut-off (src/solver.jl:82) and steps_to_eps (src/solver.jl:100)
+  h->log_ratio = std::log(sp->eps) / std::log(p->discount);
+  long long d = 0;
+  while (std::pow(p->discount, (double)d) >= sp->eps && d <= 0xffff) ++d;
+  if (d > 0xfff0) { h->err = "horizon log(eps)/log(discount) too long (> 65520 levels)"; return bail(POMCP_ERR_INVALID_ARG); }
+  h->levels = (int)std::min<long long>(d, sp->max_depth);
+  std::vector<double> gp((size_t)d + 1);
+  for (long long i = 0; i <= d; ++i) gp[(size_t)i] = std::pow(p->discount, (double)i);
+  CKC(dev_alloc(h, &h->d_gpow, gp.size()));
+  CKU(cudaMemcpy(h->d_gpow, gp.data(), gp.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+  // device model block
+  DevModel& m = h->dm;
+  m.pid = p->problem_id; m.nA = nA; m.nO = nO; m.state_bytes = sb; m.gamma = p->discount;
+  m.t_r_listen = p->tiger_r_listen; m.t_r_find = p->tiger_r_findtiger; m.t_r_escape = p->tiger_r_escapetiger;
+  m.t_p_correct = p->tiger_p_listen_correctly;
+  m.b_r_feed = p->baby_r_feed; m.b_r_hungry = p->baby_r_hungry; m.b_p_hungry = p->baby_p_become_hungry;
+  m.b_p_cry_h = p->baby_p_cry_when_hungry; m.b_p_cry_nh = p->baby_p_cry_when_not_hungry;
+  m.b_thr_hungry = (unsigned long long)std::ceil(std::min(std::max(p->baby_p_become_hungry, 0.0), 1.0) * 4294967296.0);
+  m.rs_n = p->rs_n; m.rs_k = p->rs_k;
+  m.rs_start = (unsigned)p->rs_start_x | ((unsigned)p->rs_start_y << 4);
+  m.rs_r_good = p->rs_r_good; m.rs_r_bad = p->rs_r_bad; m.rs_r_exit = p->rs_r_exit;
+  m.ld_correct = p->ld_correct_r; m.ld_incorrect = p->ld_incorrect_r; m.ld_mean = p->ld_init_mean; m.ld_std = p->ld_init_std;
+  std::memset(m.rock_at, -1, sizeof(m.rock_at));
+  if (p->problem_id == POMCP_ROCKSAMPLE) {
+    std::vector<double> eta(256 * POMCP_MAX_ROCKS, 0.0);
+    for (int i = 0; i < p->rs_k; ++i) {
+      if (p->rs_rock_x[i] < 0 || p->rs_rock_x[i] >= p->rs_n || p->rs_rock_y[i] < 0 || p->rs_rock_y[i] >= p->rs_n) {
+        h->err = "rock outside the grid";
+        return bail(POMCP_ERR_INVALID_ARG);
+      }
+      m.rock_at[p->rs_rock_y[i] * 16 + p->rs_rock_x[i]] = (signed char)i;
+    }
+    if (p->rs_start_x < 0 || p->rs_start_x >= p->rs_n || p->rs_start_y < 0 || p->rs_start_y >= p->rs_n) {
+      h->err = "start outside the grid";
+      return bail(POMCP_ERR_INVALID_ARG);
+    }
+    for (int y = 0; y < p->rs_n; ++y)
+      for (int x = 0; x < p->rs_n; ++x)
+        for (int i = 0; i < p->rs_k; ++i) {
+          double dx = (double)(x - p->rs_rock_x[i]), dy = (double)(y - p->rs_rock_y[i]);
+          double dist = std::sqrt(dx * dx + dy * dy);
+          eta[(size_t)(y * 16 + x) * POMCP_MAX_ROCKS + i] = 0.5 * (1.0 + std::exp2(-dist / p->rs_half_eff_dist));
+        }
+    CKC(dev_alloc(h, &h->d_eta, eta.size()));
+    CKU(cudaMemcpy(h->d_eta, eta.data(), eta.size() * sizeof(double), cudaMemcpyHostToDevice));
+    m.rs_eta = h->d_eta;
+  }
+
+  // wave schedule
+  h->wave_min = sp->wave_min > 0 ? sp->wave_min : 32;
+  h->wave_max = sp->wave_max > 0 ? sp->wave_max : 32768;
+  h->wave_min = std::min(h->wave_min, h->wave_max);
+  h->ramp_div = sp->wave_ramp_div > 0 ? sp->wave_ramp_div : 8;
+  h->wave_cap = h->exact ? 1 : h->wave_max;
+
+  // pool sizing
+  size_t free_b = 0, total_b = 0;
+  CKU(cudaMemGetInfo(&free_b, &total_b));
+  long long Q = std::max<long long>(sp->tree_queries, 1);
+  size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4);
+  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 16 * Q : 2 * Q) + 4096;
+  long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
+  want = std::min<long long>(want, std::min<long long>(cap_mem, (1ll << 31) - 2));
+  if (want < 16) { h->err = "not enough device memory for the node pool"; return bail(POMCP_ERR_CUDA); }
+  Pool& P = h->pool;
+  P.max_nodes = (uint32_t)want;
+  CKC(dev_alloc(h, &P.node_N, (size_t)want));
+  CKC(dev_alloc(h, &P.node_flags, (size_t)want));
+  CKC(dev_alloc(h, &P.act_N, (size_t)want * nA));
+  CKC(dev_alloc(h, &P.act_M, (size_t)want * nA));
+  CKC(dev_alloc(h, &P.act_V, (size_t)want * nA));
+  if (h->hashed) {
+    size_t e = 1;
+    while (e < (size_t)want * 2) e <<= 1;
+    h->ht_entries = e;
+    P.ht_mask = e - 1;
+    CKC(dev_alloc(h, &P.ht, e));
+    CKC(dev_alloc(h, &P.node_pslot, (size_t)want));
+    CKC(dev_alloc(h, &P.node_obs, (size_t)want));
+    CKU(cudaMemset(P.ht, 0, e * sizeof(uint32_t)));
+  } else {
+    CKC(dev_alloc(h, &P.child, (size_t)want * nA * nO));
+  }
+  long long log_want = 0;
+  if (h->unweighted) {
+    log_want = sp->max_log > 0 ? sp->max_log : want * 8;
+    long long cap_log = (long long)((free_b * 2 / 10) / (4 + (size_t)sb));
+    log_want = std::min(log_want, cap_log);
+  }
+  P.log_cap = (unsigned long long)log_want;
+  CKC(dev_alloc(h, &P.log_node, (size_t)log_want));
+  CKU(cudaMalloc(&P.log_state, std::max<size_t>((size_t)log_want * sb, 16)));
+  CKC(dev_alloc(h, &P.ctr, 1));
+  CKU(cudaMemset(P.ctr, 0, sizeof(DevCtr)));
+
+  // wave scratch
+  size_t pw = (size_t)std::max(h->levels, 1) * h->wave_cap;
+  h->wb.stride = h->wave_cap;
+  CKC(dev_alloc(h, &h->wb.path_slot, pw));
+  CKC(dev_alloc(h, &h->wb.path_node, pw));
+  CKC(dev_alloc(h, &h->wb.path_r, pw));
+  CKU(cudaMalloc(&h->wb.path_state, pw * sb));
+  CKU(cudaMalloc(&h->wb.leaf_state, (size_t)h->wave_cap * sb));
+  CKC(dev_alloc(h, &h->wb.leaf_info, (size_t)h->wave_cap));
+
+  CKC(dev_alloc(h, &h->d_res, 1));
+  CKC(dev_alloc(h, &h->d_pfctl, 1));
+  CKC(dev_alloc(h, &h->d_ns, 1));
+  CKU(cudaMallocHost((void**)&h->h_res, sizeof(SearchResult)));
+  CKU(cudaMallocHost((void**)&h->h_ctr, sizeof(DevCtr)));
+  CKU(cudaMallocHost((void**)&h->h_pfctl, sizeof(PfCtl)));
+  CKU(cudaMallocHost((void**)&h->h_ns, sizeof(NodeStats)));
+  std::memset(h->h_res, 0, sizeof(SearchResult));
+
+  h->nodes_used = want;  // first fill covers the whole pool
+  CKC(fresh_root(h));
+  CKU(cudaStreamSynchronize(h->stream));
+#undef CKC
+#undef CKU
+  *out = h;
+  return POMCP_OK;
+}
+
+int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t n) {
+  if (!h || !states || n <= 0 || n >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "bad particle array");
+  cudaSetDevice(h->device);
+  int b = h->bel_cur;
+  int rc = ensure_bytes(h, &h->d_bel[b], &h->bel_cap[b], (size_t)n * h->state_bytes);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_bel[b], states, (size_t)n * h->state_bytes, cudaMemcpyHostToDevice, h->stream));
+  h->n_bel = n;
+  h->bel_kind = 2;
+  return fresh_root(h);
+}
+
+int32_t pomcp_set_belief_initial(pomcp_handle* h) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  h->bel_kind = 1;
+  h->n_bel = 0;
+  return fresh_root(h);
+}
+
+int32_t pomcp_get_belief_particles(pomcp_handle* h, void* out, int64_t cap, int64_t* n) {
+  if (!h || !n) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  *n = (h->bel_kind == 2) ? h->n_bel : 0;
+  if (out && cap > 0 && h->bel_kind == 2) {
+    size_t cnt = (size_t)std::min<int64_t>(cap, h->n_bel);
+    CK(cudaMemcpyAsync(out, h->d_bel[h->bel_cur], cnt * h->state_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return POMCP_OK;
+}
+
+int32_t pomcp_search_async(pomcp_handle* h, int64_t Q) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  return enqueue_search(h, Q, nullptr, 0, nullptr, 0);
+}
+
+int32_t pomcp_sync(pomcp_handle* h) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->pending) return finish_search(h);
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
+}
+
+int32_t pomcp_search(pomcp_handle* h, int64_t Q, int32_t* action_out, int64_t* N, double* V, int32_t nA) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  int rc = enqueue_search(h, Q, nullptr, 0, nullptr, 0);
+  if (rc) return rc;
+  rc = finish_search(h);
+  if (rc == POMCP_OK || rc == POMCP_ERR_NAN_VALUE) copy_out(h, action_out, N, V, nA);
+  return rc;
+}
+
+int32_t pomcp_search_replay(pomcp_handle* h, int64_t Q, const double* uni, int64_t nu, const double* rets, int64_t nr,
+                            int32_t* action_out, int64_t* N, double* V, int32_t nA, int64_t* u_used,
+                            int64_t* r_used) {
+  if (!h || !uni || nu < 0 || nr < 0) return fail(h, POMCP_ERR_INVALID_ARG, "bad replay arrays");
+  cudaSetDevice(h->device);
+  if (!h->exact) return fail(h, POMCP_ERR_INVALID_ARG, "replay needs search_mode = exact");
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, (size_t)std::max<int64_t>(nu, 1) * sizeof(double));
+  if (rc) return rc;
+  rc = ensure_bytes(h, &h->d_tmp2, &h->tmp2_cap, (size_t)std::max<int64_t>(nr, 1) * sizeof(double));
+  if (rc) return rc;
+  if (nu) CK(cudaMemcpyAsync(h->d_tmp, uni, (size_t)nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (nr) CK(cudaMemcpyAsync(h->d_tmp2, rets, (size_t)nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  rc = enqueue_search(h, Q, (const double*)h->d_tmp, nu, (const double*)h->d_tmp2, nr);
+  if (rc) return rc;
+  h->epoch--;  // replay does not consume a Philox epoch
+  rc = finish_search(h);
+  if (u_used) *u_used = h->h_res->ucur;
+  if (r_used) *r_used = h->h_res->rcur;
+  if (rc == POMCP_OK) copy_out(h, action_out, N, V, nA);
+  return rc;
+}
+
+static int node_stats_impl(pomcp_handle* h, const int32_t* actions, const uint64_t* obs, int32_t depth) {
+  if (depth < 0 || depth > 64) return fail(h, POMCP_ERR_INVALID_ARG, "history depth must be in [0,64]");
+  NodeQuery q{};
+  q.depth = depth;
+  for (int d = 0; d < depth; ++d) {
+    if (actions[d] < 0 || actions[d] >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad action in history");
+    q.actions[d] = actions[d];
+    q.obs[d] = obs[d];
+  }
+  long long nb = (h->bel_kind == 2) ? h->n_bel : 0;
+  DISPATCH_PID(h->prob.problem_id, {
+    k_node_stats<PID><<<1, 32, 0, h->stream>>>(h->pool, h->dm, h->root, q, h->exact ? 1 : 0, h->sp.init_V, nb,
+                                               h->unweighted ? 1 : 0, h->d_ns);
+  });
+  int rc = launch_check(h, "k_node_stats");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_ns, h->d_ns, sizeof(NodeStats), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
+}
+
+int32_t pomcp_get_node_stats(pomcp_handle* h, const int32_t* actions, const uint64_t* obs, int32_t depth,
+                             int64_t* node_N, int64_t* n_particles, int64_t* act_N, double* act_V, int32_t nA) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  int rc = node_stats_impl(h, actions, obs, depth);
+  if (rc) return rc;
+  if (h->h_ns->node < 0) {
+    if (node_N) *node_N = -1;
+    return POMCP_OK;
+  }
+  if (node_N) *node_N = h->h_ns->N;
+  if (n_particles) *n_particles = h->h_ns->n_particles;
+  for (int a = 0; a < h->nA && a < nA; ++a) {
+    if (act_N) act_N[a] = h->h_ns->act_N[a];
+    if (act_V) act_V[a] = h->h_ns->act_V[a];
+  }
+  return POMCP_OK;
+}
+
+int32_t pomcp_get_root_stats(pomcp_handle* h, int64_t* root_N, int64_t* act_N, double* act_V, int32_t nA) {
+  return pomcp_get_node_stats(h, nullptr, nullptr, 0, root_N, nullptr, act_N, act_V, nA);
+}
+
+// update(::RootUpdater{<:ParticleReinvigorator}, b_old, a, o): src/updater.jl:13-27
+int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
+  if (a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad action");
+  PhaseTimer& t = h->timers[POMCP_PHASE_REROOT];
+  t.reset();
+  CK(cudaEventRecord(t.next(), h->stream));
+  int32_t acts[1] = {a};
+  uint64_t obs[1] = {obs_bits};
+  int rc = node_stats_impl(h, acts, obs, 1);
+  if (rc) return rc;
+  // missing child -> handle_unseen_observation; empty collection -> reinvigorate! (src/particle_filter.jl:85-92)
+  if (h->h_ns->node < 0 || h->h_ns->N == 0) return POMCP_ERR_PARTICLE_DEPLETION;
+  uint32_t child = (uint32_t)h->h_ns->node;
+  long long cnt = h->h_ns->N;
+  int nb = 1 - h->bel_cur;
+  rc = ensure_bytes(h, &h->d_bel[nb], &h->bel_cap[nb], (size_t)cnt * h->state_bytes);
+  if (rc) return rc;
+  long long n_log = (long long)h->log_used;
+  rc = ensure_scan(h, n_log);
+  if (rc) return rc;
+  int tiles = (int)((n_log + SCAN_TILE - 1) / SCAN_TILE);
+  if (tiles > 0) {
+    if (h->state_bytes == 4)
+      k_log_gather<uint32_t><<<tiles, SCAN_THREADS, 0, h->stream>>>(h->pool.log_node, (const uint32_t*)h->pool.log_state,
+                                                                  child, n_log, (uint32_t*)h->d_bel[nb], cnt,
+                                                                  h->d_scan_status + 1, h->d_scan_status);
+    else
+      k_log_gather<LDState><<<tiles, SCAN_THREADS, 0, h->stream>>>(h->pool.log_node, (const LDState*)h->pool.log_state,
+                                                                 child, n_log, (LDState*)h->d_bel[nb], cnt,
+                                                                 h->d_scan_status + 1, h->d_scan_status);
+    rc = launch_check(h, "k_log_gather");
+    if (rc) return rc;
+    k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 1, tiles, &h->d_pfctl->total);
+    rc = launch_check(h, "k_scan_total");
+    if (rc) return rc;
+    t.launches += 3;
+  }
+  CK(cudaEventRecord(t.next(), h->stream));
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  long long found = tiles > 0 ? (long long)h->h_pfctl->total : 0;
+  if (found != cnt) {
+    char buf[160];
+    std::snprintf(buf, sizeof buf, "particle log holds %lld states for the new root but N = %lld", found, cnt);
+    return fail(h, POMCP_ERR_POOL_EXHAUSTED, buf);
+  }
+  h->bel_cur = nb;
+  h->n_bel = cnt;
+  h->bel_kind = 2;
+  h->root = child;
+  h->root_visits = cnt;
+  return POMCP_OK;
+}
+
+// update(::SIRParticleFilter, b, a, o): propagate, weight, systematic resample (test/runtests.jl:57)
+int32_t pomcp_pf_update_sir(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint64_t seed, int64_t n_out) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->bel_kind != 2) return fail(h, POMCP_ERR_INVALID_ARG, "SIR update needs a particle belief");
+  if (a < 0 || a >= h->nA || n_out <= 0 || n_out >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "bad a / n_out");
+  const long long n = h->n_bel;
+  int nb = 1 - h->bel_cur;
+  int rc = ensure_bytes(h, &h->d_bel[nb], &h->bel_cap[nb], (size_t)n_out * h->state_bytes);
+  if (rc) return rc;
+  Philox4 pr = philox4x32_10(0u, TAG_RESAMPLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  PhaseTimer& t = h->timers[POMCP_PHASE_PF];
+  t.reset();
+  CK(cudaEventRecord(t.next(), h->stream));
+  DISPATCH_PID(h->prob.problem_id, {
+    auto src = make_src<PID>(h, h->d_bel[h->bel_cur], a, obs_bits, seed);
+    rc = run_resample(h, src, n, pr.w[0], n_out, (typename ModelT<PID>::State*)h->d_bel[nb]);
+  });
+  if (rc) return rc;
+  CK(cudaEventRecord(t.next(), h->stream));
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_pfctl->status != POMCP_OK) return h->h_pfctl->status;
+  h->bel_cur = nb;
+  h->n_bel = n_out;
+  return fresh_root(h);  // a ParticleCollection is not a BeliefNode: new RootNode (src/solver.jl:278-281)
+}
+
+int32_t pomcp_resample_systematic(pomcp_handle* h, const double* w, int64_t n, double r, int64_t n_out, int32_t mode,
+                                  int64_t* idx_out) {
+  if (!h || !w || !idx_out || n <= 0 || n_out <= 0 || n >= (1ll << 32) || n_out >= (1ll << 32) || !(r >= 0.0) ||
+      !(r < 1.0))
+    return fail(h, POMCP_ERR_INVALID_ARG, "bad resample arguments");
+  cudaSetDevice(h->device);
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, (size_t)n * sizeof(double));
+  if (rc) return rc;
+  rc = ensure_bytes(h, &h->d_tmp2, &h->tmp2_cap, (size_t)n_out * sizeof(long long));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tmp, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->d_tmp2, 0xff, (size_t)n_out * sizeof(long long), h->stream));
+  if (mode == 0) {
+    ArraySrc src{(const double*)h->d_tmp};
+    rc = run_resample(h, src, n, (uint32_t)(r * 4294967296.0), n_out, (long long*)h->d_tmp2);
+    if (rc) return rc;
+  } else {
+    PfCtl z{};
+    *h->h_pfctl = z;
+    CK(cudaMemcpyAsync(h->d_pfctl, h->h_pfctl, sizeof(PfCtl), cudaMemcpyHostToDevice, h->stream));
+    k_resample_seq_f64<<<1, 32, 0, h->stream>>>((const double*)h->d_tmp, n, r, n_out, (long long*)h->d_tmp2, h->d_pfctl);
+    rc = launch_check(h, "k_resample_seq_f64");
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(idx_out, h->d_tmp2, (size_t)n_out * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return h->h_pfctl->status;
+}
+
+int32_t pomcp_rollout_batch(pomcp_handle* h, const void* states, int64_t n, int32_t steps, uint64_t seed,
+                            double* ret, int32_t* steps_out) {
+  if (!h || !states || !ret || n <= 0 || n >= (1ll << 32) || steps < 0) return fail(h, POMCP_ERR_INVALID_ARG, "bad rollout batch");
+  cudaSetDevice(h->device);
+  size_t sbytes = (size_t)n * h->state_bytes;
+  size_t off_ret = (sbytes + 255) & ~(size_t)255;
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, off_ret + (size_t)n * sizeof(double));
+  if (rc) return rc;
+  rc = ensure_bytes(h, &h->d_tmp2, &h->tmp2_cap, (size_t)n * sizeof(int));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tmp, states, sbytes, cudaMemcpyHostToDevice, h->stream));
+  double* d_ret = (double*)((char*)h->d_tmp + off_ret);
+  PhaseTimer& t = h->timers[POMCP_PHASE_ROLLOUT];
+  t.reset();
+  CK(cudaEventRecord(t.next(), h->stream));
+  DISPATCH_PID(h->prob.problem_id, {
+    k_rollout_batch<PID><<<(int)((n + 255) / 256), 256, 0, h->stream>>>(
+        h->dm, (const typename ModelT<PID>::State*)h->d_tmp, n, steps, (uint32_t)seed, (uint32_t)(seed >> 32), d_ret,
+        (int*)h->d_tmp2);
+  });
+  rc = launch_check(h, "k_rollout_batch");
+  if (rc) return rc;
+  CK(cudaEventRecord(t.next(), h->stream));
+  t.launches = 1;
+  CK(cudaMemcpyAsync(ret, d_ret, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (steps_out) CK(cudaMemcpyAsync(steps_out, h->d_tmp2, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
+}
+
+int32_t pomcp_pf_weights(pomcp_handle* h, const void* states, int64_t n, int32_t a, uint64_t obs_bits, uint64_t seed,
+                         double* w_out, void* sp_out) {
+  if (!h || !states || !w_out || n <= 0 || a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad pf_weights arguments");
+  cudaSetDevice(h->device);
+  size_t sbytes = (size_t)n * h->state_bytes;
+  size_t off2 = (sbytes + 255) & ~(size_t)255;
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, off2 + sbytes);
+  if (rc) return rc;
+  rc = ensure_bytes(h, &h->d_tmp2, &h->tmp2_cap, (size_t)n * sizeof(double));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tmp, states, sbytes, cudaMemcpyHostToDevice, h->stream));
+  void* d_sp = (char*)h->d_tmp + off2;
+  DISPATCH_PID(h->prob.problem_id, {
+    auto src = make_src<PID>(h, h->d_tmp, a, obs_bits, seed);
+    k_pf_weights<PID><<<(int)((n + 255) / 256), 256, 0, h->stream>>>(src, n, (double*)h->d_tmp2,
+                                                                    (typename ModelT<PID>::State*)d_sp);
+  });
+  rc = launch_check(h, "k_pf_weights");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(w_out, h->d_tmp2, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (sp_out) CK(cudaMemcpyAsync(sp_out, d_sp, sbytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
+}
+
+int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap, int64_t* n_nodes, int64_t* node_N, int64_t* act_N, double* act_V,
+                        int32_t* child) {
+  if (!h || !n_nodes) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpy(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost));
+  long long nn = (long long)std::min<unsigned long long>(h->h_ctr->node_count, h->pool.max_nodes);
+  *n_nodes = nn;
+  long long n = std::min<long long>(nn, cap);
+  if (n <= 0) return POMCP_OK;
+  const int nA = h->nA, nO = h->nO;
+  std::vector<uint32_t> t32((size_t)n * nA * std::max(nO, 1));
+  std::vector<uint32_t> m32((size_t)n * nA);
+  std::vector<double> tv((size_t)n * nA);
+  if (node_N) {
+    CK(cudaMemcpy(t32.data(), h->pool.node_N, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; ++i) node_N[i] = t32[(size_t)i];
+  }
+  if (act_N) {
+    CK(cudaMemcpy(t32.data(), h->pool.act_N, (size_t)n * nA * 4, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n * nA; ++i) act_N[i] = t32[(size_t)i];
+  }
+  if (act_V) {
+    CK(cudaMemcpy(tv.data(), h->pool.act_V, (size_t)n * nA * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(m32.data(), h->pool.act_M, (size_t)n * nA * 4, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n * nA; ++i) {
+      double v = tv[(size_t)i];
+      if (!h->exact) v = (m32[(size_t)i] > 0 && std::isfinite(h->sp.init_V)) ? v / (double)m32[(size_t)i] : h->sp.init_V;
+      act_V[i] = v;
+    }
+  }
+  if (child && nO > 0) {
+    CK(cudaMemcpy(t32.data(), h->pool.child, (size_t)n * nA * nO * 4, cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n * nA * nO; ++i) child[i] = t32[(size_t)i] ? (int32_t)t32[(size_t)i] : -1;
+  }
+  return POMCP_OK;
+}
+
+int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out) {
+  if (!h || !out) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const DevCtr& c = *h->h_ctr;
+  out->simulations = (int64_t)c.sims;
+  out->terminal_skips = (int64_t)c.skips;
+  out->rollouts = (int64_t)c.rollouts;
+  out->rollout_steps = (int64_t)c.rollout_steps;
+  out->tree_steps = (int64_t)c.tree_steps;
+  out->nodes = (int64_t)c.node_count;
+  out->log_entries = (int64_t)c.log_count;
+  out->max_depth_seen = (int64_t)c.max_depth;
+  out->waves = h->last_waves;
+  out->kernel_launches = h->launches;
+  return POMCP_OK;
+}
+
+int32_t pomcp_reset_counters(pomcp_handle* h) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  size_t off = offsetof(DevCtr, sims), end = offsetof(DevCtr, scan_ticket);
+  CK(cudaMemsetAsync((char*)h->pool.ctr + off, 0, end - off, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->launches = 0;
+  return POMCP_OK;
+}
+
+int32_t pomcp_last_phase_ms(pomcp_handle* h, int32_t phase, double* ms, int64_t* launches) {
+  if (!h || phase < 0 || phase >= POMCP_PHASE_COUNT) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  if (ms) *ms = h->timers[phase].total_ms();
+  if (launches) *launches = h->timers[phase].launches;
+  return POMCP_OK;
+}
+
+int32_t pomcp_flush_l2(pomcp_handle* h) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->d_flush) {
+    h->flush_n = (size_t)256 * 1024 * 1024 / sizeof(float4);  // 256 MiB > 126 MB of L2
+    CK(cudaMalloc((void**)&h->d_flush, h->flush_n * sizeof(float4)));
+  }
+  k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_n);
+  return launch_check(h, "k_flush_l2");
+}
+
+// ---- K10: root-parallel merge over NCCL
+int32_t pomcp_nccl_unique_id(void* id_out) {
+  std::string err;
+  if (!id_out) return POMCP_ERR_INVALID_ARG;
+  if (!g_nccl.load(err)) return fail(nullptr, POMCP_ERR_NCCL, err);
+  nccl_uid id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclGetUniqueId");
+  std::memcpy(id_out, &id, sizeof(id));
+  return POMCP_OK;
+}
+
+int32_t pomcp_comm_init(pomcp_handle* h, const void* uid, int32_t rank, int32_t nranks) {
+  if (!h || !uid || rank < 0 || rank >= nranks) return fail(h, POMCP_ERR_INVALID_ARG, "bad comm arguments");
+  cudaSetDevice(h->device);
+  if (!g_nccl.load(h->err)) return POMCP_ERR_NCCL;
+  nccl_uid id;
+  std::memcpy(&id, uid, sizeof(id));
+  int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+  if (rc != 0) return fail(h, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
+  h->nranks = nranks;
+  h->sp.rank = rank;  // distinct Philox streams per tree
+  return POMCP_OK;
+}
+
+int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t Q, int32_t* action_out, int64_t* N, double* V, int32_t nA) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->comm) return fail(h, POMCP_ERR_INVALID_ARG, "pomcp_comm_init has not been called");
+  int rc = enqueue_search(h, Q, nullptr, 0, nullptr, 0);
+  if (rc) return rc;
+  // one fused all-reduce of [N_a ..., N_a*V_a ...] (2|A| doubles) before the arg-max of src/solver.jl:60-70
+  int nrc = g_nccl.AllReduce(h->d_res->merge, h->d_res->merge, (size_t)(2 * h->nA), NCCL_FLOAT64, NCCL_SUM, h->comm,
+                             h->stream);
+  if (nrc != 0) return fail(h, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce");
+  k_root_merge_finish<<<1, 32, 0, h->stream>>>(h->nA, h->sp.init_V, h->d_res);
+  rc = launch_check(h, "k_root_merge_finish");
+  if (rc) return rc;
+  rc = finish_search(h);
+  if (rc == POMCP_OK) copy_out(h, action_out, N, V, nA);
+  return rc;
+}
+
+}  // extern "C"

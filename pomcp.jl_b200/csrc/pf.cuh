@@ -1,0 +1,368 @@
+// K6/K7/K8 — SIR particle-filter update on the device, and K9's particle gather.
+// Replaces ParticleFilters.jl's SimpleParticleFilter.update + LowVarianceResampler.resample
+// (not vendored in the reference; call site test/runtests.jl:57, semantics SURVEY.md App. B.3)
+// and the per-node ParticleCollection of the unweighted filter (src/particle_filter.jl:27-30).
+//
+// HBM-bound design, three streaming passes, none of which stores the propagated state or the
+// fp64 weight:
+//   K6 pf_max:   read s_i                       -> max weight, first alive particle
+//   K7 pf_scan:  read s_i (L2), write C_i (8 B) -> single-pass decoupled-look-back scan of the
+//                fixed-point weights q_i = trunc(w_i * 2^s)
+//   K8 pf_emit:  read C_i (8 B), s_i (L2)       -> write the resampled states (S bytes each)
+// Fixed point makes the cumulative sums associative, so the systematic-resampling indices are
+// identical for every scan order (the oracle walks the same integers sequentially).
+#pragma once
+#include <cstdint>
+#include "models.cuh"
+#include "tree.cuh"
+
+namespace pomcp {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr unsigned long long SCAN_VAL_MASK = (1ull << 62) - 1;
+
+struct PfCtl {
+  unsigned long long max_bits;     // bits of the largest weight (weights >= 0: order-preserving)
+  unsigned long long first_alive;  // index of the first non-terminal particle
+  unsigned long long total;        // T = sum q_i
+  unsigned int any_alive, status;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+
+// Decoupled look-back (Merrill & Garland): warp 0 of the tile publishes its aggregate, then
+// polls 32 predecessors at a time until it meets an inclusive prefix.
+__device__ __forceinline__ unsigned long long scan_lookback(unsigned long long* status, int tile,
+                                                            unsigned long long aggregate) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) {
+    if (lane == 0) atomicExch(&status[0], (2ull << 62) | aggregate);
+    return 0ull;
+  }
+  if (lane == 0) atomicExch(&status[tile], (1ull << 62) | aggregate);
+  unsigned long long exclusive = 0;
+  int pos = tile - 1;
+  for (;;) {
+    int idx = pos - lane;
+    unsigned long long st = (idx >= 0) ? ld_volatile_u64(&status[idx]) : (2ull << 62);
+    unsigned flag = (unsigned)(st >> 62);
+    unsigned pref = __ballot_sync(0xffffffffu, flag == 2u);
+    unsigned none = __ballot_sync(0xffffffffu, flag == 0u);
+    int p = pref ? (__ffs(pref) - 1) : -1;
+    unsigned need = (p >= 0) ? ((p == 31) ? 0xffffffffu : ((2u << p) - 1u)) : 0xffffffffu;
+    if (none & need) continue;  // a needed predecessor has not published yet
+    unsigned long long v = ((need >> lane) & 1u) ? (st & SCAN_VAL_MASK) : 0ull;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    exclusive += v;
+    if (p >= 0) break;
+    pos -= 32;
+  }
+  if (lane == 0) atomicExch(&status[tile], (2ull << 62) | ((exclusive + aggregate) & SCAN_VAL_MASK));
+  return exclusive;
+}
+
+// Generic single-pass inclusive scan: src(i) -> u64 value (< 2^62 in total), sink(i, inclusive, value).
+// Items are warp-striped so that every load/store instruction is coalesced.
+template <class Src, class Sink>
+__device__ __forceinline__ void chained_scan(Src& src, Sink& sink, long long n, unsigned long long* status,
+                                             unsigned long long* ticket) {
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_warp[SCAN_THREADS / 32];
+  __shared__ unsigned long long s_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = (unsigned)atomicAdd(ticket, 1ull);
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const long long base = (long long)tile * SCAN_TILE + (long long)warp * 32 * SCAN_ITEMS;
+  unsigned long long v[SCAN_ITEMS], inc[SCAN_ITEMS];
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    long long i = base + j * 32 + lane;
+    v[j] = (i < n) ? src(i) : 0ull;
+    unsigned long long x = v[j];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    inc[j] = x + carry;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) s_warp[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0ull;
+    unsigned long long x = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    unsigned long long aggregate = __shfl_sync(0xffffffffu, x, 31);
+    if (lane < SCAN_THREADS / 32) s_warp[lane] = x - w;  // exclusive over warps
+    unsigned long long excl = scan_lookback(status, tile, aggregate);
+    if (lane == 0) s_excl = excl;
+  }
+  __syncthreads();
+  const unsigned long long off0 = s_excl + s_warp[warp];
+#pragma unroll
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    long long i = base + j * 32 + lane;
+    if (i < n) sink(i, off0 + inc[j], v[j]);
+  }
+}
+
+// ---- weight sources
+template <int PID>
+struct ModelSrc {
+  using M = ModelT<PID>;
+  using State = typename M::State;
+  const State* states;
+  DevModel m;
+  int a;
+  uint64_t obs;
+  uint32_t k0, k1;
+  // propagate + weight one particle: generate_s then pdf(observation(a, sp), o)
+  __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
+    State s = states[i];
+    if (M::terminal(m, s)) { sp = s; w = 0.0; return false; }  // dropped before weighting
+    Philox4 p = philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1);
+    uint64_t o;
+    double r;
+    M::template step<false, double>(m, s, a, u01(p.w[0]), 0.0, 0.0, sp, o, r);
+    w = M::obs_weight(m, a, sp, obs);
+    return true;
+  }
+};
+
+struct ArraySrc {  // replayed weights (parity hook): payload is the index itself
+  using State = long long;
+  const double* w_in;
+  __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
+    sp = i;
+    w = w_in[i];
+    return true;
+  }
+};
+
+__device__ __forceinline__ int pf_scale(unsigned long long max_bits, long long n) {
+  int e = (int)((max_bits >> 52) & 0x7ffull) - 1023;
+  int L = 0;
+  while ((1ll << L) < n) ++L;
+  return 61 - L - e;
+}
+__device__ __forceinline__ unsigned long long pf_quantise(double w, int s) {
+  return (w > 0.0) ? __double2ull_rz(ldexp(w, s)) : 0ull;
+}
+
+// K6
+template <class Src>
+__global__ void __launch_bounds__(256) k_pf_max(const __grid_constant__ Src src, long long n, PfCtl* ctl) {
+  __shared__ unsigned long long s_max[8];
+  __shared__ unsigned long long s_first[8];
+  unsigned long long mx = 0, first = ~0ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    typename Src::State sp;
+    double w;
+    bool alive = src.eval(i, sp, w);
+    if (alive) {
+      if ((unsigned long long)i < first) first = (unsigned long long)i;
+      unsigned long long b = (w > 0.0) ? d2u(w) : 0ull;
+      if (b > mx) mx = b;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, off), of = __shfl_xor_sync(0xffffffffu, first, off);
+    mx = om > mx ? om : mx;
+    first = of < first ? of : first;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_max[warp] = mx; s_first[warp] = first; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+      mx = s_max[k] > mx ? s_max[k] : mx;
+      first = s_first[k] < first ? s_first[k] : first;
+    }
+    if (first != ~0ull) {
+      atomicMax(&ctl->max_bits, mx);
+      atomicMin(&ctl->first_alive, first);
+      ctl->any_alive = 1;
+    }
+  }
+}
+
+// K7
+template <class Src>
+struct PfScanSrc {
+  Src src;
+  int scale;
+  __device__ __forceinline__ unsigned long long operator()(long long i) const {
+    typename Src::State sp;
+    double w;
+    bool alive = src.eval(i, sp, w);
+    return alive ? pf_quantise(w, scale) : 0ull;
+  }
+};
+struct CumSink {
+  unsigned long long* cum;
+  __device__ __forceinline__ void operator()(long long i, unsigned long long inc, unsigned long long) const {
+    cum[i] = inc;
+  }
+};
+template <class Src>
+__global__ void __launch_bounds__(SCAN_THREADS) k_pf_scan(const __grid_constant__ Src src, long long n,
+                                                          const PfCtl* ctl, unsigned long long* cum,
+                                                          unsigned long long* status, unsigned long long* ticket) {
+  PfScanSrc<Src> s{src, pf_scale(ctl->max_bits, n)};
+  CumSink k{cum};
+  chained_scan(s, k, n, status, ticket);
+}
+
+// number of systematic points U_m = (ru/2^32 + m) * T / n_out, m in [0, n_out), with U_m <= C
+__device__ __forceinline__ long long pf_points_below(unsigned long long C, unsigned long long T, uint32_t ru,
+                                                     long long n_out) {
+  unsigned __int128 lhs = ((unsigned __int128)C * (unsigned long long)n_out) << 32;
+  unsigned __int128 r0 = (unsigned __int128)ru * T;
+  if (lhs < r0) return 0;
+  unsigned __int128 x = (lhs - r0) >> 32;  // floor(floor(X / 2^32) / T) == floor(X / (2^32 T))
+  // quotient < 2^33: estimate in fp64, then correct exactly
+  double est = ((double)(unsigned long long)(x >> 64) * 18446744073709551616.0 + (double)(unsigned long long)x) / (double)T;
+  long long qq = (long long)est;
+  if (qq < 0) qq = 0;
+  for (;;) {
+    unsigned __int128 prod = (unsigned __int128)(unsigned long long)qq * T;
+    if (prod > x) { --qq; continue; }
+    if (x - prod >= T) { ++qq; continue; }
+    break;
+  }
+  long long cnt = qq + 1;
+  return cnt < n_out ? cnt : n_out;
+}
+
+// K8: particle i owns the output range [M(C_{i-1}), M(C_i)) and writes that many copies.
+template <class Src, class Out>
+__global__ void __launch_bounds__(256) k_pf_emit(const __grid_constant__ Src src, long long n, const PfCtl* ctl,
+                                                 const unsigned long long* cum, uint32_t ru, long long n_out,
+                                                 Out* out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long T = cum[n - 1];
+  if (T == 0) return;
+  unsigned long long C = cum[i];
+  unsigned long long Cp = i > 0 ? cum[i - 1] : 0ull;
+  typename Src::State sp;
+  double w;
+  bool alive = src.eval(i, sp, w);
+  if (!alive) return;
+  const bool is_first = (unsigned long long)i == ctl->first_alive;
+  if (C == Cp && !is_first) return;
+  long long hi = pf_points_below(C, T, ru, n_out);
+  long long lo = is_first ? 0 : pf_points_below(Cp, T, ru, n_out);
+  for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+}
+
+__global__ void k_pf_finalize(const unsigned long long* cum, long long n, PfCtl* ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ctl->total = cum[n - 1];
+  int st = POMCP_OK;
+  if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;  // "all states in the particle collection were terminal"
+  else if (ctl->max_bits == 0 || ctl->total == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
+  ctl->status = st;
+}
+
+// Upstream running-sum semantics on one thread (verification mode of pomcp_resample_systematic).
+__global__ void k_resample_seq_f64(const double* w, long long n, double r01, long long n_out, long long* idx,
+                                   PfCtl* ctl) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double W = 0.0;
+  for (long long i = 0; i < n; ++i) W += w[i];
+  if (!(W > 0.0)) { ctl->status = POMCP_ERR_PARTICLE_DEPLETION; return; }
+  double step = W / (double)n_out;
+  double U = r01 * W / (double)n_out;
+  double c = w[0];
+  long long i = 0;
+  for (long long mth = 0; mth < n_out; ++mth) {
+    while (U > c) {
+      if (i + 1 >= n) break;
+      ++i;
+      c += w[i];
+    }
+    U += step;
+    idx[mth] = i;
+  }
+  ctl->status = POMCP_OK;
+}
+
+// pomcp_pf_weights parity hook
+template <int PID>
+__global__ void k_pf_weights(const __grid_constant__ ModelSrc<PID> src, long long n, double* w_out,
+                             typename ModelT<PID>::State* sp_out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename ModelT<PID>::State sp;
+  double w;
+  src.eval(i, sp, w);
+  w_out[i] = w;
+  sp_out[i] = sp;
+}
+
+// ---- K9: gather the particles pushed at one belief node (stable stream compaction of the
+// append-only log, fused into the scan's sink).
+struct LogMatchSrc {
+  const uint32_t* log_node;
+  uint32_t target;
+  __device__ __forceinline__ unsigned long long operator()(long long i) const {
+    return log_node[i] == target ? 1ull : 0ull;
+  }
+};
+template <class State>
+struct LogGatherSink {
+  const State* log_state;
+  State* out;
+  long long cap;
+  __device__ __forceinline__ void operator()(long long i, unsigned long long inc, unsigned long long v) const {
+    if (v && (long long)inc <= cap) out[inc - 1] = log_state[i];
+  }
+};
+template <class State>
+__global__ void __launch_bounds__(SCAN_THREADS) k_log_gather(const uint32_t* log_node, const State* log_state,
+                                                             uint32_t target, long long n, State* out,
+                                                             long long cap, unsigned long long* status,
+                                                             unsigned long long* ticket) {
+  LogMatchSrc s{log_node, target};
+  LogGatherSink<State> k{log_state, out, cap};
+  chained_scan(s, k, n, status, ticket);
+}
+__global__ void k_scan_total(const unsigned long long* status, int n_tiles, unsigned long long* total_out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *total_out = status[n_tiles - 1] & SCAN_VAL_MASK;
+}
+
+// pomcp_rollout_batch parity hook (K3 alone)
+template <int PID>
+__global__ void __launch_bounds__(256) k_rollout_batch(const __grid_constant__ DevModel m,
+                                                       const typename ModelT<PID>::State* states, long long n,
+                                                       int steps, uint32_t k0, uint32_t k1, double* ret, int* ns) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int nsteps = 0;
+  ret[i] = rollout_random<PID>(m, states[i], steps, k0, k1, TAG_ROLLOUT, (uint32_t)i, 0u, nsteps);
+  ns[i] = nsteps;
+}
+
+__global__ void k_flush_l2(float4* buf, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) buf[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+}
+
+}  // namespace pomcp

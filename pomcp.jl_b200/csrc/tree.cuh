@@ -1,0 +1,610 @@
+// K1/K2/K3/K4/K5 — the search core: root sampling, warp-per-path descent with UCB1 selection
+// and child lookup/insert on the SoA node pool, thread-per-trajectory random rollouts, backup.
+// Replaces search()/simulate() (src/solver.jl:41-157), the tree node types (src/tree.jl:7-26)
+// and rollout() (src/rollout.jl:77-84) of the reference.
+//
+// Node pool in HBM (struct of arrays, ids are u32, id 0 is the first root):
+//   node_N[n]            visits of belief node n (arrivals; == reference N once a wave has drained)
+//   node_flags[n]        bit0: children expanded (src/solver.jl:87-94)
+//   act_N[n*A+a]         visits of action node (n,a), counted at descent (in-flight included)
+//   act_M[n*A+a]         completed backups (batched mode)
+//   act_V[n*A+a]         exact mode: running mean V; batched mode: W = sum of returns
+//   child[(n*A+a)*nO+o]  discrete observations: child belief node id, 0 = none
+//   ht[] / node_pslot[] / node_obs[]   continuous observations: open-addressed (slot,obs)->id
+//   log_node[] / log_state[]           append-only particle log = push!(hao.B, sp) (src/solver.jl:146-148)
+#pragma once
+#include <cstdint>
+#include "models.cuh"
+
+namespace pomcp {
+
+struct DevCtr {
+  unsigned long long node_count, log_count;
+  unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
+  unsigned long long scan_ticket;
+  unsigned int pool_overflow, log_overflow, replay_overflow, any_nonterminal;
+};
+
+struct Pool {
+  uint32_t* node_N;
+  uint32_t* node_flags;
+  uint32_t* act_N;
+  uint32_t* act_M;
+  double* act_V;
+  uint32_t* child;
+  uint32_t* ht;
+  uint32_t* node_pslot;
+  unsigned long long* node_obs;
+  uint32_t* log_node;
+  void* log_state;
+  DevCtr* ctr;
+  unsigned long long ht_mask, log_cap;
+  uint32_t max_nodes;
+};
+
+struct SearchCfg {
+  double c, init_V, log_ratio, est_value;
+  long long max_depth, init_N;
+  const double* gpow;  // gamma^d, d = 0..levels
+  int levels;          // first depth at which gamma^depth < eps (src/solver.jl:82), capped by max_depth
+  int belief_unweighted, estimator;
+  uint32_t key0, key1, rank, epoch;
+  const void* bel;  // root belief particles (NULL: the problem's initial distribution)
+  long long n_bel;
+  uint32_t root;
+  // replay (exact mode only)
+  const double* uni;
+  long long n_uni;
+  const double* rets;
+  long long n_rets;
+};
+
+// Per-wave scratch: path[level][i] and leaf[i], i = index of the simulation inside the wave.
+struct WaveBuf {
+  uint32_t* path_slot;
+  uint32_t* path_node;
+  double* path_r;
+  void* path_state;
+  void* leaf_state;
+  int* leaf_info;  // depth | flags
+  int stride;
+};
+enum : int { LEAF_ROLLOUT = 1 << 16, LEAF_SKIPPED = 1 << 17, LEAF_ABORTED = 1 << 18, LEAF_DEPTH_MASK = 0xffff };
+
+struct ReplayCursor {
+  long long ucur, rcur;
+};
+
+struct SearchResult {
+  int status, action;
+  long long root_N;
+  long long N[POMCP_MAX_ACTIONS];
+  double V[POMCP_MAX_ACTIONS];
+  double merge[2 * POMCP_MAX_ACTIONS];  // [N_a..., N_a*V_a...] for the root-parallel all-reduce
+  long long ucur, rcur;
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+  return x;
+}
+
+template <bool REPLAY>
+__device__ __forceinline__ void get_draws(const SearchCfg& cfg, ReplayCursor& rc, uint32_t tag, uint32_t idx,
+                                          uint32_t q, double out[4]) {
+  if (REPLAY) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (rc.ucur < cfg.n_uni) out[i] = cfg.uni[rc.ucur]; else out[i] = 0.0;
+      rc.ucur++;
+    }
+  } else {
+    Philox4 p = philox4x32_10(idx, tag | (cfg.rank << 8), q, cfg.epoch, cfg.key0, cfg.key1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = u01(p.w[i]);
+  }
+}
+
+// ---- K3: RolloutSimulator loop under the uniform-random policy (src/rollout.jl:77-84;
+// loop body = POMDPToolbox.RolloutSimulator).  One thread = one trajectory,
+// state in registers, one Philox block feeds 4/DPS steps; the observation is never generated
+// (VoidUpdater discards it, src/rollout.jl:104).
+template <int PID>
+__device__ __forceinline__ double rollout_random(const DevModel& m, typename ModelT<PID>::State s, long long steps,
+                                                 uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
+                                                 uint32_t epoch, int& nsteps) {
+  using M = ModelT<PID>;
+  constexpr int DPS = M::DPS;
+  const double gamma = m.gamma;
+  double disc = 1.0, total = 0.0;
+  long long step = 0;
+  bool live = !M::terminal(m, s) && steps > 0;
+  for (uint32_t blk = 0; live; ++blk) {
+    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4 / DPS; ++j) {
+      if (live) {
+        uint32_t wa = p.w[j * DPS];
+        uint32_t wt = p.w[j * DPS + (DPS - 1)];
+        int a = (int)__umulhi(wa, (uint32_t)m.nA);  // rand(rng, actions): floor(u * nA)
+        typename M::State sp;
+        uint64_t o;
+        double r;
+        M::template step<false, uint32_t>(m, s, a, wt, 0.0, 0.0, sp, o, r);
+        total += disc * r;
+        s = sp;
+        disc *= gamma;
+        ++step;
+        live = disc > 0.0 && !M::terminal(m, s) && step < steps;
+      }
+    }
+  }
+  nsteps = (int)step;
+  return total;
+}
+
+// ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only; `spare` recycles a node id
+// that lost an insertion race.
+template <int PID>
+__device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const DevModel& m, uint32_t slot,
+                                                         uint64_t obs, uint32_t& spare) {
+  using M = ModelT<PID>;
+  if (!M::HASHED) {
+    uint32_t* cs = &P.child[(size_t)slot * m.nO + (uint32_t)obs];
+    uint32_t c = __ldcg(cs);
+    if (c != 0) return c;
+    uint32_t fresh = spare ? spare : (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+    if (fresh >= P.max_nodes) {
+      P.ctr->pool_overflow = 1;
+      return 0;
+    }
+    uint32_t old = atomicCAS(cs, 0u, fresh);
+    if (old == 0) { spare = 0; return fresh; }
+    spare = fresh;
+    return old;
+  } else {
+    uint64_t h = mix64((uint64_t)slot * 0x9E3779B97F4A7C15ull ^ obs) & P.ht_mask;
+    for (;;) {
+      uint32_t id = __ldcg(&P.ht[h]);
+      if (id == 0) {
+        uint32_t fresh = spare ? spare : (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+        if (fresh >= P.max_nodes) {
+          P.ctr->pool_overflow = 1;
+          return 0;
+        }
+        P.node_pslot[fresh] = slot;
+        P.node_obs[fresh] = obs;
+        __threadfence();
+        uint32_t old = atomicCAS(&P.ht[h], 0u, fresh);
+        if (old == 0) { spare = 0; return fresh; }
+        spare = fresh;
+        id = old;
+      }
+      if (__ldcg(&P.node_pslot[id]) == slot && __ldcg(&P.node_obs[id]) == obs) return id;
+      h = (h + 1) & P.ht_mask;
+    }
+  }
+}
+
+// read-only lookup used by update / inspection
+template <int PID>
+__device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m, uint32_t slot, uint64_t obs) {
+  using M = ModelT<PID>;
+  if (!M::HASHED) {
+    if (obs >= (uint64_t)m.nO) return 0;
+    return __ldcg(&P.child[(size_t)slot * m.nO + (uint32_t)obs]);
+  } else {
+    uint64_t h = mix64((uint64_t)slot * 0x9E3779B97F4A7C15ull ^ obs) & P.ht_mask;
+    for (;;) {
+      uint32_t id = __ldcg(&P.ht[h]);
+      if (id == 0) return 0;
+      if (__ldcg(&P.node_pslot[id]) == slot && __ldcg(&P.node_obs[id]) == obs) return id;
+      h = (h + 1) & P.ht_mask;
+    }
+  }
+}
+
+// ---- K1 + K2: one warp walks one tree path (src/solver.jl:48-49, 82-142).
+// Control flow is warp-uniform; lanes hold the actions for the UCB arg-max; lane 0 issues the
+// atomics.  Visits are counted on arrival: the value returned by the node_N ticket is exactly
+// the reference's h.N for a sequential run, and in batched mode it makes concurrent simulations
+// see each other's in-flight visits (so they spread over actions instead of piling up).
+template <int PID, bool EXACT, bool REPLAY>
+__device__ __forceinline__ void descend_one(const Pool& P, const DevModel& m, const SearchCfg& cfg,
+                                            const WaveBuf& wb, int widx, uint32_t q, uint32_t root_ticket,
+                                            ReplayCursor& rc, uint32_t& spare) {
+  using M = ModelT<PID>;
+  using State = typename M::State;
+  const int lane = threadIdx.x & 31;
+  const int nA = m.nA;
+  State* path_state = (State*)wb.path_state;
+  State* leaf_state = (State*)wb.leaf_state;
+
+  // rand(rng, b): src/solver.jl:48 -> src/updater.jl:53-55
+  double u[4];
+  get_draws<REPLAY>(cfg, rc, TAG_ROOT, 0, q, u);
+  if (REPLAY) rc.ucur -= 2;  // the root draw consumes two uniforms
+  State s;
+  if (cfg.bel != nullptr) {
+    long long idx = (long long)(u[0] * (double)cfg.n_bel);
+    s = ((const State*)cfg.bel)[idx];
+  } else {
+    s = M::initial(m, u[0], u[1]);
+  }
+  if (M::terminal(m, s)) {  // src/solver.jl:49: the query is consumed
+    if (lane == 0) {
+      wb.leaf_info[widx] = LEAF_SKIPPED;
+    }
+    return;
+  }
+
+  uint32_t h = cfg.root;
+  uint32_t hN = root_ticket;
+  int depth = 0;
+  int flags = 0;
+  for (;;) {
+    // src/solver.jl:82-86
+    if (depth >= cfg.levels || M::terminal(m, s)) break;
+    // src/solver.jl:87-107: first non-cut-off visitor expands and evaluates the leaf
+    uint32_t fl = __ldcg(&P.node_flags[h]);
+    if (!(fl & 1u)) {
+      uint32_t old = 0;
+      if (lane == 0) old = EXACT ? fl : atomicOr(&P.node_flags[h], 1u);
+      if (EXACT && lane == 0) P.node_flags[h] = fl | 1u;
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (!(old & 1u)) {
+        if (depth > 0) flags |= LEAF_ROLLOUT;
+        break;
+      }
+    }
+    // UCB1: src/solver.jl:109-124
+    double crit = 0.0;
+    bool valid = false;
+    if (lane < nA) {
+      uint32_t slot = h * (uint32_t)nA + (uint32_t)lane;
+      uint32_t n = __ldcg(&P.act_N[slot]);
+      double v = __ldcg(&P.act_V[slot]);
+      if (!EXACT) {
+        uint32_t mm = __ldcg(&P.act_M[slot]);
+        v = (mm > 0 && v == v && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
+      }
+      uint32_t hn = EXACT ? hN : (hN < 1u ? 1u : hN);
+      if (n == 0 && hn == 1) crit = v;
+      else if (n == 0 && v == -INFINITY) crit = INFINITY;
+      else crit = v + cfg.c * sqrt(det_log((double)hn) / (double)n);
+      valid = (crit == crit);
+    }
+    int best_a = lane;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double oc = __shfl_xor_sync(0xffffffffu, crit, off);
+      int oa = __shfl_xor_sync(0xffffffffu, best_a, off);
+      bool ov = __shfl_xor_sync(0xffffffffu, (int)valid, off) != 0;
+      bool take = ov && (!valid || oc > crit || (oc == crit && oa > best_a));  // ">=": last index wins ties
+      if (take) { crit = oc; best_a = oa; valid = true; }
+    }
+    valid = __shfl_sync(0xffffffffu, (int)valid, 0) != 0;
+    best_a = __shfl_sync(0xffffffffu, best_a, 0);
+    if (!valid) best_a = nA - 1;
+    const uint32_t slot = h * (uint32_t)nA + (uint32_t)best_a;
+
+    // src/solver.jl:126
+    get_draws<REPLAY>(cfg, rc, TAG_TREE, (uint32_t)depth, q, u);
+    State sp;
+    uint64_t o;
+    double r;
+    M::template step<true, double>(m, s, best_a, u[0], u[2], u[3], sp, o, r);
+
+    // src/solver.jl:132-142 + arrival counting
+    uint32_t hao = 0, ticket = 0;
+    if (lane == 0) {
+      if (EXACT) P.act_N[slot] = __ldcg(&P.act_N[slot]) + 1u; else atomicAdd(&P.act_N[slot], 1u);
+      hao = find_or_insert_child<PID>(P, m, slot, o, spare);
+      if (hao != 0) {
+        if (EXACT) { ticket = __ldcg(&P.node_N[hao]); P.node_N[hao] = ticket + 1u; }
+        else ticket = atomicAdd(&P.node_N[hao], 1u);
+        size_t pi = (size_t)depth * wb.stride + widx;
+        wb.path_slot[pi] = slot;
+        wb.path_node[pi] = hao;
+        wb.path_r[pi] = r;
+        path_state[pi] = sp;
+      }
+    }
+    hao = __shfl_sync(0xffffffffu, hao, 0);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (hao == 0) { flags |= LEAF_ABORTED; break; }
+    h = hao;
+    hN = ticket;
+    s = sp;
+    ++depth;
+  }
+  if (lane == 0) {
+    leaf_state[widx] = s;
+    wb.leaf_info[widx] = depth | flags;
+  }
+}
+
+// ---- K3 + K4 for one simulation (one thread): leaf evaluation (src/solver.jl:97-103), then the
+// backup R = r + gamma*R' bottom-up (src/solver.jl:144-156) and the particle pushes.
+// AGG: level-0 (root action) sums go through shared memory first, one global atomic per CTA/action.
+template <int PID, bool EXACT, bool REPLAY, bool AGG>
+__device__ __forceinline__ void finish_one(const Pool& P, const DevModel& m, const SearchCfg& cfg, const WaveBuf& wb,
+                                           int widx, uint32_t q, bool active, ReplayCursor& rc, double* sW,
+                                           unsigned* sM, unsigned long long* sCtr) {
+  using M = ModelT<PID>;
+  using State = typename M::State;
+  const State* path_state = (const State*)wb.path_state;
+  const State* leaf_state = (const State*)wb.leaf_state;
+  int info = active ? wb.leaf_info[widx] : LEAF_SKIPPED;
+  int depth = info & LEAF_DEPTH_MASK;
+  bool skipped = (info & LEAF_SKIPPED) != 0 || !active;
+  bool aborted = (info & LEAF_ABORTED) != 0;
+  double leaf = 0.0;
+  int nsteps = 0;
+  bool did_rollout = false;
+  if (!skipped && !aborted && (info & LEAF_ROLLOUT)) {
+    long long steps_to_eps = (long long)ceil(cfg.log_ratio - (double)depth);
+    long long steps = min(cfg.max_depth - (long long)depth, steps_to_eps);
+    double est;
+    if (REPLAY) {
+      est = (rc.rcur < cfg.n_rets) ? cfg.rets[rc.rcur] : 0.0;
+      rc.rcur++;
+    } else if (cfg.estimator == POMCP_EST_CONSTANT) {
+      est = cfg.est_value;  // src/rollout.jl:10
+    } else {
+      est = rollout_random<PID>(m, leaf_state[widx], steps, cfg.key0, cfg.key1, TAG_ROLLOUT | (cfg.rank << 8), q,
+                                cfg.epoch, nsteps);
+    }
+    leaf = cfg.gpow[depth] * est;  // src/solver.jl:103
+    did_rollout = true;
+  }
+  const bool live = !skipped && !aborted;
+
+  // particle log reservation: one atomic per warp
+  unsigned long long log_base = 0;
+  if (cfg.belief_unweighted) {
+    int len = live ? depth : 0;
+    int incl = len;
+    const int lane = threadIdx.x & 31;
+    if (AGG) {
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      int total = __shfl_sync(0xffffffffu, incl, 31);
+      unsigned long long base = 0;
+      if (lane == 0 && total > 0) base = atomicAdd(&P.ctr->log_count, (unsigned long long)total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      log_base = base + (unsigned long long)(incl - len);
+    } else if (len > 0) {
+      log_base = P.ctr->log_count;
+      P.ctr->log_count = log_base + len;
+    }
+    if (len > 0 && log_base + len > P.log_cap) {
+      P.ctr->log_overflow = 1;
+      log_base = ~0ull;
+    }
+  }
+
+  if (live) {
+    double R = leaf;
+    State* log_state = (State*)P.log_state;
+    for (int d = depth - 1; d >= 0; --d) {
+      size_t pi = (size_t)d * wb.stride + widx;
+      R = wb.path_r[pi] + m.gamma * R;
+      uint32_t slot = wb.path_slot[pi];
+      if (cfg.belief_unweighted && log_base != ~0ull) {
+        // deepest level first, like the unwinding recursion (src/solver.jl:146-148)
+        unsigned long long li = log_base + (unsigned long long)(depth - 1 - d);
+        P.log_node[li] = wb.path_node[pi];
+        log_state[li] = path_state[pi];
+      }
+      if (EXACT) {
+        double v = P.act_V[slot];
+        if (v != -INFINITY) P.act_V[slot] = v + (R - v) / (double)P.act_N[slot];  // src/solver.jl:151-154
+      } else if (AGG && d == 0) {
+        uint32_t a = slot - cfg.root * (uint32_t)m.nA;
+        atomicAdd(&sW[a], R);
+        atomicAdd(&sM[a], 1u);
+      } else {
+        atomicAdd(&P.act_V[slot], R);
+        atomicAdd(&P.act_M[slot], 1u);
+      }
+    }
+  }
+  // counters
+  if (AGG) {
+    if (live) atomicAdd(&sCtr[0], 1ull);
+    if (skipped && active) atomicAdd(&sCtr[1], 1ull);
+    if (did_rollout) { atomicAdd(&sCtr[2], 1ull); atomicAdd(&sCtr[3], (unsigned long long)nsteps); }
+    if (live) { atomicAdd(&sCtr[4], (unsigned long long)depth); atomicMax(&sCtr[5], (unsigned long long)depth); }
+  } else {
+    DevCtr* c = P.ctr;
+    if (live) { c->sims++; c->tree_steps += depth; if ((unsigned long long)depth > c->max_depth) c->max_depth = depth; }
+    if (skipped && active) c->skips++;
+    if (did_rollout) { c->rollouts++; c->rollout_steps += nsteps; }
+    if (live) { P.node_N[cfg.root] += 1u; c->any_nonterminal = 1; }  // b.N += 1, src/solver.jl:51
+  }
+}
+
+// ---- batched mode: one wave = descend kernel (warp per path) + finish kernel (thread per path)
+template <int PID>
+__global__ void __launch_bounds__(128) k_descend(const __grid_constant__ Pool P, const __grid_constant__ DevModel m,
+                                                 const __grid_constant__ SearchCfg cfg,
+                                                 const __grid_constant__ WaveBuf wb, int wave, uint32_t q_base) {
+  int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (warp >= wave) return;
+  ReplayCursor rc{0, 0};
+  uint32_t spare = 0;
+  uint32_t root_ticket = __ldcg(&P.node_N[cfg.root]) + (uint32_t)warp;
+  descend_one<PID, false, false>(P, m, cfg, wb, warp, q_base + (uint32_t)warp, root_ticket, rc, spare);
+}
+
+template <int PID>
+__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Pool P, const __grid_constant__ DevModel m,
+                                                const __grid_constant__ SearchCfg cfg,
+                                                const __grid_constant__ WaveBuf wb, int wave, uint32_t q_base) {
+  __shared__ double sW[POMCP_MAX_ACTIONS];
+  __shared__ unsigned sM[POMCP_MAX_ACTIONS];
+  __shared__ unsigned long long sCtr[6];
+  if (threadIdx.x < POMCP_MAX_ACTIONS) { sW[threadIdx.x] = 0.0; sM[threadIdx.x] = 0u; }
+  if (threadIdx.x < 6) sCtr[threadIdx.x] = 0ull;
+  __syncthreads();
+  int widx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  ReplayCursor rc{0, 0};
+  finish_one<PID, false, false, true>(P, m, cfg, wb, widx, q_base + (uint32_t)widx, widx < wave, rc, sW, sM, sCtr);
+  __syncthreads();
+  if (threadIdx.x < m.nA && sM[threadIdx.x] > 0) {
+    uint32_t slot = cfg.root * (uint32_t)m.nA + threadIdx.x;
+    atomicAdd(&P.act_V[slot], sW[threadIdx.x]);
+    atomicAdd(&P.act_M[slot], sM[threadIdx.x]);
+  }
+  if (threadIdx.x == 0) {
+    DevCtr* c = P.ctr;
+    if (sCtr[0]) {
+      atomicAdd(&c->sims, sCtr[0]);
+      atomicAdd(&P.node_N[cfg.root], (uint32_t)sCtr[0]);  // b.N += 1 per simulation, src/solver.jl:51
+      c->any_nonterminal = 1;
+    }
+    if (sCtr[1]) atomicAdd(&c->skips, sCtr[1]);
+    if (sCtr[2]) { atomicAdd(&c->rollouts, sCtr[2]); atomicAdd(&c->rollout_steps, sCtr[3]); }
+    if (sCtr[4]) atomicAdd(&c->tree_steps, sCtr[4]);
+    atomicMax(&c->max_depth, sCtr[5]);
+  }
+}
+
+// ---- exact mode: one warp runs the queries strictly one after another (bit-parity with the
+// sequential reference; also the replay hook).
+template <int PID, bool REPLAY>
+__global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Pool P,
+                                                     const __grid_constant__ DevModel m,
+                                                     const __grid_constant__ SearchCfg cfg,
+                                                     const __grid_constant__ WaveBuf wb, long long queries,
+                                                     SearchResult* res) {
+  ReplayCursor rc{0, 0};
+  uint32_t spare = 0;
+  const int lane = threadIdx.x & 31;
+  for (long long q = 0; q < queries; ++q) {
+    uint32_t root_ticket = __ldcg(&P.node_N[cfg.root]);
+    descend_one<PID, true, REPLAY>(P, m, cfg, wb, 0, (uint32_t)q, root_ticket, rc, spare);
+    __syncwarp();
+    if (lane == 0) finish_one<PID, true, REPLAY, false>(P, m, cfg, wb, 0, (uint32_t)q, true, rc, nullptr, nullptr, nullptr);
+    rc.rcur = __shfl_sync(0xffffffffu, rc.rcur, 0);
+    __threadfence_block();
+    __syncwarp();
+  }
+  if (lane == 0) {
+    res->ucur = rc.ucur;
+    res->rcur = rc.rcur;
+    if (REPLAY && (rc.ucur > cfg.n_uni || rc.rcur > cfg.n_rets)) P.ctr->replay_overflow = 1;
+  }
+}
+
+// ---- K5: root statistics + arg-max V with ">=" (src/solver.jl:60-70); also packs the
+// [N_a, N_a*V_a] vector for the root-parallel merge (K10).
+__global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t root, int exact, double init_V,
+                              SearchResult* res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  DevCtr* c = P.ctr;
+  res->root_N = P.node_N[root];
+  int best = 0;
+  double best_V = 0.0;
+  for (int a = 0; a < nA; ++a) {
+    uint32_t slot = root * (uint32_t)nA + a;
+    double v = P.act_V[slot];
+    long long n = P.act_N[slot];
+    if (!exact) {
+      uint32_t mm = P.act_M[slot];
+      v = (mm > 0 && fabs(init_V) != INFINITY) ? v / (double)mm : init_V;
+    }
+    res->N[a] = n;
+    res->V[a] = v;
+    res->merge[a] = (double)n;
+    res->merge[nA + a] = (double)n * v;
+    if (a == 0 || v >= best_V) { best_V = v; best = a; }
+  }
+  res->action = best;
+  int st = POMCP_OK;
+  if (res->V[0] != res->V[0]) st = POMCP_ERR_NAN_VALUE;           // @assert !isnan(best_V), src/solver.jl:62
+  if (!c->any_nonterminal) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;    // src/solver.jl:56-58
+  if (c->pool_overflow || c->log_overflow) st = POMCP_ERR_POOL_EXHAUSTED;
+  if (c->replay_overflow) st = POMCP_ERR_INVALID_ARG;
+  res->status = st;
+}
+
+// after the all-reduce: V_a = sum(N*V)/sum(N), then the reference's arg-max rule
+__global__ void k_root_merge_finish(int nA, double init_V, SearchResult* res) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int best = 0;
+  double best_V = 0.0;
+  for (int a = 0; a < nA; ++a) {
+    double n = res->merge[a], nv = res->merge[nA + a];
+    double v = n > 0.0 ? nv / n : init_V;
+    res->N[a] = (long long)n;
+    res->V[a] = v;
+    if (a == 0 || v >= best_V) { best_V = v; best = a; }
+  }
+  res->action = best;
+}
+
+// ---- pool (re)initialisation: ActNode(a, init_N, init_V, {}) for every slot (src/solver.jl:89-93)
+__global__ void k_pool_fill(const __grid_constant__ Pool P, int nA, int nO, unsigned long long n_nodes,
+                            uint32_t init_N, double init_V, int exact) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  double v0 = exact ? init_V : (init_N > 0 && fabs(init_V) != INFINITY ? init_V * (double)init_N : 0.0);
+  for (unsigned long long k = i; k < n_nodes * nA; k += stride) {
+    P.act_N[k] = init_N;
+    P.act_M[k] = init_N;
+    P.act_V[k] = v0;
+  }
+  for (unsigned long long k = i; k < n_nodes; k += stride) {
+    P.node_N[k] = 0;
+    P.node_flags[k] = 0;
+    if (P.node_pslot) { P.node_pslot[k] = 0; P.node_obs[k] = 0; }
+  }
+  if (P.child)
+    for (unsigned long long k = i; k < n_nodes * nA * nO; k += stride) P.child[k] = 0;
+}
+
+// ---- inspection / update helpers (single thread)
+struct NodeQuery {
+  int depth;
+  int actions[64];
+  unsigned long long obs[64];
+};
+struct NodeStats {
+  long long node;  // -1: absent
+  long long N, n_particles;
+  long long act_N[POMCP_MAX_ACTIONS];
+  double act_V[POMCP_MAX_ACTIONS];
+};
+
+template <int PID>
+__global__ void k_node_stats(const __grid_constant__ Pool P, const __grid_constant__ DevModel m, uint32_t root,
+                             const __grid_constant__ NodeQuery qy, int exact, double init_V, long long n_bel,
+                             int unweighted, NodeStats* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t h = root;
+  for (int d = 0; d < qy.depth; ++d) {
+    uint32_t c = find_child<PID>(P, m, h * (uint32_t)m.nA + (uint32_t)qy.actions[d], qy.obs[d]);
+    if (c == 0) { out->node = -1; return; }
+    h = c;
+  }
+  out->node = h;
+  out->N = P.node_N[h];
+  out->n_particles = (h == root) ? n_bel : (unweighted ? (long long)P.node_N[h] : 0);
+  for (int a = 0; a < m.nA; ++a) {
+    uint32_t slot = h * (uint32_t)m.nA + a;
+    double v = P.act_V[slot];
+    if (!exact) {
+      uint32_t mm = P.act_M[slot];
+      v = (mm > 0 && fabs(init_V) != INFINITY) ? v / (double)mm : init_V;
+    }
+    out->act_N[a] = P.act_N[slot];
+    out->act_V[a] = v;
+  }
+}
+
+}  // namespace pomcp

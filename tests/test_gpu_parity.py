@@ -1,0 +1,375 @@
+"""GPU parity tests: every CUDA path is called through the C ABI (via the host mirror) and compared
+with the CPU oracle on the same seeded inputs.  Integer / index / count results must be bit-exact;
+fp64 values that go through identical IEEE operation sequences must be bit-exact too; the batched
+search (atomics, waves in flight) is compared statistically with the tolerance written in the test."""
+import numpy as np
+import pytest
+
+import pomcp_jl_b200 as pj
+from pomcp_jl_b200 import _abi as abi
+
+from helpers import make_pair, problems, random_states
+
+pytestmark = pytest.mark.gpu
+
+PROBS = problems()
+
+
+def _bits(a):
+    return np.asarray(a, dtype=np.float64).view(np.uint64)
+
+
+# ----------------------------------------------------------------------------- K3 rollouts
+@pytest.mark.parametrize("name", list(PROBS))
+def test_rollout_batch_bit_exact(oracle, gpu_lib, name):
+    pomdp, c = PROBS[name]
+    gp, _ = make_pair(oracle, pomdp, c, seed=3)
+    rng = np.random.default_rng(1)
+    states = random_states(pomdp, 20000, rng)
+    for steps in (0, 1, 7, 89):
+        ret_g, ns_g = gp.rollout_batch(states, steps, seed=0xDEADBEEF12345)
+        ret_o, ns_o = oracle.rollout_batch(pomdp, states, steps, seed=0xDEADBEEF12345)
+        assert np.array_equal(ns_g, ns_o), (name, steps)
+        assert np.array_equal(_bits(ret_g), _bits(ret_o)), (name, steps, np.abs(ret_g - ret_o).max())
+    assert ns_g.max() <= 89 and (ns_g > 0).any()
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- K6 weights
+@pytest.mark.parametrize("name", list(PROBS))
+def test_pf_weights_bit_exact(oracle, gpu_lib, name):
+    pomdp, c = PROBS[name]
+    gp, _ = make_pair(oracle, pomdp, c, seed=3)
+    rng = np.random.default_rng(2)
+    states = random_states(pomdp, 30000, rng)
+    obs_list = [3.0, -1.25, 7.5] if pomdp.continuous_obs else list(range(pomdp.n_observations))
+    for a in range(pomdp.n_actions):
+        for o in obs_list[:2]:
+            w_g, sp_g = gp.pf_weights(states, a, o, seed=77)
+            w_o, sp_o = oracle.pf_weights(pomdp, states, a, o, seed=77)
+            assert np.array_equal(_bits(w_g), _bits(w_o)), (name, a, o)
+            assert sp_g.tobytes() == sp_o.tobytes(), (name, a, o)
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- K7/K8 resampling
+def _weight_cases(rng):
+    yield "uniform", np.ones(1000), 0.37, 1000
+    yield "random", rng.random(5000), 0.9123, 5000
+    yield "skewed", rng.random(4097) ** 12, 0.5, 3000
+    yield "zeros", np.where(rng.random(7000) < 0.8, 0.0, rng.random(7000)), 0.001, 9000
+    yield "leading_zero_r0", np.concatenate([[0.0, 0.0], rng.random(100)]), 0.0, 64
+    yield "single", np.array([0.3]), 0.99, 17
+    yield "one_heavy", np.concatenate([rng.random(3000) * 1e-9, [5.0], rng.random(2000) * 1e-9]), 0.25, 4000
+    yield "tiny", rng.random(2500) * 1e-200, 0.6, 2500
+    yield "big", rng.random(300000), 0.4242, 300000
+    yield "ragged", rng.random(1025), 0.75, 7
+
+
+def test_resample_fixed_bit_exact(oracle, gpu_lib):
+    pomdp, c = PROBS["baby"]
+    gp, _ = make_pair(oracle, pomdp, c, seed=3)
+    rng = np.random.default_rng(5)
+    for tag, w, r, n_out in _weight_cases(rng):
+        idx_g = gp.resample_systematic(w, r, n_out, mode=0)
+        rc, idx_o = oracle.resample_systematic(w, r, n_out, fixed=True)
+        assert rc == 0
+        assert np.array_equal(idx_g, idx_o), tag
+        assert np.all(np.diff(idx_g) >= 0), tag  # sortedness
+        # agreement with the upstream fp64 running-sum semantics (not guaranteed bit-exact: re-association)
+        rc, idx_f = oracle.resample_systematic(w, r, n_out, fixed=False)
+        assert rc == 0
+        assert np.mean(idx_f != idx_g) <= 1e-3, (tag, np.mean(idx_f != idx_g))
+    gp.close()
+
+
+def test_resample_sequential_fp64_bit_exact(oracle, gpu_lib):
+    """Verification mode: the upstream running fp64 sums on one device thread."""
+    pomdp, c = PROBS["baby"]
+    gp, _ = make_pair(oracle, pomdp, c, seed=3)
+    rng = np.random.default_rng(6)
+    for tag, w, r, n_out in _weight_cases(rng):
+        if len(w) > 50000:
+            continue
+        idx_g = gp.resample_systematic(w, r, n_out, mode=1)
+        rc, idx_o = oracle.resample_systematic(w, r, n_out, fixed=False)
+        assert rc == 0
+        assert np.array_equal(idx_g, idx_o), tag
+    gp.close()
+
+
+def test_resample_zero_weight_is_depletion(oracle, gpu_lib):
+    gp, _ = make_pair(oracle, PROBS["baby"][0], 10.0, seed=3)
+    with pytest.raises(pj.ParticleDepletion):
+        gp.resample_systematic(np.zeros(100), 0.5, 100, mode=0)
+    rc, _ = oracle.resample_systematic(np.zeros(100), 0.5, 100, fixed=True)
+    assert rc == abi.ERR_PARTICLE_DEPLETION
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- exact search
+@pytest.mark.parametrize("name,queries", [("tiger", 1000), ("baby", 3000), ("rs78", 4000), ("rs44", 4000),
+                                          ("lightdark", 1500)])
+def test_exact_search_bit_exact(oracle, gpu_lib, name, queries):
+    """Same Philox streams => identical trees: N counts, V bits, structure."""
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=11, mode="exact", tree_queries=queries)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(queries)
+    rc, a_o, N_o, V_o = op.search(queries)
+    assert rc == 0
+    assert np.array_equal(N_g, N_o), (N_g, N_o)
+    assert np.array_equal(_bits(V_g), _bits(V_o)), (V_g, V_o)
+    assert a_g == a_o
+    tg, to = gp.dump_tree(), op.dump_tree()
+    assert np.array_equal(tg[0], to[0])
+    assert np.array_equal(tg[1], to[1])
+    assert np.array_equal(_bits(tg[2]), _bits(to[2]))
+    if to[3] is not None:
+        assert np.array_equal(tg[3], to[3])
+    cg, co = gp.counters(), op.counters()
+    for k in ("simulations", "rollouts", "rollout_steps", "tree_steps", "nodes", "log_entries", "max_depth_seen"):
+        assert cg[k] == co[k], (k, cg[k], co[k])
+    gp.close()
+
+
+@pytest.mark.parametrize("name", ["tiger", "baby", "rs44", "lightdark"])
+def test_replay_tree_counts_bit_exact(oracle, gpu_lib, name):
+    """north_star criterion 1: replayed uniform stream + injected rollout returns => identical counts."""
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=0, mode="exact")
+    rng = np.random.default_rng(123)
+    Q = 800
+    uniforms = rng.random(Q * (2 + 4 * 90))
+    returns = rng.normal(-5.0, 10.0, Q)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g, uu_g, ru_g = gp.search_replay(Q, uniforms, returns)
+    rc, a_o, N_o, V_o, uu_o, ru_o = op.search_replay(Q, uniforms, returns)
+    assert rc == 0
+    assert (uu_g, ru_g) == (uu_o, ru_o)
+    assert np.array_equal(N_g, N_o)
+    assert np.array_equal(_bits(V_g), _bits(V_o))
+    assert a_g == a_o
+    tg, to = gp.dump_tree(), op.dump_tree()
+    assert np.array_equal(tg[0], to[0]) and np.array_equal(tg[1], to[1])
+    gp.close()
+
+
+@pytest.mark.parametrize("name", ["tiger", "baby", "rs44"])
+def test_unweighted_update_episode_bit_exact(oracle, gpu_lib, name):
+    """search -> re-root at (a,o) -> search ... : particles (in push order), counts and values agree."""
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=21, mode="exact", tree_queries=1500)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    for step in range(4):
+        a_g, N_g, V_g = gp.search(1500)
+        rc, a_o, N_o, V_o = op.search(1500)
+        assert rc == 0 and a_g == a_o
+        assert np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o))
+        # choose the most visited observation child of the chosen action (exists in both trees)
+        best_o, best_n = None, 0
+        for o in range(pomdp.n_observations):
+            n, npart, _, _ = op.node_stats([(a_o, o)])
+            if n > best_n:
+                best_o, best_n = o, n
+        assert best_o is not None
+        ng, npg, Ng, Vg = gp.node_stats([(a_g, best_o)])
+        no, npo, No, Vo = op.node_stats([(a_o, best_o)])
+        assert (ng, npg) == (no, npo) and np.array_equal(Ng, No) and np.array_equal(_bits(Vg), _bits(Vo))
+        gp.update_unweighted(a_g, best_o)
+        assert op.update_unweighted(a_o, best_o) == 0
+        pg, po = gp.belief_particles(), op.belief_particles()
+        assert len(pg) == best_n == len(po)
+        assert np.array_equal(pg, po)
+    gp.close()
+
+
+def test_unweighted_update_depletion(oracle, gpu_lib):
+    """@test_throws ErrorException (test/Belief_and_Particle_Filter_Options.jl:35-36, test/runtests.jl:35-41)."""
+    pomdp, c = PROBS["rs78"]
+    gp, op = make_pair(oracle, pomdp, c, seed=2, mode="exact", tree_queries=5)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a, _, _ = gp.search(5)
+    op.search(5)
+    # an observation never generated under action `a` in 5 queries
+    missing = None
+    for o in range(3):
+        if op.node_stats([(a, o)])[0] < 0:
+            missing = o
+            break
+    assert missing is not None
+    assert op.update_unweighted(a, missing) == abi.ERR_PARTICLE_DEPLETION
+    with pytest.raises(pj.ParticleDepletion):
+        gp.update_unweighted(a, missing)
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- SIR update
+@pytest.mark.parametrize("name,n", [("baby", 10000), ("tiger", 4096), ("rs78", 50000), ("lightdark", 100000)])
+def test_sir_update_bit_exact(oracle, gpu_lib, name, n):
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=4, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
+    rng = np.random.default_rng(9)
+    states = random_states(pomdp, n, rng)
+    gp.set_belief_particles(states)
+    op.set_belief_particles(states)
+    script = {"baby": [(0, 1), (1, 0), (0, 0)], "tiger": [(0, 1), (0, 1), (1, 0)],
+              "rs78": [(5, 0), (0, 2), (7, 1)], "lightdark": [(2, 3.0), (2, 4.2), (0, 2.9)]}[name]
+    for k, (a, o) in enumerate(script):
+        n_out = n if k != 1 else n // 2 + 1
+        gp.pf_update_sir(a, o, seed=1000 + k, n_out=n_out)
+        assert op.pf_update_sir(a, o, seed=1000 + k, n_out=n_out, mode=0) == 0
+        pg, po = gp.belief_particles(), op.belief_particles()
+        assert len(pg) == n_out == len(po)
+        assert pg.tobytes() == po.tobytes(), (name, k)
+    gp.close()
+
+
+def test_sir_baby_posterior_matches_golden_chain(oracle, gpu_lib):
+    """D2: exact Baby belief chain 0 -> 0.0240964 -> 0.0298684 (notebooks/Display_Tree.ipynb:385):
+    the 10^4-particle... here 2^20-particle SIR posterior mean must approach it within MC error."""
+    pomdp = pj.BabyPOMDP(-5.0, -10.0)
+    gp, _ = make_pair(oracle, pomdp, 10.0, seed=4, belief_mode=abi.BELIEF_EXTERNAL)
+    n = 1 << 20
+    gp.set_belief_particles(np.zeros(n, dtype=np.uint32))
+    for k, want in enumerate([0.02409638554216867, 0.029868401596924436, 0.03128309542601844]):
+        gp.pf_update_sir(0, 0, seed=50 + k, n_out=n)
+        got = gp.belief_particles().mean()
+        assert abs(got - want) < 5 * np.sqrt(want * (1 - want) / n) + 2e-4, (k, got, want)
+    gp.close()
+
+
+def test_sir_all_terminal(oracle, gpu_lib):
+    pomdp = pj.LightDark1D()
+    gp, op = make_pair(oracle, pomdp, 1.0, seed=4, belief_mode=abi.BELIEF_EXTERNAL)
+    s = np.zeros(100, dtype=pomdp.state_dtype)
+    s["status"] = -1
+    gp.set_belief_particles(s)
+    op.set_belief_particles(s)
+    assert op.pf_update_sir(2, 3.0, 1, 100, 0) == abi.ERR_ALL_SAMPLES_TERMINAL
+    with pytest.raises(pj.AllSamplesTerminal):
+        gp.pf_update_sir(2, 3.0, 1, 100)
+    with pytest.raises(pj.AllSamplesTerminal):
+        gp.search(100)
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- batched search
+def _tree_invariants(node_N, act_N, child, root=0):
+    """Q10: N(ha) = sum_o N(hao); N(h) = [expanded] + sum_a N(h,a) for visited h."""
+    nn, nA = act_N.shape
+    for n in range(nn):
+        for a in range(nA):
+            kids = child[n, a][child[n, a] >= 0]
+            assert act_N[n, a] == node_N[kids].sum(), (n, a)
+
+
+@pytest.mark.parametrize("name,queries", [("tiger", 20000), ("baby", 50000), ("rs78", 100000)])
+def test_batched_search_invariants_and_values(oracle, gpu_lib, name, queries):
+    """Batched mode: structural invariants hold exactly; root statistics agree with the sequential
+    oracle statistically.  Tolerance: total visits exact; the oracle's best root action is the
+    batched best action or within 3 standard errors of it; per-action |Q_gpu - Q_oracle| <= 4 SE + 2%
+    of the reward scale, for actions with >= 200 visits on both sides."""
+    pomdp, c = PROBS[name]
+    if name == "tiger":
+        c = 50.0  # c=1 against rewards of -100 never explores: nothing to compare
+    gp, op = make_pair(oracle, pomdp, c, seed=31, mode="batched", tree_queries=queries)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(queries)
+    rc, a_o, N_o, V_o = op.search(queries)
+    assert rc == 0
+    rootN, _, _ = gp.root_stats()
+    assert rootN == queries
+    assert N_g.sum() == queries - 1  # the root expansion consumes one query (src/solver.jl:104-106)
+    node_N, act_N, act_V, child = gp.dump_tree()
+    _tree_invariants(node_N, act_N, child)
+    cg = gp.counters()
+    assert cg["simulations"] == queries and cg["rollouts"] <= queries - 1
+    scale = {"tiger": 100.0, "baby": 15.0, "rs78": 10.0}[name]
+    both = (N_g >= 200) & (N_o >= 200)
+    assert both.any()
+    se = scale / np.sqrt(np.minimum(N_g, N_o).clip(1))
+    assert np.all(np.abs(V_g - V_o)[both] <= 4 * se[both] + 0.02 * scale), (V_g, V_o, N_g, N_o)
+    assert V_g[a_o] >= V_g[a_g] - 3 * se[a_o] - 0.02 * scale, (a_g, a_o, V_g, V_o)
+    gp.close()
+
+
+def test_batched_lightdark_continuous_obs(oracle, gpu_lib):
+    pomdp, c = PROBS["lightdark"]
+    gp, op = make_pair(oracle, pomdp, c, seed=8, mode="batched", tree_queries=30000)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(30000)
+    rc, a_o, N_o, V_o = op.search(30000)
+    assert N_g.sum() == 29999
+    cg, co = gp.counters(), op.counters()
+    assert cg["max_depth_seen"] == co["max_depth_seen"] == 1  # Float64 observations never repeat
+    assert cg["nodes"] == 30000
+    assert abs(V_g[N_g.argmax()] - V_o[N_o.argmax()]) < 1.0
+    gp.close()
+
+
+def test_batched_particle_belief_and_update(oracle, gpu_lib):
+    """Batched search from a particle belief, then the unweighted re-root: the new belief holds
+    exactly N(child) states, all consistent with the model."""
+    pomdp, c = PROBS["baby"]
+    gp, _ = make_pair(oracle, pomdp, c, seed=5, mode="batched", tree_queries=20000)
+    rng = np.random.default_rng(3)
+    gp.set_belief_particles((rng.random(10000) < 0.1).astype(np.uint32))
+    a, N, V = gp.search(20000)
+    n_child, npart, _, _ = gp.node_stats([(a, 0)])
+    assert n_child > 0
+    gp.update_unweighted(a, 0)
+    p = gp.belief_particles()
+    assert len(p) == n_child
+    assert set(np.unique(p)) <= {0, 1}
+    rootN, _, _ = gp.root_stats()
+    assert rootN == n_child
+    a2, N2, V2 = gp.search(20000)
+    rootN2, _, _ = gp.root_stats()
+    assert rootN2 == n_child + 20000  # tree reuse: counts continue (src/solver.jl:276)
+    gp.close()
+
+
+# ----------------------------------------------------------------------------- API surface
+def test_api_episode_baby(gpu_lib):
+    """Basic_Usage notebook flow through the mirrored API: solve / action / updater / update."""
+    pomdp = pj.BabyPOMDP(-5.0, -10.0)
+    solver = pj.POMCPSolver(tree_queries=3000, c=10.0, rng=7)
+    policy = pj.solve(solver, pomdp)
+    up = pj.updater(policy)
+    b = pj.initialize_belief(up, pj.initial_state_distribution(pomdp))
+    a = pj.action(policy, b)
+    assert a in (0, 1)
+    assert b.N == 3000
+    kids = b.children
+    assert sum(n for n, _ in kids.values()) == 2999
+    b2 = pj.update(up, b, a, 0)
+    assert len(b2.particles()) == b2.N > 0
+    with pytest.raises(ValueError):
+        _ = b.N  # stale node
+    a2 = pj.action(policy, b2)
+    assert a2 in (0, 1)
+    policy.close()
+
+
+def test_api_default_action_and_errors(gpu_lib):
+    pomdp = pj.LightDark1D()
+    s = np.zeros(10, dtype=pomdp.state_dtype)
+    s["status"] = -1
+    policy = pj.solve(pj.POMCPSolver(tree_queries=50, rng=1), pomdp)
+    with pytest.raises(pj.AllSamplesTerminal):
+        pj.action(policy, pj.ParticleCollection(s))
+    policy.close()
+    policy = pj.solve(pj.POMCPSolver(tree_queries=50, rng=1, default_action=2), pomdp)
+    assert pj.action(policy, pj.ParticleCollection(s)) == 2
+    policy.close()
+    with pytest.raises(ValueError):
+        pj.solve(pj.POMCPSolver(), pj.BabyPOMDP(discount_factor=1.0))
+    with pytest.raises(NotImplementedError):
+        pj.solve(pj.POMCPSolver(num_sparse_actions=3), pj.BabyPOMDP())
