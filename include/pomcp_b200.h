@@ -224,6 +224,9 @@ typedef enum pomcp_phase { POMCP_PHASE_SEARCH = 0, POMCP_PHASE_ROLLOUT = 1, POMC
 int32_t pomcp_last_phase_ms(pomcp_handle* h, int32_t phase, double* ms_out, int64_t* launches_out);
 /* Device-resident variants used by the bench's kernel-only timing: run on
  * whatever belief is already in HBM and leave results there. */
+/* Generic CUDA-event stopwatch on the handle's stream (8 slots). */
+int32_t pomcp_event_record(pomcp_handle* h, int32_t slot);
+int32_t pomcp_event_elapsed_ms(pomcp_handle* h, int32_t slot_start, int32_t slot_stop, double* ms_out);
 int32_t pomcp_search_async(pomcp_handle* h, int64_t tree_queries);
 int32_t pomcp_sync(pomcp_handle* h);
 int32_t pomcp_flush_l2(pomcp_handle* h);

@@ -60,6 +60,8 @@ def lib():
     L.pomcp_comm_init.argtypes = [vp, vp, i32, i32]
     L.pomcp_search_rootparallel.argtypes = [vp, i64, P(i32), vp, vp, i32]
     L.pomcp_last_phase_ms.argtypes = [vp, i32, P(dbl), P(i64)]
+    L.pomcp_event_record.argtypes = [vp, i32]
+    L.pomcp_event_elapsed_ms.argtypes = [vp, i32, i32, P(dbl)]
     L.pomcp_search_async.argtypes = [vp, i64]
     L.pomcp_sync.argtypes = [vp]
     L.pomcp_flush_l2.argtypes = [vp]

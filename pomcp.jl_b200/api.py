@@ -371,6 +371,24 @@ class POMCPPlanner:
         _check(lib().pomcp_last_phase_ms(self._h, phase, C.byref(ms), C.byref(n)), self._h)
         return ms.value, n.value
 
+    def event_record(self, slot):
+        _check(lib().pomcp_event_record(self._h, slot), self._h)
+
+    def event_elapsed_ms(self, s0, s1):
+        ms = C.c_double(0.0)
+        _check(lib().pomcp_event_elapsed_ms(self._h, s0, s1, C.byref(ms)), self._h)
+        return ms.value
+
+    def search_async(self, tree_queries=-1):
+        _check(lib().pomcp_search_async(self._h, tree_queries), self._h)
+
+    def sync(self):
+        rc = lib().pomcp_sync(self._h)
+        _check(rc, self._h)
+
+    def flush_l2(self):
+        _check(lib().pomcp_flush_l2(self._h), self._h)
+
     def rollout_batch(self, states, steps, seed):
         states = np.ascontiguousarray(states, dtype=self.problem.state_dtype)
         ret = np.zeros(len(states), dtype=np.float64)

@@ -122,6 +122,7 @@ struct pomcp_handle {
   float4* d_flush = nullptr;
   size_t flush_n = 0;
   PhaseTimer timers[POMCP_PHASE_COUNT];
+  cudaEvent_t user_ev[8] = {};
   pomcp_counters host_ctr{};
   long long launches = 0, last_waves = 0;
   bool pending = false;
@@ -463,6 +464,8 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   if (h->h_pfctl) cudaFreeHost(h->h_pfctl);
   if (h->h_ns) cudaFreeHost(h->h_ns);
   for (auto& t : h->timers) t.destroy();
+  for (auto e : h->user_ev)
+    if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return POMCP_OK;
@@ -995,6 +998,25 @@ int32_t pomcp_last_phase_ms(pomcp_handle* h, int32_t phase, double* ms, int64_t*
   CK(cudaStreamSynchronize(h->stream));
   if (ms) *ms = h->timers[phase].total_ms();
   if (launches) *launches = h->timers[phase].launches;
+  return POMCP_OK;
+}
+
+int32_t pomcp_event_record(pomcp_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot >= 8) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->user_ev[slot]) CK(cudaEventCreate(&h->user_ev[slot]));
+  CK(cudaEventRecord(h->user_ev[slot], h->stream));
+  return POMCP_OK;
+}
+
+int32_t pomcp_event_elapsed_ms(pomcp_handle* h, int32_t s0, int32_t s1, double* ms_out) {
+  if (!h || s0 < 0 || s0 >= 8 || s1 < 0 || s1 >= 8 || !ms_out || !h->user_ev[s0] || !h->user_ev[s1])
+    return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaEventSynchronize(h->user_ev[s1]));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->user_ev[s0], h->user_ev[s1]));
+  *ms_out = ms;
   return POMCP_OK;
 }
 
