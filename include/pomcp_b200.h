@@ -114,10 +114,12 @@ typedef struct pomcp_solver_params {
   /* ---- device knobs ---- */
   int64_t max_nodes;     /* belief-node pool capacity (0 = derive from tree_queries) */
   int64_t max_log;       /* particle-log capacity in entries (0 = derive) */
-  int32_t wave_min;      /* batched: smallest wave (0 = default 32) */
-  int32_t wave_max;      /* batched: largest wave (0 = default 32768) */
-  int32_t wave_ramp_div; /* batched: wave = clamp(visits_so_far / div) (0 = default 8) */
-  int32_t rank;          /* root-parallel rank, mixed into the Philox key */
+  int32_t inflight_min;      /* batched: simulations in flight while the tree is empty (0 = default) */
+  int32_t inflight_max;      /* batched: cap on simulations (warp workers) in flight (0 = default) */
+  int32_t inflight_ramp_div; /* batched: in flight = clamp(root visits / div, min, max) (0 = default) */
+  int32_t rollouts_per_leaf; /* R in 1..32 rollouts averaged per leaf evaluation, one lane each (0 = default) */
+  int32_t rank;              /* root-parallel rank, mixed into the Philox counter */
+  int32_t _pad1;
 } pomcp_solver_params;
 
 typedef struct pomcp_counters {

@@ -662,7 +662,20 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
         } else if (sol->estimator == POMCP_EST_CONSTANT) {
           est = sol->estimator_value; /* src/rollout.jl:10 */
         } else {
-          est = rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8), q, g->epoch, &pl->ctr.rollout_steps);
+          /* R rollouts per leaf (device extension; R = 1 is the reference).  Rollout r draws from the
+           * stream tagged r<<16; the R returns are added in the butterfly order of a 32-lane warp. */
+          int R = sol->rollouts_per_leaf > 0 ? sol->rollouts_per_leaf : 1;
+          double x[32], y[32];
+          for (int r = 0; r < 32; ++r)
+            x[r] = r < R ? rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
+                                          g->epoch, &pl->ctr.rollout_steps)
+                         : 0.0;
+          for (int off = 16; off > 0; off >>= 1) {
+            for (int i = 0; i < 32; ++i) y[i] = x[i] + x[i ^ off];
+            memcpy(x, y, sizeof(x));
+          }
+          est = x[0] / (double)R;
+          pl->ctr.rollouts += R - 1;
         }
         pl->ctr.rollouts++;
         leaf = pl->gpow[depth] * est;

@@ -58,7 +58,8 @@ class SolverParams(C.Structure):
         ("num_sparse_actions", C.c_int32), ("estimator", C.c_int32), ("estimator_value", C.c_double),
         ("belief_mode", C.c_int32), ("search_mode", C.c_int32),
         ("max_nodes", C.c_int64), ("max_log", C.c_int64),
-        ("wave_min", C.c_int32), ("wave_max", C.c_int32), ("wave_ramp_div", C.c_int32), ("rank", C.c_int32),
+        ("inflight_min", C.c_int32), ("inflight_max", C.c_int32), ("inflight_ramp_div", C.c_int32),
+        ("rollouts_per_leaf", C.c_int32), ("rank", C.c_int32), ("_pad1", C.c_int32),
     ]
 
 

@@ -130,12 +130,13 @@ class DefaultReinvigoratorStub:
 class POMCPSolver:
     """Keyword constructor with the reference defaults (src/constructor.jl:8-18; fields documented
     at src/POMCP.jl:75-136).  `rng` is an integer seed (Philox key) instead of an AbstractRNG.
-    Device-only keywords: search_mode ("batched"|"exact"), wave_min, wave_max, wave_ramp_div,
+    Device-only keywords: search_mode ("batched"|"exact"), inflight_min, inflight_max, inflight_ramp_div, rollouts_per_leaf,
     max_nodes, max_log, device, rank."""
 
     def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0,
                  node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
-                 default_action=None, search_mode="batched", wave_min=0, wave_max=0, wave_ramp_div=0, max_nodes=0,
+                 default_action=None, search_mode="batched", inflight_min=0, inflight_max=0, inflight_ramp_div=0, rollouts_per_leaf=0,
+                 max_nodes=0,
                  max_log=0, device=0, rank=0):
         self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
         self.rng = rng
@@ -145,7 +146,8 @@ class POMCPSolver:
         self.init_V, self.init_N, self.num_sparse_actions = init_V, init_N, num_sparse_actions
         self.default_action = default_action if default_action is not None else ExceptionRethrow()
         self.search_mode = search_mode
-        self.wave_min, self.wave_max, self.wave_ramp_div = wave_min, wave_max, wave_ramp_div
+        self.inflight_min, self.inflight_max, self.inflight_ramp_div = inflight_min, inflight_max, inflight_ramp_div
+        self.rollouts_per_leaf = rollouts_per_leaf
         self.max_nodes, self.max_log, self.device, self.rank = max_nodes, max_log, device, rank
 
     def c_params(self, belief_mode):
@@ -170,7 +172,8 @@ class POMCPSolver:
         sp.belief_mode = belief_mode
         sp.search_mode = {"exact": abi.MODE_EXACT, "batched": abi.MODE_BATCHED}[self.search_mode]
         sp.max_nodes, sp.max_log = int(self.max_nodes), int(self.max_log)
-        sp.wave_min, sp.wave_max, sp.wave_ramp_div = self.wave_min, self.wave_max, self.wave_ramp_div
+        sp.inflight_min, sp.inflight_max = self.inflight_min, self.inflight_max
+        sp.inflight_ramp_div, sp.rollouts_per_leaf = self.inflight_ramp_div, self.rollouts_per_leaf
         sp.rank = self.rank
         return sp
 

@@ -95,8 +95,8 @@ struct pomcp_handle {
   double* d_gpow = nullptr;
   Pool pool{};
   size_t ht_entries = 0;
-  WaveBuf wb{};
-  int wave_cap = 0, wave_min = 32, wave_max = 32768, ramp_div = 8;
+  PathBuf pb{};
+  int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32;
   void* d_bel[2] = {nullptr, nullptr};
   size_t bel_cap[2] = {0, 0};
   int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles
@@ -243,12 +243,17 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.bel = (h->bel_kind == 2) ? h->d_bel[h->bel_cur] : nullptr;
   c.n_bel = h->n_bel;
   c.root = h->root;
+  c.root_N0 = (uint32_t)h->root_visits;
+  c.rollouts = h->rollouts;
+  c.inflight_min = h->inflight_min;
+  c.inflight_max = h->inflight_max;
+  c.ramp_div = h->ramp_div;
   return c;
 }
 
 int reset_search_flags(pomcp_handle* h) {
-  // any_nonterminal / overflow flags are per search
-  size_t off = offsetof(DevCtr, pool_overflow);
+  // query / worker tickets, any_nonterminal and the overflow flags are per search
+  size_t off = offsetof(DevCtr, next_query);
   CK(cudaMemsetAsync((char*)h->pool.ctr + off, 0, sizeof(DevCtr) - off, h->stream));
   return POMCP_OK;
 }
@@ -271,40 +276,28 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
   if (h->exact || replay) {
     if (!h->exact) return fail(h, POMCP_ERR_INVALID_ARG, "replay needs search_mode = exact");
     DISPATCH_PID(h->prob.problem_id, {
-      if (replay) k_search_exact<PID, true><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, Q, h->d_res);
-      else k_search_exact<PID, false><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, Q, h->d_res);
+      if (replay) k_search_exact<PID, true><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q, h->d_res);
+      else k_search_exact<PID, false><<<1, 32, 0, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q, h->d_res);
     });
     rc = launch_check(h, "k_search_exact");
     if (rc) return rc;
     ts.launches++;
-    h->root_visits += Q;
   } else {
-    long long q = 0;
-    while (q < Q) {
-      long long B = h->root_visits / h->ramp_div;
-      B = std::max<long long>(B, h->wave_min);
-      B = std::min<long long>(B, h->wave_max);
-      B = std::min<long long>(B, Q - q);
-      int wave = (int)B;
-      DISPATCH_PID(h->prob.problem_id, {
-        k_descend<PID><<<(wave * 32 + 127) / 128, 128, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, wave, (uint32_t)q);
-      });
-      rc = launch_check(h, "k_descend");
-      if (rc) return rc;
-      CK(cudaEventRecord(tr.next(), h->stream));
-      DISPATCH_PID(h->prob.problem_id, {
-        k_finish<PID><<<(wave + 255) / 256, 256, 0, h->stream>>>(h->pool, h->dm, cfg, h->wb, wave, (uint32_t)q);
-      });
-      rc = launch_check(h, "k_finish");
-      if (rc) return rc;
-      CK(cudaEventRecord(tr.next(), h->stream));
-      tr.launches++;
-      ts.launches += 2;
-      q += B;
-      h->root_visits += B;
-      h->last_waves++;
-    }
+    // one persistent launch: every warp is a worker, admission is ramped on the device
+    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
+    int blocks = (int)((workers + 3) / 4);
+    CK(cudaEventRecord(tr.next(), h->stream));
+    DISPATCH_PID(h->prob.problem_id, {
+      k_search_workers<PID><<<blocks, 128, 0, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+    });
+    rc = launch_check(h, "k_search_workers");
+    if (rc) return rc;
+    CK(cudaEventRecord(tr.next(), h->stream));
+    tr.launches++;
+    ts.launches++;
+    h->last_waves = 1;
   }
+  h->root_visits += Q;
   k_root_result<<<1, 32, 0, h->stream>>>(h->pool, h->nA, h->root, h->exact ? 1 : 0, h->sp.init_V, h->d_res);
   rc = launch_check(h, "k_root_result");
   if (rc) return rc;
@@ -454,8 +447,8 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   void* ptrs[] = {h->d_eta, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
-                  h->pool.log_state, h->pool.ctr, h->wb.path_slot, h->wb.path_node, h->wb.path_r, h->wb.path_state,
-                  h->wb.leaf_state, h->wb.leaf_info, h->d_bel[0], h->d_bel[1], h->d_res, h->d_pfctl, h->d_ns,
+                  h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
+                  h->d_bel[0], h->d_bel[1], h->d_res, h->d_pfctl, h->d_ns,
                   h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -559,12 +552,17 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     m.rs_eta = h->d_eta;
   }
 
-  // wave schedule
-  h->wave_min = sp->wave_min > 0 ? sp->wave_min : 32;
-  h->wave_max = sp->wave_max > 0 ? sp->wave_max : 32768;
-  h->wave_min = std::min(h->wave_min, h->wave_max);
-  h->ramp_div = sp->wave_ramp_div > 0 ? sp->wave_ramp_div : 8;
-  h->wave_cap = h->exact ? 1 : h->wave_max;
+  // simulations in flight (batched mode) and rollouts per leaf
+  h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096) : 1024;
+  h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
+  h->inflight_min = std::max(1, std::min(h->inflight_min, h->inflight_max));
+  h->ramp_div = sp->inflight_ramp_div > 0 ? sp->inflight_ramp_div : 32;
+  if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 32) {
+    h->err = "rollouts_per_leaf must be in 1..32";
+    return bail(POMCP_ERR_INVALID_ARG);
+  }
+  h->rollouts = sp->rollouts_per_leaf > 0 ? sp->rollouts_per_leaf : (h->exact ? 1 : 32);
+  h->n_slots = h->exact ? 1 : h->inflight_max;
 
   // pool sizing
   size_t free_b = 0, total_b = 0;
@@ -606,15 +604,13 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &P.ctr, 1));
   CKU(cudaMemset(P.ctr, 0, sizeof(DevCtr)));
 
-  // wave scratch
-  size_t pw = (size_t)std::max(h->levels, 1) * h->wave_cap;
-  h->wb.stride = h->wave_cap;
-  CKC(dev_alloc(h, &h->wb.path_slot, pw));
-  CKC(dev_alloc(h, &h->wb.path_node, pw));
-  CKC(dev_alloc(h, &h->wb.path_r, pw));
-  CKU(cudaMalloc(&h->wb.path_state, pw * sb));
-  CKU(cudaMalloc(&h->wb.leaf_state, (size_t)h->wave_cap * sb));
-  CKC(dev_alloc(h, &h->wb.leaf_info, (size_t)h->wave_cap));
+  // per-worker path scratch
+  size_t pw = (size_t)std::max(h->levels, 1) * h->n_slots;
+  h->pb.stride = h->n_slots;
+  CKC(dev_alloc(h, &h->pb.path_slot, pw));
+  CKC(dev_alloc(h, &h->pb.path_node, pw));
+  CKC(dev_alloc(h, &h->pb.path_r, pw));
+  CKU(cudaMalloc(&h->pb.path_state, pw * sb));
 
   CKC(dev_alloc(h, &h->d_res, 1));
   CKC(dev_alloc(h, &h->d_pfctl, 1));

@@ -1,10 +1,10 @@
 // K1/K2/K3/K4/K5 — the search core: root sampling, warp-per-path descent with UCB1 selection
-// and child lookup/insert on the SoA node pool, thread-per-trajectory random rollouts, backup.
-// Replaces search()/simulate() (src/solver.jl:41-157), the tree node types (src/tree.jl:7-26)
-// and rollout() (src/rollout.jl:77-84) of the reference.
+// and child lookup/insert on the SoA node pool, one-thread-per-trajectory random rollouts reduced
+// by warp shuffles, backup with atomics.  Replaces search()/simulate() (src/solver.jl:41-157),
+// the tree node types (src/tree.jl:7-26) and rollout() (src/rollout.jl:77-84) of the reference.
 //
 // Node pool in HBM (struct of arrays, ids are u32, id 0 is the first root):
-//   node_N[n]            visits of belief node n (arrivals; == reference N once a wave has drained)
+//   node_N[n]            visits of belief node n, counted on arrival (== reference N once drained)
 //   node_flags[n]        bit0: children expanded (src/solver.jl:87-94)
 //   act_N[n*A+a]         visits of action node (n,a), counted at descent (in-flight included)
 //   act_M[n*A+a]         completed backups (batched mode)
@@ -22,7 +22,9 @@ struct DevCtr {
   unsigned long long node_count, log_count;
   unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
   unsigned long long scan_ticket;
+  unsigned long long next_query, worker_ticket;
   unsigned int pool_overflow, log_overflow, replay_overflow, any_nonterminal;
+  unsigned long long dbg[8];
 };
 
 struct Pool {
@@ -48,10 +50,14 @@ struct SearchCfg {
   const double* gpow;  // gamma^d, d = 0..levels
   int levels;          // first depth at which gamma^depth < eps (src/solver.jl:82), capped by max_depth
   int belief_unweighted, estimator;
+  int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
   uint32_t key0, key1, rank, epoch;
   const void* bel;  // root belief particles (NULL: the problem's initial distribution)
   long long n_bel;
   uint32_t root;
+  uint32_t root_N0;  // root visits when the search started
+  // asynchronous workers: in flight = clamp(root visits / ramp_div, inflight_min, inflight_max)
+  int inflight_min, inflight_max, ramp_div;
   // replay (exact mode only)
   const double* uni;
   long long n_uni;
@@ -59,20 +65,21 @@ struct SearchCfg {
   long long n_rets;
 };
 
-// Per-wave scratch: path[level][i] and leaf[i], i = index of the simulation inside the wave.
-struct WaveBuf {
+// Per-worker scratch: path[level][slot], slot = worker index
+struct PathBuf {
   uint32_t* path_slot;
   uint32_t* path_node;
   double* path_r;
   void* path_state;
-  void* leaf_state;
-  int* leaf_info;  // depth | flags
   int stride;
 };
-enum : int { LEAF_ROLLOUT = 1 << 16, LEAF_SKIPPED = 1 << 17, LEAF_ABORTED = 1 << 18, LEAF_DEPTH_MASK = 0xffff };
 
 struct ReplayCursor {
   long long ucur, rcur;
+};
+
+struct LocalCtr {
+  unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
 };
 
 struct SearchResult {
@@ -204,21 +211,32 @@ __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m,
   }
 }
 
-// ---- K1 + K2: one warp walks one tree path (src/solver.jl:48-49, 82-142).
-// Control flow is warp-uniform; lanes hold the actions for the UCB arg-max; lane 0 issues the
-// atomics.  Visits are counted on arrival: the value returned by the node_N ticket is exactly
-// the reference's h.N for a sequential run, and in batched mode it makes concurrent simulations
-// see each other's in-flight visits (so they spread over actions instead of piling up).
+// fixed-shape butterfly sum over the warp: the oracle adds in the same binary tree
+__device__ __forceinline__ double warp_tree_sum(double x) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+
+// ---- one simulation, run by one warp: simulate() of src/solver.jl:78-157.
+//  * K1 root draw (src/solver.jl:48-49);
+//  * K2 descent: control flow is warp-uniform, lanes hold the actions for the UCB arg-max, lane 0
+//    issues the atomics.  Visits are counted on arrival: the value returned by the node_N ticket
+//    is exactly the reference's h.N in a sequential run, and with many simulations in flight it
+//    lets each one see the others' unfinished visits, so they spread over actions like sequential
+//    UCB would instead of piling up on one arm;
+//  * K3 leaf evaluation: lane r runs rollout r (R <= 32), returns are reduced by shuffles;
+//  * K4 backup bottom-up (src/solver.jl:144-156) and particle pushes.
+// Returns false when the query was consumed by a terminal root sample.
 template <int PID, bool EXACT, bool REPLAY>
-__device__ __forceinline__ void descend_one(const Pool& P, const DevModel& m, const SearchCfg& cfg,
-                                            const WaveBuf& wb, int widx, uint32_t q, uint32_t root_ticket,
-                                            ReplayCursor& rc, uint32_t& spare) {
+__device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, const SearchCfg& cfg,
+                                             const PathBuf& pb, int slot_idx, uint32_t q, uint32_t root_ticket,
+                                             ReplayCursor& rc, uint32_t& spare, LocalCtr& lc) {
   using M = ModelT<PID>;
   using State = typename M::State;
   const int lane = threadIdx.x & 31;
   const int nA = m.nA;
-  State* path_state = (State*)wb.path_state;
-  State* leaf_state = (State*)wb.leaf_state;
+  State* path_state = (State*)pb.path_state;
 
   // rand(rng, b): src/solver.jl:48 -> src/updater.jl:53-55
   double u[4];
@@ -232,41 +250,46 @@ __device__ __forceinline__ void descend_one(const Pool& P, const DevModel& m, co
     s = M::initial(m, u[0], u[1]);
   }
   if (M::terminal(m, s)) {  // src/solver.jl:49: the query is consumed
-    if (lane == 0) {
-      wb.leaf_info[widx] = LEAF_SKIPPED;
-    }
-    return;
+    lc.skips++;
+    return false;
   }
 
   uint32_t h = cfg.root;
   uint32_t hN = root_ticket;
   int depth = 0;
-  int flags = 0;
+  bool want_rollout = false, aborted = false;
   for (;;) {
     // src/solver.jl:82-86
     if (depth >= cfg.levels || M::terminal(m, s)) break;
     // src/solver.jl:87-107: first non-cut-off visitor expands and evaluates the leaf
-    uint32_t fl = __ldcg(&P.node_flags[h]);
-    if (!(fl & 1u)) {
-      uint32_t old = 0;
-      if (lane == 0) old = EXACT ? fl : atomicOr(&P.node_flags[h], 1u);
-      if (EXACT && lane == 0) P.node_flags[h] = fl | 1u;
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (!(old & 1u)) {
-        if (depth > 0) flags |= LEAF_ROLLOUT;
-        break;
+    // The flag races with other workers: lane 0 reads (and claims) it and broadcasts the outcome.
+    // A per-lane load could return different values to different lanes of this warp (lanes are
+    // not guaranteed to execute the load together) and split the warp across shuffle sites.
+    int i_expand = 0;
+    if (lane == 0) {
+      uint32_t fl = __ldcg(&P.node_flags[h]);
+      if (!(fl & 1u)) {
+        uint32_t old;
+        if (EXACT) { old = fl; P.node_flags[h] = fl | 1u; }
+        else old = atomicOr(&P.node_flags[h], 1u);
+        i_expand = !(old & 1u);
       }
+    }
+    i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
+    if (i_expand) {
+      want_rollout = depth > 0;
+      break;
     }
     // UCB1: src/solver.jl:109-124
     double crit = 0.0;
     bool valid = false;
     if (lane < nA) {
-      uint32_t slot = h * (uint32_t)nA + (uint32_t)lane;
-      uint32_t n = __ldcg(&P.act_N[slot]);
-      double v = __ldcg(&P.act_V[slot]);
+      uint32_t sl = h * (uint32_t)nA + (uint32_t)lane;
+      uint32_t n = __ldcg(&P.act_N[sl]);
+      double v = __ldcg(&P.act_V[sl]);
       if (!EXACT) {
-        uint32_t mm = __ldcg(&P.act_M[slot]);
-        v = (mm > 0 && v == v && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
+        uint32_t mm = __ldcg(&P.act_M[sl]);
+        v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
       }
       uint32_t hn = EXACT ? hN : (hN < 1u ? 1u : hN);
       if (n == 0 && hn == 1) crit = v;
@@ -303,175 +326,159 @@ __device__ __forceinline__ void descend_one(const Pool& P, const DevModel& m, co
       if (hao != 0) {
         if (EXACT) { ticket = __ldcg(&P.node_N[hao]); P.node_N[hao] = ticket + 1u; }
         else ticket = atomicAdd(&P.node_N[hao], 1u);
-        size_t pi = (size_t)depth * wb.stride + widx;
-        wb.path_slot[pi] = slot;
-        wb.path_node[pi] = hao;
-        wb.path_r[pi] = r;
+        size_t pi = (size_t)depth * pb.stride + slot_idx;
+        pb.path_slot[pi] = slot;
+        pb.path_node[pi] = hao;
+        pb.path_r[pi] = r;
         path_state[pi] = sp;
       }
     }
     hao = __shfl_sync(0xffffffffu, hao, 0);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (hao == 0) { flags |= LEAF_ABORTED; break; }
+    if (hao == 0) { aborted = true; break; }
     h = hao;
     hN = ticket;
     s = sp;
     ++depth;
   }
-  if (lane == 0) {
-    leaf_state[widx] = s;
-    wb.leaf_info[widx] = depth | flags;
-  }
-}
+  if (aborted) return true;  // pool exhausted: the search reports POOL_EXHAUSTED
 
-// ---- K3 + K4 for one simulation (one thread): leaf evaluation (src/solver.jl:97-103), then the
-// backup R = r + gamma*R' bottom-up (src/solver.jl:144-156) and the particle pushes.
-// AGG: level-0 (root action) sums go through shared memory first, one global atomic per CTA/action.
-template <int PID, bool EXACT, bool REPLAY, bool AGG>
-__device__ __forceinline__ void finish_one(const Pool& P, const DevModel& m, const SearchCfg& cfg, const WaveBuf& wb,
-                                           int widx, uint32_t q, bool active, ReplayCursor& rc, double* sW,
-                                           unsigned* sM, unsigned long long* sCtr) {
-  using M = ModelT<PID>;
-  using State = typename M::State;
-  const State* path_state = (const State*)wb.path_state;
-  const State* leaf_state = (const State*)wb.leaf_state;
-  int info = active ? wb.leaf_info[widx] : LEAF_SKIPPED;
-  int depth = info & LEAF_DEPTH_MASK;
-  bool skipped = (info & LEAF_SKIPPED) != 0 || !active;
-  bool aborted = (info & LEAF_ABORTED) != 0;
+  // leaf evaluation, src/solver.jl:97-103
   double leaf = 0.0;
-  int nsteps = 0;
-  bool did_rollout = false;
-  if (!skipped && !aborted && (info & LEAF_ROLLOUT)) {
+  if (want_rollout) {
     long long steps_to_eps = (long long)ceil(cfg.log_ratio - (double)depth);
     long long steps = min(cfg.max_depth - (long long)depth, steps_to_eps);
     double est;
     if (REPLAY) {
       est = (rc.rcur < cfg.n_rets) ? cfg.rets[rc.rcur] : 0.0;
       rc.rcur++;
+      lc.rollouts++;
     } else if (cfg.estimator == POMCP_EST_CONSTANT) {
       est = cfg.est_value;  // src/rollout.jl:10
+      lc.rollouts++;
     } else {
-      est = rollout_random<PID>(m, leaf_state[widx], steps, cfg.key0, cfg.key1, TAG_ROLLOUT | (cfg.rank << 8), q,
-                                cfg.epoch, nsteps);
+      double ret = 0.0;
+      int nsteps = 0;
+      if (lane < cfg.rollouts)
+        ret = rollout_random<PID>(m, s, steps, cfg.key0, cfg.key1,
+                                  TAG_ROLLOUT | (cfg.rank << 8) | ((uint32_t)lane << 16), q, cfg.epoch, nsteps);
+      est = warp_tree_sum(ret) / (double)cfg.rollouts;
+      nsteps = __reduce_add_sync(0xffffffffu, nsteps);
+      lc.rollouts += cfg.rollouts;
+      lc.rollout_steps += nsteps;
     }
-    leaf = cfg.gpow[depth] * est;  // src/solver.jl:103
-    did_rollout = true;
-  }
-  const bool live = !skipped && !aborted;
-
-  // particle log reservation: one atomic per warp
-  unsigned long long log_base = 0;
-  if (cfg.belief_unweighted) {
-    int len = live ? depth : 0;
-    int incl = len;
-    const int lane = threadIdx.x & 31;
-    if (AGG) {
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-      }
-      int total = __shfl_sync(0xffffffffu, incl, 31);
-      unsigned long long base = 0;
-      if (lane == 0 && total > 0) base = atomicAdd(&P.ctr->log_count, (unsigned long long)total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      log_base = base + (unsigned long long)(incl - len);
-    } else if (len > 0) {
-      log_base = P.ctr->log_count;
-      P.ctr->log_count = log_base + len;
-    }
-    if (len > 0 && log_base + len > P.log_cap) {
-      P.ctr->log_overflow = 1;
-      log_base = ~0ull;
-    }
+    leaf = cfg.gpow[depth] * est;  // src/solver.jl:103 (the reference's extra gamma^depth is kept)
   }
 
-  if (live) {
-    double R = leaf;
+  // particle log reservation (lane 0), then lanes write one level each
+  unsigned long long log_base = ~0ull;
+  if (cfg.belief_unweighted && depth > 0) {
+    if (lane == 0) {
+      if (EXACT) { log_base = P.ctr->log_count; P.ctr->log_count = log_base + depth; }
+      else log_base = atomicAdd(&P.ctr->log_count, (unsigned long long)depth);
+      if (log_base + depth > P.log_cap) { P.ctr->log_overflow = 1; log_base = ~0ull; }
+    }
+    log_base = __shfl_sync(0xffffffffu, log_base, 0);
+  }
+  __syncwarp();
+  if (log_base != ~0ull) {
     State* log_state = (State*)P.log_state;
+    for (int d = depth - 1 - lane; d >= 0; d -= 32) {
+      // deepest level first, like the unwinding recursion (src/solver.jl:146-148)
+      size_t pi = (size_t)d * pb.stride + slot_idx;
+      unsigned long long li = log_base + (unsigned long long)(depth - 1 - d);
+      P.log_node[li] = pb.path_node[pi];
+      log_state[li] = path_state[pi];
+    }
+  }
+  // backup, src/solver.jl:144-156
+  if (lane == 0) {
+    double R = leaf;
     for (int d = depth - 1; d >= 0; --d) {
-      size_t pi = (size_t)d * wb.stride + widx;
-      R = wb.path_r[pi] + m.gamma * R;
-      uint32_t slot = wb.path_slot[pi];
-      if (cfg.belief_unweighted && log_base != ~0ull) {
-        // deepest level first, like the unwinding recursion (src/solver.jl:146-148)
-        unsigned long long li = log_base + (unsigned long long)(depth - 1 - d);
-        P.log_node[li] = wb.path_node[pi];
-        log_state[li] = path_state[pi];
-      }
+      size_t pi = (size_t)d * pb.stride + slot_idx;
+      R = pb.path_r[pi] + m.gamma * R;
+      uint32_t slot = pb.path_slot[pi];
       if (EXACT) {
         double v = P.act_V[slot];
         if (v != -INFINITY) P.act_V[slot] = v + (R - v) / (double)P.act_N[slot];  // src/solver.jl:151-154
-      } else if (AGG && d == 0) {
-        uint32_t a = slot - cfg.root * (uint32_t)m.nA;
-        atomicAdd(&sW[a], R);
-        atomicAdd(&sM[a], 1u);
       } else {
         atomicAdd(&P.act_V[slot], R);
         atomicAdd(&P.act_M[slot], 1u);
       }
     }
+    // b.N += 1 after simulate (src/solver.jl:51)
+    if (EXACT) P.node_N[cfg.root] = __ldcg(&P.node_N[cfg.root]) + 1u;
+    else { __threadfence(); atomicAdd(&P.node_N[cfg.root], 1u); }
   }
-  // counters
-  if (AGG) {
-    if (live) atomicAdd(&sCtr[0], 1ull);
-    if (skipped && active) atomicAdd(&sCtr[1], 1ull);
-    if (did_rollout) { atomicAdd(&sCtr[2], 1ull); atomicAdd(&sCtr[3], (unsigned long long)nsteps); }
-    if (live) { atomicAdd(&sCtr[4], (unsigned long long)depth); atomicMax(&sCtr[5], (unsigned long long)depth); }
+  lc.sims++;
+  lc.tree_steps += depth;
+  if ((unsigned long long)depth > lc.max_depth) lc.max_depth = depth;
+  return true;
+}
+
+__device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc, bool exact) {
+  DevCtr* c = P.ctr;
+  if (exact) {
+    c->sims += lc.sims; c->skips += lc.skips; c->rollouts += lc.rollouts; c->rollout_steps += lc.rollout_steps;
+    c->tree_steps += lc.tree_steps;
+    if (lc.max_depth > c->max_depth) c->max_depth = lc.max_depth;
+    if (lc.sims) c->any_nonterminal = 1;
   } else {
-    DevCtr* c = P.ctr;
-    if (live) { c->sims++; c->tree_steps += depth; if ((unsigned long long)depth > c->max_depth) c->max_depth = depth; }
-    if (skipped && active) c->skips++;
-    if (did_rollout) { c->rollouts++; c->rollout_steps += nsteps; }
-    if (live) { P.node_N[cfg.root] += 1u; c->any_nonterminal = 1; }  // b.N += 1, src/solver.jl:51
+    if (lc.sims) { atomicAdd(&c->sims, lc.sims); atomicAdd(&c->tree_steps, lc.tree_steps); c->any_nonterminal = 1; }
+    if (lc.skips) atomicAdd(&c->skips, lc.skips);
+    if (lc.rollouts) { atomicAdd(&c->rollouts, lc.rollouts); atomicAdd(&c->rollout_steps, lc.rollout_steps); }
+    atomicMax(&c->max_depth, lc.max_depth);
   }
 }
 
-// ---- batched mode: one wave = descend kernel (warp per path) + finish kernel (thread per path)
+// ---- batched mode: persistent asynchronous warp workers.  Every warp of the grid is a worker;
+// a worker repeatedly takes the next query id, runs one whole simulation and publishes its
+// statistics with atomics.  There is no barrier anywhere: the number of simulations in flight is
+// the number of admitted workers, clamp(root visits / ramp_div, inflight_min, inflight_max), so
+// the tree is never more than that many simulations stale (small while the tree is small).
 template <int PID>
-__global__ void __launch_bounds__(128) k_descend(const __grid_constant__ Pool P, const __grid_constant__ DevModel m,
-                                                 const __grid_constant__ SearchCfg cfg,
-                                                 const __grid_constant__ WaveBuf wb, int wave, uint32_t q_base) {
-  int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (warp >= wave) return;
+__global__ void __launch_bounds__(128) k_search_workers(const __grid_constant__ Pool P,
+                                                        const __grid_constant__ DevModel m,
+                                                        const __grid_constant__ SearchCfg cfg,
+                                                        const __grid_constant__ PathBuf pb, long long queries) {
+  const int lane = threadIdx.x & 31;
+  DevCtr* c = P.ctr;
+  // worker ids are handed out in start order, so the admitted (lowest) ids are always resident
+  unsigned wid = 0;
+  if (lane == 0) wid = (unsigned)atomicAdd(&c->worker_ticket, 1ull);
+  wid = __shfl_sync(0xffffffffu, wid, 0);
   ReplayCursor rc{0, 0};
+  LocalCtr lc{0, 0, 0, 0, 0, 0};
   uint32_t spare = 0;
-  uint32_t root_ticket = __ldcg(&P.node_N[cfg.root]) + (uint32_t)warp;
-  descend_one<PID, false, false>(P, m, cfg, wb, warp, q_base + (uint32_t)warp, root_ticket, rc, spare);
-}
-
-template <int PID>
-__global__ void __launch_bounds__(256) k_finish(const __grid_constant__ Pool P, const __grid_constant__ DevModel m,
-                                                const __grid_constant__ SearchCfg cfg,
-                                                const __grid_constant__ WaveBuf wb, int wave, uint32_t q_base) {
-  __shared__ double sW[POMCP_MAX_ACTIONS];
-  __shared__ unsigned sM[POMCP_MAX_ACTIONS];
-  __shared__ unsigned long long sCtr[6];
-  if (threadIdx.x < POMCP_MAX_ACTIONS) { sW[threadIdx.x] = 0.0; sM[threadIdx.x] = 0u; }
-  if (threadIdx.x < 6) sCtr[threadIdx.x] = 0ull;
-  __syncthreads();
-  int widx = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  ReplayCursor rc{0, 0};
-  finish_one<PID, false, false, true>(P, m, cfg, wb, widx, q_base + (uint32_t)widx, widx < wave, rc, sW, sM, sCtr);
-  __syncthreads();
-  if (threadIdx.x < m.nA && sM[threadIdx.x] > 0) {
-    uint32_t slot = cfg.root * (uint32_t)m.nA + threadIdx.x;
-    atomicAdd(&P.act_V[slot], sW[threadIdx.x]);
-    atomicAdd(&P.act_M[slot], sM[threadIdx.x]);
-  }
-  if (threadIdx.x == 0) {
-    DevCtr* c = P.ctr;
-    if (sCtr[0]) {
-      atomicAdd(&c->sims, sCtr[0]);
-      atomicAdd(&P.node_N[cfg.root], (uint32_t)sCtr[0]);  // b.N += 1 per simulation, src/solver.jl:51
-      c->any_nonterminal = 1;
+  for (;;) {
+    // admission: ramp the number of simulations in flight with the size of the tree
+    long long q = -1;
+    if (lane == 0) {
+      unsigned spins = 0;
+      for (;;) {
+        if (__ldcg((const unsigned long long*)&c->next_query) >= (unsigned long long)queries) break;
+        if (__ldcg(&c->pool_overflow)) break;
+        if (++spins > (1u << 22)) {  // ~2 s without being admitted: give up instead of hanging the device
+          c->pool_overflow = 2;
+          break;
+        }
+        long long visits = (long long)__ldcg(&P.node_N[cfg.root]);
+        long long allowed = visits / cfg.ramp_div;
+        allowed = allowed < cfg.inflight_min ? cfg.inflight_min : allowed;
+        allowed = allowed > cfg.inflight_max ? cfg.inflight_max : allowed;
+        if ((long long)wid < allowed) {
+          unsigned long long t = atomicAdd(&c->next_query, 1ull);
+          if (t < (unsigned long long)queries) q = (long long)t;
+          break;
+        }
+        __nanosleep(400);
+      }
     }
-    if (sCtr[1]) atomicAdd(&c->skips, sCtr[1]);
-    if (sCtr[2]) { atomicAdd(&c->rollouts, sCtr[2]); atomicAdd(&c->rollout_steps, sCtr[3]); }
-    if (sCtr[4]) atomicAdd(&c->tree_steps, sCtr[4]);
-    atomicMax(&c->max_depth, sCtr[5]);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q < 0) break;
+    simulate_one<PID, false, false>(P, m, cfg, pb, (int)wid, (uint32_t)q, cfg.root_N0 + (uint32_t)q, rc, spare, lc);
   }
+  if (lane == 0) flush_counters(P, lc, false);
 }
 
 // ---- exact mode: one warp runs the queries strictly one after another (bit-parity with the
@@ -480,21 +487,20 @@ template <int PID, bool REPLAY>
 __global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Pool P,
                                                      const __grid_constant__ DevModel m,
                                                      const __grid_constant__ SearchCfg cfg,
-                                                     const __grid_constant__ WaveBuf wb, long long queries,
+                                                     const __grid_constant__ PathBuf pb, long long queries,
                                                      SearchResult* res) {
   ReplayCursor rc{0, 0};
+  LocalCtr lc{0, 0, 0, 0, 0, 0};
   uint32_t spare = 0;
   const int lane = threadIdx.x & 31;
   for (long long q = 0; q < queries; ++q) {
     uint32_t root_ticket = __ldcg(&P.node_N[cfg.root]);
-    descend_one<PID, true, REPLAY>(P, m, cfg, wb, 0, (uint32_t)q, root_ticket, rc, spare);
-    __syncwarp();
-    if (lane == 0) finish_one<PID, true, REPLAY, false>(P, m, cfg, wb, 0, (uint32_t)q, true, rc, nullptr, nullptr, nullptr);
-    rc.rcur = __shfl_sync(0xffffffffu, rc.rcur, 0);
+    simulate_one<PID, true, REPLAY>(P, m, cfg, pb, 0, (uint32_t)q, root_ticket, rc, spare, lc);
     __threadfence_block();
     __syncwarp();
   }
   if (lane == 0) {
+    flush_counters(P, lc, true);
     res->ucur = rc.ucur;
     res->rcur = rc.rcur;
     if (REPLAY && (rc.ucur > cfg.n_uni || rc.rcur > cfg.n_rets)) P.ctr->replay_overflow = 1;
@@ -529,6 +535,7 @@ __global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t r
   if (res->V[0] != res->V[0]) st = POMCP_ERR_NAN_VALUE;           // @assert !isnan(best_V), src/solver.jl:62
   if (!c->any_nonterminal) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;    // src/solver.jl:56-58
   if (c->pool_overflow || c->log_overflow) st = POMCP_ERR_POOL_EXHAUSTED;
+  if (c->pool_overflow == 2) st = POMCP_ERR_CUDA;  // worker watchdog fired
   if (c->replay_overflow) st = POMCP_ERR_INVALID_ARG;
   res->status = st;
 }

@@ -1,0 +1,20 @@
+"""One warmed-up decision (search 1e6 + SIR 2^20) on RockSample(7,8): the ncu target."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pomcp_jl_b200 as pj
+from pomcp_jl_b200 import _abi as abi
+import bench
+
+Q = int(sys.argv[1]) if len(sys.argv) > 1 else bench.TREE_QUERIES
+pomdp = pj.RockSamplePOMDP(bench.RS_N, bench.RS_K, seed=bench.RS_SEED)
+solver = pj.POMCPSolver(c=bench.UCB_C, rng=bench.SOLVER_SEED, tree_queries=Q, search_mode="batched", max_nodes=3 * Q)
+policy = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
+parts, _ = bench.initial_particles(pomdp, bench.N_PARTICLES)
+policy.set_belief_particles(parts)
+for k in range(2):
+    a, N, V = policy.search(Q)
+    policy.pf_update_sir(5, k & 1, seed=k, n_out=bench.N_PARTICLES)
+cs = policy.counters()
+print("ok", a, cs["rollout_steps"], cs["waves"], cs["kernel_launches"])
+policy.close()

@@ -108,12 +108,14 @@ def test_resample_zero_weight_is_depletion(oracle, gpu_lib):
 
 
 # ----------------------------------------------------------------------------- exact search
-@pytest.mark.parametrize("name,queries", [("tiger", 1000), ("baby", 3000), ("rs78", 4000), ("rs44", 4000),
-                                          ("lightdark", 1500)])
-def test_exact_search_bit_exact(oracle, gpu_lib, name, queries):
-    """Same Philox streams => identical trees: N counts, V bits, structure."""
+@pytest.mark.parametrize("name,queries,R", [("tiger", 1000, 1), ("baby", 3000, 1), ("rs78", 4000, 1), ("rs44", 4000, 1),
+                                            ("lightdark", 1500, 1), ("baby", 2000, 32), ("rs78", 3000, 32),
+                                            ("tiger", 1000, 5), ("lightdark", 1000, 32)])
+def test_exact_search_bit_exact(oracle, gpu_lib, name, queries, R):
+    """Same Philox streams => identical trees: N counts, V bits, structure.  R = rollouts averaged per
+    leaf (R = 1 is the reference; lane r runs rollout r and the returns are added in butterfly order)."""
     pomdp, c = PROBS[name]
-    gp, op = make_pair(oracle, pomdp, c, seed=11, mode="exact", tree_queries=queries)
+    gp, op = make_pair(oracle, pomdp, c, seed=11, mode="exact", tree_queries=queries, rollouts_per_leaf=R)
     gp.set_belief_initial()
     op.set_belief_initial()
     a_g, N_g, V_g = gp.search(queries)
@@ -289,7 +291,7 @@ def test_batched_search_invariants_and_values(oracle, gpu_lib, name, queries):
     node_N, act_N, act_V, child = gp.dump_tree()
     _tree_invariants(node_N, act_N, child)
     cg = gp.counters()
-    assert cg["simulations"] == queries and cg["rollouts"] <= queries - 1
+    assert cg["simulations"] == queries and cg["rollouts"] <= 32 * (queries - 1)
     scale = {"tiger": 300.0, "baby": 15.0, "rs78": 10.0}[name]
     both = (N_g >= 200) & (N_o >= 200)
     assert both.any()
