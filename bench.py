@@ -74,11 +74,18 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -87,7 +94,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -99,7 +106,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = (self.t0 or 0) + 0.02
+        hi = (self.t1 or 1e30) + 0.05
+        for ts, r in self.rows:
+            if not (lo <= ts <= hi):
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -249,13 +260,14 @@ def run_gpu(args):
         policy.pf_update_sir(5, k & 1, seed=1000 + k, n_out=N_PARTICLES)  # check rock 0, alternating answers
         return a
 
+    sampler = ClockSampler(device)
+    if rank == 0:
+        sampler.start()
     for k in range(args.warmup):
         resident_step(k)
     policy.reset_counters()
-    sampler = ClockSampler(device)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     step_ms, pf_ms, search_ms, rollout_ms, pf_launches = [], [], [], [], 0
     for k in range(args.steps):
         policy.flush_l2()
@@ -270,6 +282,7 @@ def run_gpu(args):
         search_ms.append(policy.phase_ms(abi.PHASE_SEARCH)[0])
         rollout_ms.append(policy.phase_ms(abi.PHASE_ROLLOUT)[0])
     barrier()
+    sampler.mark_stop()
     clocks = sampler.stop() if rank == 0 else None
     cs = policy.counters()
     total_ms = sum(step_ms)
@@ -349,15 +362,24 @@ def run_gpu(args):
                 "launches_per_update": pf_launches, "peak_source": peak_src,
             },
             "roofline_rollout": {
-                "kernel": "k_finish (K3 rollout + K4 backup), one thread per trajectory", "bound": "issue",
+                "kernel": "k_search_workers (K1-K4: warp-per-path descent, lane-per-trajectory rollouts, backup)",
+                "bound": "issue",
                 "achieved": steps_rank0 / roll_s if roll_s > 0 else None, "unit": "rollout steps/s inside the kernel",
                 "share_of_step": roll_s * 1e3 / total_ms,
                 "thread_inst_per_step": prof.get("rollout_thread_inst_per_step"),
                 "peak": (148 * 4 * 32 * sm_max * 1e6 / prof["rollout_thread_inst_per_step"])
                 if prof.get("rollout_thread_inst_per_step") else None,
+                "frac": (steps_rank0 / roll_s) / (148 * 4 * 32 * sm_max * 1e6 / prof["rollout_thread_inst_per_step"])
+                if (prof.get("rollout_thread_inst_per_step") and roll_s > 0) else None,
                 "warp_efficiency": prof.get("rollout_warp_efficiency"),
+                "issue_active_pct": prof.get("workers_issue_active_pct"),
+                "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
+                        "keep the tree no more than that many simulations stale",
             },
-            "phase_ms_per_step": {"search": statistics.mean(search_ms), "finish_kernels": statistics.mean(rollout_ms),
+            "solver": {"inflight_max": policy._sp.inflight_max or 1024, "inflight_ramp_div": policy._sp.inflight_ramp_div
+                       or 32, "rollouts_per_leaf": policy._sp.rollouts_per_leaf or 32, "search_mode": "batched"},
+            "rollouts_per_sec": cs["rollouts"] * n_gpus / (total_ms_max * 1e-3),
+            "phase_ms_per_step": {"search": statistics.mean(search_ms), "worker_kernel": statistics.mean(rollout_ms),
                                   "sir_update": statistics.mean(pf_ms), "step": statistics.mean(step_ms)},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
@@ -372,7 +394,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
