@@ -126,6 +126,7 @@ struct pomcp_handle {
   pomcp_counters host_ctr{};
   long long launches = 0, last_waves = 0;
   bool pending = false;
+  bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
   nccl_comm comm = nullptr;
   int nranks = 1;
   std::string err;
@@ -361,6 +362,29 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   z.first_alive = ~0ull;
   *h->h_pfctl = z;
   CK(cudaMemcpyAsync(h->d_pfctl, h->h_pfctl, sizeof(PfCtl), cudaMemcpyHostToDevice, h->stream));
+  // fused single-launch path when the whole set fits one co-resident grid
+  static int max_grid = -1;  // per <Src,Out> instantiation
+  if (max_grid < 0) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    max_grid = per_sm * sms;
+  }
+  long long grid = (n + PF_CTA_ITEMS - 1) / PF_CTA_ITEMS;
+  if (grid <= max_grid && !h->force_streaming_pf) {
+    PfCtl* ctl = h->d_pfctl;
+    unsigned long long* cta_tot = h->d_scan_status + 1;
+    unsigned int* bar = (unsigned int*)h->d_scan_status;
+    Src src_copy = src;
+    void* args[] = {(void*)&src_copy, (void*)&n, (void*)&ctl, (void*)&ru, (void*)&n_out, (void*)&d_out,
+                    (void*)&cta_tot, (void*)&bar};
+    CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args, 0,
+                                   h->stream));
+    rc = launch_check(h, "k_pf_fused");
+    if (rc) return rc;
+    h->timers[POMCP_PHASE_PF].launches += 1;
+    return POMCP_OK;
+  }
   int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
   k_pf_max<Src><<<blocks, 256, 0, h->stream>>>(src, n, h->d_pfctl);
   rc = launch_check(h, "k_pf_max");
@@ -500,6 +524,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->hashed = (nO == 0);
   h->exact = sp->search_mode == POMCP_MODE_EXACT;
   h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
+  h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
   CKU(cudaSetDevice(device));
   CKU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 

@@ -141,11 +141,20 @@ struct ModelSrc {
     w = M::obs_weight(m, a, sp, obs);
     return true;
   }
+  // generate_s only (the emit phase needs the state, not the weight, of the particles it copies)
+  __device__ __forceinline__ void propagate(long long i, State& sp) const {
+    State s = states[i];
+    Philox4 p = philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1);
+    uint64_t o;
+    double r;
+    M::template step<false, double>(m, s, a, u01(p.w[0]), 0.0, 0.0, sp, o, r);
+  }
 };
 
 struct ArraySrc {  // replayed weights (parity hook): payload is the index itself
   using State = long long;
   const double* w_in;
+  __device__ __forceinline__ void propagate(long long i, State& sp) const { sp = i; }
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
     sp = i;
     w = w_in[i];
@@ -301,6 +310,162 @@ __global__ void k_resample_seq_f64(const double* w, long long n, double r01, lon
     idx[mth] = i;
   }
   ctl->status = POMCP_OK;
+}
+
+// ---- K6+K7+K8 fused: one persistent cooperative launch for particle sets that fit the grid
+// (n <= gridDim * PF_CTA_ITEMS; 148 SMs x 2 CTAs x 4096 items = 1.2 M particles on B200).
+// Every CTA owns 4096 consecutive particles and keeps their fp64 weights in registers across two
+// grid-wide barriers, so HBM sees each input state once and each output state once:
+//   phase A  read s_i, propagate + weight          -> global max weight, first alive particle
+//   barrier  phase B  quantise, warp/CTA scan      -> per-CTA totals (gridDim values)
+//   barrier  phase C  offsets from the CTA totals, closed-form output ranges, write the copies
+// Same integers as the streaming path (k_pf_max / k_pf_scan / k_pf_emit), so the same indices.
+constexpr int PF_THREADS = 512;
+constexpr int PF_ITEMS = 8;
+constexpr int PF_CTA_ITEMS = PF_THREADS * PF_ITEMS;
+
+__device__ __forceinline__ void pf_grid_barrier(unsigned int* bar, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar));
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class Src, class Out>
+__global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constant__ Src src, long long n, PfCtl* ctl,
+                                                            uint32_t ru, long long n_out, Out* out,
+                                                            unsigned long long* cta_tot, unsigned int* bar) {
+  __shared__ unsigned long long s_a[PF_THREADS / 32];
+  __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_off, s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long base = (long long)blockIdx.x * PF_CTA_ITEMS + (long long)warp * 32 * PF_ITEMS;
+
+  // ---- phase A: propagate + weight
+  double w[PF_ITEMS];
+  unsigned alive_mask = 0;
+  unsigned long long mx = 0, first = ~0ull;
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    long long i = base + j * 32 + lane;
+    w[j] = 0.0;
+    if (i < n) {
+      typename Src::State sp;
+      bool alive = src.eval(i, sp, w[j]);
+      if (alive) {
+        alive_mask |= 1u << j;
+        if ((unsigned long long)i < first) first = (unsigned long long)i;
+        unsigned long long b = (w[j] > 0.0) ? d2u(w[j]) : 0ull;
+        mx = b > mx ? b : mx;
+      } else {
+        w[j] = 0.0;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, off), of = __shfl_xor_sync(0xffffffffu, first, off);
+    mx = om > mx ? om : mx;
+    first = of < first ? of : first;
+  }
+  if (lane == 0) { s_a[warp] = mx; s_b[warp] = first; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < PF_THREADS / 32; ++k) {
+      mx = s_a[k] > mx ? s_a[k] : mx;
+      first = s_b[k] < first ? s_b[k] : first;
+    }
+    if (first != ~0ull) {
+      atomicMax(&ctl->max_bits, mx);
+      atomicMin(&ctl->first_alive, first);
+      ctl->any_alive = 1;
+    }
+  }
+  pf_grid_barrier(bar, gridDim.x);
+
+  // ---- phase B: quantise and scan inside the CTA
+  const unsigned long long max_bits = ld_volatile_u64(&ctl->max_bits);
+  const int scale = pf_scale(max_bits, n);
+  unsigned long long inc[PF_ITEMS];
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    unsigned long long x = ((alive_mask >> j) & 1u) ? pf_quantise(w[j], scale) : 0ull;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    inc[j] = x + carry;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) s_a[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = (lane < PF_THREADS / 32) ? s_a[lane] : 0ull, x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    if (lane < PF_THREADS / 32) s_a[lane] = x - v;  // exclusive over warps
+    if (lane == 31) atomicExch(&cta_tot[blockIdx.x], x);
+  }
+  pf_grid_barrier(bar, 2u * gridDim.x);
+
+  // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
+  if (warp == 0) {
+    unsigned long long before = 0, all = 0;
+    for (int k = lane; k < (int)gridDim.x; k += 32) {
+      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
+      all += t;
+      if (k < (int)blockIdx.x) before += t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, off);
+      all += __shfl_xor_sync(0xffffffffu, all, off);
+    }
+    if (lane == 0) { s_off = before; s_total = all; }
+  }
+  __syncthreads();
+  const unsigned long long T = s_total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->total = T;
+    int st = POMCP_OK;
+    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+    else if (max_bits == 0 || T == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
+    ctl->status = st;
+  }
+  if (T == 0) return;
+
+  // ---- phase C: particle i owns outputs [M(C_{i-1}), M(C_i))
+  const unsigned long long first_alive = ld_volatile_u64(&ctl->first_alive);
+  const unsigned long long off0 = s_off + s_a[warp];
+  long long prev_hi = pf_points_below(off0, T, ru, n_out);  // M at the start of this warp's range
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    long long i = base + j * 32 + lane;
+    long long hi = pf_points_below(off0 + inc[j], T, ru, n_out);
+    long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
+    if (lane == 0) lo = prev_hi;
+    prev_hi = __shfl_sync(0xffffffffu, hi, 31);
+    if (i < n && ((alive_mask >> j) & 1u)) {
+      if ((unsigned long long)i == first_alive) lo = 0;
+      if (lo < hi) {
+        typename Src::State sp;
+        src.propagate(i, sp);
+        for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+      }
+    }
+  }
 }
 
 // pomcp_pf_weights parity hook

@@ -21,7 +21,7 @@ def probe_search(pomdp, c, Q, n_part, **kw):
         t = time.time(); a, N, V = gp.search(Q); dt = time.time() - t
         cs = gp.counters()
         ms_s, ls = gp.phase_ms(abi.PHASE_SEARCH); ms_r, lr = gp.phase_ms(abi.PHASE_ROLLOUT)
-        print(f"{type(pomdp).__name__} Q={Q} it={it} wall={dt*1e3:.2f}ms search={ms_s:.2f}ms finish-kernels={ms_r:.2f}ms waves={cs['waves']} "
+        print(f"{type(pomdp).__name__} Q={Q} it={it} wall={dt*1e3:.2f}ms search={ms_s:.2f}ms worker-kernel={ms_r:.2f}ms waves={cs['waves']} "
               f"rollout_steps={cs['rollout_steps']} steps/s={cs['rollout_steps']/(ms_s*1e-3):.3e} sims/s={Q/(ms_s*1e-3):.3e} "
               f"nodes={cs['nodes']} maxdepth={cs['max_depth_seen']} a={a} Nmax={N.max()} V={np.round(V,2)}")
     return gp, parts
@@ -47,6 +47,6 @@ if __name__ == "__main__":
     gp, parts = probe_search(pj.BabyPOMDP(), 10.0, 100000, 10000)
     probe_sir(gp, pj.BabyPOMDP(), parts, 0, 1)
     gp.close()
-    for wm in (4096, 16384, 65536):
-        gp, parts = probe_search(rs, 20.0, Q, 1 << 20, wave_max=wm)
+    for im in (256, 4096):
+        gp, parts = probe_search(rs, 20.0, Q, 1 << 20, inflight_max=im)
         gp.close()

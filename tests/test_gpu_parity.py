@@ -64,9 +64,17 @@ def _weight_cases(rng):
     yield "tiny", rng.random(2500) * 1e-200, 0.6, 2500
     yield "big", rng.random(300000), 0.4242, 300000
     yield "ragged", rng.random(1025), 0.75, 7
+    yield "max_single_grid", rng.random(148 * 2 * 4096), 0.123, 1 << 20   # largest set of the fused kernel
+    yield "beyond_single_grid", rng.random(1_500_000), 0.321, 1_000_000   # falls back to the streaming kernels
+    yield "heavy_runs", np.where(rng.random(20000) < 0.002, 1.0, 1e-12), 0.5, 400000  # few particles, long copy runs
 
 
-def test_resample_fixed_bit_exact(oracle, gpu_lib):
+@pytest.mark.parametrize("streaming", [False, True])
+def test_resample_fixed_bit_exact(oracle, gpu_lib, streaming, monkeypatch):
+    """Fixed-point systematic resampling: fused single-launch kernel and the three streaming kernels
+    (POMCP_PF_STREAMING=1 forces the latter) give the oracle's indices bit for bit."""
+    if streaming:
+        monkeypatch.setenv("POMCP_PF_STREAMING", "1")
     pomdp, c = PROBS["baby"]
     gp, _ = make_pair(oracle, pomdp, c, seed=3)
     rng = np.random.default_rng(5)
@@ -211,8 +219,12 @@ def test_unweighted_update_depletion(oracle, gpu_lib):
 
 
 # ----------------------------------------------------------------------------- SIR update
-@pytest.mark.parametrize("name,n", [("baby", 10000), ("tiger", 4096), ("rs78", 50000), ("lightdark", 100000)])
-def test_sir_update_bit_exact(oracle, gpu_lib, name, n):
+@pytest.mark.parametrize("streaming", [False, True])
+@pytest.mark.parametrize("name,n", [("baby", 10000), ("tiger", 4096), ("rs78", 50000), ("lightdark", 100000),
+                                    ("lightdark", 1000000), ("rs78", 1 << 20)])
+def test_sir_update_bit_exact(oracle, gpu_lib, name, n, streaming, monkeypatch):
+    if streaming:
+        monkeypatch.setenv("POMCP_PF_STREAMING", "1")
     pomdp, c = PROBS[name]
     gp, op = make_pair(oracle, pomdp, c, seed=4, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
     rng = np.random.default_rng(9)
