@@ -113,7 +113,8 @@ struct pomcp_handle {
   NodeStats* h_ns = nullptr;
   unsigned long long* d_cum = nullptr;
   size_t cum_cap = 0;
-  unsigned long long* d_scan_status = nullptr;  // [0] = ticket, [1..] = tile status
+  // one zero-initialised control block per scan / resample: [0..7] PfCtl, [8] ticket or barrier, [9..] tile status
+  unsigned long long* d_scan_status = nullptr;
   size_t scan_cap = 0;
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
@@ -344,9 +345,11 @@ ModelSrc<PID> make_src(pomcp_handle* h, const void* states, int a, uint64_t obs,
 }
 
 int ensure_scan(pomcp_handle* h, long long n) {
-  size_t tiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 2;
-  int rc = ensure_bytes(h, (void**)&h->d_scan_status, &h->scan_cap, tiles * sizeof(unsigned long long));
+  static_assert(sizeof(PfCtl) <= 64, "PfCtl must fit the first 8 words of the control block");
+  size_t tiles = (size_t)((n + SCAN_TILE - 1) / SCAN_TILE) + 12;
+  int rc = ensure_bytes(h, (void**)&h->d_scan_status, &h->scan_cap, std::max<size_t>(tiles, 512) * sizeof(unsigned long long));
   if (rc) return rc;
+  h->d_pfctl = (PfCtl*)h->d_scan_status;
   CK(cudaMemsetAsync(h->d_scan_status, 0, tiles * sizeof(unsigned long long), h->stream));
   return POMCP_OK;
 }
@@ -358,10 +361,6 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   if (rc) return rc;
   rc = ensure_scan(h, n);
   if (rc) return rc;
-  PfCtl z{};
-  z.first_alive = ~0ull;
-  *h->h_pfctl = z;
-  CK(cudaMemcpyAsync(h->d_pfctl, h->h_pfctl, sizeof(PfCtl), cudaMemcpyHostToDevice, h->stream));
   // fused single-launch path when the whole set fits one co-resident grid
   static int max_grid = -1;  // per <Src,Out> instantiation
   if (max_grid < 0) {
@@ -370,16 +369,22 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     max_grid = per_sm * sms;
   }
-  long long grid = (n + PF_CTA_ITEMS - 1) / PF_CTA_ITEMS;
-  if (grid <= max_grid && !h->force_streaming_pf) {
+  // split the set evenly over the co-resident grid: rows of 32 particles per warp (<= PF_ITEMS)
+  long long rows_ll = max_grid > 0 ? (n + (long long)max_grid * PF_THREADS - 1) / ((long long)max_grid * PF_THREADS) : 99;
+  int rows = (int)std::max<long long>(rows_ll, 1);
+  long long grid = (n + (long long)PF_THREADS * rows - 1) / ((long long)PF_THREADS * rows);
+  if (rows <= PF_ITEMS && grid <= max_grid && !h->force_streaming_pf) {
     PfCtl* ctl = h->d_pfctl;
-    unsigned long long* cta_tot = h->d_scan_status + 1;
-    unsigned int* bar = (unsigned int*)h->d_scan_status;
+    unsigned long long* cta_tot = h->d_scan_status + 9;
+    unsigned int* bar = (unsigned int*)(h->d_scan_status + 8);
     Src src_copy = src;
     void* args[] = {(void*)&src_copy, (void*)&n, (void*)&ctl, (void*)&ru, (void*)&n_out, (void*)&d_out,
-                    (void*)&cta_tot, (void*)&bar};
-    CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args, 0,
-                                   h->stream));
+                    (void*)&cta_tot, (void*)&bar, (void*)&rows};
+    if (std::getenv("POMCP_PF_NONCOOP"))  // measurement only: plain launch (co-residency not guaranteed)
+      k_pf_fused<Src, Out><<<(unsigned)grid, PF_THREADS, 0, h->stream>>>(src_copy, n, ctl, ru, n_out, d_out, cta_tot, bar, rows);
+    else
+      CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
+                                     0, h->stream));
     rc = launch_check(h, "k_pf_fused");
     if (rc) return rc;
     h->timers[POMCP_PHASE_PF].launches += 1;
@@ -390,8 +395,8 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   rc = launch_check(h, "k_pf_max");
   if (rc) return rc;
   int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-  k_pf_scan<Src><<<tiles, SCAN_THREADS, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, h->d_scan_status + 1,
-                                                        h->d_scan_status);
+  k_pf_scan<Src><<<tiles, SCAN_THREADS, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, h->d_scan_status + 9,
+                                                        h->d_scan_status + 8);
   rc = launch_check(h, "k_pf_scan");
   if (rc) return rc;
   k_pf_finalize<<<1, 32, 0, h->stream>>>(h->d_cum, n, h->d_pfctl);
@@ -472,7 +477,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   void* ptrs[] = {h->d_eta, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
-                  h->d_bel[0], h->d_bel[1], h->d_res, h->d_pfctl, h->d_ns,
+                  h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
                   h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -594,7 +599,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKU(cudaMemGetInfo(&free_b, &total_b));
   long long Q = std::max<long long>(sp->tree_queries, 1);
   size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4);
-  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 16 * Q : 2 * Q) + 4096;
+  // unweighted mode keeps the tree across decisions (re-rooting, no compaction yet): room for ~64 of them
+  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) + 65536;
   long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
   want = std::min<long long>(want, std::min<long long>(cap_mem, (1ll << 31) - 2));
   if (want < 16) { h->err = "not enough device memory for the node pool"; return bail(POMCP_ERR_CUDA); }
@@ -638,7 +644,6 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKU(cudaMalloc(&h->pb.path_state, pw * sb));
 
   CKC(dev_alloc(h, &h->d_res, 1));
-  CKC(dev_alloc(h, &h->d_pfctl, 1));
   CKC(dev_alloc(h, &h->d_ns, 1));
   CKU(cudaMallocHost((void**)&h->h_res, sizeof(SearchResult)));
   CKU(cudaMallocHost((void**)&h->h_ctr, sizeof(DevCtr)));
@@ -646,6 +651,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKU(cudaMallocHost((void**)&h->h_ns, sizeof(NodeStats)));
   std::memset(h->h_res, 0, sizeof(SearchResult));
 
+  CKC(ensure_scan(h, 1));
   h->nodes_used = want;  // first fill covers the whole pool
   CKC(fresh_root(h));
   CKU(cudaStreamSynchronize(h->stream));
@@ -805,14 +811,14 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
     if (h->state_bytes == 4)
       k_log_gather<uint32_t><<<tiles, SCAN_THREADS, 0, h->stream>>>(h->pool.log_node, (const uint32_t*)h->pool.log_state,
                                                                   child, n_log, (uint32_t*)h->d_bel[nb], cnt,
-                                                                  h->d_scan_status + 1, h->d_scan_status);
+                                                                  h->d_scan_status + 9, h->d_scan_status + 8);
     else
       k_log_gather<LDState><<<tiles, SCAN_THREADS, 0, h->stream>>>(h->pool.log_node, (const LDState*)h->pool.log_state,
                                                                  child, n_log, (LDState*)h->d_bel[nb], cnt,
-                                                                 h->d_scan_status + 1, h->d_scan_status);
+                                                                 h->d_scan_status + 9, h->d_scan_status + 8);
     rc = launch_check(h, "k_log_gather");
     if (rc) return rc;
-    k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 1, tiles, &h->d_pfctl->total);
+    k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 9, tiles, &h->d_pfctl->total);
     rc = launch_check(h, "k_scan_total");
     if (rc) return rc;
     t.launches += 3;
@@ -879,9 +885,8 @@ int32_t pomcp_resample_systematic(pomcp_handle* h, const double* w, int64_t n, d
     rc = run_resample(h, src, n, (uint32_t)(r * 4294967296.0), n_out, (long long*)h->d_tmp2);
     if (rc) return rc;
   } else {
-    PfCtl z{};
-    *h->h_pfctl = z;
-    CK(cudaMemcpyAsync(h->d_pfctl, h->h_pfctl, sizeof(PfCtl), cudaMemcpyHostToDevice, h->stream));
+    rc = ensure_scan(h, 1);
+    if (rc) return rc;
     k_resample_seq_f64<<<1, 32, 0, h->stream>>>((const double*)h->d_tmp, n, r, n_out, (long long*)h->d_tmp2, h->d_pfctl);
     rc = launch_check(h, "k_resample_seq_f64");
     if (rc) return rc;

@@ -53,6 +53,8 @@ struct ModelT<POMCP_TIGER> {
   using State = uint32_t;  // 1: tiger behind the left door
   static constexpr int DPS = 2;  // Philox words per rollout step: action, transition
   static constexpr bool HASHED = false;
+  static constexpr int NO = 2;
+  static constexpr bool T_DRAW = true;  // the transition consumes a uniform
   __device__ __forceinline__ static bool terminal(const DevModel&, State) { return false; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State s, int a, U ut0, double uo0, double,
@@ -82,6 +84,8 @@ struct ModelT<POMCP_BABY> {
   using State = uint32_t;  // 1: hungry
   static constexpr int DPS = 2;
   static constexpr bool HASHED = false;
+  static constexpr int NO = 2;
+  static constexpr bool T_DRAW = true;  // the transition consumes a uniform
   __device__ __forceinline__ static bool terminal(const DevModel&, State) { return false; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State s, int a, U ut0, double uo0, double,
@@ -109,34 +113,31 @@ struct ModelT<POMCP_ROCKSAMPLE> {
   using State = uint32_t;  // bits 0-3 x, 4-7 y, 8-23 rocks (1 good), bit 31 terminal
   static constexpr int DPS = 1;
   static constexpr bool HASHED = false;
+  static constexpr int NO = 3;
+  static constexpr bool T_DRAW = false;  // deterministic transitions
   __device__ __forceinline__ static bool terminal(const DevModel&, State s) { return (s & POMCP_RS_TERMINAL) != 0; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State st, int a, U, double uo0, double, State& sp,
                                               uint64_t& o, double& r) {
     int x = (int)(st & 15u), y = (int)((st >> 4) & 15u);
-    r = 0.0;
     o = 2;  // none
-    if (a == 0) {
-      y = min(y + 1, m.rs_n - 1);
-    } else if (a == 2) {
-      y = max(y - 1, 0);
-    } else if (a == 3) {
-      x = max(x - 1, 0);
-    } else if (a == 1) {
-      if (x == m.rs_n - 1) {
-        st |= POMCP_RS_TERMINAL;
-        r = m.rs_r_exit;
-      } else {
-        ++x;
-      }
-    } else if (a == 4) {
+    // moves without branches: lanes of a rollout warp hold different actions, so every arm of an
+    // if-chain would be executed by the warp on every step
+    const int nmax = m.rs_n - 1;
+    y = min(max(y + (int)(a == 0) - (int)(a == 2), 0), nmax);
+    const int nx = x + (int)(a == 1) - (int)(a == 3);
+    const bool exits = nx > nmax;  // only a == 1 on the east edge
+    x = min(max(nx, 0), nmax);
+    st |= exits ? POMCP_RS_TERMINAL : 0u;
+    r = exits ? m.rs_r_exit : 0.0;
+    if (a == 4) {
       int ri = m.rock_at[y * 16 + x];
       if (ri >= 0) {
         uint32_t good = (st >> (8 + ri)) & 1u;
         r = good ? m.rs_r_good : m.rs_r_bad;
         st &= ~(good << (8 + ri));
       }
-    } else {
+    } else if (a >= 5) {
       if (OBS) {
         int ri = a - 5;
         int good = (int)((st >> (8 + ri)) & 1u);
@@ -170,6 +171,8 @@ struct ModelT<POMCP_LIGHTDARK1D> {
   using State = LDState;
   static constexpr int DPS = 1;
   static constexpr bool HASHED = true;  // Float64 observations: children live in a hash table
+  static constexpr int NO = 0;
+  static constexpr bool T_DRAW = false;  // deterministic transitions
   __device__ __forceinline__ static bool terminal(const DevModel&, const State& s) { return s.status < 0; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, const State& s, int a, U, double uo0, double uo1,

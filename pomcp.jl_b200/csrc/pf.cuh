@@ -25,7 +25,7 @@ constexpr unsigned long long SCAN_VAL_MASK = (1ull << 62) - 1;
 
 struct PfCtl {
   unsigned long long max_bits;     // bits of the largest weight (weights >= 0: order-preserving)
-  unsigned long long first_alive;  // index of the first non-terminal particle
+  unsigned long long first_alive_inv;  // ~(index of the first non-terminal particle); 0 = none yet
   unsigned long long total;        // T = sum q_i
   unsigned int any_alive, status;
 };
@@ -134,20 +134,22 @@ struct ModelSrc {
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
     State s = states[i];
     if (M::terminal(m, s)) { sp = s; w = 0.0; return false; }  // dropped before weighting
-    Philox4 p = philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1);
+    double ut0 = 0.0;
+    if (M::T_DRAW) ut0 = u01(philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1).w[0]);
     uint64_t o;
     double r;
-    M::template step<false, double>(m, s, a, u01(p.w[0]), 0.0, 0.0, sp, o, r);
+    M::template step<false, double>(m, s, a, ut0, 0.0, 0.0, sp, o, r);
     w = M::obs_weight(m, a, sp, obs);
     return true;
   }
   // generate_s only (the emit phase needs the state, not the weight, of the particles it copies)
   __device__ __forceinline__ void propagate(long long i, State& sp) const {
     State s = states[i];
-    Philox4 p = philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1);
+    double ut0 = 0.0;
+    if (M::T_DRAW) ut0 = u01(philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1).w[0]);
     uint64_t o;
     double r;
-    M::template step<false, double>(m, s, a, u01(p.w[0]), 0.0, 0.0, sp, o, r);
+    M::template step<false, double>(m, s, a, ut0, 0.0, 0.0, sp, o, r);
   }
 };
 
@@ -164,8 +166,7 @@ struct ArraySrc {  // replayed weights (parity hook): payload is the index itsel
 
 __device__ __forceinline__ int pf_scale(unsigned long long max_bits, long long n) {
   int e = (int)((max_bits >> 52) & 0x7ffull) - 1023;
-  int L = 0;
-  while ((1ll << L) < n) ++L;
+  int L = (n <= 1) ? 0 : 64 - __clzll(n - 1);  // ceil(log2 n)
   return 61 - L - e;
 }
 __device__ __forceinline__ unsigned long long pf_quantise(double w, int s) {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) k_pf_max(const __grid_constant__ Src src,
     }
     if (first != ~0ull) {
       atomicMax(&ctl->max_bits, mx);
-      atomicMin(&ctl->first_alive, first);
+      atomicMax(&ctl->first_alive_inv, ~first);
       ctl->any_alive = 1;
     }
   }
@@ -237,26 +238,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_pf_scan(const __grid_constant_
   chained_scan(s, k, n, status, ticket);
 }
 
-// number of systematic points U_m = (ru/2^32 + m) * T / n_out, m in [0, n_out), with U_m <= C
-__device__ __forceinline__ long long pf_points_below(unsigned long long C, unsigned long long T, uint32_t ru,
-                                                     long long n_out) {
-  unsigned __int128 lhs = ((unsigned __int128)C * (unsigned long long)n_out) << 32;
-  unsigned __int128 r0 = (unsigned __int128)ru * T;
-  if (lhs < r0) return 0;
-  unsigned __int128 x = (lhs - r0) >> 32;  // floor(floor(X / 2^32) / T) == floor(X / (2^32 T))
-  // quotient < 2^33: estimate in fp64, then correct exactly
-  double est = ((double)(unsigned long long)(x >> 64) * 18446744073709551616.0 + (double)(unsigned long long)x) / (double)T;
-  long long qq = (long long)est;
-  if (qq < 0) qq = 0;
-  for (;;) {
-    unsigned __int128 prod = (unsigned __int128)(unsigned long long)qq * T;
-    if (prod > x) { --qq; continue; }
-    if (x - prod >= T) { ++qq; continue; }
-    break;
+// Number of systematic points U_m = (ru/2^32 + m) * T / n_out, m in [0, n_out), with U_m <= C, i.e.
+//   M(C) = floor((C*n_out*2^32 - ru*T) / (2^32*T)) + 1   (0 when the numerator is negative).
+// Write C*n_out = k*T + rem (0 <= rem < T).  Then M(C) = k + [rem*2^32 >= ru*T] = k + [rem >= thr]
+// with thr = ceil(ru*T / 2^32).  k < 2^32 comes from one fp64 multiply (relative error 2^-51, so at
+// most one off) and is corrected with rem computed in wrapping 64-bit arithmetic: the true
+// remainder of a k that is one off lies in (-T, 2T), well inside int64 since T < 2^62.
+struct PfDiv {
+  unsigned long long T, thr;
+  long long n_out;
+  double ratio;  // n_out / T
+  __device__ __forceinline__ PfDiv(unsigned long long T_, uint32_t ru, long long n_out_) : T(T_), n_out(n_out_) {
+    thr = (unsigned long long)(((unsigned __int128)ru * T_ + 0xffffffffull) >> 32);
+    ratio = (double)n_out_ / (double)T_;
   }
-  long long cnt = qq + 1;
-  return cnt < n_out ? cnt : n_out;
-}
+  __device__ __forceinline__ long long points_below(unsigned long long C) const {
+    unsigned long long k = (unsigned long long)((double)C * ratio);
+    long long rem = (long long)(C * (unsigned long long)n_out - k * T);
+    while (rem < 0) { --k; rem += (long long)T; }
+    while ((unsigned long long)rem >= T) { ++k; rem -= (long long)T; }
+    long long cnt = (long long)k + ((unsigned long long)rem >= thr ? 1 : 0);
+    return cnt < n_out ? cnt : n_out;
+  }
+};
 
 // K8: particle i owns the output range [M(C_{i-1}), M(C_i)) and writes that many copies.
 template <class Src, class Out>
@@ -273,10 +277,11 @@ __global__ void __launch_bounds__(256) k_pf_emit(const __grid_constant__ Src src
   double w;
   bool alive = src.eval(i, sp, w);
   if (!alive) return;
-  const bool is_first = (unsigned long long)i == ctl->first_alive;
+  const bool is_first = (unsigned long long)i == ~ctl->first_alive_inv;
   if (C == Cp && !is_first) return;
-  long long hi = pf_points_below(C, T, ru, n_out);
-  long long lo = is_first ? 0 : pf_points_below(Cp, T, ru, n_out);
+  const PfDiv dv(T, ru, n_out);
+  long long hi = dv.points_below(C);
+  long long lo = is_first ? 0 : dv.points_below(Cp);
   for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
 }
 
@@ -313,8 +318,9 @@ __global__ void k_resample_seq_f64(const double* w, long long n, double r01, lon
 }
 
 // ---- K6+K7+K8 fused: one persistent cooperative launch for particle sets that fit the grid
-// (n <= gridDim * PF_CTA_ITEMS; 148 SMs x 2 CTAs x 4096 items = 1.2 M particles on B200).
-// Every CTA owns 4096 consecutive particles and keeps their fp64 weights in registers across two
+// (n <= co-resident CTAs * 4096; 148 SMs x 2 CTAs x 4096 items = 1.2 M particles on B200).
+// The particles are split evenly over the grid (`rows` warp-rows of 32 per warp, <= 8); every CTA
+// owns 512*rows consecutive particles and keeps their fp64 weights in registers across two
 // grid-wide barriers, so HBM sees each input state once and each output state once:
 //   phase A  read s_i, propagate + weight          -> global max weight, first alive particle
 //   barrier  phase B  quantise, warp/CTA scan      -> per-CTA totals (gridDim values)
@@ -341,12 +347,13 @@ __device__ __forceinline__ void pf_grid_barrier(unsigned int* bar, unsigned int 
 template <class Src, class Out>
 __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constant__ Src src, long long n, PfCtl* ctl,
                                                             uint32_t ru, long long n_out, Out* out,
-                                                            unsigned long long* cta_tot, unsigned int* bar) {
+                                                            unsigned long long* cta_tot, unsigned int* bar,
+                                                            int rows) {
   __shared__ unsigned long long s_a[PF_THREADS / 32];
   __shared__ unsigned long long s_b[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long base = (long long)blockIdx.x * PF_CTA_ITEMS + (long long)warp * 32 * PF_ITEMS;
+  const long long base = ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * rows;
 
   // ---- phase A: propagate + weight
   double w[PF_ITEMS];
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   for (int j = 0; j < PF_ITEMS; ++j) {
     long long i = base + j * 32 + lane;
     w[j] = 0.0;
-    if (i < n) {
+    if (j < rows && i < n) {
       typename Src::State sp;
       bool alive = src.eval(i, sp, w[j]);
       if (alive) {
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
     }
     if (first != ~0ull) {
       atomicMax(&ctl->max_bits, mx);
-      atomicMin(&ctl->first_alive, first);
+      atomicMax(&ctl->first_alive_inv, ~first);
       ctl->any_alive = 1;
     }
   }
@@ -447,17 +454,19 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   if (T == 0) return;
 
   // ---- phase C: particle i owns outputs [M(C_{i-1}), M(C_i))
-  const unsigned long long first_alive = ld_volatile_u64(&ctl->first_alive);
+  const unsigned long long first_alive = ~ld_volatile_u64(&ctl->first_alive_inv);
   const unsigned long long off0 = s_off + s_a[warp];
-  long long prev_hi = pf_points_below(off0, T, ru, n_out);  // M at the start of this warp's range
+  const PfDiv dv(T, ru, n_out);
+  long long prev_hi = dv.points_below(off0);  // M at the start of this warp's range
 #pragma unroll
   for (int j = 0; j < PF_ITEMS; ++j) {
+    if (j >= rows) break;  // uniform
     long long i = base + j * 32 + lane;
-    long long hi = pf_points_below(off0 + inc[j], T, ru, n_out);
+    long long hi = dv.points_below(off0 + inc[j]);
     long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
     if (lane == 0) lo = prev_hi;
     prev_hi = __shfl_sync(0xffffffffu, hi, 31);
-    if (i < n && ((alive_mask >> j) & 1u)) {
+    if (j < rows && i < n && ((alive_mask >> j) & 1u)) {
       if ((unsigned long long)i == first_alive) lo = 0;
       if (lo < hi) {
         typename Src::State sp;

@@ -258,39 +258,46 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
   uint32_t hN = root_ticket;
   int depth = 0;
   bool want_rollout = false, aborted = false;
+  // Two dependent L2 round trips per level: (1) the node's action statistics together with its
+  // child ids, (2) the arrival ticket of the chosen child together with that child's expansion flag.
+  uint32_t fl = 0;  // lane 0 only: expansion flag of h
+  if (lane == 0) fl = __ldcg(&P.node_flags[h]);
   for (;;) {
     // src/solver.jl:82-86
     if (depth >= cfg.levels || M::terminal(m, s)) break;
-    // src/solver.jl:87-107: first non-cut-off visitor expands and evaluates the leaf
+    // src/solver.jl:87-107: first non-cut-off visitor expands and evaluates the leaf.
     // The flag races with other workers: lane 0 reads (and claims) it and broadcasts the outcome.
     // A per-lane load could return different values to different lanes of this warp (lanes are
     // not guaranteed to execute the load together) and split the warp across shuffle sites.
     int i_expand = 0;
-    if (lane == 0) {
-      uint32_t fl = __ldcg(&P.node_flags[h]);
-      if (!(fl & 1u)) {
-        uint32_t old;
-        if (EXACT) { old = fl; P.node_flags[h] = fl | 1u; }
-        else old = atomicOr(&P.node_flags[h], 1u);
-        i_expand = !(old & 1u);
-      }
+    if (lane == 0 && !(fl & 1u)) {
+      uint32_t old;
+      if (EXACT) { old = fl; P.node_flags[h] = fl | 1u; }
+      else old = atomicOr(&P.node_flags[h], 1u);
+      i_expand = !(old & 1u);
     }
     i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
     if (i_expand) {
       want_rollout = depth > 0;
       break;
     }
-    // UCB1: src/solver.jl:109-124
+    // UCB1: src/solver.jl:109-124 (child ids of every action are fetched by the same lanes)
     double crit = 0.0;
     bool valid = false;
+    uint32_t kid[M::NO > 0 ? M::NO : 1];
+#pragma unroll
+    for (int k = 0; k < (M::NO > 0 ? M::NO : 1); ++k) kid[k] = 0;
     if (lane < nA) {
       uint32_t sl = h * (uint32_t)nA + (uint32_t)lane;
       uint32_t n = __ldcg(&P.act_N[sl]);
       double v = __ldcg(&P.act_V[sl]);
-      if (!EXACT) {
-        uint32_t mm = __ldcg(&P.act_M[sl]);
-        v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
+      uint32_t mm = 0;
+      if (!EXACT) mm = __ldcg(&P.act_M[sl]);
+      if (!M::HASHED) {
+#pragma unroll
+        for (int k = 0; k < M::NO; ++k) kid[k] = __ldcg(&P.child[(size_t)sl * M::NO + k]);
       }
+      if (!EXACT) v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
       uint32_t hn = EXACT ? hN : (hN < 1u ? 1u : hN);
       if (n == 0 && hn == 1) crit = v;
       else if (n == 0 && v == -INFINITY) crit = INFINITY;
@@ -319,13 +326,21 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     M::template step<true, double>(m, s, best_a, u[0], u[2], u[3], sp, o, r);
 
     // src/solver.jl:132-142 + arrival counting
+    uint32_t pre = 0;  // prefetched child id (ids never change once published; 0 = not there yet)
+    if (!M::HASHED) {
+      uint32_t mine = kid[0];
+#pragma unroll
+      for (int k = 1; k < M::NO; ++k) mine = (o == (uint64_t)k) ? kid[k] : mine;
+      pre = __shfl_sync(0xffffffffu, mine, best_a);
+    }
     uint32_t hao = 0, ticket = 0;
     if (lane == 0) {
       if (EXACT) P.act_N[slot] = __ldcg(&P.act_N[slot]) + 1u; else atomicAdd(&P.act_N[slot], 1u);
-      hao = find_or_insert_child<PID>(P, m, slot, o, spare);
+      hao = pre ? pre : find_or_insert_child<PID>(P, m, slot, o, spare);
       if (hao != 0) {
         if (EXACT) { ticket = __ldcg(&P.node_N[hao]); P.node_N[hao] = ticket + 1u; }
         else ticket = atomicAdd(&P.node_N[hao], 1u);
+        fl = __ldcg(&P.node_flags[hao]);  // independent of the ticket: both are in flight together
         size_t pi = (size_t)depth * pb.stride + slot_idx;
         pb.path_slot[pi] = slot;
         pb.path_node[pi] = hao;

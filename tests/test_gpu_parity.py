@@ -284,33 +284,38 @@ def _tree_invariants(node_N, act_N, child, root=0):
 
 @pytest.mark.parametrize("name,queries", [("tiger", 20000), ("baby", 50000), ("rs78", 100000)])
 def test_batched_search_invariants_and_values(oracle, gpu_lib, name, queries):
-    """Batched mode: structural invariants hold exactly; root statistics agree with the sequential
-    oracle statistically.  Tolerance: total visits exact; the oracle's best root action is the
-    batched best action or within 3 standard errors of it; per-action |Q_gpu - Q_oracle| <= 4 SE + 2%
-    of the reward scale, for actions with >= 200 visits on both sides."""
+    """Batched mode (asynchronous workers, atomics): structural invariants hold exactly in every run;
+    root statistics agree with the sequential oracle statistically.  Both solvers are randomised, so
+    the comparison is between their distributions over 6 seeds.  Stated tolerance: the batched
+    planner picks the oracle's modal root action in >= 5 of 6 runs, and the mean root value of that
+    action differs by no more than 3 standard errors of the difference + 3% of the reward scale."""
     pomdp, c = PROBS[name]
     if name == "tiger":
         c = 1000.0  # random-rollout returns are O(-500): smaller c never revisits an action
-    gp, op = make_pair(oracle, pomdp, c, seed=31, mode="batched", tree_queries=queries)
-    gp.set_belief_initial()
-    op.set_belief_initial()
-    a_g, N_g, V_g = gp.search(queries)
-    rc, a_o, N_o, V_o = op.search(queries)
-    assert rc == 0
-    rootN, _, _ = gp.root_stats()
-    assert rootN == queries
-    assert N_g.sum() == queries - 1  # the root expansion consumes one query (src/solver.jl:104-106)
-    node_N, act_N, act_V, child = gp.dump_tree()
-    _tree_invariants(node_N, act_N, child)
-    cg = gp.counters()
-    assert cg["simulations"] == queries and cg["rollouts"] <= 32 * (queries - 1)
     scale = {"tiger": 300.0, "baby": 15.0, "rs78": 10.0}[name]
-    both = (N_g >= 200) & (N_o >= 200)
-    assert both.any()
-    se = scale / np.sqrt(np.minimum(N_g, N_o).clip(1))
-    assert np.all(np.abs(V_g - V_o)[both] <= 4 * se[both] + 0.02 * scale), (V_g, V_o, N_g, N_o)
-    assert V_g[a_o] >= V_g[a_g] - 3 * se[a_o] - 0.02 * scale, (a_g, a_o, V_g, V_o)
-    gp.close()
+    acts_g, acts_o, Vg, Vo = [], [], [], []
+    for seed in range(6):
+        gp, op = make_pair(oracle, pomdp, c, seed=31 + seed, mode="batched", tree_queries=queries)
+        gp.set_belief_initial()
+        op.set_belief_initial()
+        a_g, N_g, V_g = gp.search(queries)
+        rc, a_o, N_o, V_o = op.search(queries)
+        assert rc == 0
+        rootN, _, _ = gp.root_stats()
+        assert rootN == queries
+        assert N_g.sum() == queries - 1  # the root expansion consumes one query (src/solver.jl:104-106)
+        if seed == 0:
+            node_N, act_N, act_V, child = gp.dump_tree()
+            _tree_invariants(node_N, act_N, child)
+        cg = gp.counters()
+        assert cg["simulations"] == queries and cg["rollouts"] <= 32 * (queries - 1)
+        acts_g.append(a_g); acts_o.append(a_o); Vg.append(V_g); Vo.append(V_o)
+        gp.close()
+    modal = int(np.bincount(acts_o).argmax())
+    assert sum(a == modal for a in acts_g) >= 5, (acts_g, acts_o)
+    vg = np.array([v[modal] for v in Vg]); vo = np.array([v[modal] for v in Vo])
+    se = np.sqrt(vg.var(ddof=1) / len(vg) + vo.var(ddof=1) / len(vo))
+    assert abs(vg.mean() - vo.mean()) <= 3 * se + 0.03 * scale, (vg, vo)
 
 
 def test_batched_lightdark_continuous_obs(oracle, gpu_lib):
@@ -387,3 +392,125 @@ def test_api_default_action_and_errors(gpu_lib):
         pj.solve(pj.POMCPSolver(), pj.BabyPOMDP(discount_factor=1.0))
     with pytest.raises(NotImplementedError):
         pj.solve(pj.POMCPSolver(num_sparse_actions=3), pj.BabyPOMDP())
+
+
+# ----------------------------------------------------------------------------- episode reward (criterion 3)
+def _run_episodes(oracle, pomdp, make_planner, n_episodes, max_steps, seed0, use_gpu, n_part=0):
+    """RolloutSimulator outer loop: action -> environment step -> belief update.
+    The environment is stepped by the oracle's generative model with a host RNG shared by both arms."""
+    rewards = []
+    for ep in range(n_episodes):
+        env = np.random.default_rng(seed0 + ep)
+        pl = make_planner(ep)
+        if n_part:
+            s0 = pl_init_particles(pomdp, n_part, env)
+            pl.set_belief_particles(s0)
+            s = s0[0].copy()
+        else:
+            pl.set_belief_initial()
+            s = np.zeros(1, dtype=pomdp.state_dtype)[0]
+        disc, total = 1.0, 0.0
+        for t in range(max_steps):
+            if use_gpu:
+                try:
+                    a = pl.search(-1)[0]
+                except pj.AllSamplesTerminal:
+                    break
+            else:
+                rc, a, _, _ = pl.search(-1)
+                if rc == abi.ERR_ALL_SAMPLES_TERMINAL:
+                    break
+                assert rc == 0
+            if oracle.lib().orc_is_terminal(pomdp.c_struct(), np.array([s]).ctypes.data):
+                break
+            s, o, r = oracle.model_step(pomdp, s, a, ut=(env.random(), 0), uo=(env.random(), env.random()))
+            total += disc * r
+            disc *= pomdp.discount
+            o = pj.obs_from_bits(pomdp, o)
+            try:
+                if n_part:
+                    if use_gpu:
+                        pl.pf_update_sir(a, o, seed=ep * 1000 + t, n_out=n_part)
+                    else:
+                        rc = pl.pf_update_sir(a, o, seed=ep * 1000 + t, n_out=n_part, mode=0)
+                        if rc != 0:
+                            break
+                else:
+                    if use_gpu:
+                        pl.update_unweighted(a, o)
+                    elif pl.update_unweighted(a, o) != 0:
+                        total = None
+                        break
+            except (pj.ParticleDepletion, pj.AllSamplesTerminal):
+                if not n_part:
+                    total = None
+                break
+        if total is not None:
+            rewards.append(total)
+        pl.close()
+    return np.array(rewards)
+
+
+def pl_init_particles(pomdp, n, rng):
+    rocks = rng.integers(0, 1 << pomdp.k, n).astype(np.uint32)
+    return (np.uint32(pomdp.start[0]) | np.uint32(pomdp.start[1] << 4) | (rocks << 8)).astype(np.uint32)
+
+
+def test_episode_reward_baby_not_worse(oracle, gpu_lib):
+    """north_star criterion 3 on the reference's own sanity setting (Baby, tree_queries=300, c=10,
+    tree reuse through the RootUpdater): the batched GPU planner's mean discounted reward must not be
+    worse than the sequential oracle's (one-sided, 3 standard errors of the difference)."""
+    pomdp = pj.BabyPOMDP(-5.0, -10.0)
+
+    def gpu(ep):
+        return pj.solve(pj.POMCPSolver(c=10.0, rng=500 + ep, tree_queries=300, search_mode="batched"), pomdp)
+
+    def cpu(ep):
+        return oracle.OraclePlanner(pomdp, oracle.default_params(c=10.0, seed=500 + ep, tree_queries=300))
+
+    rg = _run_episodes(oracle, pomdp, gpu, 80, 44, 9000, True)
+    ro = _run_episodes(oracle, pomdp, cpu, 80, 44, 9000, False)
+    assert len(rg) >= 70 and len(ro) >= 70
+    se = np.sqrt(rg.var() / len(rg) + ro.var() / len(ro))
+    assert rg.mean() >= ro.mean() - 3 * se, (rg.mean(), ro.mean(), se)
+    assert -22.0 < rg.mean() < -13.0  # reference band (notebooks/Sanity_Checks.ipynb:197,239,134)
+
+
+def test_episode_reward_rocksample_not_worse(oracle, gpu_lib):
+    """Same criterion on RockSample(4,4) with the SIR belief (fresh root every step)."""
+    pomdp = pj.RockSamplePOMDP(4, 4, seed=44)
+    Q, n_part = 3000, 2000
+
+    def gpu(ep):
+        return pj.solve(pj.POMCPSolver(c=20.0, rng=700 + ep, tree_queries=Q, search_mode="batched"), pomdp,
+                        belief_mode=abi.BELIEF_EXTERNAL)
+
+    def cpu(ep):
+        return oracle.OraclePlanner(pomdp, oracle.default_params(c=20.0, seed=700 + ep, tree_queries=Q,
+                                                                 belief_mode=abi.BELIEF_EXTERNAL))
+
+    rg = _run_episodes(oracle, pomdp, gpu, 40, 30, 9500, True, n_part)
+    ro = _run_episodes(oracle, pomdp, cpu, 40, 30, 9500, False, n_part)
+    se = np.sqrt(rg.var() / len(rg) + ro.var() / len(ro))
+    assert rg.mean() >= ro.mean() - 3 * se, (rg.mean(), ro.mean(), se)
+    assert rg.mean() > 0.0  # a useful policy: exits and samples good rocks
+
+
+def test_rocksample_11_11_exact_and_batched(oracle, gpu_lib):
+    """BASELINE config 5 problem (16 actions): exact parity and batched agreement on one GPU."""
+    pomdp = pj.RockSamplePOMDP(11, 11, seed=11011)
+    gp, op = make_pair(oracle, pomdp, 20.0, seed=3, mode="exact", tree_queries=3000)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(3000)
+    rc, a_o, N_o, V_o = op.search(3000)
+    assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o))
+    gp.close()
+    gp, op = make_pair(oracle, pomdp, 20.0, seed=3, mode="batched", tree_queries=60000)
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(60000)
+    rc, a_o, N_o, V_o = op.search(60000)
+    assert N_g.sum() == 59999
+    assert V_g[a_o] >= V_g.max() - 0.5 and abs(V_g.max() - V_o.max()) < 0.15 * abs(V_o.max()) + 0.3, (V_g, V_o)
+    gp.close()
