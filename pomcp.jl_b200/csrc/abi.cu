@@ -15,6 +15,7 @@
 
 #include "../../include/pomcp_b200.h"
 #include "pf.cuh"
+#include "reroot.cuh"
 #include "tree.cuh"
 
 using namespace pomcp;
@@ -127,6 +128,10 @@ struct pomcp_handle {
   pomcp_counters host_ctr{};
   long long launches = 0, last_waves = 0;
   bool pending = false;
+  uint32_t* d_newid = nullptr;
+  size_t newid_cap = 0;
+  bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
+  long long compactions = 0;
   bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
   nccl_comm comm = nullptr;
   int nranks = 1;
@@ -409,6 +414,110 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   return POMCP_OK;
 }
 
+// Pool compaction after a re-root (see reroot.cuh): keeps the sub-tree under h->root, which becomes node 0.
+int compact_pool(pomcp_handle* h) {
+  const long long n_nodes = (long long)std::min<unsigned long long>(h->nodes_used, h->pool.max_nodes);
+  const long long n_log = (long long)h->log_used;
+  const int nA = h->nA, nO = h->nO, sb = h->state_bytes;
+  Pool& P = h->pool;
+  int rc = ensure_bytes(h, (void**)&h->d_newid, &h->newid_cap, (size_t)n_nodes * sizeof(uint32_t));
+  if (rc) return rc;
+  // 1. mark + rank
+  rc = ensure_scan(h, n_nodes);
+  if (rc) return rc;
+  int tiles = (int)((n_nodes + SCAN_TILE - 1) / SCAN_TILE);
+  k_rank_subtree<<<tiles, SCAN_THREADS, 0, h->stream>>>(P.node_pslot, h->root, (uint32_t)nA, n_nodes, h->d_newid,
+                                                        h->d_scan_status + 9, h->d_scan_status + 8);
+  rc = launch_check(h, "k_rank_subtree");
+  if (rc) return rc;
+  k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 9, tiles, &h->d_pfctl->total);
+  rc = launch_check(h, "k_scan_total");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const long long kept = (long long)h->h_pfctl->total;
+  if (kept <= 0 || kept > n_nodes) return fail(h, POMCP_ERR_CUDA, "pool compaction: bad sub-tree size");
+  // 2. copy the kept nodes through a scratch block
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o_N = 0, o_fl = o_N + al((size_t)kept * 4), o_ps = o_fl + al((size_t)kept * 4),
+         o_obs = o_ps + al((size_t)kept * 4), o_aN = o_obs + al(h->hashed ? (size_t)kept * 8 : 0),
+         o_aM = o_aN + al((size_t)kept * nA * 4), o_aV = o_aM + al((size_t)kept * nA * 4),
+         o_ch = o_aV + al((size_t)kept * nA * 8), total = o_ch + al((size_t)kept * nA * nO * 4);
+  rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, total);
+  if (rc) return rc;
+  char* base = (char*)h->d_tmp;
+  PoolScratch T{(uint32_t*)(base + o_N), (uint32_t*)(base + o_fl), (uint32_t*)(base + o_ps),
+                (unsigned long long*)(base + o_obs), (uint32_t*)(base + o_aN), (uint32_t*)(base + o_aM),
+                (double*)(base + o_aV), (uint32_t*)(base + o_ch)};
+  k_copy_kept<<<(int)((n_nodes + 255) / 256), 256, 0, h->stream>>>(P, T, h->d_newid, h->root, nA, nO, n_nodes);
+  rc = launch_check(h, "k_copy_kept");
+  if (rc) return rc;
+  auto d2d = [&](void* dst, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, h->stream) : cudaSuccess;
+  };
+  CK(d2d(P.node_N, T.node_N, (size_t)kept * 4));
+  CK(d2d(P.node_flags, T.node_flags, (size_t)kept * 4));
+  CK(d2d(P.node_pslot, T.node_pslot, (size_t)kept * 4));
+  if (h->hashed) CK(d2d(P.node_obs, T.node_obs, (size_t)kept * 8));
+  CK(d2d(P.act_N, T.act_N, (size_t)kept * nA * 4));
+  CK(d2d(P.act_M, T.act_M, (size_t)kept * nA * 4));
+  CK(d2d(P.act_V, T.act_V, (size_t)kept * nA * 8));
+  if (!h->hashed) CK(d2d(P.child, T.child, (size_t)kept * nA * nO * 4));
+  if (n_nodes > kept) {
+    unsigned long long cnt = (unsigned long long)(n_nodes - kept);
+    int blocks = (int)std::min<unsigned long long>((cnt * nA * std::max(nO, 1) + 255) / 256, 148ull * 16);
+    k_pool_fill_range<<<blocks, 256, 0, h->stream>>>(P, nA, nO, (unsigned long long)kept, cnt, (uint32_t)h->sp.init_N,
+                                                     h->sp.init_V, h->exact ? 1 : 0);
+    rc = launch_check(h, "k_pool_fill_range");
+    if (rc) return rc;
+  }
+  if (h->hashed) {
+    CK(cudaMemsetAsync(P.ht, 0, h->ht_entries * sizeof(uint32_t), h->stream));
+    k_rehash<<<(int)((kept + 255) / 256), 256, 0, h->stream>>>(P, kept);
+    rc = launch_check(h, "k_rehash");
+    if (rc) return rc;
+  }
+  // 3. the particle log
+  long long kept_log = 0;
+  if (n_log > 0) {
+    size_t o_st = al((size_t)n_log * 4);
+    rc = ensure_bytes(h, &h->d_tmp2, &h->tmp2_cap, o_st + (size_t)n_log * sb);
+    if (rc) return rc;
+    rc = ensure_scan(h, n_log);
+    if (rc) return rc;
+    int ltiles = (int)((n_log + SCAN_TILE - 1) / SCAN_TILE);
+    uint32_t* out_node = (uint32_t*)h->d_tmp2;
+    void* out_state = (char*)h->d_tmp2 + o_st;
+    if (sb == 4)
+      k_log_compact<uint32_t><<<ltiles, SCAN_THREADS, 0, h->stream>>>(P.log_node, (const uint32_t*)P.log_state,
+                                                                     h->d_newid, n_log, out_node, (uint32_t*)out_state,
+                                                                     h->d_scan_status + 9, h->d_scan_status + 8);
+    else
+      k_log_compact<LDState><<<ltiles, SCAN_THREADS, 0, h->stream>>>(P.log_node, (const LDState*)P.log_state,
+                                                                    h->d_newid, n_log, out_node, (LDState*)out_state,
+                                                                    h->d_scan_status + 9, h->d_scan_status + 8);
+    rc = launch_check(h, "k_log_compact");
+    if (rc) return rc;
+    k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 9, ltiles, &h->d_pfctl->total);
+    rc = launch_check(h, "k_scan_total");
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    kept_log = (long long)h->h_pfctl->total;
+    CK(d2d(P.log_node, out_node, (size_t)kept_log * 4));
+    CK(d2d(P.log_state, out_state, (size_t)kept_log * sb));
+  }
+  k_set_counts<<<1, 32, 0, h->stream>>>(P.ctr, (unsigned long long)kept, (unsigned long long)kept_log);
+  rc = launch_check(h, "k_set_counts");
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->root = 0;
+  h->nodes_used = (unsigned long long)kept;
+  h->log_used = (unsigned long long)kept_log;
+  h->compactions++;
+  return POMCP_OK;
+}
+
 }  // namespace
 
 // ===================================================================== C ABI
@@ -478,7 +587,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
-                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush};
+                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
@@ -530,6 +639,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->exact = sp->search_mode == POMCP_MODE_EXACT;
   h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
   h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
+  h->compact_always = std::getenv("POMCP_COMPACT_ALWAYS") != nullptr;
   CKU(cudaSetDevice(device));
   CKU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 
@@ -611,13 +721,13 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &P.act_N, (size_t)want * nA));
   CKC(dev_alloc(h, &P.act_M, (size_t)want * nA));
   CKC(dev_alloc(h, &P.act_V, (size_t)want * nA));
+  CKC(dev_alloc(h, &P.node_pslot, (size_t)want));
   if (h->hashed) {
     size_t e = 1;
     while (e < (size_t)want * 2) e <<= 1;
     h->ht_entries = e;
     P.ht_mask = e - 1;
     CKC(dev_alloc(h, &P.ht, e));
-    CKC(dev_alloc(h, &P.node_pslot, (size_t)want));
     CKC(dev_alloc(h, &P.node_obs, (size_t)want));
     CKU(cudaMemset(P.ht, 0, e * sizeof(uint32_t)));
   } else {
@@ -837,6 +947,11 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
   h->bel_kind = 2;
   h->root = child;
   h->root_visits = cnt;
+  // reclaim the dead part of the pool / particle log once a quarter of either is used
+  if (h->compact_always || h->nodes_used * 4 >= h->pool.max_nodes || h->log_used * 4 >= h->pool.log_cap) {
+    rc = compact_pool(h);
+    if (rc) return rc;
+  }
   return POMCP_OK;
 }
 

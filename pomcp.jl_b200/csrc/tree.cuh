@@ -150,8 +150,9 @@ __device__ __forceinline__ double rollout_random(const DevModel& m, typename Mod
   return total;
 }
 
-// ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only; `spare` recycles a node id
-// that lost an insertion race.
+// ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
+// race is not recycled (it stays an unreachable, zero-initialised slot): ids therefore grow along
+// every root-to-leaf path, which the pool compaction (reroot.cuh) relies on.
 template <int PID>
 __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const DevModel& m, uint32_t slot,
                                                          uint64_t obs, uint32_t& spare) {
@@ -160,21 +161,22 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
     uint32_t* cs = &P.child[(size_t)slot * m.nO + (uint32_t)obs];
     uint32_t c = __ldcg(cs);
     if (c != 0) return c;
-    uint32_t fresh = spare ? spare : (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+    uint32_t fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
     if (fresh >= P.max_nodes) {
       P.ctr->pool_overflow = 1;
       return 0;
     }
+    P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
     uint32_t old = atomicCAS(cs, 0u, fresh);
-    if (old == 0) { spare = 0; return fresh; }
-    spare = fresh;
+    if (old == 0) return fresh;
+    P.node_pslot[fresh] = 0;  // lost the race: leave the slot detached
     return old;
   } else {
     uint64_t h = mix64((uint64_t)slot * 0x9E3779B97F4A7C15ull ^ obs) & P.ht_mask;
     for (;;) {
       uint32_t id = __ldcg(&P.ht[h]);
       if (id == 0) {
-        uint32_t fresh = spare ? spare : (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+        uint32_t fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
         if (fresh >= P.max_nodes) {
           P.ctr->pool_overflow = 1;
           return 0;
@@ -183,8 +185,8 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
         P.node_obs[fresh] = obs;
         __threadfence();
         uint32_t old = atomicCAS(&P.ht[h], 0u, fresh);
-        if (old == 0) { spare = 0; return fresh; }
-        spare = fresh;
+        if (old == 0) return fresh;
+        P.node_pslot[fresh] = 0;  // lost the race: leave the slot detached
         id = old;
       }
       if (__ldcg(&P.node_pslot[id]) == slot && __ldcg(&P.node_obs[id]) == obs) return id;
@@ -584,7 +586,8 @@ __global__ void k_pool_fill(const __grid_constant__ Pool P, int nA, int nO, unsi
   for (unsigned long long k = i; k < n_nodes; k += stride) {
     P.node_N[k] = 0;
     P.node_flags[k] = 0;
-    if (P.node_pslot) { P.node_pslot[k] = 0; P.node_obs[k] = 0; }
+    P.node_pslot[k] = 0;
+    if (P.node_obs) P.node_obs[k] = 0;
   }
   if (P.child)
     for (unsigned long long k = i; k < n_nodes * nA * nO; k += stride) P.child[k] = 0;
