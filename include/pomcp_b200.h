@@ -81,7 +81,9 @@ typedef struct pomcp_problem {
 /* estimate_value kinds (src/rollout.jl:8-69). */
 typedef enum pomcp_estimator {
   POMCP_EST_RANDOM_ROLLOUT = 0, /* RolloutEstimator(RandomSolver()), src/constructor.jl:14 */
-  POMCP_EST_CONSTANT = 1        /* estimate_value(n::Number,...), src/rollout.jl:10 */
+  POMCP_EST_CONSTANT = 1,       /* estimate_value(n::Number,...), src/rollout.jl:10 */
+  POMCP_EST_FWC_ROLLOUT = 2     /* Baby only: RolloutEstimator(FeedWhenCrying()) with the previous-observation
+                                   "belief" of src/rollout.jl:105-108 (test/runtests.jl:13-19) */
 } pomcp_estimator;
 
 /* node_belief_updater kinds (src/solver.jl:135-139). */

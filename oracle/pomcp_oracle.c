@@ -397,6 +397,36 @@ static double rollout_random(const model* m, ostate s, int64_t steps, const uint
   return total;
 }
 
+/* Rollout under POMDPModels.FeedWhenCrying: feed iff the previous observation was crying; the
+ * "belief" starts as the label of the leaf node (extract_belief for PreviousObservationUpdater,
+ * src/rollout.jl:105-106).  Two Philox words per step: transition, observation. */
+static double rollout_fwc(const model* m, ostate s, int64_t steps, uint64_t last_obs, const uint32_t key[2],
+                          uint32_t tagword, uint32_t q, uint32_t epoch, int64_t* nsteps) {
+  const double gamma = m->p.discount;
+  double disc = 1.0, total = 0.0;
+  int64_t step = 0;
+  uint32_t w[4];
+  int64_t blk = -1;
+  while (disc > 0.0 && !is_terminal(m, s) && step < steps) {
+    int64_t word = step * 2;
+    if ((word >> 2) != blk) {
+      blk = word >> 2;
+      uint32_t ctr[4] = {(uint32_t)blk, tagword, q, epoch};
+      orc_philox4x32_10(ctr, key, w);
+    }
+    int a = last_obs ? 1 : 0;
+    ostate sp; uint64_t o; double r;
+    model_step(m, s, a, u01(w[word & 3]), u01(w[(word & 3) + 1]), 0.0, 1, &sp, &o, &r);
+    total += disc * r;
+    s = sp;
+    last_obs = o;
+    disc *= gamma;
+    ++step;
+  }
+  if (nsteps) *nsteps += step;
+  return total;
+}
+
 /* ------------------------------------------------------------------ */
 /* planner / tree (src/tree.jl:7-26 as flat arrays)                     */
 /* ------------------------------------------------------------------ */
@@ -535,6 +565,7 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   if (model_init(&pl->m, p) != POMCP_OK) { free(pl); return NULL; }
   pl->sp = *sp;
   if (sp->num_sparse_actions > 0 || !(sp->eps > 0.0) || !(sp->eps < 1.0)) { free(pl); return NULL; }
+  if (sp->estimator == POMCP_EST_FWC_ROLLOUT && p->problem_id != POMCP_BABY) { free(pl); return NULL; }
   pl->nA = pl->m.nA; pl->nO = pl->m.nO;
   /* cut-off gamma^depth < eps (src/solver.jl:82) and steps_to_eps (src/solver.jl:100) */
   pl->log_ratio = log(sp->eps) / log(p->discount);
@@ -667,9 +698,13 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
           int R = sol->rollouts_per_leaf > 0 ? sol->rollouts_per_leaf : 1;
           double x[32], y[32];
           for (int r = 0; r < 32; ++r)
-            x[r] = r < R ? rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
-                                          g->epoch, &pl->ctr.rollout_steps)
-                         : 0.0;
+            x[r] = r >= R ? 0.0
+                   : sol->estimator == POMCP_EST_FWC_ROLLOUT
+                       ? rollout_fwc(m, s, steps, pl->node_obs[h], g->key,
+                                     TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q, g->epoch,
+                                     &pl->ctr.rollout_steps)
+                       : rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
+                                        g->epoch, &pl->ctr.rollout_steps);
           for (int off = 16; off > 0; off >>= 1) {
             for (int i = 0; i < 32; ++i) y[i] = x[i] + x[i ^ off];
             memcpy(x, y, sizeof(x));

@@ -23,7 +23,7 @@ ERR_NAN_VALUE = 8
 TIGER, BABY, ROCKSAMPLE, LIGHTDARK1D = 0, 1, 2, 3
 RS_TERMINAL = 0x80000000
 
-EST_RANDOM_ROLLOUT, EST_CONSTANT = 0, 1
+EST_RANDOM_ROLLOUT, EST_CONSTANT, EST_FWC_ROLLOUT = 0, 1, 2
 BELIEF_UNWEIGHTED, BELIEF_EXTERNAL = 0, 1
 MODE_EXACT, MODE_BATCHED = 0, 1
 PHASE_SEARCH, PHASE_ROLLOUT, PHASE_PF, PHASE_REROOT = 0, 1, 2, 3

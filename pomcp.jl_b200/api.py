@@ -18,7 +18,7 @@ from ._lib import lib
 from .problems import POMDP, obs_bits
 
 __all__ = [
-    "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "RandomSolver", "DefaultReinvigoratorStub",
+    "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
     "DeadReinvigorator", "ParticleReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
@@ -89,6 +89,10 @@ class ExceptionRethrow:
 
 class RandomSolver:
     """POMDPToolbox.RandomSolver: uniform-random rollout policy (src/constructor.jl:14)."""
+
+
+class FeedWhenCrying:
+    """POMDPModels.FeedWhenCrying: feed iff the previous observation was crying (Baby only)."""
 
 
 class RolloutEstimator:
@@ -163,6 +167,8 @@ class POMCPSolver:
         ev = self.estimate_value
         if isinstance(ev, RolloutEstimator) and isinstance(ev.solver, RandomSolver):
             sp.estimator = abi.EST_RANDOM_ROLLOUT
+        elif isinstance(ev, RolloutEstimator) and isinstance(ev.solver, FeedWhenCrying):
+            sp.estimator = abi.EST_FWC_ROLLOUT  # test/runtests.jl:13-19, notebooks/Display_Tree.ipynb:31-39
         elif isinstance(ev, (int, float)):
             sp.estimator, sp.estimator_value = abi.EST_CONSTANT, float(ev)  # src/rollout.jl:10
         else:

@@ -612,8 +612,9 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   if (!(sp->eps > 0.0) || !(sp->eps < 1.0)) return fail(nullptr, POMCP_ERR_INVALID_ARG, "eps must be in (0,1)");
   if (sp->num_sparse_actions > 0)
     return fail(nullptr, POMCP_ERR_UNSUPPORTED, "num_sparse_actions > 0 (random action sub-sampling) is not supported");
-  if (sp->estimator != POMCP_EST_RANDOM_ROLLOUT && sp->estimator != POMCP_EST_CONSTANT)
-    return fail(nullptr, POMCP_ERR_UNSUPPORTED, "estimator");
+  if (sp->estimator != POMCP_EST_RANDOM_ROLLOUT && sp->estimator != POMCP_EST_CONSTANT &&
+      !(sp->estimator == POMCP_EST_FWC_ROLLOUT && p->problem_id == POMCP_BABY))
+    return fail(nullptr, POMCP_ERR_UNSUPPORTED, "estimator (FeedWhenCrying rollouts exist for BabyPOMDP only)");
   if (sp->init_N < 0 || sp->max_depth < 0) return fail(nullptr, POMCP_ERR_INVALID_ARG, "init_N/max_depth < 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

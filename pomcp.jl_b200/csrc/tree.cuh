@@ -150,6 +150,39 @@ __device__ __forceinline__ double rollout_random(const DevModel& m, typename Mod
   return total;
 }
 
+// Baby only: rollout under FeedWhenCrying (feed iff the previous observation was crying), starting
+// from the leaf node's observation label (src/rollout.jl:105-106).  Words per step: transition, observation.
+__device__ __forceinline__ double rollout_fwc(const DevModel& m, uint32_t s, long long steps, uint64_t last_obs,
+                                              uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q, uint32_t epoch,
+                                              int& nsteps) {
+  using M = ModelT<POMCP_BABY>;
+  const double gamma = m.gamma;
+  double disc = 1.0, total = 0.0;
+  long long step = 0;
+  bool live = steps > 0;
+  for (uint32_t blk = 0; live; ++blk) {
+    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (live) {
+        int a = last_obs ? 1 : 0;
+        uint32_t sp;
+        uint64_t o;
+        double r;
+        M::template step<true, double>(m, s, a, u01(p.w[2 * j]), u01(p.w[2 * j + 1]), 0.0, sp, o, r);
+        total += disc * r;
+        s = sp;
+        last_obs = o;
+        disc *= gamma;
+        ++step;
+        live = disc > 0.0 && step < steps;
+      }
+    }
+  }
+  nsteps = (int)step;
+  return total;
+}
+
 // ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
 // race is not recycled (it stays an unreachable, zero-initialised slot): ids therefore grow along
 // every root-to-leaf path, which the pool compaction (reroot.cuh) relies on.
@@ -213,6 +246,9 @@ __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m,
   }
 }
 
+__device__ __forceinline__ uint32_t baby_state(uint32_t s) { return s; }
+__device__ __forceinline__ uint32_t baby_state(const LDState&) { return 0u; }  // never called for LightDark
+
 // fixed-shape butterfly sum over the warp: the oracle adds in the same binary tree
 __device__ __forceinline__ double warp_tree_sum(double x) {
 #pragma unroll
@@ -258,6 +294,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
 
   uint32_t h = cfg.root;
   uint32_t hN = root_ticket;
+  uint64_t last_o = 0;  // observation label of h (the leaf's label seeds the FeedWhenCrying rollout)
   int depth = 0;
   bool want_rollout = false, aborted = false;
   // Two dependent L2 round trips per level: (1) the node's action statistics together with its
@@ -356,6 +393,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     h = hao;
     hN = ticket;
     s = sp;
+    last_o = o;
     ++depth;
   }
   if (aborted) return true;  // pool exhausted: the search reports POOL_EXHAUSTED
@@ -376,9 +414,13 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     } else {
       double ret = 0.0;
       int nsteps = 0;
-      if (lane < cfg.rollouts)
-        ret = rollout_random<PID>(m, s, steps, cfg.key0, cfg.key1,
-                                  TAG_ROLLOUT | (cfg.rank << 8) | ((uint32_t)lane << 16), q, cfg.epoch, nsteps);
+      if (lane < cfg.rollouts) {
+        const uint32_t tagword = TAG_ROLLOUT | (cfg.rank << 8) | ((uint32_t)lane << 16);
+        if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
+          ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+        else
+          ret = rollout_random<PID>(m, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+      }
       est = warp_tree_sum(ret) / (double)cfg.rollouts;
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       lc.rollouts += cfg.rollouts;

@@ -22,7 +22,7 @@ class ActNode:
 
 
 class Twin:
-    def __init__(self, pomdp, c, seed, eps=0.01, max_depth=2 ** 62, log_fn=math.log):
+    def __init__(self, pomdp, c, seed, eps=0.01, max_depth=2 ** 62, log_fn=math.log, fwc=False):
         self.p, self.c, self.eps, self.max_depth = pomdp, c, eps, max_depth
         self.key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
         self.gamma = pomdp.discount
@@ -30,6 +30,7 @@ class Twin:
         self.epoch = 0
         self.log = log_fn
         self.kind = type(pomdp).__name__
+        self.fwc = fwc  # Baby: RolloutEstimator(FeedWhenCrying()), test/runtests.jl:13-19
 
     # ---- generative model (Tiger / Baby), transition draw first, observation draw second
     def step(self, s, a, ut, uo, need_obs=True):
@@ -64,7 +65,24 @@ class Twin:
             step += 1
         return total
 
-    def simulate(self, h, s, depth, q):
+    def rollout_fwc(self, s, steps, q, last_obs):
+        """feed iff the previous observation was crying; starts from the leaf's observation label
+        (src/rollout.jl:105-106).  Two words per step: transition, observation."""
+        disc, total, step, blk, w = 1.0, 0.0, 0, -1, None
+        while step < steps:
+            word = step * 2
+            if word >> 2 != blk:
+                blk = word >> 2
+                w = philox4x32_10((blk, TAG_ROLLOUT, q, self.epoch), self.key)
+            a = 1 if last_obs else 0
+            sp, o, r = self.step(s, a, w[word & 3] * U, w[(word & 3) + 1] * U)
+            total += disc * r
+            s, last_obs = sp, o
+            disc *= self.gamma
+            step += 1
+        return total
+
+    def simulate(self, h, s, depth, q, label=0):
         if self.gamma ** depth < self.eps or depth >= self.max_depth:
             return 0.0
         if not h.children:
@@ -72,6 +90,8 @@ class Twin:
                 h.children[a] = ActNode(a, 0, 0.0)
             if depth > 0:
                 steps = min(self.max_depth - depth, math.ceil(math.log(self.eps) / math.log(self.gamma) - depth))
+                if self.fwc:
+                    return self.gamma ** depth * self.rollout_fwc(s, steps, q, label)
                 return self.gamma ** depth * self.rollout(s, steps, q)
             return 0.0
         best, best_node = -math.inf, None
@@ -91,7 +111,7 @@ class Twin:
         if o not in best_node.children:
             best_node.children[o] = Node()
         hao = best_node.children[o]
-        R = r + self.gamma * self.simulate(hao, sp, depth + 1, q)
+        R = r + self.gamma * self.simulate(hao, sp, depth + 1, q, o)
         hao.particles.append(sp)
         hao.N += 1
         best_node.N += 1

@@ -224,6 +224,42 @@ def test_baby_reward_band(oracle):
     assert -21.0 < m < -14.0, m
 
 
+def test_fwc_rollout_estimator_oracle(oracle):
+    """RolloutEstimator(FeedWhenCrying()) (test/runtests.jl:13-19; notebooks/Display_Tree.ipynb:31-39 uses it
+    for the golden tree, whose 20-query root values are false: -14.61, true: -24.23).  The oracle's
+    FeedWhenCrying leaf estimates must (i) be well above the uniform-random ones, (ii) rank not
+    feeding first at the never-hungry initial belief, (iii) put the root values in the band the
+    notebook prints (FeedWhenCrying alone scores -15.06 +- 1, notebooks/Sanity_Checks.ipynb:98)."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    vals = {}
+    for est in (abi.EST_RANDOM_ROLLOUT, abi.EST_FWC_ROLLOUT):
+        V = []
+        for seed in range(6):
+            pl = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=seed, estimator=est))
+            pl.set_belief_initial()
+            rc, a, N, Vs = pl.search(3000)
+            assert rc == 0
+            V.append(Vs)
+            pl.close()
+        vals[est] = np.mean(V, axis=0)
+    fwc, rnd = vals[abi.EST_FWC_ROLLOUT], vals[abi.EST_RANDOM_ROLLOUT]
+    assert fwc[0] > fwc[1] and fwc[0] > rnd[0] + 1.0, (fwc, rnd)
+    assert -19.0 < fwc[0] < -12.0 and -27.0 < fwc[1] < -17.0, fwc
+    # independent recursive twin, same Philox draw map: bit-identical tree statistics
+    for seed in (0, 3):
+        tw = Twin(baby, 10.0, seed, log_fn=oracle.lib().orc_det_log, fwc=True)
+        op = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=seed, estimator=abi.EST_FWC_ROLLOUT))
+        op.set_belief_initial()
+        for Q in (500, 200):
+            a_t, N_t, V_t = tw.search(Q)
+            rc, a_o, N_o, V_o = op.search(Q)
+            assert rc == 0 and a_t == a_o and list(N_o) == N_t
+            assert np.array_equal(np.array(V_t).view(np.uint64), V_o.view(np.uint64))
+    # only Baby has this policy
+    with pytest.raises(ValueError):
+        oracle.OraclePlanner(pj.TigerPOMDP(), oracle.default_params(estimator=abi.EST_FWC_ROLLOUT))
+
+
 # ----------------------------------------------------------------------------- independent twin
 @pytest.mark.parametrize("name,c,Q", [("tiger", 1000.0, 400), ("baby", 10.0, 600), ("baby", 1.0, 300)])
 def test_python_twin_matches_oracle(oracle, name, c, Q):
