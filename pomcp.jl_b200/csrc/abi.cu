@@ -290,12 +290,15 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     if (rc) return rc;
     ts.launches++;
   } else {
-    // one persistent launch: every warp is a worker, admission is ramped on the device
+    // one persistent launch: every warp (= CTA) is a worker, admission is ramped on the device
     long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
-    int blocks = (int)((workers + 3) / 4);
+    int blocks = (int)workers;
+    size_t path_bytes = (size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes);
+    cfg.path_smem = path_bytes <= 40 * 1024 ? 1 : 0;
+    size_t smem = cfg.path_smem ? path_bytes : 0;
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
-      k_search_workers<PID><<<blocks, 128, 0, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+      k_search_workers<PID><<<blocks, 32, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
     });
     rc = launch_check(h, "k_search_workers");
     if (rc) return rc;
@@ -666,6 +669,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   m.rs_n = p->rs_n; m.rs_k = p->rs_k;
   m.rs_start = (unsigned)p->rs_start_x | ((unsigned)p->rs_start_y << 4);
   m.rs_r_good = p->rs_r_good; m.rs_r_bad = p->rs_r_bad; m.rs_r_exit = p->rs_r_exit;
+  m.rs_rtab[0] = 0.0; m.rs_rtab[1] = p->rs_r_exit; m.rs_rtab[2] = p->rs_r_bad; m.rs_rtab[3] = p->rs_r_good;
   m.ld_correct = p->ld_correct_r; m.ld_incorrect = p->ld_incorrect_r; m.ld_mean = p->ld_init_mean; m.ld_std = p->ld_init_std;
   std::memset(m.rock_at, -1, sizeof(m.rock_at));
   if (p->problem_id == POMCP_ROCKSAMPLE) {

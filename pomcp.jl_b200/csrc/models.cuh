@@ -26,6 +26,7 @@ struct DevModel {
   int rs_n, rs_k;
   unsigned rs_start;  // packed x | y<<4
   double rs_r_good, rs_r_bad, rs_r_exit;
+  double rs_rtab[4];  // rollout reward by event: 0 none, 1 exit, 2 sampled a bad rock, 3 sampled a good rock
   const double* rs_eta;  // device table [cell(y*16+x)][rock]: P(check correct)
   signed char rock_at[256];
   double ld_correct, ld_incorrect, ld_mean, ld_std;

@@ -526,10 +526,12 @@ template <int PID>
 __global__ void __launch_bounds__(256) k_rollout_batch(const __grid_constant__ DevModel m,
                                                        const typename ModelT<PID>::State* states, long long n,
                                                        int steps, uint32_t k0, uint32_t k1, double* ret, int* ns) {
+  __shared__ RsTab rs_tab;
+  if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int nsteps = 0;
-  ret[i] = rollout_random<PID>(m, states[i], steps, k0, k1, TAG_ROLLOUT, (uint32_t)i, 0u, nsteps);
+  ret[i] = rollout_random<PID>(m, &rs_tab, states[i], steps, k0, k1, TAG_ROLLOUT, (uint32_t)i, 0u, nsteps);
   ns[i] = nsteps;
 }
 

@@ -58,6 +58,7 @@ struct SearchCfg {
   uint32_t root_N0;  // root visits when the search started
   // asynchronous workers: in flight = clamp(root visits / ramp_div, inflight_min, inflight_max)
   int inflight_min, inflight_max, ramp_div;
+  int path_smem;  // batched mode: the worker's recorded path lives in shared memory (else in PathBuf)
   // replay (exact mode only)
   const double* uni;
   long long n_uni;
@@ -112,20 +113,19 @@ __device__ __forceinline__ void get_draws(const SearchCfg& cfg, ReplayCursor& rc
   }
 }
 
-// ---- K3: RolloutSimulator loop under the uniform-random policy (src/rollout.jl:77-84;
-// loop body = POMDPToolbox.RolloutSimulator, SURVEY.md App. B.1).  One thread = one trajectory,
-// state in registers, one Philox block feeds 4/DPS steps; the observation is never generated
-// (VoidUpdater discards it, src/rollout.jl:104).
-template <int PID>
-__device__ __forceinline__ double rollout_random(const DevModel& m, typename ModelT<PID>::State s, long long steps,
-                                                 uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
-                                                 uint32_t epoch, int& nsteps) {
+// CHECK_DISC: keep RolloutSimulator's `disc > eps` test (eps = 0).  Inside the tree
+// steps <= ceil(log(eps)/log(gamma)), so disc >= eps * gamma > 0 and the test can never fire.
+template <int PID, bool CHECK_DISC>
+__device__ __forceinline__ double rollout_generic(const DevModel& m, typename ModelT<PID>::State s, long long steps,
+                                                  uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
+                                                  uint32_t epoch, int& nsteps) {
   using M = ModelT<PID>;
   constexpr int DPS = M::DPS;
   const double gamma = m.gamma;
   double disc = 1.0, total = 0.0;
-  long long step = 0;
-  bool live = !M::terminal(m, s) && steps > 0;
+  const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
+  int step = 0;
+  bool live = !M::terminal(m, s) && nstep_max > 0;
   for (uint32_t blk = 0; live; ++blk) {
     Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
 #pragma unroll
@@ -142,12 +142,97 @@ __device__ __forceinline__ double rollout_random(const DevModel& m, typename Mod
         s = sp;
         disc *= gamma;
         ++step;
-        live = disc > 0.0 && !M::terminal(m, s) && step < steps;
+        live = (!CHECK_DISC || disc > 0.0) && !M::terminal(m, s) && step < nstep_max;
       }
     }
   }
-  nsteps = (int)step;
+  nsteps = step;
   return total;
+}
+
+// RockSample lookup tables staged in shared memory: 32 lanes index them with 32 different cells,
+// which the constant cache would serialise (one address per access) and shared memory does not.
+struct RsTab {
+  double rtab[4];           // reward by event: 0 none, 1 exit, 2 sampled a bad rock, 3 sampled a good rock
+  signed char rock_at[256]; // rock index at cell y*16+x, -1 none
+};
+__device__ __forceinline__ void rs_tab_init(RsTab* t, const DevModel& m) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t->rock_at[i] = m.rock_at[i];
+  if (threadIdx.x < 4) t->rtab[threadIdx.x] = m.rs_rtab[threadIdx.x];
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t shr_clamped(uint32_t x, uint32_t n) {  // 0 for n >= 32
+  uint32_t y;
+  asm("shr.u32 %0, %1, %2;" : "=r"(y) : "r"(x), "r"(n));
+  return y;
+}
+__device__ __forceinline__ int sbfe2(uint32_t x, int pos) {  // signed 2-bit field
+  int y;
+  asm("bfe.s32 %0, %1, %2, 2;" : "=r"(y) : "r"(x), "r"(pos));
+  return y;
+}
+
+// RockSample rollouts: the same draws, transitions, rewards and fp64 operation order as
+// ModelT<ROCKSAMPLE>::step<false> (bit-identical returns, checked against the oracle through
+// pomcp_rollout_batch), arranged for the issue slots: position and rock bits stay unpacked in
+// registers, the move comes out of a nibble table, the rock lookup and the reward are
+// branch-free (32 lanes hold 32 different actions, so a branch would be taken by the warp on
+// almost every step anyway).
+template <bool CHECK_DISC>
+__device__ __forceinline__ double rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
+                                                     uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
+                                                     uint32_t epoch, int& nsteps) {
+  const double gamma = m.gamma;
+  const uint32_t nA = (uint32_t)m.nA;
+  const int nmax = m.rs_n - 1;
+  int x = (int)(s & 15u), y = (int)((s >> 4) & 15u);
+  uint32_t rocks = s >> 8;  // bit i: rock i is good
+  double disc = 1.0, total = 0.0;
+  const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
+  int step = 0;
+  bool live = !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
+  for (uint32_t blk = 0; live; ++blk) {
+    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (live) {
+        const uint32_t a = __umulhi(p.w[j], nA);  // rand(rng, actions): floor(u * nA)
+        // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
+        const uint32_t t = shr_clamped(0x3C14u, a * 4u);
+        y = min(max(y + sbfe2(t, 2), 0), nmax);
+        const int nx = x + sbfe2(t, 0);
+        const bool exits = nx > nmax;  // moving east off the grid
+        x = min(max(nx, 0), nmax);
+        const int ri = tb->rock_at[y * 16 + x];
+        const bool hit = (a == 4u) & (ri >= 0);  // sample on a rock
+        const uint32_t sh = (uint32_t)ri & 31u;
+        const uint32_t good = (rocks >> sh) & 1u;
+        rocks &= ~((hit ? good : 0u) << sh);  // a sampled rock turns bad
+        const int ev = exits ? 1 : (hit ? 2 + (int)good : 0);
+        total += disc * tb->rtab[ev];
+        disc *= gamma;
+        ++step;
+        live = (!CHECK_DISC || disc > 0.0) && !exits && step < nstep_max;
+      }
+    }
+  }
+  nsteps = step;
+  return total;
+}
+
+// ---- K3: RolloutSimulator loop under the uniform-random policy (src/rollout.jl:77-84;
+// loop body = POMDPToolbox.RolloutSimulator, SURVEY.md App. B.1).  One thread = one trajectory,
+// state in registers, one Philox block feeds 4/DPS steps; the observation is never generated
+// (VoidUpdater discards it, src/rollout.jl:104).
+template <int PID, bool CHECK_DISC = true>
+__device__ __forceinline__ double rollout_random(const DevModel& m, const RsTab* tb, typename ModelT<PID>::State s,
+                                                 long long steps, uint32_t k0, uint32_t k1, uint32_t tagword,
+                                                 uint32_t q, uint32_t epoch, int& nsteps) {
+  if constexpr (PID == POMCP_ROCKSAMPLE)
+    return rollout_rocksample<CHECK_DISC>(m, tb, s, steps, k0, k1, tagword, q, epoch, nsteps);
+  else
+    return rollout_generic<PID, CHECK_DISC>(m, s, steps, k0, k1, tagword, q, epoch, nsteps);
 }
 
 // Baby only: rollout under FeedWhenCrying (feed iff the previous observation was crying), starting
@@ -186,14 +271,20 @@ __device__ __forceinline__ double rollout_fwc(const DevModel& m, uint32_t s, lon
 // ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
 // race is not recycled (it stays an unreachable, zero-initialised slot): ids therefore grow along
 // every root-to-leaf path, which the pool compaction (reroot.cuh) relies on.
-template <int PID>
+// SKIP_LOAD: the caller has just read the child slot as empty (direct table only), go straight to the insert.
+// `created` tells the caller that it published the node itself (then it is, like in the reference,
+// the natural first visitor of that node).
+template <int PID, bool SKIP_LOAD = false>
 __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const DevModel& m, uint32_t slot,
-                                                         uint64_t obs, uint32_t& spare) {
+                                                         uint64_t obs, bool& created) {
   using M = ModelT<PID>;
+  created = false;
   if (!M::HASHED) {
     uint32_t* cs = &P.child[(size_t)slot * m.nO + (uint32_t)obs];
-    uint32_t c = __ldcg(cs);
-    if (c != 0) return c;
+    if (!SKIP_LOAD) {
+      uint32_t c = __ldcg(cs);
+      if (c != 0) return c;
+    }
     uint32_t fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
     if (fresh >= P.max_nodes) {
       P.ctr->pool_overflow = 1;
@@ -201,28 +292,33 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
     }
     P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
     uint32_t old = atomicCAS(cs, 0u, fresh);
-    if (old == 0) return fresh;
+    if (old == 0) { created = true; return fresh; }
     P.node_pslot[fresh] = 0;  // lost the race: leave the slot detached
     return old;
   } else {
     uint64_t h = mix64((uint64_t)slot * 0x9E3779B97F4A7C15ull ^ obs) & P.ht_mask;
+    uint32_t fresh = 0;  // allocated at the first empty slot; kept while probing past other keys' insertions
     for (;;) {
       uint32_t id = __ldcg(&P.ht[h]);
       if (id == 0) {
-        uint32_t fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
-        if (fresh >= P.max_nodes) {
-          P.ctr->pool_overflow = 1;
-          return 0;
+        if (fresh == 0) {
+          fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+          if (fresh >= P.max_nodes) {
+            P.ctr->pool_overflow = 1;
+            return 0;
+          }
+          P.node_pslot[fresh] = slot;
+          P.node_obs[fresh] = obs;
+          __threadfence();
         }
-        P.node_pslot[fresh] = slot;
-        P.node_obs[fresh] = obs;
-        __threadfence();
         uint32_t old = atomicCAS(&P.ht[h], 0u, fresh);
-        if (old == 0) return fresh;
-        P.node_pslot[fresh] = 0;  // lost the race: leave the slot detached
-        id = old;
+        if (old == 0) { created = true; return fresh; }
+        id = old;  // another insertion took this slot: same key -> use it, other key -> keep probing
       }
-      if (__ldcg(&P.node_pslot[id]) == slot && __ldcg(&P.node_obs[id]) == obs) return id;
+      if (__ldcg(&P.node_pslot[id]) == slot && __ldcg(&P.node_obs[id]) == obs) {
+        if (fresh != 0) P.node_pslot[fresh] = 0;  // lost the race for this very key: leave the slot detached
+        return id;
+      }
       h = (h + 1) & P.ht_mask;
     }
   }
@@ -267,7 +363,7 @@ __device__ __forceinline__ double warp_tree_sum(double x) {
 //  * K4 backup bottom-up (src/solver.jl:144-156) and particle pushes.
 // Returns false when the query was consumed by a terminal root sample.
 template <int PID, bool EXACT, bool REPLAY>
-__device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, const SearchCfg& cfg,
+__device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
                                              const PathBuf& pb, int slot_idx, uint32_t q, uint32_t root_ticket,
                                              ReplayCursor& rc, uint32_t& spare, LocalCtr& lc) {
   using M = ModelT<PID>;
@@ -375,7 +471,8 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     uint32_t hao = 0, ticket = 0;
     if (lane == 0) {
       if (EXACT) P.act_N[slot] = __ldcg(&P.act_N[slot]) + 1u; else atomicAdd(&P.act_N[slot], 1u);
-      hao = pre ? pre : find_or_insert_child<PID>(P, m, slot, o, spare);
+      bool created_;
+      hao = pre ? pre : find_or_insert_child<PID>(P, m, slot, o, created_);
       if (hao != 0) {
         if (EXACT) { ticket = __ldcg(&P.node_N[hao]); P.node_N[hao] = ticket + 1u; }
         else ticket = atomicAdd(&P.node_N[hao], 1u);
@@ -419,7 +516,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
         if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
           ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
         else
-          ret = rollout_random<PID>(m, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+          ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
       }
       est = warp_tree_sum(ret) / (double)cfg.rollouts;
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
@@ -475,6 +572,254 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
   return true;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched mode.  Same algorithm as simulate_one, arranged for latency: a simulation is a chain of
+// dependent L2/HBM accesses, and with a bounded number of simulations in flight the search rate
+// is (simulations in flight) / (latency of one simulation).
+//  * one memory round trip per level: the child id of every (action, observation) is fetched with
+//    the node's statistics, so once the action and the observation are known the arrival ticket of
+//    the child, its expansion flag and its statistics are all requested together (the statistics
+//    speculatively: they are unused if this worker then expands the child);
+//  * the recorded path lives in shared memory, the backup does not touch global memory for it;
+//  * UCB1 in fp32 with the SFU (lg2/rcp/sqrt approx): the exploration term does not need 53 bits,
+//    and the arg-max with the reference's tie rule is one REDUX.MAX on an order-preserving key plus
+//    one ballot (highest lane among the maxima = "last wins on >=");
+//  * the next query id is requested before the rollouts start, so that atomic is off the path.
+template <class State>
+struct PathView {
+  uint32_t* slot;
+  uint32_t* node;
+  double* r;
+  State* state;
+  int stride;
+};
+
+__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_rcp(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_sqrt(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// order-preserving map float -> u32 (callers send NaN to 0)
+__device__ __forceinline__ uint32_t f2ord(float x) {
+  uint32_t b = __float_as_uint(x);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+template <int PID>
+struct ActStats {
+  static constexpr int K = ModelT<PID>::NO > 0 ? ModelT<PID>::NO : 1;
+  uint32_t n, mm;
+  double w;
+  uint32_t kid[K];
+  __device__ __forceinline__ void load(const Pool& P, uint32_t h, int nA, int lane) {
+    n = 0; mm = 0; w = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) kid[k] = 0;
+    if (lane < nA) {
+      const uint32_t sl = h * (uint32_t)nA + (uint32_t)lane;
+      n = __ldcg(&P.act_N[sl]);
+      w = __ldcg(&P.act_V[sl]);
+      mm = __ldcg(&P.act_M[sl]);
+      if (!ModelT<PID>::HASHED) {
+#pragma unroll
+        for (int k = 0; k < ModelT<PID>::NO; ++k) kid[k] = __ldcg(&P.child[(size_t)sl * ModelT<PID>::NO + k]);
+      }
+    }
+  }
+};
+
+// One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
+// (lane 0; requested early so its latency hides behind the rollouts).
+template <int PID>
+__device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
+                                               const PathView<typename ModelT<PID>::State>& pv, uint32_t q,
+                                               LocalCtr& lc, unsigned long long& next_q) {
+  using M = ModelT<PID>;
+  using State = typename M::State;
+  const int lane = threadIdx.x & 31;
+  const int nA = m.nA;
+  const uint32_t tag_rank = cfg.rank << 8;
+  const float c_f = (float)cfg.c;
+  const bool v_finite = fabs(cfg.init_V) != INFINITY;
+  const float initV_f = (float)cfg.init_V;
+
+  // root statistics are requested first: they do not depend on the draw
+  uint32_t h = cfg.root;
+  uint32_t hN = cfg.root_N0 + q;
+  ActStats<PID> st;
+  st.load(P, h, nA, lane);
+  uint32_t fl = 0;
+  if (lane == 0) fl = __ldcg(&P.node_flags[h]);
+
+  // rand(rng, b): src/solver.jl:48 -> src/updater.jl:53-55
+  Philox4 pr = philox4x32_10(0u, TAG_ROOT | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+  const double u0 = u01(pr.w[0]), u1 = u01(pr.w[1]);
+  State s;
+  if (cfg.bel != nullptr) s = ((const State*)cfg.bel)[(long long)(u0 * (double)cfg.n_bel)];
+  else s = M::initial(m, u0, u1);
+  fl = __shfl_sync(0xffffffffu, fl, 0);
+  if (M::terminal(m, s)) {  // src/solver.jl:49: the query is consumed
+    lc.skips++;
+    if (lane == 0) next_q = atomicAdd(&P.ctr->next_query, 1ull);
+    return;
+  }
+
+  uint64_t last_o = 0;  // observation label of h (seeds the FeedWhenCrying rollout)
+  int depth = 0;
+  bool want_rollout = false, aborted = false;
+  for (;;) {
+    if (depth >= cfg.levels || M::terminal(m, s)) break;  // src/solver.jl:82-86
+    if (!(fl & 1u)) {  // src/solver.jl:87-107: the first visitor that is not cut off expands the node
+      int i_expand = 0;
+      if (lane == 0) i_expand = !(atomicOr(&P.node_flags[h], 1u) & 1u);
+      i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
+      if (i_expand) {
+        want_rollout = depth > 0;
+        break;
+      }
+    }
+    // UCB1, src/solver.jl:109-124 (lanes = actions)
+    uint32_t key = 0;
+    if (lane < nA) {
+      const float v = (st.mm > 0 && v_finite) ? (float)st.w * sfu_rcp((float)st.mm) : initV_f;
+      const uint32_t hn = hN < 1u ? 1u : hN;
+      float crit;
+      if (st.n == 0 && hn == 1) crit = v;
+      else if (st.n == 0 && v == -INFINITY) crit = INFINITY;
+      else crit = v + c_f * sfu_sqrt(sfu_lg2((float)hn) * 0.69314718f * sfu_rcp((float)st.n));
+      key = (crit == crit) ? f2ord(crit) : 0u;
+    }
+    const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
+    const unsigned tied = __ballot_sync(0xffffffffu, key == mx && lane < nA);
+    const int best_a = mx ? 31 - __clz((int)tied) : nA - 1;  // ">=": the last maximal index wins
+    const uint32_t slot = h * (uint32_t)nA + (uint32_t)best_a;
+
+    // src/solver.jl:126
+    Philox4 pt = philox4x32_10((uint32_t)depth, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    State sp;
+    uint64_t o;
+    double r;
+    M::template step<true, double>(m, s, best_a, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp, o, r);
+
+    // src/solver.jl:132-142: child ids came with the statistics; ids never change once published
+    uint32_t hao = 0;
+    if (!M::HASHED) {
+      uint32_t mine = st.kid[0];
+#pragma unroll
+      for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o == (uint64_t)k) ? st.kid[k] : mine;
+      hao = __shfl_sync(0xffffffffu, mine, best_a);
+    }
+    int created = 0;
+    if (hao == 0) {
+      if (lane == 0) {
+        bool cr;
+        hao = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr);
+        created = cr;
+      }
+      hao = __shfl_sync(0xffffffffu, hao, 0);
+      created = __shfl_sync(0xffffffffu, created, 0);
+      if (hao == 0) { aborted = true; break; }
+    }
+    // Arrival ticket, expansion flag and statistics of the child: one round trip.  The worker that
+    // created the child (and is not cut off there) claims its expansion in the same round trip and
+    // does not need the statistics of a brand-new node.
+    const bool try_claim = created && !(depth + 1 >= cfg.levels || M::terminal(m, sp));
+    uint32_t ticket = 0, nfl = 0;
+    if (lane == 0) {
+      atomicAdd(&P.act_N[slot], 1u);
+      ticket = atomicAdd(&P.node_N[hao], 1u);
+      if (try_claim) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;  // bit1: the claim was attempted here
+      else nfl = __ldcg(&P.node_flags[hao]);
+      const int pi = depth * pv.stride;
+      pv.slot[pi] = slot;
+      pv.r[pi] = r;
+      if (cfg.belief_unweighted) {
+        pv.node[pi] = hao;
+        pv.state[pi] = sp;
+      }
+    }
+    if (!try_claim) st.load(P, hao, nA, lane);
+    hN = __shfl_sync(0xffffffffu, ticket, 0);
+    fl = __shfl_sync(0xffffffffu, nfl, 0);
+    h = hao;
+    s = sp;
+    last_o = o;
+    ++depth;
+    if (fl & 2u) {
+      if (!(fl & 1u)) {  // claimed: expand + evaluate the leaf (src/solver.jl:87-103)
+        want_rollout = true;
+        break;
+      }
+      st.load(P, hao, nA, lane);  // somebody else got there first (rare): descend through it
+      fl = 1u;
+    }
+  }
+  if (lane == 0) {
+    if (aborted) atomicMax(&P.ctr->next_query, 1ull << 62);  // pool exhausted: stop every worker
+    next_q = atomicAdd(&P.ctr->next_query, 1ull);
+  }
+  if (aborted) return;
+
+  // leaf evaluation, src/solver.jl:97-103
+  double leaf = 0.0;
+  if (want_rollout) {
+    long long steps_to_eps = (long long)ceil(cfg.log_ratio - (double)depth);
+    long long steps = min(cfg.max_depth - (long long)depth, steps_to_eps);
+    double est;
+    if (cfg.estimator == POMCP_EST_CONSTANT) {
+      est = cfg.est_value;  // src/rollout.jl:10
+      lc.rollouts++;
+    } else {
+      double ret = 0.0;
+      int nsteps = 0;
+      if (lane < cfg.rollouts) {
+        const uint32_t tagword = TAG_ROLLOUT | tag_rank | ((uint32_t)lane << 16);
+        if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
+          ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+        else
+          ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+      }
+      est = warp_tree_sum(ret) / (double)cfg.rollouts;
+      nsteps = __reduce_add_sync(0xffffffffu, nsteps);
+      lc.rollouts += cfg.rollouts;
+      lc.rollout_steps += nsteps;
+    }
+    leaf = cfg.gpow[depth] * est;  // src/solver.jl:103 (the reference's extra gamma^depth is kept)
+  }
+
+  // particle pushes, deepest level first like the unwinding recursion (src/solver.jl:146-148)
+  if (cfg.belief_unweighted && depth > 0) {
+    unsigned long long log_base = 0;
+    if (lane == 0) {
+      log_base = atomicAdd(&P.ctr->log_count, (unsigned long long)depth);
+      if (log_base + depth > P.log_cap) { P.ctr->log_overflow = 1; log_base = ~0ull; }
+    }
+    log_base = __shfl_sync(0xffffffffu, log_base, 0);
+    if (log_base != ~0ull) {
+      State* log_state = (State*)P.log_state;
+      for (int d = depth - 1 - lane; d >= 0; d -= 32) {
+        const unsigned long long li = log_base + (unsigned long long)(depth - 1 - d);
+        P.log_node[li] = pv.node[d * pv.stride];
+        log_state[li] = pv.state[d * pv.stride];
+      }
+    }
+  }
+  // backup, src/solver.jl:144-156: W += R, M += 1 (V = W / M)
+  if (lane == 0) {
+    double R = leaf;
+    for (int d = depth - 1; d >= 0; --d) {
+      const int pi = d * pv.stride;
+      R = pv.r[pi] + m.gamma * R;
+      const uint32_t slot = pv.slot[pi];
+      atomicAdd(&P.act_V[slot], R);
+      atomicAdd(&P.act_M[slot], 1u);
+    }
+    atomicAdd(&P.node_N[cfg.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
+  }
+  __syncwarp();
+  lc.sims++;
+  lc.tree_steps += depth;
+  if ((unsigned long long)depth > lc.max_depth) lc.max_depth = depth;
+}
+
 __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc, bool exact) {
   DevCtr* c = P.ctr;
   if (exact) {
@@ -490,52 +835,65 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
   }
 }
 
-// ---- batched mode: persistent asynchronous warp workers.  Every warp of the grid is a worker;
-// a worker repeatedly takes the next query id, runs one whole simulation and publishes its
-// statistics with atomics.  There is no barrier anywhere: the number of simulations in flight is
-// the number of admitted workers, clamp(root visits / ramp_div, inflight_min, inflight_max), so
-// the tree is never more than that many simulations stale (small while the tree is small).
+// ---- batched mode: persistent asynchronous warp workers, one warp per CTA.  A worker repeatedly
+// takes the next query id, runs one whole simulation and publishes its statistics with atomics.
+// There is no barrier anywhere: the number of simulations in flight is the number of admitted
+// workers, clamp(root visits / ramp_div, inflight_min, inflight_max), so the tree is never more than
+// that many simulations stale (small while the tree is small).  Root visits only grow, so a worker
+// waits for admission once: worker w starts when root visits >= (w + 1) * ramp_div.
 template <int PID>
-__global__ void __launch_bounds__(128) k_search_workers(const __grid_constant__ Pool P,
-                                                        const __grid_constant__ DevModel m,
-                                                        const __grid_constant__ SearchCfg cfg,
-                                                        const __grid_constant__ PathBuf pb, long long queries) {
+__global__ void __launch_bounds__(32) k_search_workers(const __grid_constant__ Pool P,
+                                                       const __grid_constant__ DevModel m,
+                                                       const __grid_constant__ SearchCfg cfg,
+                                                       const __grid_constant__ PathBuf pb, long long queries) {
+  using State = typename ModelT<PID>::State;
+  extern __shared__ __align__(16) unsigned char path_smem[];
+  __shared__ RsTab rs_tab;
+  if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
   const int lane = threadIdx.x & 31;
   DevCtr* c = P.ctr;
   // worker ids are handed out in start order, so the admitted (lowest) ids are always resident
   unsigned wid = 0;
   if (lane == 0) wid = (unsigned)atomicAdd(&c->worker_ticket, 1ull);
   wid = __shfl_sync(0xffffffffu, wid, 0);
-  ReplayCursor rc{0, 0};
+  PathView<State> pv;
+  if (cfg.path_smem) {
+    const int L = cfg.levels > 0 ? cfg.levels : 1;
+    pv.r = (double*)path_smem;
+    pv.state = (State*)(path_smem + (size_t)L * 8);
+    pv.slot = (uint32_t*)(path_smem + (size_t)L * (8 + sizeof(State)));
+    pv.node = pv.slot + L;
+    pv.stride = 1;
+  } else {
+    pv.r = pb.path_r + wid;
+    pv.state = (State*)pb.path_state + wid;
+    pv.slot = pb.path_slot + wid;
+    pv.node = pb.path_node + wid;
+    pv.stride = pb.stride;
+  }
   LocalCtr lc{0, 0, 0, 0, 0, 0};
-  uint32_t spare = 0;
-  for (;;) {
+  unsigned long long next_q = ~0ull;
+  if (lane == 0) {
     // admission: ramp the number of simulations in flight with the size of the tree
-    long long q = -1;
-    if (lane == 0) {
-      unsigned spins = 0;
-      for (;;) {
-        if (__ldcg((const unsigned long long*)&c->next_query) >= (unsigned long long)queries) break;
-        if (__ldcg(&c->pool_overflow)) break;
-        if (++spins > (1u << 22)) {  // ~2 s without being admitted: give up instead of hanging the device
-          c->pool_overflow = 2;
-          break;
-        }
-        long long visits = (long long)__ldcg(&P.node_N[cfg.root]);
-        long long allowed = visits / cfg.ramp_div;
-        allowed = allowed < cfg.inflight_min ? cfg.inflight_min : allowed;
-        allowed = allowed > cfg.inflight_max ? cfg.inflight_max : allowed;
-        if ((long long)wid < allowed) {
-          unsigned long long t = atomicAdd(&c->next_query, 1ull);
-          if (t < (unsigned long long)queries) q = (long long)t;
-          break;
-        }
-        __nanosleep(400);
+    const unsigned long long need =
+        (long long)wid < (long long)cfg.inflight_min ? 0ull : ((unsigned long long)wid + 1ull) * (unsigned long long)cfg.ramp_div;
+    bool go = true;
+    unsigned spins = 0;
+    while ((unsigned long long)__ldcg(&P.node_N[cfg.root]) < need) {
+      if (__ldcg((const unsigned long long*)&c->next_query) >= (unsigned long long)queries) { go = false; break; }
+      if (++spins > (1u << 22)) {  // ~2 s without being admitted: give up instead of hanging the device
+        c->pool_overflow = 2;
+        go = false;
+        break;
       }
+      __nanosleep(2000);
     }
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q < 0) break;
-    simulate_one<PID, false, false>(P, m, cfg, pb, (int)wid, (uint32_t)q, cfg.root_N0 + (uint32_t)q, rc, spare, lc);
+    if (go) next_q = atomicAdd(&c->next_query, 1ull);
+  }
+  for (;;) {
+    const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
+    if (q >= (unsigned long long)queries) break;
+    simulate_async<PID>(P, m, &rs_tab, cfg, pv, (uint32_t)q, lc, next_q);
   }
   if (lane == 0) flush_counters(P, lc, false);
 }
@@ -548,13 +906,15 @@ __global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Poo
                                                      const __grid_constant__ SearchCfg cfg,
                                                      const __grid_constant__ PathBuf pb, long long queries,
                                                      SearchResult* res) {
+  __shared__ RsTab rs_tab;
+  if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
   ReplayCursor rc{0, 0};
   LocalCtr lc{0, 0, 0, 0, 0, 0};
   uint32_t spare = 0;
   const int lane = threadIdx.x & 31;
   for (long long q = 0; q < queries; ++q) {
     uint32_t root_ticket = __ldcg(&P.node_N[cfg.root]);
-    simulate_one<PID, true, REPLAY>(P, m, cfg, pb, 0, (uint32_t)q, root_ticket, rc, spare, lc);
+    simulate_one<PID, true, REPLAY>(P, m, &rs_tab, cfg, pb, 0, (uint32_t)q, root_ticket, rc, spare, lc);
     __threadfence_block();
     __syncwarp();
   }
