@@ -213,6 +213,10 @@ int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap_nodes, int64_t* n_nodes, in
                         int64_t* act_N, double* act_V, int32_t* child /* [node][action][obs], -1 none; NULL ok */);
 int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out);
 int32_t pomcp_reset_counters(pomcp_handle* h);
+/* Diagnostics: SM cycles summed over the batched workers since the last reset: [0] descent,
+ * [1] child insertion, [2] leaf rollouts, [3] backup + particle pushes, [4] waiting for admission,
+ * [5] admitted life time. */
+int32_t pomcp_worker_cycles(pomcp_handle* h, uint64_t* out8);
 
 /* Root-parallel multi-GPU search: one tree per rank, root statistics merged by
  * one NCCL all-reduce before the arg-max of src/solver.jl:60-70. */

@@ -56,6 +56,7 @@ def lib():
     L.pomcp_dump_tree.argtypes = [vp, i64, P(i64), vp, vp, vp, vp]
     L.pomcp_get_counters.argtypes = [vp, P(abi.Counters)]
     L.pomcp_reset_counters.argtypes = [vp]
+    L.pomcp_worker_cycles.argtypes = [vp, vp]
     L.pomcp_nccl_unique_id.argtypes = [vp]
     L.pomcp_comm_init.argtypes = [vp, vp, i32, i32]
     L.pomcp_search_rootparallel.argtypes = [vp, i64, P(i32), vp, vp, i32]

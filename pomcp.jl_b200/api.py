@@ -372,6 +372,11 @@ class POMCPPlanner:
         _check(lib().pomcp_get_counters(self._h, C.byref(c)), self._h)
         return c.as_dict()
 
+    def worker_cycles(self):
+        out = np.zeros(8, dtype=np.uint64)
+        _check(lib().pomcp_worker_cycles(self._h, out.ctypes.data_as(C.c_void_p)), self._h)
+        return out
+
     def reset_counters(self):
         _check(lib().pomcp_reset_counters(self._h), self._h)
 

@@ -90,6 +90,8 @@ struct pomcp_handle {
   pomcp_solver_params sp{};
   DevModel dm{};
   double* d_eta = nullptr;
+  uint32_t* d_eta_thr = nullptr;  // RockSample sensor thresholds, compact [(y*n+x)*k+rock]
+  int eta_n = 0;
   int nA = 0, nO = 0, state_bytes = 4, levels = 0;
   bool hashed = false, exact = false, unweighted = true;
   double log_ratio = 0;
@@ -293,9 +295,13 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     // one persistent launch: every warp (= CTA) is a worker, admission is ramped on the device
     long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
     int blocks = (int)workers;
-    size_t path_bytes = (size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes);
-    cfg.path_smem = path_bytes <= 40 * 1024 ? 1 : 0;
+    size_t path_bytes = ((size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes) + 15) & ~(size_t)15;
+    cfg.path_smem = path_bytes <= 28 * 1024 ? 1 : 0;
     size_t smem = cfg.path_smem ? path_bytes : 0;
+    cfg.eta_off = (int)smem;
+    cfg.eta_n = h->eta_n;
+    cfg.eta_thr = h->d_eta_thr;
+    smem += (size_t)h->eta_n * sizeof(uint32_t);
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
       k_search_workers<PID><<<blocks, 32, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
@@ -586,7 +592,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  void* ptrs[] = {h->d_eta, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
+  void* ptrs[] = {h->d_eta, h->d_eta_thr, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
@@ -695,6 +701,17 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     CKC(dev_alloc(h, &h->d_eta, eta.size()));
     CKU(cudaMemcpy(h->d_eta, eta.data(), eta.size() * sizeof(double), cudaMemcpyHostToDevice));
     m.rs_eta = h->d_eta;
+    // the same event as u < eta for u = word * 2^-32:  word <= ceil(eta * 2^32) - 1  (eta >= 0.5)
+    h->eta_n = p->rs_n * p->rs_n * p->rs_k;
+    std::vector<uint32_t> thr((size_t)std::max(h->eta_n, 1), 0u);
+    for (int y = 0; y < p->rs_n; ++y)
+      for (int x = 0; x < p->rs_n; ++x)
+        for (int i = 0; i < p->rs_k; ++i) {
+          double e = eta[(size_t)(y * 16 + x) * POMCP_MAX_ROCKS + i];
+          thr[(size_t)(y * p->rs_n + x) * p->rs_k + i] = (uint32_t)(std::ceil(e * 4294967296.0) - 1.0);
+        }
+    CKC(dev_alloc(h, &h->d_eta_thr, thr.size()));
+    CKU(cudaMemcpy(h->d_eta_thr, thr.data(), thr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   }
 
   // simulations in flight (batched mode) and rollouts per leaf
@@ -1104,7 +1121,7 @@ int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap, int64_t* n_nodes, int64_t*
   }
   if (child && nO > 0) {
     CK(cudaMemcpy(t32.data(), h->pool.child, (size_t)n * nA * nO * 4, cudaMemcpyDeviceToHost));
-    for (long long i = 0; i < n * nA * nO; ++i) child[i] = t32[(size_t)i] ? (int32_t)t32[(size_t)i] : -1;
+    for (long long i = 0; i < n * nA * nO; ++i) child[i] = t32[(size_t)i] ? (int32_t)(t32[(size_t)i] & CHILD_ID_MASK) : -1;
   }
   return POMCP_OK;
 }
@@ -1128,11 +1145,24 @@ int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out) {
   return POMCP_OK;
 }
 
+// Diagnostics: SM cycles summed over the batched workers since the counters were reset:
+// [0] descent, [1] child insertion, [2] leaf rollouts, [3] backup + particle pushes,
+// [4] waiting for admission, [5] admitted life time (includes fetching query ids).
+int32_t pomcp_worker_cycles(pomcp_handle* h, uint64_t* out8) {
+  if (!h || !out8) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 8; ++i) out8[i] = h->h_ctr->dbg[i];
+  return POMCP_OK;
+}
+
 int32_t pomcp_reset_counters(pomcp_handle* h) {
   if (!h) return POMCP_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   size_t off = offsetof(DevCtr, sims), end = offsetof(DevCtr, scan_ticket);
   CK(cudaMemsetAsync((char*)h->pool.ctr + off, 0, end - off, h->stream));
+  CK(cudaMemsetAsync((char*)h->pool.ctr + offsetof(DevCtr, dbg), 0, sizeof(((DevCtr*)0)->dbg), h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->launches = 0;
   return POMCP_OK;

@@ -73,7 +73,7 @@ __global__ void k_copy_kept(const __grid_constant__ Pool P, const __grid_constan
     T.act_V[sn] = P.act_V[so];
     for (int o = 0; o < nO; ++o) {
       uint32_t c = P.child[so * nO + o];
-      T.child[sn * nO + o] = c ? newid[c] : 0u;
+      T.child[sn * nO + o] = c ? (newid[c & CHILD_ID_MASK] | (c & CHILD_EXPANDED)) : 0u;
     }
   }
 }

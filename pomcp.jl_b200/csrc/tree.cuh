@@ -18,6 +18,12 @@
 
 namespace pomcp {
 
+// Direct child table (discrete observations): bit 31 of a child id says that the worker which
+// created the node also expands it (it was not cut off there) — later visitors need not read the
+// node's expansion flag, and the creator needs no claim round trip.
+constexpr uint32_t CHILD_EXPANDED = 0x80000000u;
+constexpr uint32_t CHILD_ID_MASK = 0x7fffffffu;
+
 struct DevCtr {
   unsigned long long node_count, log_count;
   unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
@@ -59,6 +65,8 @@ struct SearchCfg {
   // asynchronous workers: in flight = clamp(root visits / ramp_div, inflight_min, inflight_max)
   int inflight_min, inflight_max, ramp_div;
   int path_smem;  // batched mode: the worker's recorded path lives in shared memory (else in PathBuf)
+  int eta_off, eta_n;  // RockSample: byte offset / entry count of the sensor thresholds in dynamic shared memory
+  const uint32_t* eta_thr;  // [(y*n+x)*k+rock]: check is correct iff obs word <= threshold  (== u < eta)
   // replay (exact mode only)
   const double* uni;
   long long n_uni;
@@ -81,6 +89,8 @@ struct ReplayCursor {
 
 struct LocalCtr {
   unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
+  // batched workers: SM cycles spent per phase (pomcp_worker_cycles): descent, insert, rollout, backup
+  unsigned long long cyc[4];
 };
 
 struct SearchResult {
@@ -115,6 +125,11 @@ __device__ __forceinline__ void get_draws(const SearchCfg& cfg, ReplayCursor& rc
 
 // CHECK_DISC: keep RolloutSimulator's `disc > eps` test (eps = 0).  Inside the tree
 // steps <= ceil(log(eps)/log(gamma)), so disc >= eps * gamma > 0 and the test can never fire.
+// Both rollout loops below are branch-free inside a Philox block: every step of the block is
+// computed by every lane, and a lane that has finished (terminal state or step budget) only adds
+// +0.0 to its return.  That leaves one basic block per Philox block, in which the next block's
+// Philox rounds (independent of the trajectory) are interleaved with the dependent chain of the
+// steps — a single trajectory is a latency chain, the issue slots next to it are free.
 template <int PID, bool CHECK_DISC>
 __device__ __forceinline__ double rollout_generic(const DevModel& m, typename ModelT<PID>::State s, long long steps,
                                                   uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
@@ -126,25 +141,25 @@ __device__ __forceinline__ double rollout_generic(const DevModel& m, typename Mo
   const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
   int step = 0;
   bool live = !M::terminal(m, s) && nstep_max > 0;
+  Philox4 p = philox4x32_10(0u, tagword, q, epoch, k0, k1);
   for (uint32_t blk = 0; live; ++blk) {
-    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+    const Philox4 pn = philox4x32_10(blk + 1u, tagword, q, epoch, k0, k1);
 #pragma unroll
     for (int j = 0; j < 4 / DPS; ++j) {
-      if (live) {
-        uint32_t wa = p.w[j * DPS];
-        uint32_t wt = p.w[j * DPS + (DPS - 1)];
-        int a = (int)__umulhi(wa, (uint32_t)m.nA);  // rand(rng, actions): floor(u * nA)
-        typename M::State sp;
-        uint64_t o;
-        double r;
-        M::template step<false, uint32_t>(m, s, a, wt, 0.0, 0.0, sp, o, r);
-        total += disc * r;
-        s = sp;
-        disc *= gamma;
-        ++step;
-        live = (!CHECK_DISC || disc > 0.0) && !M::terminal(m, s) && step < nstep_max;
-      }
+      uint32_t wa = p.w[j * DPS];
+      uint32_t wt = p.w[j * DPS + (DPS - 1)];
+      int a = (int)__umulhi(wa, (uint32_t)m.nA);  // rand(rng, actions): floor(u * nA)
+      typename M::State sp;
+      uint64_t o;
+      double r;
+      M::template step<false, uint32_t>(m, s, a, wt, 0.0, 0.0, sp, o, r);
+      total += disc * (live ? r : 0.0);
+      s = sp;
+      disc *= gamma;
+      step += live ? 1 : 0;
+      live = live && (!CHECK_DISC || disc > 0.0) && !M::terminal(m, s) && step < nstep_max;
     }
+    p = pn;
   }
   nsteps = step;
   return total;
@@ -192,30 +207,30 @@ __device__ __forceinline__ double rollout_rocksample(const DevModel& m, const Rs
   const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
   int step = 0;
   bool live = !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
+  Philox4 p = philox4x32_10(0u, tagword, q, epoch, k0, k1);
   for (uint32_t blk = 0; live; ++blk) {
-    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+    const Philox4 pn = philox4x32_10(blk + 1u, tagword, q, epoch, k0, k1);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (live) {
-        const uint32_t a = __umulhi(p.w[j], nA);  // rand(rng, actions): floor(u * nA)
-        // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
-        const uint32_t t = shr_clamped(0x3C14u, a * 4u);
-        y = min(max(y + sbfe2(t, 2), 0), nmax);
-        const int nx = x + sbfe2(t, 0);
-        const bool exits = nx > nmax;  // moving east off the grid
-        x = min(max(nx, 0), nmax);
-        const int ri = tb->rock_at[y * 16 + x];
-        const bool hit = (a == 4u) & (ri >= 0);  // sample on a rock
-        const uint32_t sh = (uint32_t)ri & 31u;
-        const uint32_t good = (rocks >> sh) & 1u;
-        rocks &= ~((hit ? good : 0u) << sh);  // a sampled rock turns bad
-        const int ev = exits ? 1 : (hit ? 2 + (int)good : 0);
-        total += disc * tb->rtab[ev];
-        disc *= gamma;
-        ++step;
-        live = (!CHECK_DISC || disc > 0.0) && !exits && step < nstep_max;
-      }
+      const uint32_t a = __umulhi(p.w[j], nA);  // rand(rng, actions): floor(u * nA)
+      // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
+      const uint32_t t = shr_clamped(0x3C14u, a * 4u);
+      y = min(max(y + sbfe2(t, 2), 0), nmax);
+      const int nx = x + sbfe2(t, 0);
+      const bool exits = nx > nmax;  // moving east off the grid
+      x = min(max(nx, 0), nmax);
+      const int ri = tb->rock_at[y * 16 + x];
+      const bool hit = (a == 4u) & (ri >= 0);  // sample on a rock
+      const uint32_t sh = (uint32_t)ri & 31u;
+      const uint32_t good = (rocks >> sh) & 1u;
+      rocks &= ~((hit ? good : 0u) << sh);  // a sampled rock turns bad
+      const int ev = exits ? 1 : (hit ? 2 + (int)good : 0);
+      total += disc * tb->rtab[live ? ev : 0];  // a finished lane adds +0.0
+      disc *= gamma;
+      step += live ? 1 : 0;
+      live = live && (!CHECK_DISC || disc > 0.0) && !exits && step < nstep_max;
     }
+    p = pn;
   }
   nsteps = step;
   return total;
@@ -274,9 +289,10 @@ __device__ __forceinline__ double rollout_fwc(const DevModel& m, uint32_t s, lon
 // SKIP_LOAD: the caller has just read the child slot as empty (direct table only), go straight to the insert.
 // `created` tells the caller that it published the node itself (then it is, like in the reference,
 // the natural first visitor of that node).
+// `claim` (direct table only): publish the id with CHILD_EXPANDED; the returned value keeps that bit.
 template <int PID, bool SKIP_LOAD = false>
 __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const DevModel& m, uint32_t slot,
-                                                         uint64_t obs, bool& created) {
+                                                         uint64_t obs, bool& created, bool claim = false) {
   using M = ModelT<PID>;
   created = false;
   if (!M::HASHED) {
@@ -291,8 +307,9 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
       return 0;
     }
     P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
-    uint32_t old = atomicCAS(cs, 0u, fresh);
-    if (old == 0) { created = true; return fresh; }
+    const uint32_t pub = claim ? (fresh | CHILD_EXPANDED) : fresh;
+    uint32_t old = atomicCAS(cs, 0u, pub);
+    if (old == 0) { created = true; return pub; }
     P.node_pslot[fresh] = 0;  // lost the race: leave the slot detached
     return old;
   } else {
@@ -330,7 +347,7 @@ __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m,
   using M = ModelT<PID>;
   if (!M::HASHED) {
     if (obs >= (uint64_t)m.nO) return 0;
-    return __ldcg(&P.child[(size_t)slot * m.nO + (uint32_t)obs]);
+    return __ldcg(&P.child[(size_t)slot * m.nO + (uint32_t)obs]) & CHILD_ID_MASK;
   } else {
     uint64_t h = mix64((uint64_t)slot * 0x9E3779B97F4A7C15ull ^ obs) & P.ht_mask;
     for (;;) {
@@ -585,6 +602,35 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
 //    and the arg-max with the reference's tie rule is one REDUX.MAX on an order-preserving key plus
 //    one ballot (highest lane among the maxima = "last wins on >=");
 //  * the next query id is requested before the rollouts start, so that atomic is off the path.
+// RockSample generative step for the tree (batched mode): same transition, reward and observation as
+// ModelT<ROCKSAMPLE>::step<true>, on the shared-memory tables.  The sensor draw compares the Philox
+// word with ceil(eta * 2^32) - 1, which is the same event as word * 2^-32 < eta.
+__device__ __forceinline__ void rs_tree_step(const DevModel& m, const RsTab* tb, const uint32_t* eta_thr, uint32_t st,
+                                             int a, uint32_t w_obs, uint32_t& sp, uint64_t& o, double& r) {
+  const int nmax = m.rs_n - 1;
+  int x = (int)(st & 15u), y = (int)((st >> 4) & 15u);
+  const uint32_t t = shr_clamped(0x3C14u, (uint32_t)a * 4u);
+  y = min(max(y + sbfe2(t, 2), 0), nmax);
+  const int nx = x + sbfe2(t, 0);
+  const bool exits = nx > nmax;
+  x = min(max(nx, 0), nmax);
+  st |= exits ? POMCP_RS_TERMINAL : 0u;
+  const int ri = tb->rock_at[y * 16 + x];
+  const bool hit = (a == 4) & (ri >= 0);
+  const uint32_t sh = 8u + ((uint32_t)ri & 15u);
+  const uint32_t good = (st >> sh) & 1u;
+  st &= ~((hit ? good : 0u) << sh);
+  r = tb->rtab[exits ? 1 : (hit ? 2 + (int)good : 0)];
+  o = 2;  // none
+  if (a >= 5) {
+    const int rk = a - 5;
+    const uint32_t g = (st >> (8 + rk)) & 1u;
+    const uint32_t correct = w_obs <= eta_thr[(y * m.rs_n + x) * m.rs_k + rk] ? 1u : 0u;
+    o = (g == correct) ? 0 : 1;
+  }
+  sp = (st & ~0xffu) | (uint32_t)x | ((uint32_t)y << 4);
+}
+
 template <class State>
 struct PathView {
   uint32_t* slot;
@@ -629,7 +675,8 @@ struct ActStats {
 // One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
 // (lane 0; requested early so its latency hides behind the rollouts).
 template <int PID>
-__device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
+__device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
+                                               const uint32_t* eta_thr, const SearchCfg& cfg,
                                                const PathView<typename ModelT<PID>::State>& pv, uint32_t q,
                                                LocalCtr& lc, unsigned long long& next_q) {
   using M = ModelT<PID>;
@@ -665,6 +712,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   uint64_t last_o = 0;  // observation label of h (seeds the FeedWhenCrying rollout)
   int depth = 0;
   bool want_rollout = false, aborted = false;
+  long long t0 = clock64(), t_ins = 0;
+  // draws of the tree step at `depth`: computed while the node's statistics are in flight
+  Philox4 pt = philox4x32_10(0u, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
   for (;;) {
     if (depth >= cfg.levels || M::terminal(m, s)) break;  // src/solver.jl:82-86
     if (!(fl & 1u)) {  // src/solver.jl:87-107: the first visitor that is not cut off expands the node
@@ -693,41 +743,50 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     const uint32_t slot = h * (uint32_t)nA + (uint32_t)best_a;
 
     // src/solver.jl:126
-    Philox4 pt = philox4x32_10((uint32_t)depth, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
     State sp;
     uint64_t o;
     double r;
-    M::template step<true, double>(m, s, best_a, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp, o, r);
+    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, best_a, pt.w[2], sp, o, r);
+    else M::template step<true, double>(m, s, best_a, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp, o, r);
+    const bool cut_next = depth + 1 >= cfg.levels || M::terminal(m, sp);
 
     // src/solver.jl:132-142: child ids came with the statistics; ids never change once published
-    uint32_t hao = 0;
+    uint32_t raw = 0;
     if (!M::HASHED) {
       uint32_t mine = st.kid[0];
 #pragma unroll
       for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o == (uint64_t)k) ? st.kid[k] : mine;
-      hao = __shfl_sync(0xffffffffu, mine, best_a);
+      raw = __shfl_sync(0xffffffffu, mine, best_a);
     }
     int created = 0;
-    if (hao == 0) {
+    if (raw == 0) {
+      const long long ti = clock64();
       if (lane == 0) {
         bool cr;
-        hao = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr);
+        raw = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr, !M::HASHED && !cut_next);
         created = cr;
       }
-      hao = __shfl_sync(0xffffffffu, hao, 0);
+      raw = __shfl_sync(0xffffffffu, raw, 0);
       created = __shfl_sync(0xffffffffu, created, 0);
-      if (hao == 0) { aborted = true; break; }
+      t_ins += clock64() - ti;
+      if (raw == 0) { aborted = true; break; }
     }
-    // Arrival ticket, expansion flag and statistics of the child: one round trip.  The worker that
-    // created the child (and is not cut off there) claims its expansion in the same round trip and
-    // does not need the statistics of a brand-new node.
-    const bool try_claim = created && !(depth + 1 >= cfg.levels || M::terminal(m, sp));
-    uint32_t ticket = 0, nfl = 0;
+    const uint32_t hao = raw & CHILD_ID_MASK;
+    const bool i_expand_child = created && (raw & CHILD_EXPANDED);  // direct table: the creator expands
+    const bool try_claim = created && !i_expand_child && !cut_next;  // hashed table: claim now
+    const bool flag_known = (raw & CHILD_EXPANDED) != 0;
+    // Arrival ticket, expansion flag and statistics of the child: one round trip.
+    uint32_t ticket = 0, nfl = flag_known ? 1u : 0u;
     if (lane == 0) {
       atomicAdd(&P.act_N[slot], 1u);
-      ticket = atomicAdd(&P.node_N[hao], 1u);
-      if (try_claim) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;  // bit1: the claim was attempted here
-      else nfl = __ldcg(&P.node_flags[hao]);
+      if (i_expand_child) {
+        atomicAdd(&P.node_N[hao], 1u);    // nobody waits for these two
+        atomicOr(&P.node_flags[hao], 1u);
+      } else {
+        ticket = atomicAdd(&P.node_N[hao], 1u);
+        if (try_claim) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;  // bit1: the claim was attempted here
+        else if (!flag_known) nfl = __ldcg(&P.node_flags[hao]);
+      }
       const int pi = depth * pv.stride;
       pv.slot[pi] = slot;
       pv.r[pi] = r;
@@ -736,15 +795,20 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         pv.state[pi] = sp;
       }
     }
-    if (!try_claim) st.load(P, hao, nA, lane);
-    hN = __shfl_sync(0xffffffffu, ticket, 0);
-    fl = __shfl_sync(0xffffffffu, nfl, 0);
     h = hao;
     s = sp;
     last_o = o;
     ++depth;
+    if (i_expand_child) {  // expand + evaluate the leaf (src/solver.jl:87-103)
+      want_rollout = true;
+      break;
+    }
+    if (!try_claim) st.load(P, hao, nA, lane);
+    pt = philox4x32_10((uint32_t)depth, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    hN = __shfl_sync(0xffffffffu, ticket, 0);
+    fl = __shfl_sync(0xffffffffu, nfl, 0);
     if (fl & 2u) {
-      if (!(fl & 1u)) {  // claimed: expand + evaluate the leaf (src/solver.jl:87-103)
+      if (!(fl & 1u)) {  // claimed
         want_rollout = true;
         break;
       }
@@ -757,6 +821,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     next_q = atomicAdd(&P.ctr->next_query, 1ull);
   }
   if (aborted) return;
+  const long long t1 = clock64();
+  lc.cyc[0] += (unsigned long long)(t1 - t0 - t_ins);
+  lc.cyc[1] += (unsigned long long)t_ins;
 
   // leaf evaluation, src/solver.jl:97-103
   double leaf = 0.0;
@@ -784,6 +851,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
     leaf = cfg.gpow[depth] * est;  // src/solver.jl:103 (the reference's extra gamma^depth is kept)
   }
+  const long long t2 = clock64();
+  lc.cyc[2] += (unsigned long long)(t2 - t1);
 
   // particle pushes, deepest level first like the unwinding recursion (src/solver.jl:146-148)
   if (cfg.belief_unweighted && depth > 0) {
@@ -815,6 +884,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     atomicAdd(&P.node_N[cfg.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
   }
   __syncwarp();
+  lc.cyc[3] += (unsigned long long)(clock64() - t2);
   lc.sims++;
   lc.tree_steps += depth;
   if ((unsigned long long)depth > lc.max_depth) lc.max_depth = depth;
@@ -832,6 +902,8 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
     if (lc.skips) atomicAdd(&c->skips, lc.skips);
     if (lc.rollouts) { atomicAdd(&c->rollouts, lc.rollouts); atomicAdd(&c->rollout_steps, lc.rollout_steps); }
     atomicMax(&c->max_depth, lc.max_depth);
+    for (int i = 0; i < 4; ++i)
+      if (lc.cyc[i]) atomicAdd(&c->dbg[i], lc.cyc[i]);
   }
 }
 
@@ -871,8 +943,16 @@ __global__ void __launch_bounds__(32) k_search_workers(const __grid_constant__ P
     pv.node = pb.path_node + wid;
     pv.stride = pb.stride;
   }
-  LocalCtr lc{0, 0, 0, 0, 0, 0};
+  const uint32_t* eta_thr = nullptr;
+  if (PID == POMCP_ROCKSAMPLE) {
+    uint32_t* e = (uint32_t*)(path_smem + cfg.eta_off);
+    for (int i = lane; i < cfg.eta_n; i += 32) e[i] = cfg.eta_thr[i];
+    __syncwarp();
+    eta_thr = e;
+  }
+  LocalCtr lc{};
   unsigned long long next_q = ~0ull;
+  const long long t_start = clock64();
   if (lane == 0) {
     // admission: ramp the number of simulations in flight with the size of the tree
     const unsigned long long need =
@@ -890,12 +970,17 @@ __global__ void __launch_bounds__(32) k_search_workers(const __grid_constant__ P
     }
     if (go) next_q = atomicAdd(&c->next_query, 1ull);
   }
+  const long long t_admitted = clock64();
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID>(P, m, &rs_tab, cfg, pv, (uint32_t)q, lc, next_q);
+    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, (uint32_t)q, lc, next_q);
   }
-  if (lane == 0) flush_counters(P, lc, false);
+  if (lane == 0) {
+    flush_counters(P, lc, false);
+    atomicAdd(&c->dbg[4], (unsigned long long)(t_admitted - t_start));  // waiting for admission
+    atomicAdd(&c->dbg[5], (unsigned long long)(clock64() - t_admitted));  // working
+  }
 }
 
 // ---- exact mode: one warp runs the queries strictly one after another (bit-parity with the
@@ -909,7 +994,7 @@ __global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Poo
   __shared__ RsTab rs_tab;
   if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
   ReplayCursor rc{0, 0};
-  LocalCtr lc{0, 0, 0, 0, 0, 0};
+  LocalCtr lc{};
   uint32_t spare = 0;
   const int lane = threadIdx.x & 31;
   for (long long q = 0; q < queries; ++q) {
