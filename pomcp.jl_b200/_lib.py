@@ -9,7 +9,8 @@ import os
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libpomcp_b200.so")
+# POMCP_B200_LIB: developer override (A/B timing of two builds); the default is the in-tree library
+SO_PATH = os.environ.get("POMCP_B200_LIB") or os.path.join(_HERE, "libpomcp_b200.so")
 _lib = None
 
 

@@ -170,9 +170,13 @@ __device__ __forceinline__ double rollout_generic(const DevModel& m, typename Mo
 struct RsTab {
   double rtab[4];           // reward by event: 0 none, 1 exit, 2 sampled a bad rock, 3 sampled a good rock
   signed char rock_at[256]; // rock index at cell y*16+x, -1 none
+  unsigned char rock_sh[256];  // the same as a shift amount: rock index, or 32 (-> empty mask) where there is no rock
 };
 __device__ __forceinline__ void rs_tab_init(RsTab* t, const DevModel& m) {
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) t->rock_at[i] = m.rock_at[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    t->rock_at[i] = m.rock_at[i];
+    t->rock_sh[i] = m.rock_at[i] >= 0 ? (unsigned char)m.rock_at[i] : (unsigned char)32;
+  }
   if (threadIdx.x < 4) t->rtab[threadIdx.x] = m.rs_rtab[threadIdx.x];
   __syncthreads();
 }
@@ -180,6 +184,11 @@ __device__ __forceinline__ void rs_tab_init(RsTab* t, const DevModel& m) {
 __device__ __forceinline__ uint32_t shr_clamped(uint32_t x, uint32_t n) {  // 0 for n >= 32
   uint32_t y;
   asm("shr.u32 %0, %1, %2;" : "=r"(y) : "r"(x), "r"(n));
+  return y;
+}
+__device__ __forceinline__ uint32_t shl_clamped(uint32_t x, uint32_t n) {  // 0 for n >= 32
+  uint32_t y;
+  asm("shl.b32 %0, %1, %2;" : "=r"(y) : "r"(x), "r"(n));
   return y;
 }
 __device__ __forceinline__ int sbfe2(uint32_t x, int pos) {  // signed 2-bit field
@@ -210,6 +219,8 @@ __device__ __forceinline__ double rollout_rocksample(const DevModel& m, const Rs
   Philox4 p = philox4x32_10(0u, tagword, q, epoch, k0, k1);
   for (uint32_t blk = 0; live; ++blk) {
     const Philox4 pn = philox4x32_10(blk + 1u, tagword, q, epoch, k0, k1);
+    // Loop-carried chains per step are kept minimal: position (add + clamp), rock bits (one and-not
+    // with a mask that comes from the position only), return (one add), discount (one multiply).
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t a = __umulhi(p.w[j], nA);  // rand(rng, actions): floor(u * nA)
@@ -219,12 +230,11 @@ __device__ __forceinline__ double rollout_rocksample(const DevModel& m, const Rs
       const int nx = x + sbfe2(t, 0);
       const bool exits = nx > nmax;  // moving east off the grid
       x = min(max(nx, 0), nmax);
-      const int ri = tb->rock_at[y * 16 + x];
-      const bool hit = (a == 4u) & (ri >= 0);  // sample on a rock
-      const uint32_t sh = (uint32_t)ri & 31u;
-      const uint32_t good = (rocks >> sh) & 1u;
-      rocks &= ~((hit ? good : 0u) << sh);  // a sampled rock turns bad
-      const int ev = exits ? 1 : (hit ? 2 + (int)good : 0);
+      // sample (a == 4) on a rock: +good / -bad, and the rock is bad afterwards either way
+      const uint32_t mask = shl_clamped(a == 4u ? 1u : 0u, tb->rock_sh[y * 16 + x]);
+      const uint32_t goodbit = rocks & mask;
+      rocks &= ~mask;
+      const int ev = exits ? 1 : (mask ? (goodbit ? 3 : 2) : 0);
       total += disc * tb->rtab[live ? ev : 0];  // a finished lane adds +0.0
       disc *= gamma;
       step += live ? 1 : 0;
@@ -631,6 +641,14 @@ __device__ __forceinline__ void rs_tree_step(const DevModel& m, const RsTab* tb,
   sp = (st & ~0xffu) | (uint32_t)x | ((uint32_t)y << 4);
 }
 
+__device__ __forceinline__ uint32_t shfl_state(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ LDState shfl_state(const LDState& v, int src) {
+  LDState o;
+  o.status = __shfl_sync(0xffffffffu, v.status, src);
+  o.y = __shfl_sync(0xffffffffu, v.y, src);
+  return o;
+}
+
 template <class State>
 struct PathView {
   uint32_t* slot;
@@ -713,8 +731,19 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   int depth = 0;
   bool want_rollout = false, aborted = false;
   long long t0 = clock64(), t_ins = 0;
-  // draws of the tree step at `depth`: computed while the node's statistics are in flight
-  Philox4 pt = philox4x32_10(0u, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+  // Generative step of every action, one per lane (src/solver.jl:126 for whichever action UCB
+  // will pick): it depends on the state and on this level's draws only, not on the node's
+  // statistics, so it runs while those are in flight and is off the critical path.
+  State sp_l;
+  uint64_t o_l;
+  double r_l;
+  auto spec_step = [&](int d) {
+    const Philox4 pt = philox4x32_10((uint32_t)d, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    const int a_l = lane < nA ? lane : nA - 1;
+    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, pt.w[2], sp_l, o_l, r_l);
+    else M::template step<true, double>(m, s, a_l, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp_l, o_l, r_l);
+  };
+  spec_step(0);
   for (;;) {
     if (depth >= cfg.levels || M::terminal(m, s)) break;  // src/solver.jl:82-86
     if (!(fl & 1u)) {  // src/solver.jl:87-107: the first visitor that is not cut off expands the node
@@ -742,22 +771,20 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     const int best_a = mx ? 31 - __clz((int)tied) : nA - 1;  // ">=": the last maximal index wins
     const uint32_t slot = h * (uint32_t)nA + (uint32_t)best_a;
 
-    // src/solver.jl:126
-    State sp;
-    uint64_t o;
-    double r;
-    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, best_a, pt.w[2], sp, o, r);
-    else M::template step<true, double>(m, s, best_a, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp, o, r);
+    // outcome of the chosen action; child ids came with the statistics (ids never change once published)
+    uint32_t mine = 0;
+    if (!M::HASHED) {
+      mine = st.kid[0];
+#pragma unroll
+      for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o_l == (uint64_t)k) ? st.kid[k] : mine;
+    }
+    uint32_t raw = __shfl_sync(0xffffffffu, mine, best_a);
+    const State sp = shfl_state(sp_l, best_a);
+    const uint64_t o = __shfl_sync(0xffffffffu, o_l, best_a);
+    const double r = __shfl_sync(0xffffffffu, r_l, best_a);
     const bool cut_next = depth + 1 >= cfg.levels || M::terminal(m, sp);
 
-    // src/solver.jl:132-142: child ids came with the statistics; ids never change once published
-    uint32_t raw = 0;
-    if (!M::HASHED) {
-      uint32_t mine = st.kid[0];
-#pragma unroll
-      for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o == (uint64_t)k) ? st.kid[k] : mine;
-      raw = __shfl_sync(0xffffffffu, mine, best_a);
-    }
+    // src/solver.jl:132-142
     int created = 0;
     if (raw == 0) {
       const long long ti = clock64();
@@ -775,15 +802,17 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     const bool i_expand_child = created && (raw & CHILD_EXPANDED);  // direct table: the creator expands
     const bool try_claim = created && !i_expand_child && !cut_next;  // hashed table: claim now
     const bool flag_known = (raw & CHILD_EXPANDED) != 0;
-    // Arrival ticket, expansion flag and statistics of the child: one round trip.
-    uint32_t ticket = 0, nfl = flag_known ? 1u : 0u;
+    // Visit count, expansion flag and statistics of the child: one round trip.  The count is added
+    // with a fire-and-forget reduction and read with a plain load (a load returns sooner than an
+    // atomic; whether it sees this worker's own arrival does not matter to log(h.N)).
+    uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
     if (lane == 0) {
       atomicAdd(&P.act_N[slot], 1u);
+      atomicAdd(&P.node_N[hao], 1u);
       if (i_expand_child) {
-        atomicAdd(&P.node_N[hao], 1u);    // nobody waits for these two
-        atomicOr(&P.node_flags[hao], 1u);
+        atomicOr(&P.node_flags[hao], 1u);  // nobody waits for it
       } else {
-        ticket = atomicAdd(&P.node_N[hao], 1u);
+        seen = __ldcg(&P.node_N[hao]);
         if (try_claim) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;  // bit1: the claim was attempted here
         else if (!flag_known) nfl = __ldcg(&P.node_flags[hao]);
       }
@@ -804,8 +833,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       break;
     }
     if (!try_claim) st.load(P, hao, nA, lane);
-    pt = philox4x32_10((uint32_t)depth, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
-    hN = __shfl_sync(0xffffffffu, ticket, 0);
+    if (!cut_next) spec_step(depth);
+    hN = __shfl_sync(0xffffffffu, seen, 0);
     fl = __shfl_sync(0xffffffffu, nfl, 0);
     if (fl & 2u) {
       if (!(fl & 1u)) {  // claimed

@@ -18,18 +18,24 @@ for infl in inflights:
         solver = pj.POMCPSolver(c=bench.UCB_C, rng=bench.SOLVER_SEED, tree_queries=Q, search_mode="batched",
                                 max_nodes=3 * Q, inflight_max=infl, rollouts_per_leaf=R)
         pl = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
-        for it in range(3):
+        rows = []
+        for it in range(6):
             pl.set_belief_particles(parts)
             pl.reset_counters()
             a, N, V = pl.search(Q)
             ms, _ = pl.phase_ms(abi.PHASE_ROLLOUT)
             cs = pl.counters()
             cy = pl.worker_cycles().astype(np.float64)
-        sims = max(cs["simulations"], 1)
-        per = cy[:4] / sims
-        print(f"inflight={infl} R={R}: kernel {ms:.2f} ms, sims/s {Q / ms * 1e3:.3e}, steps/s {cs['rollout_steps'] / ms * 1e3:.3e}, "
-              f"depth/sim {cs['tree_steps'] / sims:.2f}, steps/sim {cs['rollout_steps'] / sims:.0f}, nodes {cs['nodes']}, a={a} Vbest={V.max():.3f}")
-        print(f"   cycles/sim: descent {per[0]:.0f} insert {per[1]:.0f} rollout {per[2]:.0f} backup {per[3]:.0f} "
-              f"| sum {per.sum():.0f} | admitted-life/sim {cy[5] / sims:.0f} admission-wait total {cy[4]:.3e} | "
-              f"per level {per[0] / max(cs['tree_steps'] / sims, 1):.0f}")
+            sims = max(cs["simulations"], 1)
+            if it:
+                rows.append([ms, cs["rollout_steps"] / sims, cs["tree_steps"] / sims, cs["nodes"], V.max()] + list(cy[:6] / sims))
+        r = np.array(rows)
+        mean, lo, hi = r.mean(0), r.min(0), r.max(0)
+        ms = mean[0]
+        print(f"inflight={infl} R={R}: kernel {ms:.2f} ms [{lo[0]:.2f}..{hi[0]:.2f}], sims/s {Q / ms * 1e3:.3e}, "
+              f"steps/s {mean[1] * Q / ms * 1e3:.3e}, depth/sim {mean[2]:.2f}, steps/sim {mean[1]:.0f}, nodes {mean[3]:.0f}, "
+              f"Vbest {mean[4]:.3f} [{lo[4]:.2f}..{hi[4]:.2f}]")
+        print(f"   cycles/sim: descent {mean[5]:.0f} insert {mean[6]:.0f} rollout {mean[7]:.0f} backup {mean[8]:.0f} "
+              f"| sum {mean[5:9].sum():.0f} | admitted-life/sim {mean[10]:.0f} | per level {mean[5] / mean[2]:.0f} "
+              f"| rollout per lane-step {mean[7] / (mean[1] / R):.0f}")
         pl.close()
