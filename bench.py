@@ -352,10 +352,13 @@ def run_gpu(args):
             "tree_sims_per_sec": sims_sum / (total_ms_max * 1e-3),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_s / args.steps * 1e3},
+                    "ms_per_step": e2e_s / args.steps * 1e3,
+                    "tree_sims_per_sec": TREE_QUERIES * n_gpus * args.steps / e2e_s},
             "gpu_launches": launches,
             "roofline": {
-                "kernel": "SIR update: k_pf_max + k_pf_scan + k_pf_emit (K6-K8)", "bound": "hbm",
+                "kernel": "SIR update K6-K8: k_pf_fused (one cooperative launch: propagate+weight, fixed-point scan, "
+                          "systematic resample)" if pf_launches == 1 else "SIR update K6-K8: k_pf_max + k_pf_scan + "
+                          "k_pf_finalize + k_pf_emit", "bound": "hbm",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": prof.get("pf_dram_bytes_per_update"),
                 "algorithmic_bytes": alg_bytes, "bytes_per_particle": 2 * S + 16, "launch_us": pf_s * 1e6,
