@@ -147,7 +147,8 @@ def run_reference(args):
     from pomcp_jl_b200 import _abi as abi
     from oracle import oracle as O
     pomdp = pj.RockSamplePOMDP(RS_N, RS_K, seed=RS_SEED)
-    cores = O.lib().orc_max_threads()
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: not a property of the box)
+    cores = max(len(os.sched_getaffinity(0)), 1)
     sample_q = 100_000  # per tree and per step: bounded sample of the 1e6-query decision
     n_part = N_PARTICLES
     parts, _ = initial_particles(pomdp, n_part)
