@@ -404,22 +404,21 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     h->timers[POMCP_PHASE_PF].launches += 1;
     return POMCP_OK;
   }
-  int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-  k_pf_max<Src><<<blocks, 256, 0, h->stream>>>(src, n, h->d_pfctl);
-  rc = launch_check(h, "k_pf_max");
+  // streaming path: weigh -> total -> scan + emit
+  int blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
+  k_pf_weigh<Src><<<blocks, 256, 0, h->stream>>>(src, n, (double*)h->d_cum, h->d_pfctl);
+  rc = launch_check(h, "k_pf_weigh");
   if (rc) return rc;
-  int tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-  k_pf_scan<Src><<<tiles, SCAN_THREADS, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, h->d_scan_status + 9,
-                                                        h->d_scan_status + 8);
-  rc = launch_check(h, "k_pf_scan");
+  k_pf_total<<<(int)std::min<long long>((n + 2047) / 2048, 148 * 8), 256, 0, h->stream>>>((const double*)h->d_cum, n,
+                                                                                         h->d_pfctl);
+  rc = launch_check(h, "k_pf_total");
   if (rc) return rc;
-  k_pf_finalize<<<1, 32, 0, h->stream>>>(h->d_cum, n, h->d_pfctl);
-  rc = launch_check(h, "k_pf_finalize");
+  int tiles = (int)((n + PF2_TILE - 1) / PF2_TILE);
+  k_pf_scan_emit<Src, Out><<<tiles, PF2_THREADS, 0, h->stream>>>(src, n, (const double*)h->d_cum, h->d_pfctl, ru, n_out,
+                                                                 d_out, h->d_scan_status + 9, h->d_scan_status + 8);
+  rc = launch_check(h, "k_pf_scan_emit");
   if (rc) return rc;
-  k_pf_emit<Src, Out><<<(int)((n + 255) / 256), 256, 0, h->stream>>>(src, n, h->d_pfctl, h->d_cum, ru, n_out, d_out);
-  rc = launch_check(h, "k_pf_emit");
-  if (rc) return rc;
-  h->timers[POMCP_PHASE_PF].launches += 4;
+  h->timers[POMCP_PHASE_PF].launches += 3;
   return POMCP_OK;
 }
 

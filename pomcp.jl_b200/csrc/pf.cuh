@@ -3,12 +3,17 @@
 // (not vendored in the reference; call site test/runtests.jl:57, semantics SURVEY.md App. B.3)
 // and the per-node ParticleCollection of the unweighted filter (src/particle_filter.jl:27-30).
 //
-// HBM-bound design, three streaming passes, none of which stores the propagated state or the
-// fp64 weight:
-//   K6 pf_max:   read s_i                       -> max weight, first alive particle
-//   K7 pf_scan:  read s_i (L2), write C_i (8 B) -> single-pass decoupled-look-back scan of the
-//                fixed-point weights q_i = trunc(w_i * 2^s)
-//   K8 pf_emit:  read C_i (8 B), s_i (L2)       -> write the resampled states (S bytes each)
+// Two implementations of the same integers (so the same indices, bit for bit):
+//  * k_pf_fused: one persistent cooperative launch for sets that fit one co-resident grid, weights
+//    kept in registers across two grid barriers (latency-bound sizes);
+//  * streaming path for any size, three passes shaped for HBM and for the issue slots:
+//      K6 k_pf_weigh      read s_i                      -> write w_i (fp64, -1 = terminal), max weight, first alive
+//         k_pf_total      read w_i                      -> T = sum of q_i = trunc(w_i * 2^s)   (s needs the max)
+//      K7+K8 k_pf_scan_emit  read w_i, single-pass decoupled-look-back scan of q_i with 4 consecutive
+//                         particles per thread, closed-form output range of every particle from
+//                         (C_i, T), read s_i of the particles that are copied, write the copies
+//    (3S + 24 bytes per particle against the algorithmic 2S + 16: the state is read twice because the
+//    output ranges need T, which needs the scale, which needs the largest weight.)
 // Fixed point makes the cumulative sums associative, so the systematic-resampling indices are
 // identical for every scan order (the oracle walks the same integers sequentially).
 #pragma once
@@ -143,8 +148,9 @@ struct ModelSrc {
     return true;
   }
   // generate_s only (the emit phase needs the state, not the weight, of the particles it copies)
-  __device__ __forceinline__ void propagate(long long i, State& sp) const {
-    State s = states[i];
+  __device__ __forceinline__ void propagate(long long i, State& sp) const { propagate_from(i, states[i], sp); }
+  __device__ __forceinline__ State load(long long i) const { return states[i]; }
+  __device__ __forceinline__ void propagate_from(long long i, const State& s, State& sp) const {
     double ut0 = 0.0;
     if (M::T_DRAW) ut0 = u01(philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1).w[0]);
     uint64_t o;
@@ -157,6 +163,8 @@ struct ArraySrc {  // replayed weights (parity hook): payload is the index itsel
   using State = long long;
   const double* w_in;
   __device__ __forceinline__ void propagate(long long i, State& sp) const { sp = i; }
+  __device__ __forceinline__ State load(long long i) const { return i; }
+  __device__ __forceinline__ void propagate_from(long long, const State& s, State& sp) const { sp = s; }
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
     sp = i;
     w = w_in[i];
@@ -169,26 +177,43 @@ __device__ __forceinline__ int pf_scale(unsigned long long max_bits, long long n
   int L = (n <= 1) ? 0 : 64 - __clzll(n - 1);  // ceil(log2 n)
   return 61 - L - e;
 }
+// trunc(w * 2^s) like ldexp + conversion, without the library call: scaling by a power of two is exact
+// (s in [-994, 1135]; above 1000 in two exact steps, since 2^s itself would overflow), and wherever
+// a product rounds (denormal results) it is below 1 and truncates to 0 either way.
+__device__ __forceinline__ double pf_pow2(int k) { return u2d((unsigned long long)(1023 + k) << 52); }
 __device__ __forceinline__ unsigned long long pf_quantise(double w, int s) {
-  return (w > 0.0) ? __double2ull_rz(ldexp(w, s)) : 0ull;
+  const int s1 = s < 1000 ? s : 1000;
+  double x = w * pf_pow2(s1);
+  if (s > 1000) x *= pf_pow2(s - 1000);
+  return (w > 0.0) ? __double2ull_rz(x) : 0ull;
 }
 
-// K6
+// K6 (streaming): propagate + weight every particle once, keep the weight.  Striped so that every
+// load and store is a full-line coalesced access; terminal particles are stored as -1.
 template <class Src>
-__global__ void __launch_bounds__(256) k_pf_max(const __grid_constant__ Src src, long long n, PfCtl* ctl) {
+__global__ void __launch_bounds__(256) k_pf_weigh(const __grid_constant__ Src src, long long n, double* w_out,
+                                                  PfCtl* ctl) {
   __shared__ unsigned long long s_max[8];
   __shared__ unsigned long long s_first[8];
+  // n < 2^32 (checked at the ABI): 32-bit indices; the first alive particle of a thread is the first it meets
   unsigned long long mx = 0, first = ~0ull;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const uint32_t stride = gridDim.x * blockDim.x, nn = (uint32_t)n;
+  uint32_t first32 = 0xffffffffu;
+#pragma unroll 4
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nn; i += stride) {
     typename Src::State sp;
-    double w;
-    bool alive = src.eval(i, sp, w);
+    double wk;
+    const bool alive = src.eval((long long)i, sp, wk);
+    wk = alive ? (wk > 0.0 ? wk : 0.0) : -1.0;
+    w_out[i] = wk;
     if (alive) {
-      if ((unsigned long long)i < first) first = (unsigned long long)i;
-      unsigned long long b = (w > 0.0) ? d2u(w) : 0ull;
-      if (b > mx) mx = b;
+      first32 = min(first32, i);
+      const unsigned long long bts = d2u(wk);
+      mx = bts > mx ? bts : mx;
     }
+    if (i + stride < i) break;  // index wrap guard for n close to 2^32
   }
+  if (first32 != 0xffffffffu) first = first32;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, off), of = __shfl_xor_sync(0xffffffffu, first, off);
@@ -211,31 +236,22 @@ __global__ void __launch_bounds__(256) k_pf_max(const __grid_constant__ Src src,
   }
 }
 
-// K7
-template <class Src>
-struct PfScanSrc {
-  Src src;
-  int scale;
-  __device__ __forceinline__ unsigned long long operator()(long long i) const {
-    typename Src::State sp;
-    double w;
-    bool alive = src.eval(i, sp, w);
-    return alive ? pf_quantise(w, scale) : 0ull;
+// T = sum_i trunc(w_i * 2^s): the output ranges of K8 need the total before the scan reaches the end.
+__global__ void __launch_bounds__(256) k_pf_total(const double* w, long long n, PfCtl* ctl) {
+  __shared__ unsigned long long s_sum[8];
+  const int scale = pf_scale(ctl->max_bits, n);
+  unsigned long long sum = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) sum += pf_quantise(w[i], scale);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) sum += s_sum[k];
+    if (sum) atomicAdd(&ctl->total, sum);
   }
-};
-struct CumSink {
-  unsigned long long* cum;
-  __device__ __forceinline__ void operator()(long long i, unsigned long long inc, unsigned long long) const {
-    cum[i] = inc;
-  }
-};
-template <class Src>
-__global__ void __launch_bounds__(SCAN_THREADS) k_pf_scan(const __grid_constant__ Src src, long long n,
-                                                          const PfCtl* ctl, unsigned long long* cum,
-                                                          unsigned long long* status, unsigned long long* ticket) {
-  PfScanSrc<Src> s{src, pf_scale(ctl->max_bits, n)};
-  CumSink k{cum};
-  chained_scan(s, k, n, status, ticket);
 }
 
 // Number of systematic points U_m = (ru/2^32 + m) * T / n_out, m in [0, n_out), with U_m <= C, i.e.
@@ -260,38 +276,152 @@ struct PfDiv {
     long long cnt = (long long)k + ((unsigned long long)rem >= thr ? 1 : 0);
     return cnt < n_out ? cnt : n_out;
   }
+  // The same count for a run of cumulative sums C, C + q1, C + q1 + q2, ...: (k, rem) is carried and a
+  // step adds q * n_out to the remainder, so the quotient grows by the number of copies of that
+  // particle (a few subtractions) instead of being divided out again.  Falls back to the closed form
+  // when q * n_out does not fit or the particle takes many copies.
+  struct Run {
+    unsigned long long C, k, rem;
+  };
+  __device__ __forceinline__ Run start(unsigned long long C) const {
+    unsigned long long k = (unsigned long long)((double)C * ratio);
+    long long rem = (long long)(C * (unsigned long long)n_out - k * T);
+    while (rem < 0) { --k; rem += (long long)T; }
+    while ((unsigned long long)rem >= T) { ++k; rem -= (long long)T; }
+    return Run{C, k, (unsigned long long)rem};
+  }
+  __device__ __forceinline__ long long count(const Run& r) const {
+    long long cnt = (long long)r.k + (r.rem >= thr ? 1 : 0);
+    return cnt < n_out ? cnt : n_out;
+  }
+  __device__ __forceinline__ void advance(Run& r, unsigned long long q) const {
+    r.C += q;
+    const unsigned long long d = q * (unsigned long long)n_out;
+    if (__umul64hi(q, (unsigned long long)n_out) == 0ull && d < (3ull << 62)) {
+      unsigned long long x = r.rem + d;  // rem < T < 2^62 and d < 3 * 2^62: no wrap
+      unsigned long long k = r.k;
+#pragma unroll
+      for (int it = 0; it < 3; ++it)
+        if (x >= T) { x -= T; ++k; }
+      if (x < T) { r.rem = x; r.k = k; return; }
+    }
+    r = start(r.C);
+  }
 };
 
-// K8: particle i owns the output range [M(C_{i-1}), M(C_i)) and writes that many copies.
-template <class Src, class Out>
-__global__ void __launch_bounds__(256) k_pf_emit(const __grid_constant__ Src src, long long n, const PfCtl* ctl,
-                                                 const unsigned long long* cum, uint32_t ru, long long n_out,
-                                                 Out* out) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long T = cum[n - 1];
-  if (T == 0) return;
-  unsigned long long C = cum[i];
-  unsigned long long Cp = i > 0 ? cum[i - 1] : 0ull;
-  typename Src::State sp;
-  double w;
-  bool alive = src.eval(i, sp, w);
-  if (!alive) return;
-  const bool is_first = (unsigned long long)i == ~ctl->first_alive_inv;
-  if (C == Cp && !is_first) return;
-  const PfDiv dv(T, ru, n_out);
-  long long hi = dv.points_below(C);
-  long long lo = is_first ? 0 : dv.points_below(Cp);
-  for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
-}
+// K7+K8 (streaming): single-pass scan of the quantised weights fused with the resampling.  A thread owns
+// PF2_ITEMS consecutive particles (16-byte loads, a thread-local prefix and one u64 warp scan per
+// thread instead of one per particle); particle i owns the output range [M(C_{i-1}), M(C_i)) and
+// writes that many copies of its propagated state.  Ranges of neighbouring particles are adjacent,
+// so the writes of a warp land in a few consecutive lines.
+constexpr int PF2_THREADS = 256;
+constexpr int PF2_ITEMS = 8;
+constexpr int PF2_TILE = PF2_THREADS * PF2_ITEMS;
 
-__global__ void k_pf_finalize(const unsigned long long* cum, long long n, PfCtl* ctl) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ctl->total = cum[n - 1];
-  int st = POMCP_OK;
-  if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;  // "all states in the particle collection were terminal"
-  else if (ctl->max_bits == 0 || ctl->total == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
-  ctl->status = st;
+template <class Src, class Out>
+__global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_constant__ Src src, long long n,
+                                                              const double* __restrict__ w, PfCtl* ctl, uint32_t ru,
+                                                              long long n_out, Out* out, unsigned long long* status,
+                                                              unsigned long long* ticket) {
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_warp[PF2_THREADS / 32];
+  __shared__ unsigned long long s_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = (unsigned)atomicAdd(ticket, 1ull);
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const unsigned long long max_bits = ctl->max_bits;
+  const unsigned long long T = ctl->total;
+  if (tile == 0 && threadIdx.x == 0) {
+    int st = POMCP_OK;
+    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;  // "all states in the particle collection were terminal"
+    else if (max_bits == 0 || T == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
+    ctl->status = st;
+  }
+  if (T == 0) return;  // uniform: nothing to resample
+  const int scale = pf_scale(max_bits, n);
+  const long long base = (long long)tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
+  double wv[PF2_ITEMS];
+  if (base + PF2_ITEMS <= n) {
+    const double2* p = reinterpret_cast<const double2*>(w + base);  // base is a multiple of PF2_ITEMS: 64-byte aligned
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS / 2; ++k) {
+      const double2 a = p[k];
+      wv[2 * k] = a.x;
+      wv[2 * k + 1] = a.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k) wv[k] = (base + k < n) ? w[base + k] : -1.0;
+  }
+  // small states are requested now and used after the scan (16-byte states would cost 32 registers)
+  constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;
+  typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];
+  if (PRELOAD) {
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k)
+      if (base + k < n) st_in[PRELOAD ? k : 0] = src.load(base + k);
+  }
+  unsigned long long inc[PF2_ITEMS];
+  unsigned long long run = 0;
+#pragma unroll
+  for (int k = 0; k < PF2_ITEMS; ++k) {
+    run += pf_quantise(wv[k], scale);
+    inc[k] = run;
+  }
+  // exclusive prefix of the thread totals inside the warp
+  unsigned long long x = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += t;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  const unsigned long long thread_excl = x - run;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = (lane < PF2_THREADS / 32) ? s_warp[lane] : 0ull, y = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+      if (lane >= off) y += t;
+    }
+    const unsigned long long aggregate = __shfl_sync(0xffffffffu, y, 31);
+    if (lane < PF2_THREADS / 32) s_warp[lane] = y - v;  // exclusive over warps
+    const unsigned long long excl = scan_lookback(status, tile, aggregate);
+    if (lane == 0) s_excl = excl;
+  }
+  __syncthreads();
+  const unsigned long long off0 = s_excl + s_warp[warp] + thread_excl;  // C just before this thread's particles
+
+  const unsigned long long first_alive = ~ctl->first_alive_inv;
+  const PfDiv dv(T, ru, n_out);
+  PfDiv::Run rn = dv.start(off0);
+  long long lo = dv.count(rn);
+  unsigned long long prev_inc = 0;
+#pragma unroll
+  for (int k = 0; k < PF2_ITEMS; ++k) {
+    const long long i = base + k;
+    dv.advance(rn, inc[k] - prev_inc);
+    prev_inc = inc[k];
+    const long long hi = dv.count(rn);
+    if (i < n && wv[k] >= 0.0) {
+      if ((unsigned long long)i == first_alive) lo = 0;
+      const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
+      if (copies) {
+        typename Src::State sp;
+        if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
+        else src.propagate(i, sp);
+        Out* o = out + lo;
+        o[0] = (Out)sp;
+        if (copies > 1) {
+          o[1] = (Out)sp;
+          for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
+        }
+      }
+    }
+    lo = hi;
+  }
 }
 
 // Upstream running-sum semantics on one thread (verification mode of pomcp_resample_systematic).
