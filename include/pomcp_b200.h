@@ -182,6 +182,13 @@ int32_t pomcp_search_replay(pomcp_handle* h, int64_t tree_queries, const double*
  * Re-roots the tree at child (a,o); POMCP_ERR_PARTICLE_DEPLETION if absent or empty.
  * obs_bits: the observation index, or the IEEE bits of a continuous observation. */
 int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits);
+/* The same update with a device-side ParticleReinvigorator (the hooks of src/particle_filter.jl:37-73,
+ * called from src/updater.jl:14-23): a child (a,o) that is missing or empty is replaced by n_min
+ * particles drawn from the SIR posterior of the old root belief (handle_unseen_observation -> fresh
+ * root), a child with fewer than n_min particles is topped up from it (reinvigorate!).
+ * outcome: 0 plain re-root, 1 topped up, 2 rebuilt.  PARTICLE_DEPLETION only if the posterior has no mass. */
+int32_t pomcp_update_reinvigorated(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint64_t seed, int64_t n_min,
+                                   int32_t* outcome);
 
 /* update(::SIRParticleFilter, b::ParticleCollection, a, o) (call site test/runtests.jl:57):
  * propagate, weight by the observation density, systematic resample to n_out

@@ -46,6 +46,7 @@ def lib():
         L.orc_search_replay.argtypes = [vp, i64, vp, i64, vp, i64, P(i32), vp, vp, i32, P(i64), P(i64)]
         L.orc_update_unweighted.argtypes = [vp, i32, u64]
         L.orc_pf_update_sir.argtypes = [vp, i32, u64, u64, i64, i32]
+        L.orc_update_reinvigorated.argtypes = [vp, i32, u64, u64, i64, P(i32)]
         L.orc_resample_systematic_f64.argtypes = [vp, i64, dbl, i64, vp]
         L.orc_resample_systematic_fixed.argtypes = [vp, i64, dbl, i64, vp]
         L.orc_rollout_batch.argtypes = [P(abi.Problem), P(abi.SolverParams), vp, i64, i32, u64, vp, vp]
@@ -140,6 +141,11 @@ class OraclePlanner:
 
     def update_unweighted(self, a, o):
         return lib().orc_update_unweighted(self._h, a, obs_bits(o))
+
+    def update_reinvigorated(self, a, o, seed, n_min):
+        out = C.c_int32(-1)
+        rc = lib().orc_update_reinvigorated(self._h, a, obs_bits(o), seed, n_min, C.byref(out))
+        return rc, out.value
 
     def pf_update_sir(self, a, o, seed, n_out, mode=0):
         return lib().orc_pf_update_sir(self._h, a, obs_bits(o), seed, n_out, mode)

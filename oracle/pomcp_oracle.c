@@ -45,7 +45,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-enum { TAG_ROOT = 0, TAG_TREE = 1, TAG_ROLLOUT = 2, TAG_PF = 3, TAG_RESAMPLE = 4 };
+enum { TAG_ROOT = 0, TAG_TREE = 1, TAG_ROLLOUT = 2, TAG_PF = 3, TAG_RESAMPLE = 4, TAG_INIT = 5 };
 
 static inline double u01(uint32_t w) { return (double)w * 2.3283064365386963e-10; /* 2^-32 */ }
 
@@ -640,11 +640,26 @@ static void draws(orng* g, uint32_t tag, uint32_t idx, uint32_t q, int n, double
   for (int i = 0; i < n; ++i) out[i] = u01(w[i]);
 }
 
+/* rand(rng, initial_state_distribution(pomdp)) from two uniforms */
+static ostate initial_state(const pomcp_problem* p, double u0, double u1) {
+  ostate s; s.i = 0; s.y = 0.0;
+  switch (p->problem_id) {
+    case POMCP_TIGER: s.i = u0 < 0.5 ? 1 : 0; break;
+    case POMCP_BABY: s.i = 0; break; /* BoolDistribution(0.0) */
+    case POMCP_ROCKSAMPLE: {
+      uint32_t rocks = (uint32_t)(u0 * (double)(1u << p->rs_k));
+      s.i = (int64_t)((uint32_t)p->rs_start_x | ((uint32_t)p->rs_start_y << 4) | (rocks << 8));
+      break;
+    }
+    case POMCP_LIGHTDARK1D: s.i = 0; s.y = p->ld_init_mean + orc_normal_from_uniforms(u0, u1) * p->ld_init_std; break;
+  }
+  return s;
+}
+
 /* rand(rng, b) at src/solver.jl:48 -> src/updater.jl:53-55 */
 static ostate sample_root(orc_planner* pl, orng* g, uint32_t q) {
   double u[2];
   draws(g, TAG_ROOT, 0, q, 2, u);
-  ostate s; s.i = 0; s.y = 0.0;
   const pomcp_problem* p = &pl->m.p;
   if (pl->belief_kind == 2) {
     return pl->bel[(int64_t)(u[0] * (double)pl->n_bel)];
@@ -654,17 +669,7 @@ static ostate sample_root(orc_planner* pl, orng* g, uint32_t q) {
     while (k-- > 0) e = pl->log_next[e];
     return pl->log_state[e];
   }
-  switch (p->problem_id) {
-    case POMCP_TIGER: s.i = u[0] < 0.5 ? 1 : 0; break;
-    case POMCP_BABY: s.i = 0; break; /* BoolDistribution(0.0) */
-    case POMCP_ROCKSAMPLE: {
-      uint32_t rocks = (uint32_t)(u[0] * (double)(1u << p->rs_k));
-      s.i = (int64_t)((uint32_t)p->rs_start_x | ((uint32_t)p->rs_start_y << 4) | (rocks << 8));
-      break;
-    }
-    case POMCP_LIGHTDARK1D: s.i = 0; s.y = p->ld_init_mean + orc_normal_from_uniforms(u[0], u[1]) * p->ld_init_std; break;
-  }
-  return s;
+  return initial_state(p, u[0], u[1]);
 }
 
 /* simulate() for POMCPSolver, src/solver.jl:78-157, recursion unrolled into a
@@ -958,6 +963,83 @@ int32_t orc_pf_update_sir(orc_planner* pl, int32_t a, uint64_t obs, uint64_t see
     for (int64_t k = 0; k < n_out; ++k) nb[k] = sp[idx[k]];
     fresh_root(pl); /* a ParticleCollection is not a BeliefNode: new RootNode, src/solver.jl:278-281 */
     free(pl->bel); pl->bel = nb; pl->n_bel = n_out; pl->belief_kind = 2;
+  }
+  free(idx); free(sp); free(w); free(alive);
+  return rc;
+}
+
+/* update(::RootUpdater{R}, b_old, a, o) with a device-side reinvigorator R = SIRReinvigorator(n_min)
+ * (the hooks of src/particle_filter.jl:37-73, src/updater.jl:13-27):
+ *   handle_unseen_observation: child (a,o) missing or empty -> new belief = n_min particles from the SIR
+ *                              posterior of the old root belief (propagate, weight, systematic resample);
+ *   reinvigorate!:             child has fewer than n_min particles -> top it up from the same posterior.
+ * outcome: 0 plain re-root, 1 topped up, 2 rebuilt (tree discarded). */
+int32_t orc_update_reinvigorated(orc_planner* pl, int32_t a, uint64_t obs, uint64_t seed, int64_t n_min,
+                                 int32_t* outcome) {
+  if (a < 0 || a >= pl->nA || n_min <= 0) return POMCP_ERR_INVALID_ARG;
+  if (pl->sp.belief_mode != POMCP_BELIEF_UNWEIGHTED) return POMCP_ERR_UNSUPPORTED;
+  if (pl->belief_kind == 0) return POMCP_ERR_INVALID_ARG;
+  const model* m = &pl->m;
+  int64_t hao = pl->node_expanded[pl->root] ? find_child(pl, pl->root * pl->nA + a, obs) : -1;
+  int64_t cnt = hao >= 0 ? pl->node_pcount[hao] : 0;
+  int have = hao >= 0 && cnt > 0;
+  if (outcome) *outcome = 0;
+  if (have && cnt >= n_min) { pl->root = hao; pl->belief_kind = 3; return POMCP_OK; }
+  int64_t extra = n_min - cnt;
+  /* the old root belief as an array */
+  int64_t n_old;
+  ostate* old;
+  if (pl->belief_kind == 2) {
+    n_old = pl->n_bel; old = (ostate*)malloc(sizeof(ostate) * (size_t)n_old);
+    memcpy(old, pl->bel, sizeof(ostate) * (size_t)n_old);
+  } else if (pl->belief_kind == 3) {
+    n_old = pl->node_pcount[pl->root]; old = (ostate*)malloc(sizeof(ostate) * (size_t)n_old);
+    int64_t i = 0;
+    for (int64_t e = pl->node_phead[pl->root]; e >= 0; e = pl->log_next[e]) old[i++] = pl->log_state[e];
+  } else { /* initial distribution: n_min draws */
+    n_old = n_min; old = (ostate*)malloc(sizeof(ostate) * (size_t)n_old);
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int64_t i = 0; i < n_old; ++i) {
+      uint32_t ctr[4] = {0, TAG_INIT, (uint32_t)i, (uint32_t)((uint64_t)i >> 32)}, wd[4];
+      orc_philox4x32_10(ctr, key, wd);
+      old[i] = initial_state(&m->p, u01(wd[0]), u01(wd[1]));
+    }
+  }
+  void* packed = malloc((size_t)m->state_bytes * (size_t)n_old);
+  for (int64_t i = 0; i < n_old; ++i) store_state(m, packed, i, old[i]);
+  free(old);
+  ostate* sp = (ostate*)malloc(sizeof(ostate) * (size_t)n_old);
+  double* w = (double*)malloc(sizeof(double) * (size_t)n_old);
+  uint8_t* alive = (uint8_t*)malloc((size_t)n_old);
+  pf_propagate(m, packed, n_old, a, obs, seed, sp, w, alive);
+  free(packed);
+  int any_alive = 0;
+  for (int64_t i = 0; i < n_old; ++i) any_alive |= alive[i];
+  int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * (size_t)extra);
+  int32_t rc = POMCP_ERR_PARTICLE_DEPLETION;
+  if (any_alive) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {0, TAG_RESAMPLE, 0, 0}, wd[4];
+    orc_philox4x32_10(ctr, key, wd);
+    rc = resample_fixed(w, alive, n_old, wd[0], extra, idx);
+  }
+  if (rc == POMCP_OK) {
+    if (have) {
+      pl->root = hao; pl->belief_kind = 3;
+      for (int64_t k = 0; k < extra; ++k) push_particle(pl, hao, sp[idx[k]]);
+      if (outcome) *outcome = 1;
+    } else {
+      ostate* nb = (ostate*)malloc(sizeof(ostate) * (size_t)extra);
+      for (int64_t k = 0; k < extra; ++k) nb[k] = sp[idx[k]];
+      fresh_root(pl);
+      free(pl->bel); pl->bel = nb; pl->n_bel = extra; pl->belief_kind = 2;
+      if (outcome) *outcome = 2;
+    }
+  } else if (have) { /* no posterior mass to draw from: keep what the planner pushed */
+    pl->root = hao; pl->belief_kind = 3;
+    rc = POMCP_OK;
+  } else {
+    rc = POMCP_ERR_PARTICLE_DEPLETION;
   }
   free(idx); free(sp); free(w); free(alive);
   return rc;

@@ -48,6 +48,7 @@ def lib():
     L.pomcp_search.argtypes = [vp, i64, P(i32), vp, vp, i32]
     L.pomcp_search_replay.argtypes = [vp, i64, vp, i64, vp, i64, P(i32), vp, vp, i32, P(i64), P(i64)]
     L.pomcp_update_unweighted.argtypes = [vp, i32, u64]
+    L.pomcp_update_reinvigorated.argtypes = [vp, i32, u64, u64, i64, P(i32)]
     L.pomcp_pf_update_sir.argtypes = [vp, i32, u64, u64, i64]
     L.pomcp_resample_systematic.argtypes = [vp, vp, i64, dbl, i64, i32, vp]
     L.pomcp_rollout_batch.argtypes = [vp, vp, i64, i32, u64, vp, vp]

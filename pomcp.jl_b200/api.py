@@ -19,7 +19,7 @@ from .problems import POMDP, obs_bits
 
 __all__ = [
     "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
-    "DeadReinvigorator", "ParticleReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
+    "DeadReinvigorator", "ParticleReinvigorator", "SIRReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
@@ -125,6 +125,21 @@ class DeadReinvigorator(ParticleReinvigorator):
 
     def handle_unseen_observation(self, old_node, a, o):
         raise ParticleDepletion()
+
+
+class SIRReinvigorator(ParticleReinvigorator):
+    """Device-side reinvigorator: both hooks draw from the SIR posterior of the old root belief
+    (propagate with generate_s, weight with the observation pdf, systematic resample) so that the new
+    belief holds at least `n` particles; an unseen observation rebuilds the belief from `n` of them
+    (src/particle_filter.jl:37-73).  Runs inside pomcp_update_reinvigorated."""
+
+    def __init__(self, n, rng=0):
+        self.n, self.seed, self._step = int(n), int(rng), 0
+        self.last_outcome = None  # 0 plain re-root, 1 topped up, 2 rebuilt from the posterior
+
+    def next_seed(self):
+        self._step += 1
+        return (self.seed * 0x9E3779B97F4A7C15 + self._step) & (2 ** 64 - 1)
 
 
 class DefaultReinvigoratorStub:
@@ -330,6 +345,13 @@ class POMCPPlanner:
         _check(rc, self._h)
         self._generation += 1
 
+    def update_reinvigorated(self, a, o, seed, n_min):
+        out = C.c_int32(-1)
+        rc = lib().pomcp_update_reinvigorated(self._h, int(a), obs_bits(o), int(seed), int(n_min), C.byref(out))
+        _check(rc, self._h)
+        self._generation += 1
+        return out.value
+
     def pf_update_sir(self, a, o, seed, n_out):
         _check(lib().pomcp_pf_update_sir(self._h, int(a), obs_bits(o), int(seed), int(n_out)), self._h)
         self._generation += 1
@@ -518,6 +540,10 @@ def update(up, b_old, a, o):
     if not isinstance(b_old, BeliefNode):
         raise TypeError("RootUpdater.update needs the BeliefNode returned by initialize_belief/update")
     b_old._live()
+    if isinstance(up.node_belief_updater, SIRReinvigorator):  # both hooks run on the device
+        r = up.node_belief_updater
+        r.last_outcome = pl.update_reinvigorated(a, o, r.next_seed(), r.n)
+        return BeliefNode(pl, pl._generation)
     try:
         pl.update_unweighted(a, o)
     except ParticleDepletion:

@@ -132,6 +132,8 @@ struct pomcp_handle {
   bool pending = false;
   uint32_t* d_newid = nullptr;
   size_t newid_cap = 0;
+  void* d_init = nullptr;  // particles drawn from the initial distribution (reinvigorator)
+  size_t init_cap = 0;
   bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
   long long compactions = 0;
   bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
@@ -595,7 +597,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
-                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid};
+                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
@@ -914,25 +916,11 @@ int32_t pomcp_get_root_stats(pomcp_handle* h, int64_t* root_N, int64_t* act_N, d
   return pomcp_get_node_stats(h, nullptr, nullptr, 0, root_N, nullptr, act_N, act_V, nA);
 }
 
-// update(::RootUpdater{<:ParticleReinvigorator}, b_old, a, o): src/updater.jl:13-27
-int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
-  if (!h) return POMCP_ERR_INVALID_ARG;
-  cudaSetDevice(h->device);
-  if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
-  if (a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad action");
+// Gather the `cnt` states pushed at node `child` from the particle log into belief buffer `nb`
+// (room for `cap` states).  Enqueued + verified; leaves the stream synchronised.
+static int gather_child_particles(pomcp_handle* h, uint32_t child, long long cnt, int nb, long long cap) {
   PhaseTimer& t = h->timers[POMCP_PHASE_REROOT];
-  t.reset();
-  CK(cudaEventRecord(t.next(), h->stream));
-  int32_t acts[1] = {a};
-  uint64_t obs[1] = {obs_bits};
-  int rc = node_stats_impl(h, acts, obs, 1);
-  if (rc) return rc;
-  // missing child -> handle_unseen_observation; empty collection -> reinvigorate! (src/particle_filter.jl:85-92)
-  if (h->h_ns->node < 0 || h->h_ns->N == 0) return POMCP_ERR_PARTICLE_DEPLETION;
-  uint32_t child = (uint32_t)h->h_ns->node;
-  long long cnt = h->h_ns->N;
-  int nb = 1 - h->bel_cur;
-  rc = ensure_bytes(h, &h->d_bel[nb], &h->bel_cap[nb], (size_t)cnt * h->state_bytes);
+  int rc = ensure_bytes(h, &h->d_bel[nb], &h->bel_cap[nb], (size_t)std::max(cap, cnt) * h->state_bytes);
   if (rc) return rc;
   long long n_log = (long long)h->log_used;
   rc = ensure_scan(h, n_log);
@@ -963,17 +951,115 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
     std::snprintf(buf, sizeof buf, "particle log holds %lld states for the new root but N = %lld", found, cnt);
     return fail(h, POMCP_ERR_POOL_EXHAUSTED, buf);
   }
+  return POMCP_OK;
+}
+
+static int maybe_compact(pomcp_handle* h) {
+  // reclaim the dead part of the pool / particle log once a quarter of either is used
+  if (h->compact_always || h->nodes_used * 4 >= h->pool.max_nodes || h->log_used * 4 >= h->pool.log_cap)
+    return compact_pool(h);
+  return POMCP_OK;
+}
+
+// update(::RootUpdater{<:ParticleReinvigorator}, b_old, a, o): src/updater.jl:13-27
+int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
+  if (a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad action");
+  PhaseTimer& t = h->timers[POMCP_PHASE_REROOT];
+  t.reset();
+  CK(cudaEventRecord(t.next(), h->stream));
+  int32_t acts[1] = {a};
+  uint64_t obs[1] = {obs_bits};
+  int rc = node_stats_impl(h, acts, obs, 1);
+  if (rc) return rc;
+  // missing child -> handle_unseen_observation; empty collection -> reinvigorate! (src/particle_filter.jl:85-92)
+  if (h->h_ns->node < 0 || h->h_ns->N == 0) return POMCP_ERR_PARTICLE_DEPLETION;
+  uint32_t child = (uint32_t)h->h_ns->node;
+  long long cnt = h->h_ns->N;
+  int nb = 1 - h->bel_cur;
+  rc = gather_child_particles(h, child, cnt, nb, cnt);
+  if (rc) return rc;
   h->bel_cur = nb;
   h->n_bel = cnt;
   h->bel_kind = 2;
   h->root = child;
   h->root_visits = cnt;
-  // reclaim the dead part of the pool / particle log once a quarter of either is used
-  if (h->compact_always || h->nodes_used * 4 >= h->pool.max_nodes || h->log_used * 4 >= h->pool.log_cap) {
-    rc = compact_pool(h);
+  return maybe_compact(h);
+}
+
+// update(::RootUpdater{R}, b_old, a, o) with the device-side reinvigorator R = SIRReinvigorator(n_min)
+// (hooks of src/particle_filter.jl:37-73, call sites src/updater.jl:14-23):
+//   handle_unseen_observation: child (a,o) missing or empty -> n_min particles from the SIR posterior of the
+//                              old root belief become the new belief (fresh root);
+//   reinvigorate!:             fewer than n_min particles at the child -> topped up from the same posterior.
+int32_t pomcp_update_reinvigorated(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint64_t seed, int64_t n_min,
+                                   int32_t* outcome) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
+  if (a < 0 || a >= h->nA || n_min <= 0 || n_min >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "bad a / n_min");
+  if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
+  if (outcome) *outcome = 0;
+  PhaseTimer& t = h->timers[POMCP_PHASE_REROOT];
+  t.reset();
+  CK(cudaEventRecord(t.next(), h->stream));
+  int32_t acts[1] = {a};
+  uint64_t obs[1] = {obs_bits};
+  int rc = node_stats_impl(h, acts, obs, 1);
+  if (rc) return rc;
+  const bool have = h->h_ns->node >= 0 && h->h_ns->N > 0;
+  const long long cnt = have ? h->h_ns->N : 0;
+  const uint32_t child = have ? (uint32_t)h->h_ns->node : 0u;
+  if (have && cnt >= n_min) return pomcp_update_unweighted(h, a, obs_bits);
+  const long long extra = n_min - cnt;
+  // the old root belief as a particle array
+  const void* old = h->d_bel[h->bel_cur];
+  long long n_old = h->n_bel;
+  if (h->bel_kind == 1) {
+    rc = ensure_bytes(h, &h->d_init, &h->init_cap, (size_t)n_min * h->state_bytes);
+    if (rc) return rc;
+    DISPATCH_PID(h->prob.problem_id, {
+      k_init_particles<PID><<<(int)((n_min + 255) / 256), 256, 0, h->stream>>>(
+          h->dm, (typename ModelT<PID>::State*)h->d_init, n_min, (uint32_t)seed, (uint32_t)(seed >> 32));
+    });
+    rc = launch_check(h, "k_init_particles");
+    if (rc) return rc;
+    old = h->d_init;
+    n_old = n_min;
+  }
+  const int nb = 1 - h->bel_cur;
+  if (have) {
+    rc = gather_child_particles(h, child, cnt, nb, n_min);
+    if (rc) return rc;
+  } else {
+    rc = ensure_bytes(h, &h->d_bel[nb], &h->bel_cap[nb], (size_t)n_min * h->state_bytes);
     if (rc) return rc;
   }
-  return POMCP_OK;
+  // SIR posterior of the old belief: `extra` particles appended behind the gathered ones
+  Philox4 pr = philox4x32_10(0u, TAG_RESAMPLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  DISPATCH_PID(h->prob.problem_id, {
+    auto src = make_src<PID>(h, old, a, obs_bits, seed);
+    rc = run_resample(h, src, n_old, pr.w[0], extra, (typename ModelT<PID>::State*)h->d_bel[nb] + cnt);
+  });
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const bool drew = h->h_pfctl->status == POMCP_OK;
+  if (!drew && !have) return POMCP_ERR_PARTICLE_DEPLETION;  // nothing pushed by the planner and no posterior mass
+  h->bel_cur = nb;
+  h->bel_kind = 2;
+  if (have) {
+    h->n_bel = cnt + (drew ? extra : 0);
+    h->root = child;
+    h->root_visits = cnt;
+    if (outcome) *outcome = drew ? 1 : 0;
+    return maybe_compact(h);
+  }
+  h->n_bel = extra;
+  if (outcome) *outcome = 2;
+  return fresh_root(h);
 }
 
 // update(::SIRParticleFilter, b, a, o): propagate, weight, systematic resample (test/runtests.jl:57)

@@ -607,6 +607,17 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   }
 }
 
+// n draws from the problem's initial state distribution (the reinvigorator's stand-in for an old
+// belief that is still the distribution itself)
+template <int PID>
+__global__ void k_init_particles(const __grid_constant__ DevModel m, typename ModelT<PID>::State* out, long long n,
+                                 uint32_t k0, uint32_t k1) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox4 p = philox4x32_10(0u, TAG_INIT, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1);
+  out[i] = ModelT<PID>::initial(m, u01(p.w[0]), u01(p.w[1]));
+}
+
 // pomcp_pf_weights parity hook
 template <int PID>
 __global__ void k_pf_weights(const __grid_constant__ ModelSrc<PID> src, long long n, double* w_out,

@@ -277,3 +277,35 @@ def test_python_twin_matches_oracle(oracle, name, c, Q):
         a_t, N_t, V_t = tw.search(Q // 2)
         rc, a_o, N_o, V_o = op.search(Q // 2)
         assert list(N_o) == N_t and a_t == a_o
+
+
+# ----------------------------------------------------------------------------- device-side reinvigoration
+def test_sir_reinvigorator_prevents_depletion(oracle):
+    """The reference's own depletion test (test/runtests.jl:35-41: tree_queries = 5, 100 Baby steps must throw
+    with the default DeadReinvigorator) run with the SIR reinvigorator hooks instead
+    (src/particle_filter.jl:37-73): the episode completes, the belief never holds fewer than n_min
+    particles after a top-up or rebuild, and a child that already has n_min particles is taken as is."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    pl = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=2, tree_queries=5))
+    pl.set_belief_initial()
+    rng = np.random.default_rng(0)
+    s, outcomes = 0, []
+    for t in range(100):
+        rc, a, N, V = pl.search(5)
+        assert rc == 0
+        sp, o, r = oracle.model_step(baby, s, a, ut=(rng.random(), 0.0), uo=(rng.random(), 0.0))
+        n_child = pl.node_stats([(a, int(o))])[1]
+        rc, out = pl.update_reinvigorated(a, int(o), seed=1000 + t, n_min=100)
+        assert rc == 0
+        parts = pl.belief_particles()
+        assert len(parts) == (n_child if out == 0 else 100)
+        assert set(np.unique(parts)) <= {0, 1}
+        outcomes.append(out)
+        s = int(sp)
+    assert 1 in outcomes and 2 in outcomes  # both hooks fired
+    # posterior sanity: after feeding, nobody is hungry (the Baby model's exact update gives 0)
+    pl2 = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=3, tree_queries=5))
+    pl2.set_belief_initial()
+    pl2.search(5)
+    rc, out = pl2.update_reinvigorated(1, 0, seed=5, n_min=500)
+    assert rc == 0 and out in (1, 2) and pl2.belief_particles().sum() == 0
