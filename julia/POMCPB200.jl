@@ -157,6 +157,28 @@ function update(up::RootUpdater, b_old::BeliefNode, a, o)  # src/updater.jl:13-2
     return BeliefNode(pl, pl.generation)
 end
 
+"Device-side reinvigorator: pass as `node_belief_updater`; both hooks of src/particle_filter.jl:37-73 then run
+inside pomcp_update_reinvigorated (SIR posterior of the old root belief, at least `n` particles)."
+mutable struct SIRReinvigorator <: ParticleReinvigorator
+    n::Int
+    seed::UInt64
+    step::Int
+    last_outcome::Int32                                     # 0 plain re-root, 1 topped up, 2 rebuilt
+end
+SIRReinvigorator(n; seed=0) = SIRReinvigorator(n, UInt64(seed), 0, Int32(0))
+
+function update(up::RootUpdater, b_old::BeliefNode, a, o, r::SIRReinvigorator)
+    pl = up.planner
+    ai = Int32(findfirst(==(a), POMDPs.actions(pl.problem)) - 1)
+    r.step += 1
+    out = Ref{Int32}(0)
+    check(ccall((:pomcp_update_reinvigorated, LIB), Int32, (Ptr{Cvoid}, Int32, UInt64, UInt64, Int64, Ref{Int32}),
+                pl.handle, ai, obs_bits(o), r.seed * 0x9E3779B97F4A7C15 + UInt64(r.step), r.n, out), pl.handle)
+    r.last_outcome = out[]
+    pl.generation += 1
+    return BeliefNode(pl, pl.generation)
+end
+
 "SIR particle filter on the device (ParticleFilters.SIRParticleFilter, test/runtests.jl:57)."
 struct SIRParticleFilter <: POMDPs.Updater
     planner::POMCPPlanner
