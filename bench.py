@@ -381,7 +381,7 @@ def run_gpu(args):
                         "keep the tree no more than that many simulations stale",
             },
             "solver": {"inflight_max": policy._sp.inflight_max or 1024, "inflight_ramp_div": policy._sp.inflight_ramp_div
-                       or 32, "rollouts_per_leaf": policy._sp.rollouts_per_leaf or 32, "search_mode": "batched"},
+                       or 32, "rollouts_per_leaf": policy._sp.rollouts_per_leaf or 64, "search_mode": "batched"},
             "rollouts_per_sec": cs["rollouts"] * n_gpus / (total_ms_max * 1e-3),
             "phase_ms_per_step": {"search": statistics.mean(search_ms), "worker_kernel": statistics.mean(rollout_ms),
                                   "sir_update": statistics.mean(pf_ms), "step": statistics.mean(step_ms)},

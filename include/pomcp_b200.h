@@ -119,7 +119,8 @@ typedef struct pomcp_solver_params {
   int32_t inflight_min;      /* batched: simulations in flight while the tree is empty (0 = default) */
   int32_t inflight_max;      /* batched: cap on simulations (warp workers) in flight (0 = default) */
   int32_t inflight_ramp_div; /* batched: in flight = clamp(root visits / div, min, max) (0 = default) */
-  int32_t rollouts_per_leaf; /* R in 1..32 rollouts averaged per leaf evaluation, one lane each (0 = default) */
+  int32_t rollouts_per_leaf; /* R rollouts averaged per leaf evaluation (0 = default: 1 exact, 64 batched).  Batched: 1..128, a
+                              * worker is a team of ceil(R/32) warps that roll out together; exact: 1..64 on one warp */
   int32_t rank;              /* root-parallel rank, mixed into the Philox counter */
   int32_t _pad1;
 } pomcp_solver_params;

@@ -565,6 +565,7 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   if (model_init(&pl->m, p) != POMCP_OK) { free(pl); return NULL; }
   pl->sp = *sp;
   if (sp->num_sparse_actions > 0 || !(sp->eps > 0.0) || !(sp->eps < 1.0)) { free(pl); return NULL; }
+  if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 64) { free(pl); return NULL; }
   if (sp->estimator == POMCP_EST_FWC_ROLLOUT && p->problem_id != POMCP_BABY) { free(pl); return NULL; }
   pl->nA = pl->m.nA; pl->nO = pl->m.nO;
   /* cut-off gamma^depth < eps (src/solver.jl:82) and steps_to_eps (src/solver.jl:100) */
@@ -701,8 +702,8 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
           /* R rollouts per leaf (device extension; R = 1 is the reference).  Rollout r draws from the
            * stream tagged r<<16; the R returns are added in the butterfly order of a 32-lane warp. */
           int R = sol->rollouts_per_leaf > 0 ? sol->rollouts_per_leaf : 1;
-          double x[32], y[32];
-          for (int r = 0; r < 32; ++r)
+          double x[64], y[32];
+          for (int r = 0; r < 64; ++r)
             x[r] = r >= R ? 0.0
                    : sol->estimator == POMCP_EST_FWC_ROLLOUT
                        ? rollout_fwc(m, s, steps, pl->node_obs[h], g->key,
@@ -710,9 +711,11 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
                                      &pl->ctr.rollout_steps)
                        : rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
                                         g->epoch, &pl->ctr.rollout_steps);
+          if (R > 32) /* lane l of the warp holds rollouts l and l + 32 */
+            for (int i = 0; i < 32; ++i) x[i] = x[i] + x[i + 32];
           for (int off = 16; off > 0; off >>= 1) {
             for (int i = 0; i < 32; ++i) y[i] = x[i] + x[i ^ off];
-            memcpy(x, y, sizeof(x));
+            memcpy(x, y, sizeof(y));
           }
           est = x[0] / (double)R;
           pl->ctr.rollouts += R - 1;

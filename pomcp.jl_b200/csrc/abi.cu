@@ -256,6 +256,7 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.root = h->root;
   c.root_N0 = (uint32_t)h->root_visits;
   c.rollouts = h->rollouts;
+  c.team_warps = h->exact ? 1 : (h->rollouts > 64 ? 4 : (h->rollouts + 31) / 32);
   c.inflight_min = h->inflight_min;
   c.inflight_max = h->inflight_max;
   c.ramp_div = h->ramp_div;
@@ -306,7 +307,17 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     smem += (size_t)h->eta_n * sizeof(uint32_t);
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
-      k_search_workers<PID><<<blocks, 32, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+      // no more workers than CTAs that can be co-resident: a worker that is not resident does not search
+      auto launch = [&](auto kern, int threads) {
+        int per_sm = 0, sms = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
+        kern<<<blocks, threads, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+      };
+      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4>, 128);
+      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2>, 64);
+      else launch(k_search_workers<PID, 1>, 32);
     });
     rc = launch_check(h, "k_search_workers");
     if (rc) return rc;
@@ -720,11 +731,11 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
   h->inflight_min = std::max(1, std::min(h->inflight_min, h->inflight_max));
   h->ramp_div = sp->inflight_ramp_div > 0 ? sp->inflight_ramp_div : 32;
-  if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 32) {
-    h->err = "rollouts_per_leaf must be in 1..32";
+  if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > (h->exact ? 64 : 128)) {
+    h->err = "rollouts_per_leaf must be in 1..128 (1..64 in exact mode)";
     return bail(POMCP_ERR_INVALID_ARG);
   }
-  h->rollouts = sp->rollouts_per_leaf > 0 ? sp->rollouts_per_leaf : (h->exact ? 1 : 32);
+  h->rollouts = sp->rollouts_per_leaf > 0 ? sp->rollouts_per_leaf : (h->exact ? 1 : 64);
   h->n_slots = h->exact ? 1 : h->inflight_max;
 
   // pool sizing

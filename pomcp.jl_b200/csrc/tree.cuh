@@ -57,6 +57,7 @@ struct SearchCfg {
   int levels;          // first depth at which gamma^depth < eps (src/solver.jl:82), capped by max_depth
   int belief_unweighted, estimator;
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
+  int team_warps;      // batched mode: warps per worker; warp w runs rollouts 32 w .. 32 w + 31 of every leaf
   uint32_t key0, key1, rank, epoch;
   const void* bel;  // root belief particles (NULL: the problem's initial distribution)
   long long n_bel;
@@ -203,47 +204,87 @@ __device__ __forceinline__ int sbfe2(uint32_t x, int pos) {  // signed 2-bit fie
 // registers, the move comes out of a nibble table, the rock lookup and the reward are
 // branch-free (32 lanes hold 32 different actions, so a branch would be taken by the warp on
 // almost every step anyway).
-template <bool CHECK_DISC>
-__device__ __forceinline__ double rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
-                                                     uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
-                                                     uint32_t epoch, int& nsteps) {
+// NT trajectories per lane (1 or 2), interleaved (rollouts_per_leaf > 32 on a single warp).  Both start
+// at step 0, so they share the discount sequence; each accumulates exactly as it would alone.
+template <bool CHECK_DISC, int NT>
+__device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
+                                                   uint32_t k0, uint32_t k1, const uint32_t (&tagword)[NT],
+                                                   const bool (&enabled)[NT], uint32_t q, uint32_t epoch, int& nsteps,
+                                                   double (&total)[NT]) {
   const double gamma = m.gamma;
   const uint32_t nA = (uint32_t)m.nA;
   const int nmax = m.rs_n - 1;
-  int x = (int)(s & 15u), y = (int)((s >> 4) & 15u);
-  uint32_t rocks = s >> 8;  // bit i: rock i is good
-  double disc = 1.0, total = 0.0;
   const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
-  int step = 0;
-  bool live = !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
-  Philox4 p = philox4x32_10(0u, tagword, q, epoch, k0, k1);
-  for (uint32_t blk = 0; live; ++blk) {
-    const Philox4 pn = philox4x32_10(blk + 1u, tagword, q, epoch, k0, k1);
+  int x[NT], y[NT], step[NT];
+  uint32_t rocks[NT];  // bit i: rock i is good
+  bool live[NT];
+  Philox4 p[NT];
+  double disc = 1.0;
+  bool any = false;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    x[t] = (int)(s & 15u);
+    y[t] = (int)((s >> 4) & 15u);
+    rocks[t] = s >> 8;
+    total[t] = 0.0;
+    step[t] = 0;
+    live[t] = enabled[t] && !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
+    any = any || live[t];
+    p[t] = philox4x32_10(0u, tagword[t], q, epoch, k0, k1);
+  }
+  for (uint32_t blk = 0; any; ++blk) {
+    Philox4 pn[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) pn[t] = philox4x32_10(blk + 1u, tagword[t], q, epoch, k0, k1);
     // Loop-carried chains per step are kept minimal: position (add + clamp), rock bits (one and-not
     // with a mask that comes from the position only), return (one add), discount (one multiply).
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t a = __umulhi(p.w[j], nA);  // rand(rng, actions): floor(u * nA)
-      // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
-      const uint32_t t = shr_clamped(0x3C14u, a * 4u);
-      y = min(max(y + sbfe2(t, 2), 0), nmax);
-      const int nx = x + sbfe2(t, 0);
-      const bool exits = nx > nmax;  // moving east off the grid
-      x = min(max(nx, 0), nmax);
-      // sample (a == 4) on a rock: +good / -bad, and the rock is bad afterwards either way
-      const uint32_t mask = shl_clamped(a == 4u ? 1u : 0u, tb->rock_sh[y * 16 + x]);
-      const uint32_t goodbit = rocks & mask;
-      rocks &= ~mask;
-      const int ev = exits ? 1 : (mask ? (goodbit ? 3 : 2) : 0);
-      total += disc * tb->rtab[live ? ev : 0];  // a finished lane adds +0.0
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const uint32_t a = __umulhi(p[t].w[j], nA);  // rand(rng, actions): floor(u * nA)
+        // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
+        const uint32_t mv = shr_clamped(0x3C14u, a * 4u);
+        y[t] = min(max(y[t] + sbfe2(mv, 2), 0), nmax);
+        const int nx = x[t] + sbfe2(mv, 0);
+        const bool exits = nx > nmax;  // moving east off the grid
+        x[t] = min(max(nx, 0), nmax);
+        // sample (a == 4) on a rock: +good / -bad, and the rock is bad afterwards either way
+        const uint32_t mask = shl_clamped(a == 4u ? 1u : 0u, tb->rock_sh[y[t] * 16 + x[t]]);
+        const uint32_t goodbit = rocks[t] & mask;
+        rocks[t] &= ~mask;
+        const int ev = exits ? 1 : (mask ? (goodbit ? 3 : 2) : 0);
+        total[t] += disc * tb->rtab[live[t] ? ev : 0];  // a finished trajectory adds +0.0
+        step[t] += live[t] ? 1 : 0;
+        live[t] = live[t] && !exits && step[t] < nstep_max;
+      }
       disc *= gamma;
-      step += live ? 1 : 0;
-      live = live && (!CHECK_DISC || disc > 0.0) && !exits && step < nstep_max;
+      if (CHECK_DISC && !(disc > 0.0)) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) live[t] = false;
+      }
     }
-    p = pn;
+    any = false;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      p[t] = pn[t];
+      any = any || live[t];
+    }
   }
-  nsteps = step;
-  return total;
+  nsteps = 0;
+#pragma unroll
+  for (int t = 0; t < NT; ++t) nsteps += step[t];
+}
+
+template <bool CHECK_DISC>
+__device__ __forceinline__ double rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
+                                                     uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
+                                                     uint32_t epoch, int& nsteps) {
+  const uint32_t tw[1] = {tagword};
+  const bool en[1] = {true};
+  double total[1];
+  rollout_rocksample<CHECK_DISC, 1>(m, tb, s, steps, k0, k1, tw, en, q, epoch, nsteps, total);
+  return total[0];
 }
 
 // ---- K3: RolloutSimulator loop under the uniform-random policy (src/rollout.jl:77-84;
@@ -292,6 +333,14 @@ __device__ __forceinline__ double rollout_fwc(const DevModel& m, uint32_t s, lon
   nsteps = (int)step;
   return total;
 }
+
+// Leaf evaluation by one warp: lane l runs rollout r_base + l (rollout team, batched mode) or, on a
+// single warp with R > 32 (exact mode), rollouts l and l + 32; the per-lane sums are added by the fixed
+// butterfly, so the oracle reproduces the mean bit for bit.
+template <int PID>
+__device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
+                                                typename ModelT<PID>::State s, long long steps, uint64_t last_o,
+                                                uint32_t q, int lane, int& nsteps_lane, int r_base = 0);
 
 // ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
 // race is not recycled (it stays an unreachable, zero-initialised slot): ids therefore grow along
@@ -377,6 +426,48 @@ __device__ __forceinline__ double warp_tree_sum(double x) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) x = x + __shfl_xor_sync(0xffffffffu, x, off);
   return x;
+}
+
+template <int PID>
+__device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
+                                                typename ModelT<PID>::State s, long long steps, uint64_t last_o,
+                                                uint32_t q, int lane, int& nsteps_lane, int r_base) {
+  const int R = cfg.rollouts;
+  const uint32_t tag0 = TAG_ROLLOUT | (cfg.rank << 8);
+  double ret = 0.0;
+  nsteps_lane = 0;
+  if (R > 32 && cfg.team_warps <= 1) {  // one warp, two trajectories per lane (warp-uniform)
+    if constexpr (PID == POMCP_ROCKSAMPLE) {
+      const uint32_t tw[2] = {tag0 | ((uint32_t)lane << 16), tag0 | ((uint32_t)(lane + 32) << 16)};
+      const bool en[2] = {true, lane + 32 < R};
+      double tot[2];
+      rollout_rocksample<false, 2>(m, tb, s, steps, cfg.key0, cfg.key1, tw, en, q, cfg.epoch, nsteps_lane, tot);
+      ret = tot[0] + tot[1];
+    } else {
+      double tot[2] = {0.0, 0.0};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int r = lane + 32 * t;
+        int ns = 0;
+        if (r < R) {
+          const uint32_t tagword = tag0 | ((uint32_t)r << 16);
+          if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
+            tot[t] = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+          else
+            tot[t] = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+        }
+        nsteps_lane += ns;
+      }
+      ret = tot[0] + tot[1];
+    }
+  } else if (r_base + lane < R) {  // rollout team: warp w of the worker runs rollouts 32 w .. 32 w + 31
+    const uint32_t tagword = tag0 | ((uint32_t)(r_base + lane) << 16);
+    if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
+      ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+    else
+      ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+  }
+  return ret;
 }
 
 // ---- one simulation, run by one warp: simulate() of src/solver.jl:78-157.
@@ -536,15 +627,8 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       est = cfg.est_value;  // src/rollout.jl:10
       lc.rollouts++;
     } else {
-      double ret = 0.0;
       int nsteps = 0;
-      if (lane < cfg.rollouts) {
-        const uint32_t tagword = TAG_ROLLOUT | (cfg.rank << 8) | ((uint32_t)lane << 16);
-        if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
-          ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
-        else
-          ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
-      }
+      const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
       est = warp_tree_sum(ret) / (double)cfg.rollouts;
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       lc.rollouts += cfg.rollouts;
@@ -690,12 +774,32 @@ struct ActStats {
   }
 };
 
+// Rollout team: a worker is a CTA of `team_warps` warps.  Warp 0 walks the tree; at a leaf it posts the
+// leaf state and every warp of the CTA runs 32 of the R = 32 * team_warps rollouts, so the leaf
+// estimate averages up to 128 trajectories at the latency of 32 (the helpers sleep on a named
+// barrier during the descent and take no issue slots).  A simulation's latency — and with it the
+// staleness of the tree — does not grow with R.
+template <class State>
+struct LeafJob {
+  State s;
+  long long steps;
+  unsigned long long last_o;
+  uint32_t q;
+  int cmd;  // 1: roll out, 0: the worker is done
+  double partial[4];
+  int psteps[4];
+};
+__device__ __forceinline__ void team_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
 // (lane 0; requested early so its latency hides behind the rollouts).
 template <int PID>
 __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
                                                const uint32_t* eta_thr, const SearchCfg& cfg,
-                                               const PathView<typename ModelT<PID>::State>& pv, uint32_t q,
+                                               const PathView<typename ModelT<PID>::State>& pv,
+                                               LeafJob<typename ModelT<PID>::State>* job, uint32_t q,
                                                LocalCtr& lc, unsigned long long& next_q) {
   using M = ModelT<PID>;
   using State = typename M::State;
@@ -864,17 +968,29 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       est = cfg.est_value;  // src/rollout.jl:10
       lc.rollouts++;
     } else {
-      double ret = 0.0;
-      int nsteps = 0;
-      if (lane < cfg.rollouts) {
-        const uint32_t tagword = TAG_ROLLOUT | tag_rank | ((uint32_t)lane << 16);
-        if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
-          ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
-        else
-          ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps);
+      const int W = cfg.team_warps;
+      if (W > 1) {  // post the leaf to the helper warps
+        if (lane == 0) {
+          job->s = s;
+          job->steps = steps;
+          job->last_o = last_o;
+          job->q = q;
+          job->cmd = 1;
+        }
+        team_bar(1, 32 * W);
       }
-      est = warp_tree_sum(ret) / (double)cfg.rollouts;
+      int nsteps = 0;
+      const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
+      double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
+      if (W > 1) {
+        team_bar(2, 32 * W);  // the helpers' partial sums are in shared memory
+        for (int w = 1; w < W; ++w) {
+          sum += job->partial[w];
+          nsteps += job->psteps[w];
+        }
+      }
+      est = sum / (double)cfg.rollouts;
       lc.rollouts += cfg.rollouts;
       lc.rollout_steps += nsteps;
     }
@@ -942,16 +1058,37 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
 // workers, clamp(root visits / ramp_div, inflight_min, inflight_max), so the tree is never more than
 // that many simulations stale (small while the tree is small).  Root visits only grow, so a worker
 // waits for admission once: worker w starts when root visits >= (w + 1) * ramp_div.
-template <int PID>
-__global__ void __launch_bounds__(32) k_search_workers(const __grid_constant__ Pool P,
-                                                       const __grid_constant__ DevModel m,
-                                                       const __grid_constant__ SearchCfg cfg,
-                                                       const __grid_constant__ PathBuf pb, long long queries) {
+// TEAM = warps per worker (1, 2 or 4).  Four-warp teams are compiled for 7 CTAs per SM (72 registers) so
+// that 1024 workers stay co-resident on 148 SMs; the smaller teams keep the full register budget.
+template <int PID, int TEAM>
+__global__ void __launch_bounds__(32 * TEAM, TEAM == 4 ? 7 : 1) k_search_workers(const __grid_constant__ Pool P,
+                                                        const __grid_constant__ DevModel m,
+                                                        const __grid_constant__ SearchCfg cfg,
+                                                        const __grid_constant__ PathBuf pb, long long queries) {
   using State = typename ModelT<PID>::State;
   extern __shared__ __align__(16) unsigned char path_smem[];
   __shared__ RsTab rs_tab;
+  __shared__ LeafJob<State> job;
   if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int W = TEAM;
+  if (warp > 0) {
+    // helper warp of the rollout team: 32 rollouts of every leaf the tree warp posts
+    for (;;) {
+      team_bar(1, 32 * W);
+      if (job.cmd == 0) break;
+      int nsteps = 0;
+      const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, job.s, job.steps, job.last_o, job.q, lane, nsteps, 32 * warp);
+      const double sum = warp_tree_sum(ret);
+      nsteps = __reduce_add_sync(0xffffffffu, nsteps);
+      if (lane == 0) {
+        job.partial[warp] = sum;
+        job.psteps[warp] = nsteps;
+      }
+      team_bar(2, 32 * W);
+    }
+    return;
+  }
   DevCtr* c = P.ctr;
   // worker ids are handed out in start order, so the admitted (lowest) ids are always resident
   unsigned wid = 0;
@@ -1003,7 +1140,11 @@ __global__ void __launch_bounds__(32) k_search_workers(const __grid_constant__ P
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, (uint32_t)q, lc, next_q);
+    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, &job, (uint32_t)q, lc, next_q);
+  }
+  if (W > 1) {  // release the helpers
+    if (lane == 0) job.cmd = 0;
+    team_bar(1, 32 * W);
   }
   if (lane == 0) {
     flush_counters(P, lc, false);

@@ -109,7 +109,7 @@ def test_c3_rocksample_7_8_1e6_queries(oracle, gpu_lib):
     assert gp.root_stats()[0] == Q and N_g.sum() == Q - 1
     cs = gp.counters()
     assert cs["simulations"] == Q and cs["terminal_skips"] == 0
-    assert cs["rollouts"] % 32 == 0 and cs["rollouts"] // 32 <= cs["nodes"] - 1
+    assert cs["rollouts"] % 64 == 0 and cs["rollouts"] // 64 <= cs["nodes"] - 1  # R = 64 per leaf (batched default)
     assert cs["rollout_steps"] <= cs["rollouts"] * 89  # steps <= ceil(log(eps)/log(gamma) - depth), depth >= 1
     node_N, act_N, act_V, child = gp.dump_tree()
     _check_counts(node_N, act_N, child)
