@@ -295,29 +295,32 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     if (rc) return rc;
     ts.launches++;
   } else {
-    // one persistent launch: every warp (= CTA) is a worker, admission is ramped on the device
-    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
-    int blocks = (int)workers;
+    // one persistent launch of four-warp CTAs: 4 / team_warps workers per CTA, admission ramped on the device
+    const int nteams = 4 / cfg.team_warps;
     size_t path_bytes = ((size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes) + 15) & ~(size_t)15;
-    cfg.path_smem = path_bytes <= 28 * 1024 ? 1 : 0;
-    size_t smem = cfg.path_smem ? path_bytes : 0;
+    cfg.path_smem = path_bytes * nteams <= 40 * 1024 ? 1 : 0;
+    cfg.path_bytes = (int)path_bytes;
+    size_t smem = cfg.path_smem ? path_bytes * nteams : 0;
     cfg.eta_off = (int)smem;
     cfg.eta_n = h->eta_n;
     cfg.eta_thr = h->d_eta_thr;
     smem += (size_t)h->eta_n * sizeof(uint32_t);
+    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
+    int blocks = (int)((workers + nteams - 1) / nteams);
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
-      // no more workers than CTAs that can be co-resident: a worker that is not resident does not search
-      auto launch = [&](auto kern, int threads) {
+      // no more workers than can be co-resident: a worker that is not resident does not search
+      auto launch = [&](auto kern) {
         int per_sm = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
-        kern<<<blocks, threads, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+        cfg.inflight_max = std::min<long long>(cfg.inflight_max, (long long)blocks * nteams);
+        kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
       };
-      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4>, 128);
-      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2>, 64);
-      else launch(k_search_workers<PID, 1>, 32);
+      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1>);
+      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2>);
+      else launch(k_search_workers<PID, 1, 4>);
     });
     rc = launch_check(h, "k_search_workers");
     if (rc) return rc;

@@ -66,6 +66,7 @@ struct SearchCfg {
   // asynchronous workers: in flight = clamp(root visits / ramp_div, inflight_min, inflight_max)
   int inflight_min, inflight_max, ramp_div;
   int path_smem;  // batched mode: the worker's recorded path lives in shared memory (else in PathBuf)
+  int path_bytes;      // bytes of one worker's path in dynamic shared memory (16-byte multiple)
   int eta_off, eta_n;  // RockSample: byte offset / entry count of the sensor thresholds in dynamic shared memory
   const uint32_t* eta_thr;  // [(y*n+x)*k+rock]: check is correct iff obs word <= threshold  (== u < eta)
   // replay (exact mode only)
@@ -278,8 +279,8 @@ __device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTa
 
 template <bool CHECK_DISC>
 __device__ __forceinline__ double rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
-                                                     uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
-                                                     uint32_t epoch, int& nsteps) {
+                                                  uint32_t k0, uint32_t k1, uint32_t tagword, uint32_t q,
+                                                  uint32_t epoch, int& nsteps) {
   const uint32_t tw[1] = {tagword};
   const bool en[1] = {true};
   double total[1];
@@ -786,6 +787,7 @@ struct LeafJob {
   unsigned long long last_o;
   uint32_t q;
   int cmd;  // 1: roll out, 0: the worker is done
+  int bar;  // named barriers bar, bar + 1 belong to this team
   double partial[4];
   int psteps[4];
 };
@@ -977,14 +979,14 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
           job->q = q;
           job->cmd = 1;
         }
-        team_bar(1, 32 * W);
+        team_bar(job->bar, 32 * W);
       }
       int nsteps = 0;
       const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
       double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       if (W > 1) {
-        team_bar(2, 32 * W);  // the helpers' partial sums are in shared memory
+        team_bar(job->bar + 1, 32 * W);  // the helpers' partial sums are in shared memory
         for (int w = 1; w < W; ++w) {
           sum += job->partial[w];
           nsteps += job->psteps[w];
@@ -1058,37 +1060,51 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
 // workers, clamp(root visits / ramp_div, inflight_min, inflight_max), so the tree is never more than
 // that many simulations stale (small while the tree is small).  Root visits only grow, so a worker
 // waits for admission once: worker w starts when root visits >= (w + 1) * ramp_div.
-// TEAM = warps per worker (1, 2 or 4).  Four-warp teams are compiled for 7 CTAs per SM (72 registers) so
-// that 1024 workers stay co-resident on 148 SMs; the smaller teams keep the full register budget.
-template <int PID, int TEAM>
-__global__ void __launch_bounds__(32 * TEAM, TEAM == 4 ? 7 : 1) k_search_workers(const __grid_constant__ Pool P,
-                                                        const __grid_constant__ DevModel m,
-                                                        const __grid_constant__ SearchCfg cfg,
-                                                        const __grid_constant__ PathBuf pb, long long queries) {
+// TEAM = warps per worker (1, 2 or 4), NTEAMS = 4 / TEAM workers per CTA: CTAs are always four warps, one
+// per scheduler of the SM.  Launch bounds keep 1024 workers co-resident on 148 SMs (16 warps of <= 128
+// registers per SM; the four-warp teams run 7 CTAs per SM at 72 registers).
+// Measured oddity (scripts/cycle_probe.py, same rollout code as a __noinline__ function): the 32
+// rollouts of the tree warp take 18.4 k cycles when it rolls out alone (TEAM = 1) and 12.1 k when a
+// helper warp rolls out next to it (TEAM = 2), so R = 64 is not only free, it is faster per simulation.
+template <int PID, int TEAM, int NTEAMS>
+__global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_search_workers(
+    const __grid_constant__ Pool P, const __grid_constant__ DevModel m, const __grid_constant__ SearchCfg cfg,
+    const __grid_constant__ PathBuf pb, long long queries) {
   using State = typename ModelT<PID>::State;
-  extern __shared__ __align__(16) unsigned char path_smem[];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ RsTab rs_tab;
-  __shared__ LeafJob<State> job;
-  if (PID == POMCP_ROCKSAMPLE) rs_tab_init(&rs_tab, m);
+  __shared__ LeafJob<State> jobs[NTEAMS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int team = warp / TEAM, role = warp % TEAM;
   constexpr int W = TEAM;
-  if (warp > 0) {
+  // tables shared by the CTA
+  if (PID == POMCP_ROCKSAMPLE) {
+    uint32_t* e = (uint32_t*)(dyn_smem + cfg.eta_off);
+    for (int i = threadIdx.x; i < cfg.eta_n; i += blockDim.x) e[i] = cfg.eta_thr[i];
+    rs_tab_init(&rs_tab, m);  // ends with __syncthreads()
+  }
+  const uint32_t* eta_thr = (const uint32_t*)(dyn_smem + cfg.eta_off);
+  LeafJob<State>* job = &jobs[team];
+  const int bar = 1 + 2 * team;
+  if (role > 0) {
     // helper warp of the rollout team: 32 rollouts of every leaf the tree warp posts
     for (;;) {
-      team_bar(1, 32 * W);
-      if (job.cmd == 0) break;
+      team_bar(bar, 32 * W);
+      if (job->cmd == 0) break;
       int nsteps = 0;
-      const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, job.s, job.steps, job.last_o, job.q, lane, nsteps, 32 * warp);
+      const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, job->s, job->steps, job->last_o, job->q, lane, nsteps, 32 * role);
       const double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       if (lane == 0) {
-        job.partial[warp] = sum;
-        job.psteps[warp] = nsteps;
+        job->partial[role] = sum;
+        job->psteps[role] = nsteps;
       }
-      team_bar(2, 32 * W);
+      team_bar(bar + 1, 32 * W);
     }
     return;
   }
+  if (lane == 0) job->bar = bar;
+  __syncwarp();
   DevCtr* c = P.ctr;
   // worker ids are handed out in start order, so the admitted (lowest) ids are always resident
   unsigned wid = 0;
@@ -1097,9 +1113,10 @@ __global__ void __launch_bounds__(32 * TEAM, TEAM == 4 ? 7 : 1) k_search_workers
   PathView<State> pv;
   if (cfg.path_smem) {
     const int L = cfg.levels > 0 ? cfg.levels : 1;
-    pv.r = (double*)path_smem;
-    pv.state = (State*)(path_smem + (size_t)L * 8);
-    pv.slot = (uint32_t*)(path_smem + (size_t)L * (8 + sizeof(State)));
+    unsigned char* base = dyn_smem + (size_t)team * cfg.path_bytes;
+    pv.r = (double*)base;
+    pv.state = (State*)(base + (size_t)L * 8);
+    pv.slot = (uint32_t*)(base + (size_t)L * (8 + sizeof(State)));
     pv.node = pv.slot + L;
     pv.stride = 1;
   } else {
@@ -1109,17 +1126,10 @@ __global__ void __launch_bounds__(32 * TEAM, TEAM == 4 ? 7 : 1) k_search_workers
     pv.node = pb.path_node + wid;
     pv.stride = pb.stride;
   }
-  const uint32_t* eta_thr = nullptr;
-  if (PID == POMCP_ROCKSAMPLE) {
-    uint32_t* e = (uint32_t*)(path_smem + cfg.eta_off);
-    for (int i = lane; i < cfg.eta_n; i += 32) e[i] = cfg.eta_thr[i];
-    __syncwarp();
-    eta_thr = e;
-  }
   LocalCtr lc{};
   unsigned long long next_q = ~0ull;
   const long long t_start = clock64();
-  if (lane == 0) {
+  if (lane == 0 && (long long)wid < (long long)cfg.inflight_max) {
     // admission: ramp the number of simulations in flight with the size of the tree
     const unsigned long long need =
         (long long)wid < (long long)cfg.inflight_min ? 0ull : ((unsigned long long)wid + 1ull) * (unsigned long long)cfg.ramp_div;
@@ -1140,11 +1150,11 @@ __global__ void __launch_bounds__(32 * TEAM, TEAM == 4 ? 7 : 1) k_search_workers
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, &job, (uint32_t)q, lc, next_q);
+    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q);
   }
   if (W > 1) {  // release the helpers
-    if (lane == 0) job.cmd = 0;
-    team_bar(1, 32 * W);
+    if (lane == 0) job->cmd = 0;
+    team_bar(bar, 32 * W);
   }
   if (lane == 0) {
     flush_counters(P, lc, false);
