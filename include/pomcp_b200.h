@@ -82,8 +82,12 @@ typedef struct pomcp_problem {
 typedef enum pomcp_estimator {
   POMCP_EST_RANDOM_ROLLOUT = 0, /* RolloutEstimator(RandomSolver()), src/constructor.jl:14 */
   POMCP_EST_CONSTANT = 1,       /* estimate_value(n::Number,...), src/rollout.jl:10 */
-  POMCP_EST_FWC_ROLLOUT = 2     /* Baby only: RolloutEstimator(FeedWhenCrying()) with the previous-observation
+  POMCP_EST_FWC_ROLLOUT = 2,    /* Baby only: RolloutEstimator(FeedWhenCrying()) with the previous-observation
                                    "belief" of src/rollout.jl:105-108 (test/runtests.jl:13-19) */
+  POMCP_EST_FO_FWC_ROLLOUT = 3, /* Baby only: FORollout(FeedWhenCrying()) (src/rollout.jl:24-31,86-92, test/runtests.jl:25-31):
+                                   fully observable rollout, the policy sees the state, i.e. feeds iff hungry */
+  POMCP_EST_STATE_VALUE = 4     /* FOValue(policy) (src/rollout.jl:33-39,67-69): value(policy, s) read from the table
+                                   given to pomcp_set_state_values (discrete-state problems) */
 } pomcp_estimator;
 
 /* node_belief_updater kinds (src/solver.jl:135-139). */
@@ -161,6 +165,9 @@ int32_t pomcp_destroy(pomcp_handle* h);
 int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t n);
 /* ... or over the problem's initial state distribution. */
 int32_t pomcp_set_belief_initial(pomcp_handle* h);
+/* Table for POMCP_EST_STATE_VALUE: v[state_index(s)], state_index = s for Tiger/Baby (n = 2) and the packed
+ * x | y<<4 | rocks<<8 for RockSample (n = 2^(8+k)); terminal states are worth 0. */
+int32_t pomcp_set_state_values(pomcp_handle* h, const double* values, int64_t n);
 /* Copy the root belief's particles out (ParticleCollection of the root node). */
 int32_t pomcp_get_belief_particles(pomcp_handle* h, void* out, int64_t cap, int64_t* n);
 

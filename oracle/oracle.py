@@ -41,6 +41,7 @@ def lib():
         L.orc_destroy.restype = None
         L.orc_set_belief_particles.argtypes = [vp, vp, i64]
         L.orc_set_belief_initial.argtypes = [vp]
+        L.orc_set_state_values.argtypes = [vp, vp, i64]
         L.orc_get_belief_particles.argtypes = [vp, vp, i64, P(i64)]
         L.orc_search.argtypes = [vp, i64, P(i32), vp, vp, i32]
         L.orc_search_replay.argtypes = [vp, i64, vp, i64, vp, i64, P(i32), vp, vp, i32, P(i64), P(i64)]
@@ -113,6 +114,10 @@ class OraclePlanner:
 
     def set_belief_initial(self):
         return lib().orc_set_belief_initial(self._h)
+
+    def set_state_values(self, values):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        return lib().orc_set_state_values(self._h, _vp(values), len(values))
 
     def belief_particles(self):
         n = C.c_int64(0)

@@ -427,6 +427,39 @@ static double rollout_fwc(const model* m, ostate s, int64_t steps, uint64_t last
   return total;
 }
 
+/* FORollout(FeedWhenCrying()) on Baby (src/rollout.jl:86-92 -> POMDPToolbox MDP simulate): the policy is
+ * handed the state where it expects the previous observation, so it feeds iff the baby is hungry.
+ * One Philox word per step (transition); generate_sr draws no observation. */
+static double rollout_fo_fwc(const model* m, ostate s, int64_t steps, const uint32_t key[2], uint32_t tagword,
+                             uint32_t q, uint32_t epoch, int64_t* nsteps) {
+  const double gamma = m->p.discount;
+  double disc = 1.0, total = 0.0;
+  int64_t step = 0;
+  uint32_t w[4];
+  int64_t blk = -1;
+  while (disc > 0.0 && !is_terminal(m, s) && step < steps) {
+    if ((step >> 2) != blk) {
+      blk = step >> 2;
+      uint32_t ctr[4] = {(uint32_t)blk, tagword, q, epoch};
+      orc_philox4x32_10(ctr, key, w);
+    }
+    int a = s.i ? 1 : 0;
+    ostate sp; uint64_t o; double r;
+    model_step(m, s, a, u01(w[step & 3]), 0.0, 0.0, 0, &sp, &o, &r);
+    total += disc * r;
+    s = sp;
+    disc *= gamma;
+    ++step;
+  }
+  if (nsteps) *nsteps += step;
+  return total;
+}
+
+static int64_t state_index(const model* m, ostate s) {
+  if (m->p.problem_id == POMCP_ROCKSAMPLE) return (int64_t)((uint64_t)s.i & 0xffffffull);
+  return s.i;
+}
+
 /* ------------------------------------------------------------------ */
 /* planner / tree (src/tree.jl:7-26 as flat arrays)                     */
 /* ------------------------------------------------------------------ */
@@ -456,6 +489,7 @@ struct orc_planner {
   double* gpow;       /* gamma^d, d = 0..horizon */
   double log_ratio;   /* log(eps)/log(gamma) */
   uint32_t epoch;
+  double* state_values; int64_t n_state_values; /* FOValue table */
   pomcp_counters ctr;
   /* scratch path */
   int64_t cap_path; int64_t* path_slot; int64_t* path_node; double* path_r; ostate* path_sp;
@@ -566,7 +600,9 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   pl->sp = *sp;
   if (sp->num_sparse_actions > 0 || !(sp->eps > 0.0) || !(sp->eps < 1.0)) { free(pl); return NULL; }
   if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 64) { free(pl); return NULL; }
-  if (sp->estimator == POMCP_EST_FWC_ROLLOUT && p->problem_id != POMCP_BABY) { free(pl); return NULL; }
+  if ((sp->estimator == POMCP_EST_FWC_ROLLOUT || sp->estimator == POMCP_EST_FO_FWC_ROLLOUT) &&
+      p->problem_id != POMCP_BABY) { free(pl); return NULL; }
+  if (sp->estimator == POMCP_EST_STATE_VALUE && p->problem_id == POMCP_LIGHTDARK1D) { free(pl); return NULL; }
   pl->nA = pl->m.nA; pl->nO = pl->m.nO;
   /* cut-off gamma^depth < eps (src/solver.jl:82) and steps_to_eps (src/solver.jl:100) */
   pl->log_ratio = log(sp->eps) / log(p->discount);
@@ -588,6 +624,7 @@ void orc_destroy(orc_planner* pl) {
   if (!pl) return;
   free_tree(pl);
   free(pl->bel); free(pl->gpow); free(pl->path_slot); free(pl->path_node); free(pl->path_r); free(pl->path_sp);
+  free(pl->state_values);
   free(pl);
 }
 
@@ -598,6 +635,14 @@ int32_t orc_set_belief_particles(orc_planner* pl, const void* states, int64_t n)
   pl->bel = (ostate*)malloc(sizeof(ostate) * (size_t)n);
   for (int64_t i = 0; i < n; ++i) pl->bel[i] = load_state(&pl->m, states, i);
   pl->n_bel = n; pl->belief_kind = 2;
+  return POMCP_OK;
+}
+int32_t orc_set_state_values(orc_planner* pl, const double* values, int64_t n) {
+  if (!values || n <= 0) return POMCP_ERR_INVALID_ARG;
+  free(pl->state_values);
+  pl->state_values = (double*)malloc(sizeof(double) * (size_t)n);
+  memcpy(pl->state_values, values, sizeof(double) * (size_t)n);
+  pl->n_state_values = n;
   return POMCP_OK;
 }
 int32_t orc_set_belief_initial(orc_planner* pl) {
@@ -698,6 +743,9 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
           if (g->rcur < g->nret) est = g->ret[g->rcur++]; else { est = 0.0; g->overflow = 1; }
         } else if (sol->estimator == POMCP_EST_CONSTANT) {
           est = sol->estimator_value; /* src/rollout.jl:10 */
+        } else if (sol->estimator == POMCP_EST_STATE_VALUE) { /* value(policy, s), src/rollout.jl:67-69 */
+          int64_t si = state_index(m, s);
+          est = (is_terminal(m, s) || si < 0 || si >= pl->n_state_values) ? 0.0 : pl->state_values[si];
         } else {
           /* R rollouts per leaf (device extension; R = 1 is the reference).  Rollout r draws from the
            * stream tagged r<<16; the R returns are added in the butterfly order of a 32-lane warp. */
@@ -709,6 +757,9 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
                        ? rollout_fwc(m, s, steps, pl->node_obs[h], g->key,
                                      TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q, g->epoch,
                                      &pl->ctr.rollout_steps)
+                   : sol->estimator == POMCP_EST_FO_FWC_ROLLOUT
+                       ? rollout_fo_fwc(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
+                                        g->epoch, &pl->ctr.rollout_steps)
                        : rollout_random(m, s, steps, g->key, TAG_ROLLOUT | (g->rank << 8) | ((uint32_t)r << 16), q,
                                         g->epoch, &pl->ctr.rollout_steps);
           if (R > 32) /* lane l of the warp holds rollouts l and l + 32 */

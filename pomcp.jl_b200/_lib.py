@@ -44,6 +44,7 @@ def lib():
     L.pomcp_destroy.argtypes = [vp]
     L.pomcp_set_belief_particles.argtypes = [vp, vp, i64]
     L.pomcp_set_belief_initial.argtypes = [vp]
+    L.pomcp_set_state_values.argtypes = [vp, vp, i64]
     L.pomcp_get_belief_particles.argtypes = [vp, vp, i64, P(i64)]
     L.pomcp_search.argtypes = [vp, i64, P(i32), vp, vp, i32]
     L.pomcp_search_replay.argtypes = [vp, i64, vp, i64, vp, i64, P(i32), vp, vp, i32, P(i64), P(i64)]

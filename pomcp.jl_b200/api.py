@@ -18,7 +18,7 @@ from ._lib import lib
 from .problems import POMDP, obs_bits
 
 __all__ = [
-    "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
+    "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "FORollout", "FOValue", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
     "DeadReinvigorator", "ParticleReinvigorator", "SIRReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
@@ -100,6 +100,24 @@ class RolloutEstimator:
 
     def __init__(self, solver=None):
         self.solver = solver if solver is not None else RandomSolver()
+
+
+class FORollout:
+    """FORollout(solver_or_policy) (src/rollout.jl:24-31,86-92): fully observable rollout, the policy is
+    given the state.  On device: RandomSolver() (the same trajectories as the PO rollout) and
+    FeedWhenCrying() on Baby (feeds iff hungry; test/runtests.jl:25-31)."""
+
+    def __init__(self, solver):
+        self.solver = solver
+
+
+class FOValue:
+    """FOValue(policy) (src/rollout.jl:33-39,67-69): the leaf estimate is value(policy, s).  On device the
+    policy's value function is a table over the discrete state index (Tiger/Baby: the state; RockSample:
+    x | y<<4 | rocks<<8), e.g. the solution of the underlying MDP."""
+
+    def __init__(self, values):
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
 
 
 class ParticleReinvigorator:
@@ -184,12 +202,19 @@ class POMCPSolver:
             sp.estimator = abi.EST_RANDOM_ROLLOUT
         elif isinstance(ev, RolloutEstimator) and isinstance(ev.solver, FeedWhenCrying):
             sp.estimator = abi.EST_FWC_ROLLOUT  # test/runtests.jl:13-19, notebooks/Display_Tree.ipynb:31-39
+        elif isinstance(ev, FORollout) and isinstance(ev.solver, RandomSolver):
+            sp.estimator = abi.EST_RANDOM_ROLLOUT  # a random policy ignores what it is shown
+        elif isinstance(ev, FORollout) and isinstance(ev.solver, FeedWhenCrying):
+            sp.estimator = abi.EST_FO_FWC_ROLLOUT  # test/runtests.jl:25-31
+        elif isinstance(ev, FOValue):
+            sp.estimator = abi.EST_STATE_VALUE
         elif isinstance(ev, (int, float)):
             sp.estimator, sp.estimator_value = abi.EST_CONSTANT, float(ev)  # src/rollout.jl:10
         else:
             raise NotImplementedError(
-                "estimate_value: only RolloutEstimator(RandomSolver()) and numeric estimates run on device "
-                "(FORollout/FOValue/function estimators are arbitrary host callbacks, src/rollout.jl:9,24-39)")
+                "estimate_value: RolloutEstimator / FORollout over RandomSolver() or FeedWhenCrying(), FOValue(table) "
+                "and numeric estimates run on device (function estimators and arbitrary policies are host "
+                "callbacks, src/rollout.jl:9,24-39)")
         sp.belief_mode = belief_mode
         sp.search_mode = {"exact": abi.MODE_EXACT, "batched": abi.MODE_BATCHED}[self.search_mode]
         sp.max_nodes, sp.max_log = int(self.max_nodes), int(self.max_log)
@@ -275,6 +300,9 @@ class POMCPPlanner:
         if rc != abi.OK:
             _check(rc, None)
         self._h = h
+        if isinstance(solver.estimate_value, FOValue):
+            v = solver.estimate_value.values
+            _check(lib().pomcp_set_state_values(self._h, v.ctypes.data_as(C.c_void_p), len(v)), self._h)
         self._generation = 0
         self._tree_ref = None  # src/POMCP.jl:266-267
 

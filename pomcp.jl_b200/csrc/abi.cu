@@ -132,6 +132,8 @@ struct pomcp_handle {
   bool pending = false;
   uint32_t* d_newid = nullptr;
   size_t newid_cap = 0;
+  double* d_state_values = nullptr;  // FOValue table
+  long long n_state_values = 0;
   void* d_init = nullptr;  // particles drawn from the initial distribution (reinvigorator)
   size_t init_cap = 0;
   bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
@@ -242,6 +244,8 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.init_N = h->sp.init_N;
   c.log_ratio = h->log_ratio;
   c.est_value = h->sp.estimator_value;
+  c.state_values = h->d_state_values;
+  c.n_state_values = h->n_state_values;
   c.max_depth = h->sp.max_depth;
   c.gpow = h->d_gpow;
   c.levels = h->levels;
@@ -273,6 +277,8 @@ int reset_search_flags(pomcp_handle* h) {
 int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long n_uni, const double* d_rets,
                    long long n_rets) {
   if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
+  if (h->sp.estimator == POMCP_EST_STATE_VALUE && !h->d_state_values)
+    return fail(h, POMCP_ERR_INVALID_ARG, "POMCP_EST_STATE_VALUE needs pomcp_set_state_values first");
   if (Q < 0) Q = h->sp.tree_queries;
   if (Q >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "tree_queries must be < 2^32");
   int rc = reset_search_flags(h);
@@ -611,7 +617,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
-                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init};
+                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
@@ -636,9 +642,12 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   if (!(sp->eps > 0.0) || !(sp->eps < 1.0)) return fail(nullptr, POMCP_ERR_INVALID_ARG, "eps must be in (0,1)");
   if (sp->num_sparse_actions > 0)
     return fail(nullptr, POMCP_ERR_UNSUPPORTED, "num_sparse_actions > 0 (random action sub-sampling) is not supported");
+  const bool fwc = sp->estimator == POMCP_EST_FWC_ROLLOUT || sp->estimator == POMCP_EST_FO_FWC_ROLLOUT;
   if (sp->estimator != POMCP_EST_RANDOM_ROLLOUT && sp->estimator != POMCP_EST_CONSTANT &&
-      !(sp->estimator == POMCP_EST_FWC_ROLLOUT && p->problem_id == POMCP_BABY))
-    return fail(nullptr, POMCP_ERR_UNSUPPORTED, "estimator (FeedWhenCrying rollouts exist for BabyPOMDP only)");
+      !(fwc && p->problem_id == POMCP_BABY) &&
+      !(sp->estimator == POMCP_EST_STATE_VALUE && p->problem_id != POMCP_LIGHTDARK1D))
+    return fail(nullptr, POMCP_ERR_UNSUPPORTED,
+                "estimator (FeedWhenCrying rollouts exist for BabyPOMDP only, state-value tables for discrete states only)");
   if (sp->init_N < 0 || sp->max_depth < 0) return fail(nullptr, POMCP_ERR_INVALID_ARG, "init_N/max_depth < 0");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -818,6 +827,18 @@ int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t 
   h->n_bel = n;
   h->bel_kind = 2;
   return fresh_root(h);
+}
+
+int32_t pomcp_set_state_values(pomcp_handle* h, const double* values, int64_t n) {
+  if (!h || !values || n <= 0) return fail(h, POMCP_ERR_INVALID_ARG, "bad state-value table");
+  cudaSetDevice(h->device);
+  if (h->d_state_values) CK(cudaFree(h->d_state_values));
+  h->d_state_values = nullptr;
+  CK(cudaMalloc((void**)&h->d_state_values, (size_t)n * sizeof(double)));
+  CK(cudaMemcpyAsync(h->d_state_values, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->n_state_values = n;
+  return POMCP_OK;
 }
 
 int32_t pomcp_set_belief_initial(pomcp_handle* h) {

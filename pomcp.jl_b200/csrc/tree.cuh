@@ -54,6 +54,8 @@ struct SearchCfg {
   double c, init_V, log_ratio, est_value;
   long long max_depth, init_N;
   const double* gpow;  // gamma^d, d = 0..levels
+  const double* state_values;  // FOValue table (POMCP_EST_STATE_VALUE), n_state_values entries
+  long long n_state_values;
   int levels;          // first depth at which gamma^depth < eps (src/solver.jl:82), capped by max_depth
   int belief_unweighted, estimator;
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
@@ -335,6 +337,40 @@ __device__ __forceinline__ double rollout_fwc(const DevModel& m, uint32_t s, lon
   return total;
 }
 
+// Baby only: FORollout(FeedWhenCrying()) (src/rollout.jl:86-92): the policy sees the state, feeds iff hungry.
+// One Philox word per step (transition), no observation.
+__device__ __forceinline__ double rollout_fo_fwc(const DevModel& m, uint32_t s, long long steps, uint32_t k0,
+                                                 uint32_t k1, uint32_t tagword, uint32_t q, uint32_t epoch,
+                                                 int& nsteps) {
+  using M = ModelT<POMCP_BABY>;
+  const double gamma = m.gamma;
+  double disc = 1.0, total = 0.0;
+  long long step = 0;
+  bool live = steps > 0;
+  for (uint32_t blk = 0; live; ++blk) {
+    Philox4 p = philox4x32_10(blk, tagword, q, epoch, k0, k1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (live) {
+        uint32_t sp;
+        uint64_t o;
+        double r;
+        M::template step<false, double>(m, s, s ? 1 : 0, u01(p.w[j]), 0.0, 0.0, sp, o, r);
+        total += disc * r;
+        s = sp;
+        disc *= gamma;
+        ++step;
+        live = disc > 0.0 && step < steps;
+      }
+    }
+  }
+  nsteps = (int)step;
+  return total;
+}
+
+__device__ __forceinline__ long long state_index(uint32_t s) { return (long long)(s & 0xffffffu); }
+__device__ __forceinline__ long long state_index(const LDState&) { return -1; }
+
 // Leaf evaluation by one warp: lane l runs rollout r_base + l (rollout team, batched mode) or, on a
 // single warp with R > 32 (exact mode), rollouts l and l + 32; the per-lane sums are added by the fixed
 // butterfly, so the oracle reproduces the mean bit for bit.
@@ -454,6 +490,8 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
           const uint32_t tagword = tag0 | ((uint32_t)r << 16);
           if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
             tot[t] = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+          else if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FO_FWC_ROLLOUT)
+            tot[t] = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
           else
             tot[t] = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
         }
@@ -465,6 +503,8 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
     const uint32_t tagword = tag0 | ((uint32_t)(r_base + lane) << 16);
     if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
       ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+    else if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FO_FWC_ROLLOUT)
+      ret = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
     else
       ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
   }
@@ -626,6 +666,10 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       lc.rollouts++;
     } else if (cfg.estimator == POMCP_EST_CONSTANT) {
       est = cfg.est_value;  // src/rollout.jl:10
+      lc.rollouts++;
+    } else if (cfg.estimator == POMCP_EST_STATE_VALUE) {  // value(policy, s), src/rollout.jl:67-69
+      const long long si = state_index(s);
+      est = (M::terminal(m, s) || si < 0 || si >= cfg.n_state_values) ? 0.0 : cfg.state_values[si];
       lc.rollouts++;
     } else {
       int nsteps = 0;
@@ -968,6 +1012,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     double est;
     if (cfg.estimator == POMCP_EST_CONSTANT) {
       est = cfg.est_value;  // src/rollout.jl:10
+      lc.rollouts++;
+    } else if (cfg.estimator == POMCP_EST_STATE_VALUE) {  // value(policy, s), src/rollout.jl:67-69
+      const long long si = state_index(s);
+      est = (M::terminal(m, s) || si < 0 || si >= cfg.n_state_values) ? 0.0 : cfg.state_values[si];
       lc.rollouts++;
     } else {
       const int W = cfg.team_warps;

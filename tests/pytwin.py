@@ -22,7 +22,7 @@ class ActNode:
 
 
 class Twin:
-    def __init__(self, pomdp, c, seed, eps=0.01, max_depth=2 ** 62, log_fn=math.log, fwc=False):
+    def __init__(self, pomdp, c, seed, eps=0.01, max_depth=2 ** 62, log_fn=math.log, fwc=False, fo_fwc=False):
         self.p, self.c, self.eps, self.max_depth = pomdp, c, eps, max_depth
         self.key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
         self.gamma = pomdp.discount
@@ -31,6 +31,7 @@ class Twin:
         self.log = log_fn
         self.kind = type(pomdp).__name__
         self.fwc = fwc  # Baby: RolloutEstimator(FeedWhenCrying()), test/runtests.jl:13-19
+        self.fo_fwc = fo_fwc  # Baby: FORollout(FeedWhenCrying()), test/runtests.jl:25-31
 
     # ---- generative model (Tiger / Baby), transition draw first, observation draw second
     def step(self, s, a, ut, uo, need_obs=True):
@@ -82,6 +83,20 @@ class Twin:
             step += 1
         return total
 
+    def rollout_fo_fwc(self, s, steps, q):
+        """MDP rollout, the policy is shown the state: feed iff hungry.  One word per step (transition)."""
+        disc, total, step, blk, w = 1.0, 0.0, 0, -1, None
+        while step < steps:
+            if step >> 2 != blk:
+                blk = step >> 2
+                w = philox4x32_10((blk, TAG_ROLLOUT, q, self.epoch), self.key)
+            sp, _, r = self.step(s, 1 if s else 0, w[step & 3] * U, 0.0)
+            total += disc * r
+            s = sp
+            disc *= self.gamma
+            step += 1
+        return total
+
     def simulate(self, h, s, depth, q, label=0):
         if self.gamma ** depth < self.eps or depth >= self.max_depth:
             return 0.0
@@ -92,6 +107,8 @@ class Twin:
                 steps = min(self.max_depth - depth, math.ceil(math.log(self.eps) / math.log(self.gamma) - depth))
                 if self.fwc:
                     return self.gamma ** depth * self.rollout_fwc(s, steps, q, label)
+                if self.fo_fwc:
+                    return self.gamma ** depth * self.rollout_fo_fwc(s, steps, q)
                 return self.gamma ** depth * self.rollout(s, steps, q)
             return 0.0
         best, best_node = -math.inf, None

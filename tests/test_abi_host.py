@@ -80,6 +80,9 @@ def test_unsupported_estimators_are_rejected():
     with pytest.raises(NotImplementedError):
         pj.POMCPSolver(init_V=lambda *a: 0.0).c_params(abi.BELIEF_UNWEIGHTED)
     assert pj.POMCPSolver(estimate_value=3.5).c_params(0).estimator == abi.EST_CONSTANT
+    assert pj.POMCPSolver(estimate_value=pj.FORollout(pj.RandomSolver())).c_params(0).estimator == abi.EST_RANDOM_ROLLOUT
+    assert pj.POMCPSolver(estimate_value=pj.FORollout(pj.FeedWhenCrying())).c_params(0).estimator == abi.EST_FO_FWC_ROLLOUT
+    assert pj.POMCPSolver(estimate_value=pj.FOValue([0.0, 1.0])).c_params(0).estimator == abi.EST_STATE_VALUE
 
 
 def test_default_action_dispatch():

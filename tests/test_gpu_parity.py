@@ -206,6 +206,42 @@ def test_fwc_rollout_rejected_outside_baby(gpu_lib):
         pj.solve(pj.POMCPSolver(estimate_value=pj.RolloutEstimator(pj.FeedWhenCrying())), pj.TigerPOMDP())
 
 
+def test_fo_rollout_and_fo_value_bit_exact(oracle, gpu_lib):
+    """FORollout(FeedWhenCrying()) on Baby and FOValue(table) on Baby / RockSample(4,4): exact-mode trees equal
+    the oracle's bit for bit; batched mode keeps the counting invariants."""
+    baby, c = PROBS["baby"]
+    gp, op = make_pair(oracle, baby, c, seed=29, mode="exact", tree_queries=2000, estimate_value=pj.FORollout(pj.FeedWhenCrying()))
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(2000)
+    rc, a_o, N_o, V_o = op.search(2000)
+    assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o))
+    assert gp.counters()["rollout_steps"] == op.counters()["rollout_steps"]
+    gp.close()
+    rng = np.random.default_rng(9)
+    for name, n_states in (("baby", 2), ("rs44", 1 << 12)):
+        pomdp, c = PROBS[name]
+        table = rng.normal(-5.0, 3.0, n_states)
+        gp, op = make_pair(oracle, pomdp, c, seed=31, mode="exact", tree_queries=2500, estimate_value=pj.FOValue(table))
+        assert op.set_state_values(table) == 0
+        gp.set_belief_initial()
+        op.set_belief_initial()
+        a_g, N_g, V_g = gp.search(2500)
+        rc, a_o, N_o, V_o = op.search(2500)
+        assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o))
+        tg, to = gp.dump_tree(), op.dump_tree()
+        assert np.array_equal(tg[1], to[1]) and np.array_equal(_bits(tg[2]), _bits(to[2]))
+        assert gp.counters()["rollout_steps"] == 0
+        gp.close()
+        gp, _ = make_pair(oracle, pomdp, c, seed=31, mode="batched", tree_queries=30000, estimate_value=pj.FOValue(table))
+        gp.set_belief_initial()
+        a, N, V = gp.search(30000)
+        assert N.sum() == 29999 and np.isfinite(V).all()
+        gp.close()
+    with pytest.raises(NotImplementedError):
+        pj.solve(pj.POMCPSolver(estimate_value=pj.FOValue(np.zeros(4))), pj.LightDark1D())
+
+
 @pytest.mark.parametrize("name", ["tiger", "baby", "rs44", "lightdark"])
 def test_replay_tree_counts_bit_exact(oracle, gpu_lib, name):
     """north_star criterion 1: replayed uniform stream + injected rollout returns => identical counts."""

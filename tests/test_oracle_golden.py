@@ -309,3 +309,41 @@ def test_sir_reinvigorator_prevents_depletion(oracle):
     pl2.search(5)
     rc, out = pl2.update_reinvigorated(1, 0, seed=5, n_min=500)
     assert rc == 0 and out in (1, 2) and pl2.belief_particles().sum() == 0
+
+
+# ----------------------------------------------------------------------------- FORollout / FOValue
+def test_fo_rollout_and_fo_value_estimators(oracle):
+    """FORollout(FeedWhenCrying()) (test/runtests.jl:25-31, src/rollout.jl:86-92) and FOValue(policy)
+    (src/rollout.jl:67-69).  The MDP policy "feed iff hungry" has the closed-form value
+    V(hungry) = -15 / (1 - 0.9 * 0.09 / 0.19) and V(not hungry) = 0.09 / 0.19 * V(hungry): the FOValue tree fed
+    with that table and the FORollout tree that samples the same policy must agree on the root values;
+    the recursive twin reproduces the FORollout tree bit for bit."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    vh = -15.0 / (1.0 - 0.9 * 0.09 / 0.19)
+    table = np.array([0.09 / 0.19 * vh, vh])
+    roots = {}
+    for est in (abi.EST_FO_FWC_ROLLOUT, abi.EST_STATE_VALUE):
+        V = []
+        for seed in range(6):
+            pl = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=seed, estimator=est))
+            if est == abi.EST_STATE_VALUE:
+                assert pl.set_state_values(table) == 0
+            pl.set_belief_initial()
+            rc, a, N, Vs = pl.search(4000)
+            assert rc == 0
+            V.append(Vs)
+            pl.close()
+        roots[est] = np.mean(V, axis=0)
+    assert np.all(np.abs(roots[abi.EST_FO_FWC_ROLLOUT] - roots[abi.EST_STATE_VALUE]) < 0.8), roots
+    assert roots[abi.EST_STATE_VALUE][0] > roots[abi.EST_STATE_VALUE][1]  # not feeding a sated baby is better
+    for seed in (0, 5):
+        tw = Twin(baby, 10.0, seed, log_fn=oracle.lib().orc_det_log, fo_fwc=True)
+        op = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=seed, estimator=abi.EST_FO_FWC_ROLLOUT))
+        op.set_belief_initial()
+        for Q in (400, 150):
+            a_t, N_t, V_t = tw.search(Q)
+            rc, a_o, N_o, V_o = op.search(Q)
+            assert rc == 0 and a_t == a_o and list(N_o) == N_t
+            assert np.array_equal(np.array(V_t).view(np.uint64), V_o.view(np.uint64))
+    with pytest.raises(ValueError):
+        oracle.OraclePlanner(pj.LightDark1D(), oracle.default_params(estimator=abi.EST_STATE_VALUE))
