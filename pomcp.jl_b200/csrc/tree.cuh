@@ -863,6 +863,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   st.load(P, h, nA, lane);
   uint32_t fl = 0;
   if (lane == 0) fl = __ldcg(&P.node_flags[h]);
+  __syncwarp();
 
   // rand(rng, b): src/solver.jl:48 -> src/updater.jl:53-55
   Philox4 pr = philox4x32_10(0u, TAG_ROOT | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
@@ -974,6 +975,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         pv.state[pi] = sp;
       }
     }
+    // Re-converge here: without it lane 0 stays split from lanes 1..31 until the next shuffle and the
+    // warp runs everything in between twice (measured: the whole rollout loop at 15.5 active lanes).
+    __syncwarp();
     h = hao;
     s = sp;
     last_o = o;
@@ -999,6 +1003,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     if (aborted) atomicMax(&P.ctr->next_query, 1ull << 62);  // pool exhausted: stop every worker
     next_q = atomicAdd(&P.ctr->next_query, 1ull);
   }
+  __syncwarp();  // lanes re-converge before the rollouts (see above)
   if (aborted) return;
   const long long t1 = clock64();
   lc.cyc[0] += (unsigned long long)(t1 - t0 - t_ins);

@@ -7,8 +7,10 @@ from pomcp_jl_b200 import _abi as abi
 import bench
 
 Q = int(sys.argv[1]) if len(sys.argv) > 1 else bench.TREE_QUERIES
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 0  # rollouts per leaf (0 = library default)
 pomdp = pj.RockSamplePOMDP(bench.RS_N, bench.RS_K, seed=bench.RS_SEED)
-solver = pj.POMCPSolver(c=bench.UCB_C, rng=bench.SOLVER_SEED, tree_queries=Q, search_mode="batched", max_nodes=3 * Q)
+solver = pj.POMCPSolver(c=bench.UCB_C, rng=bench.SOLVER_SEED, tree_queries=Q, search_mode="batched", max_nodes=3 * Q,
+                        rollouts_per_leaf=R)
 policy = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
 parts, _ = bench.initial_particles(pomdp, bench.N_PARTICLES)
 policy.set_belief_particles(parts)
