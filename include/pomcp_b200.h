@@ -226,6 +226,14 @@ int32_t pomcp_get_node_stats(pomcp_handle* h, const int32_t* actions, const uint
 /* Whole-tree dump in allocation order (for structural invariants). */
 int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap_nodes, int64_t* n_nodes, int64_t* node_N,
                         int64_t* act_N, double* act_V, int32_t* child /* [node][action][obs], -1 none; NULL ok */);
+/* The environment side of the outer simulation loop (POMDPToolbox.RolloutSimulator / test_solver, SURVEY.md
+ * §3.5): generate_sor(pomdp, s, a, rng) and rand(rng, initial_state_distribution(pomdp)) on the same model
+ * code the planner uses.  Draws come from Philox(seed; step), independent of the planner's streams. */
+int32_t pomcp_generate_sor(pomcp_handle* h, const void* state, int32_t a, uint64_t seed, uint32_t step,
+                           void* next_state, uint64_t* obs_bits, double* reward, int32_t* terminal);
+int32_t pomcp_initial_state(pomcp_handle* h, uint64_t seed, void* state_out);
+/* Index of the current root in the arrays pomcp_dump_tree returns (0 after a fresh root or a compaction). */
+int32_t pomcp_root_node(pomcp_handle* h, int64_t* node_id);
 int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out);
 int32_t pomcp_reset_counters(pomcp_handle* h);
 /* Diagnostics: SM cycles summed over the batched workers since the last reset: [0] descent,

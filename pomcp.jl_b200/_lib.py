@@ -58,6 +58,9 @@ def lib():
     L.pomcp_get_node_stats.argtypes = [vp, vp, vp, i32, P(i64), P(i64), vp, vp, i32]
     L.pomcp_dump_tree.argtypes = [vp, i64, P(i64), vp, vp, vp, vp]
     L.pomcp_get_counters.argtypes = [vp, P(abi.Counters)]
+    L.pomcp_generate_sor.argtypes = [vp, vp, i32, u64, C.c_uint32, vp, P(u64), P(dbl), P(i32)]
+    L.pomcp_initial_state.argtypes = [vp, u64, vp]
+    L.pomcp_root_node.argtypes = [vp, P(i64)]
     L.pomcp_reset_counters.argtypes = [vp]
     L.pomcp_worker_cycles.argtypes = [vp, vp]
     L.pomcp_nccl_unique_id.argtypes = [vp]

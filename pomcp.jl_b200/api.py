@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _abi as abi
 from ._lib import lib
-from .problems import POMDP, obs_bits
+from .problems import POMDP, obs_bits, obs_from_bits
 
 __all__ = [
     "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "FORollout", "FOValue", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
@@ -23,6 +23,7 @@ __all__ = [
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
+    "RolloutSimulator", "simulate", "test_solver", "create_json",
 ]
 
 
@@ -403,6 +404,12 @@ class POMCPPlanner:
                                           V.ctypes.data_as(C.c_void_p), self.nA), self._h)
         return nN.value, npart.value, N, V
 
+    def root_node(self):
+        """index of the current root in the dump_tree arrays"""
+        n = C.c_int64(0)
+        _check(lib().pomcp_root_node(self._h, C.byref(n)), self._h)
+        return n.value
+
     def dump_tree(self):
         n = C.c_int64(0)
         _check(lib().pomcp_dump_tree(self._h, 0, C.byref(n), None, None, None, None), self._h)
@@ -416,6 +423,20 @@ class POMCPPlanner:
                                      act_N.ctypes.data_as(C.c_void_p), act_V.ctypes.data_as(C.c_void_p),
                                      None if child is None else child.ctypes.data_as(C.c_void_p)), self._h)
         return node_N, act_N, act_V, child
+
+    def generate_sor(self, state, a, seed, step):
+        """generate_sor(pomdp, s, a, rng) on the device model -> (sp, o, r, terminal)."""
+        s = np.ascontiguousarray(np.array([state], dtype=self.problem.state_dtype))
+        sp = np.zeros(1, dtype=self.problem.state_dtype)
+        o, r, t = C.c_uint64(0), C.c_double(0.0), C.c_int32(0)
+        _check(lib().pomcp_generate_sor(self._h, s.ctypes.data_as(C.c_void_p), int(a), int(seed), int(step),
+                                        sp.ctypes.data_as(C.c_void_p), C.byref(o), C.byref(r), C.byref(t)), self._h)
+        return sp[0], obs_from_bits(self.problem, o.value), r.value, bool(t.value)
+
+    def initial_state(self, seed):
+        s = np.zeros(1, dtype=self.problem.state_dtype)
+        _check(lib().pomcp_initial_state(self._h, int(seed), s.ctypes.data_as(C.c_void_p)), self._h)
+        return s[0]
 
     def counters(self):
         c = abi.Counters()
@@ -616,3 +637,86 @@ def root_parallel_action(policy):
     """Root-parallel decision: every rank searches its own tree, root N / N*V are merged by one
     NCCL all-reduce inside pomcp_search_rootparallel (needs comm_init on every rank)."""
     return policy.search_rootparallel(policy.solver.tree_queries)[0]
+
+
+# ---------------------------------------------------------------- outer simulation loop (L4)
+class RolloutSimulator:
+    """POMDPToolbox.RolloutSimulator as the reference's tests and notebooks use it (test_solver,
+    notebooks/Basic_Usage.ipynb:88-103; loop body SURVEY.md App. B.1): runs one episode and returns the
+    discounted reward.  The environment steps with pomcp_generate_sor, i.e. the same model code as the
+    planner, on its own Philox stream `rng`."""
+
+    def __init__(self, rng=0, initial_state=None, eps=None, max_steps=None):
+        self.rng, self.initial_state, self.eps, self.max_steps = int(rng), initial_state, eps, max_steps
+        self.history = []  # (s, a, o, r) of the last episode
+
+
+def simulate(sim, pomdp, policy, up=None, initial_belief=None):
+    """simulate(sim::RolloutSimulator, pomdp, policy, updater, initial_belief) -> discounted reward."""
+    if policy.problem is not pomdp:
+        raise ValueError("the planner was solved for another problem instance")
+    up = up if up is not None else updater(policy)
+    dist = initial_belief if initial_belief is not None else initial_state_distribution(pomdp)
+    s = sim.initial_state if sim.initial_state is not None else policy.initial_state(sim.rng)
+    b = initialize_belief(up, dist)
+    eps = 0.0 if sim.eps is None else sim.eps
+    max_steps = 2 ** 62 if sim.max_steps is None else sim.max_steps
+    disc, total, step, terminal = 1.0, 0.0, 1, False
+    sim.history = []
+    while disc > eps and not terminal and step <= max_steps:
+        a = action(policy, b)
+        sp, o, r, terminal = policy.generate_sor(s, a, sim.rng, step)
+        sim.history.append((s, a, o, r))
+        total += disc * r
+        s = sp
+        if not terminal and step < max_steps:
+            b = update(up, b, a, o)
+        disc *= pomdp.discount
+        step += 1
+    return total
+
+
+def test_solver(solver, pomdp, max_steps=10, updater=None, rng=0):
+    """POMDPToolbox.test_solver: solve, run a short episode, return its reward."""
+    policy = solve(solver, pomdp)
+    try:
+        up = updater(policy) if callable(updater) else updater
+        return simulate(RolloutSimulator(rng=rng, max_steps=max_steps), pomdp, policy, up)
+    finally:
+        policy.close()
+
+
+test_solver.__test__ = False  # not a pytest test
+
+
+def create_json(policy):
+    """create_json(POMCPTreeVisualizer(node)) (src/visualization.jl:12-72): the tree under the planner's root
+    as the {id: {id, type, children_ids, tag, tt_tag, N[, V]}} dictionary MCTS.jl's D3 widget reads,
+    serialised to JSON; returns (json, root_id) like the reference."""
+    import json
+    node_N, act_N, act_V, child = policy.dump_tree()
+    if child is None:
+        raise NotImplementedError("tree export needs discrete observations")
+    nd = {}
+
+    def push_belief(n, label, parent):
+        i = len(nd) + 1
+        if parent:
+            nd[parent]["children_ids"].append(i)
+        nd[i] = {"id": i, "type": "belief", "children_ids": [], "tag": str(label), "tt_tag": str(label),
+                 "N": int(node_N[n])}
+        if act_N[n].sum() == 0 and node_N[n] == 0:
+            return
+        for a in range(act_N.shape[1]):
+            j = len(nd) + 1
+            nd[i]["children_ids"].append(j)
+            nd[j] = {"id": j, "type": "action", "children_ids": [], "tag": str(a), "tt_tag": str(a),
+                     "N": int(act_N[n, a]), "V": float(act_V[n, a])}
+            for o in range(child.shape[2]):
+                if child[n, a, o] >= 0:
+                    push_belief(int(child[n, a, o]), o, j)
+
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 10000))
+    push_belief(policy.root_node(), "root", 0)
+    return json.dumps(nd), 1

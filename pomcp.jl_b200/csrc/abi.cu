@@ -1209,6 +1209,56 @@ int32_t pomcp_pf_weights(pomcp_handle* h, const void* states, int64_t n, int32_t
   return POMCP_OK;
 }
 
+// generate_sor / initial state for the outer simulation loop (the L4 simulator of SURVEY.md §3.5 runs the
+// real environment with the same model code as the planner).
+int32_t pomcp_generate_sor(pomcp_handle* h, const void* state, int32_t a, uint64_t seed, uint32_t step,
+                           void* next_state, uint64_t* obs_bits, double* reward, int32_t* terminal) {
+  if (!h || !state || !next_state || a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad generate_sor arguments");
+  cudaSetDevice(h->device);
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, 512);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_tmp, state, (size_t)h->state_bytes, cudaMemcpyHostToDevice, h->stream));
+  char host[64];
+  DISPATCH_PID(h->prob.problem_id, {
+    EnvStep<PID>* d_out = (EnvStep<PID>*)((char*)h->d_tmp + 256);
+    k_generate_sor<PID><<<1, 32, 0, h->stream>>>(h->dm, (const typename ModelT<PID>::State*)h->d_tmp, a, (uint32_t)seed,
+                                                 (uint32_t)(seed >> 32), step, d_out);
+    rc = launch_check(h, "k_generate_sor");
+    if (rc) return rc;
+    static_assert(sizeof(EnvStep<PID>) <= sizeof(host), "EnvStep too large");
+    CK(cudaMemcpyAsync(host, d_out, sizeof(EnvStep<PID>), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const EnvStep<PID>* e = (const EnvStep<PID>*)host;
+    std::memcpy(next_state, &e->sp, (size_t)h->state_bytes);
+    if (obs_bits) *obs_bits = e->obs;
+    if (reward) *reward = e->r;
+    if (terminal) *terminal = e->terminal;
+  });
+  return POMCP_OK;
+}
+
+int32_t pomcp_root_node(pomcp_handle* h, int64_t* node_id) {
+  if (!h || !node_id) return POMCP_ERR_INVALID_ARG;
+  *node_id = (int64_t)h->root;
+  return POMCP_OK;
+}
+
+int32_t pomcp_initial_state(pomcp_handle* h, uint64_t seed, void* state_out) {
+  if (!h || !state_out) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  int rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, 512);
+  if (rc) return rc;
+  DISPATCH_PID(h->prob.problem_id, {
+    k_initial_state<PID><<<1, 32, 0, h->stream>>>(h->dm, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                  (typename ModelT<PID>::State*)h->d_tmp);
+  });
+  rc = launch_check(h, "k_initial_state");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(state_out, h->d_tmp, (size_t)h->state_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
+}
+
 int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap, int64_t* n_nodes, int64_t* node_N, int64_t* act_N, double* act_V,
                         int32_t* child) {
   if (!h || !n_nodes) return POMCP_ERR_INVALID_ARG;

@@ -618,6 +618,34 @@ __global__ void k_init_particles(const __grid_constant__ DevModel m, typename Mo
   out[i] = ModelT<PID>::initial(m, u01(p.w[0]), u01(p.w[1]));
 }
 
+// generate_sor for the outer simulation loop (POMDPs.generate_sor): one environment
+// step of the problem model, drawn from the Philox stream (seed; counter (0, TAG_ENV, step)).
+template <int PID>
+struct EnvStep {
+  typename ModelT<PID>::State sp;
+  unsigned long long obs;
+  double r;
+  int terminal;
+};
+template <int PID>
+__global__ void k_generate_sor(const __grid_constant__ DevModel m, const typename ModelT<PID>::State* s_in, int a,
+                               uint32_t k0, uint32_t k1, uint32_t step, EnvStep<PID>* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  using M = ModelT<PID>;
+  Philox4 p = philox4x32_10(0u, TAG_ENV, step, 0u, k0, k1);
+  uint64_t o;
+  M::template step<true, double>(m, s_in[0], a, u01(p.w[0]), u01(p.w[2]), u01(p.w[3]), out->sp, o, out->r);
+  out->obs = o;
+  out->terminal = M::terminal(m, out->sp) ? 1 : 0;
+}
+template <int PID>
+__global__ void k_initial_state(const __grid_constant__ DevModel m, uint32_t k0, uint32_t k1,
+                                typename ModelT<PID>::State* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Philox4 p = philox4x32_10(1u, TAG_ENV, 0u, 0u, k0, k1);
+  out[0] = ModelT<PID>::initial(m, u01(p.w[0]), u01(p.w[1]));
+}
+
 // pomcp_pf_weights parity hook
 template <int PID>
 __global__ void k_pf_weights(const __grid_constant__ ModelSrc<PID> src, long long n, double* w_out,

@@ -14,7 +14,7 @@
 
 namespace pomcp {
 
-enum : uint32_t { TAG_ROOT = 0, TAG_TREE = 1, TAG_ROLLOUT = 2, TAG_PF = 3, TAG_RESAMPLE = 4, TAG_INIT = 5 };
+enum : uint32_t { TAG_ROOT = 0, TAG_TREE = 1, TAG_ROLLOUT = 2, TAG_PF = 3, TAG_RESAMPLE = 4, TAG_INIT = 5, TAG_ENV = 6 };
 
 struct Philox4 {
   uint32_t w[4];

@@ -52,12 +52,14 @@ def main():
     base = int(data[0][0], 16)
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     agg, inst, st = collections.Counter(), collections.Counter(), collections.defaultdict(collections.Counter)
+    tinst = collections.Counter()
     for r in data:
         off = int(r[0], 16) - base
         loc = sass.get(off, (None, None))[1]
         n = int(r[ix["# Samples"]])
         agg[loc] += n
         inst[loc] += int(r[ix["Instructions Executed"]])
+        tinst[loc] += int(r[ix["Thread Instructions Executed"]])
         for s in stalls:
             st[loc][s] += int(r[ix[s]])
     tot = sum(agg.values())
@@ -69,7 +71,8 @@ def main():
         f, l = loc if loc else ("?", 0)
         text = src[f][l - 1].strip()[:88] if f in src and 0 < l <= len(src[f]) else ""
         top = ", ".join(f"{k[6:]}:{v * 100 // max(n, 1)}%" for k, v in st[loc].most_common(2))
-        print(f"{f}:{l}".ljust(20), f"{n * 100 / tot:5.1f}%", str(inst[loc]).rjust(12), top.ljust(36), text)
+        lanes = tinst[loc] / max(inst[loc], 1)
+        print(f"{f}:{l}".ljust(20), f"{n * 100 / tot:5.1f}%", str(inst[loc]).rjust(12), f"{lanes:5.1f}", top.ljust(36), text)
     byfile = collections.Counter()
     for loc, n in agg.items():
         byfile[loc[0] if loc else "?"] += n

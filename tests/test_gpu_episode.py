@@ -1,0 +1,85 @@
+"""GPU tests of the outer simulation loop: RolloutSimulator + simulate +
+test_solver on the device model (pomcp_generate_sor), the reference's own smoke tests
+(test/runtests.jl:13-31) re-expressed, and the create_json tree export (src/visualization.jl:12-72)."""
+import json
+
+import numpy as np
+import pytest
+
+import pomcp_jl_b200 as pj
+
+pytestmark = pytest.mark.gpu
+
+
+def test_generate_sor_matches_oracle_model(oracle, gpu_lib):
+    """The environment step uses the same model code as the planner: with the same uniforms it equals the
+    oracle's model_step for every problem."""
+    for pomdp in (pj.TigerPOMDP(), pj.BabyPOMDP(-5.0, -10.0), pj.RockSamplePOMDP(4, 4, seed=44), pj.LightDark1D()):
+        pl = pj.solve(pj.POMCPSolver(tree_queries=10), pomdp)
+        s = pl.initial_state(seed=3)
+        for step in range(1, 30):
+            a = step % pomdp.n_actions
+            w = pj.philox4x32_10((0, 6, step, 0), (77, 0))
+            sp, o, r, term = pl.generate_sor(s, a, 77, step)
+            sp_o, o_bits, r_o = oracle.model_step(pomdp, s, a, ut=(w[0] * 2.0 ** -32, 0.0),
+                                                  uo=(w[2] * 2.0 ** -32, w[3] * 2.0 ** -32))
+            assert np.array([sp]).tobytes() == np.array([sp_o]).tobytes() and r == r_o
+            assert pj.obs_bits(o) == o_bits
+            if term:
+                break
+            s = sp
+        pl.close()
+
+
+def test_reference_smoke_tests(gpu_lib):
+    """test/runtests.jl:13-31: the three POMCPSolver smoke tests run an episode without error."""
+    for est in (pj.RolloutEstimator(pj.FeedWhenCrying()), None, pj.FORollout(pj.FeedWhenCrying())):
+        kw = {} if est is None else {"estimate_value": est, "eps": 0.01, "c": 10.0, "tree_queries": 50, "rng": 2}
+        solver = pj.POMCPSolver(**kw)
+        r = pj.test_solver(solver, pj.BabyPOMDP(-5.0, -10.0))
+        assert np.isfinite(r) and -150.0 <= r <= 0.0
+    # particle depletion contract (test/runtests.jl:35-41)
+    solver = pj.POMCPSolver(estimate_value=pj.RolloutEstimator(pj.FeedWhenCrying()), eps=0.01, c=10.0, tree_queries=5, rng=2)
+    with pytest.raises(pj.ParticleDepletion):
+        pj.test_solver(solver, pj.BabyPOMDP(-5.0, -10.0), max_steps=100)
+
+
+def test_simulate_with_sir_updater_and_rocksample(gpu_lib):
+    """simulate() with an external SIR updater (test/runtests.jl:57 pattern) on LightDark1D, and a full
+    RockSample(7,8) episode with the unweighted updater: rewards are finite, histories consistent."""
+    ld = pj.LightDark1D()
+    policy = pj.solve(pj.POMCPSolver(tree_queries=2000, c=10.0, rng=4), ld, belief_mode=pj._abi.BELIEF_EXTERNAL)
+    rng = np.random.default_rng(0)
+    parts = np.zeros(500, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, 500)
+    sim = pj.RolloutSimulator(rng=5, max_steps=15)
+    r = pj.simulate(sim, ld, policy, pj.SIRParticleFilter(policy, 500, rng=1), pj.ParticleCollection(parts))
+    assert np.isfinite(r) and len(sim.history) >= 1
+    policy.close()
+    rs = pj.RockSamplePOMDP(7, 8, seed=7008)
+    policy = pj.solve(pj.POMCPSolver(tree_queries=20000, c=20.0, rng=6,
+                                     node_belief_updater=pj.SIRReinvigorator(2000, rng=3)), rs)
+    sim = pj.RolloutSimulator(rng=11, max_steps=40)
+    r = pj.simulate(sim, rs, policy)
+    assert np.isfinite(r) and r >= -10.0
+    assert abs(sum(0.95 ** t * h[3] for t, h in enumerate(sim.history)) - r) < 1e-9
+    policy.close()
+
+
+def test_create_json_tree_export(gpu_lib):
+    """create_json: ids are 1..n in depth-first order, children_ids are consistent, N(h) = [expanded] + sum N(ha)."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    policy = pj.solve(pj.POMCPSolver(tree_queries=200, c=10.0, rng=1, search_mode="exact"), baby)
+    b = pj.initialize_belief(pj.updater(policy), pj.initial_state_distribution(baby))
+    pj.action(policy, b)
+    js, root_id = pj.create_json(policy)
+    nd = {int(k): v for k, v in json.loads(js).items()}
+    assert root_id == 1 and nd[1]["type"] == "belief" and nd[1]["N"] == 200
+    assert sorted(nd) == list(range(1, len(nd) + 1))
+    for i, n in nd.items():
+        assert all(c in nd and c > i for c in n["children_ids"])
+        if n["type"] == "belief" and n["children_ids"]:
+            assert n["N"] == 1 + sum(nd[c]["N"] for c in n["children_ids"])
+        if n["type"] == "action":
+            assert n["N"] == sum(nd[c]["N"] for c in n["children_ids"])
+    policy.close()
