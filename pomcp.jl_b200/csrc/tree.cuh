@@ -888,11 +888,23 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   State sp_l;
   uint64_t o_l;
   double r_l;
+  // One Philox block feeds several levels (batched mode keeps its own stream map: block = level / LV):
+  // RockSample needs one word per level (the sensor draw), the other models two.
+  constexpr int TW = (PID == POMCP_ROCKSAMPLE) ? 1 : 2, LV = 4 / TW;
+  Philox4 ptb;
   auto spec_step = [&](int d) {
-    const Philox4 pt = philox4x32_10((uint32_t)d, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    if (d % LV == 0) ptb = philox4x32_10((uint32_t)(d / LV), TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    const int k = d % LV;
+    uint32_t w0 = ptb.w[0], w1 = ptb.w[1];
+    if (TW == 1) {
+      w0 = k == 0 ? ptb.w[0] : k == 1 ? ptb.w[1] : k == 2 ? ptb.w[2] : ptb.w[3];
+    } else if (k == 1) {
+      w0 = ptb.w[2];
+      w1 = ptb.w[3];
+    }
     const int a_l = lane < nA ? lane : nA - 1;
-    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, pt.w[2], sp_l, o_l, r_l);
-    else M::template step<true, double>(m, s, a_l, u01(pt.w[0]), u01(pt.w[2]), u01(pt.w[3]), sp_l, o_l, r_l);
+    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, w0, sp_l, o_l, r_l);
+    else M::template step<true, double>(m, s, a_l, u01(w0), M::T_DRAW ? u01(w1) : u01(w0), u01(w1), sp_l, o_l, r_l);
   };
   spec_step(0);
   for (;;) {
