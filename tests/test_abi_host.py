@@ -122,3 +122,30 @@ def test_missing_library_fails_loudly(tmp_path):
             % (ROOT, str(tmp_path / "nope.so")))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert "MISSING True" in out.stdout, out.stdout + out.stderr
+
+
+def _build_c_client(tmp_path):
+    exe = str(tmp_path / "abi_smoke")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-std=c11", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "abi_smoke.c"), "-o", exe, "-L" + os.path.join(ROOT, "pomcp.jl_b200"),
+           "-lpomcp_b200", "-Wl,-rpath," + os.path.join(ROOT, "pomcp.jl_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_client_links(gpu_lib, tmp_path):
+    """include/pomcp_b200.h compiles as C11 and examples/abi_smoke.c (no Python, no torch) links against the
+    shared library: the boundary is a C ABI."""
+    exe = _build_c_client(tmp_path)
+    if not os.path.exists("/dev/nvidiactl"):
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device (there is no CPU fallback)" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_runs_a_decision_and_an_update(gpu_lib, tmp_path):
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi smoke ok" in r.stdout
