@@ -23,7 +23,10 @@ __all__ = [
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
-    "RolloutSimulator", "simulate", "test_solver", "create_json",
+    "RolloutSimulator", "simulate", "test_solver", "create_json", "ObsNode", "ActNode", "AbstractActNode",
+    "POMCPTreeVisualizer", "AbstractPOMCPSolver", "POMCPDPWSolver", "RandomActionGenerator", "PORollout",
+    "PORolloutEstimator", "create_policy", "create_belief", "init_V", "init_N", "sparse_actions", "next_action", "add_N",
+    "convert_estimator", "extract_belief", "estimate_value",
 ]
 
 
@@ -81,6 +84,10 @@ def _check(rc, h=None, belief=None):
     if rc == abi.ERR_NAN_VALUE:
         raise AssertionError("!isnan(best_V)")
     raise POMCPError(rc, msg)
+
+
+class AbstractPOMCPSolver:
+    """abstract AbstractPOMCPSolver <: POMDPs.Solver (src/POMCP.jl:73)."""
 
 
 # ---------------------------------------------------------------- solver pieces
@@ -165,7 +172,7 @@ class DefaultReinvigoratorStub:
     """src/particle_filter.jl:83; replaced by DeadReinvigorator in solve() (src/solver.jl:6-10)."""
 
 
-class POMCPSolver:
+class POMCPSolver(AbstractPOMCPSolver):
     """Keyword constructor with the reference defaults (src/constructor.jl:8-18; fields documented
     at src/POMCP.jl:75-136).  `rng` is an integer seed (Philox key) instead of an AbstractRNG.
     Device-only keywords: search_mode ("batched"|"exact"), inflight_min, inflight_max, inflight_ramp_div, rollouts_per_leaf,
@@ -199,7 +206,7 @@ class POMCPSolver:
         sp.init_V, sp.init_N = float(self.init_V), int(self.init_N)
         sp.num_sparse_actions = int(self.num_sparse_actions)
         ev = self.estimate_value
-        if isinstance(ev, RolloutEstimator) and isinstance(ev.solver, RandomSolver):
+        if isinstance(ev, RolloutEstimator) and isinstance(ev.solver, RandomSolver):  # includes PORollout
             sp.estimator = abi.EST_RANDOM_ROLLOUT
         elif isinstance(ev, RolloutEstimator) and isinstance(ev.solver, FeedWhenCrying):
             sp.estimator = abi.EST_FWC_ROLLOUT  # test/runtests.jl:13-19, notebooks/Display_Tree.ipynb:31-39
@@ -247,36 +254,121 @@ def initial_state_distribution(pomdp):
     return InitialStateDistribution(pomdp)
 
 
-class BeliefNode:
-    """Handle to a belief node of the device tree (src/tree.jl:14-26).  It is both the belief and
-    the search root (src/updater.jl:20-26); only the planner's current root is addressable."""
+class AbstractActNode:
+    """abstract AbstractActNode (src/tree.jl:1-5)."""
 
-    def __init__(self, planner, generation, B=None):
+
+class ActNode(AbstractActNode):
+    """View of an action node of the device tree (src/tree.jl:7-12): label, N, V, children[o] -> ObsNode."""
+
+    def __init__(self, parent, a, N, V):
+        self._parent, self.label, self.N, self.V = parent, int(a), int(N), float(V)
+
+    @property
+    def children(self):
+        return _ObsChildren(self._parent, self.label)
+
+    def __iter__(self):  # the (N, V) pair earlier versions of this mirror returned
+        return iter((self.N, self.V))
+
+    def __repr__(self):
+        return f"ActNode(label={self.label}, N={self.N}, V={self.V:.6g})"
+
+
+class _ObsChildren:
+    """children::Dict{O,ObsNode} of an ActNode, looked up on the device (pomcp_get_node_stats)."""
+
+    def __init__(self, parent, a):
+        self._parent, self._a = parent, a
+
+    def _node(self, o):
+        return ObsNode(self._parent.planner, self._parent.generation, history=self._parent._history + [(self._a, o)],
+                       label=o)
+
+    def __contains__(self, o):
+        return self._node(o)._exists()
+
+    def __getitem__(self, o):
+        n = self._node(o)
+        if not n._exists():
+            raise KeyError(o)
+        return n
+
+    def get(self, o, default=None):
+        n = self._node(o)
+        return n if n._exists() else default
+
+    def keys(self):
+        pomdp = self._parent.planner.problem
+        if pomdp.continuous_obs:
+            raise NotImplementedError("children of continuous observations cannot be enumerated through the ABI")
+        return [o for o in range(pomdp.n_observations) if o in self]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def values(self):
+        return [self[o] for o in self.keys()]
+
+    def items(self):
+        return [(o, self[o]) for o in self.keys()]
+
+
+class BeliefNode:
+    """Handle to a belief node of the device tree (src/tree.jl:14-26): the planner's current root (it is
+    both the belief and the search root, src/updater.jl:20-26) or, through `children`, any node below it.
+    `N`, `children[a] -> ActNode`, `children[a].children[o] -> ObsNode` read the device tree through
+    pomcp_get_node_stats, so the tree can be walked like the reference's."""
+
+    def __init__(self, planner, generation, B=None, history=None, label=None):
         self.planner, self.generation, self.B = planner, generation, B
+        self._history = list(history or [])
+        self.label = label
 
     def _live(self):
         if self.generation != self.planner._generation:
             raise ValueError("stale BeliefNode: the planner's tree has been re-rooted since")
 
+    def _stats(self):
+        self._live()
+        return self.planner.node_stats(self._history)
+
+    def _exists(self):
+        return self._stats()[0] >= 0
+
     @property
     def N(self):
-        self._live()
-        return self.planner.root_stats()[0]
+        return self._stats()[0]
 
     @property
     def children(self):
-        """{action: (N, V)} of the root's ActNodes."""
-        self._live()
-        _, N, V = self.planner.root_stats()
-        return {a: (int(N[a]), float(V[a])) for a in range(len(N))}
+        """{action: ActNode} (all actions are expanded together, src/solver.jl:87-94)."""
+        _, _, N, V = self._stats()
+        return {a: ActNode(self, a, N[a], V[a]) for a in range(len(N))}
 
     def particles(self):
         self._live()
+        if self._history:
+            raise NotImplementedError("only the root's particle collection is materialised (pomcp_get_belief_particles)")
         return self.planner.belief_particles()
 
 
 class RootNode(BeliefNode):
     pass
+
+
+class ObsNode(BeliefNode):
+    pass
+
+
+class POMCPTreeVisualizer:
+    """POMCPTreeVisualizer(node) (src/visualization.jl:4-6); create_json(visualizer) exports the tree."""
+
+    def __init__(self, node):
+        self.node = node
 
 
 # ---------------------------------------------------------------- planner
@@ -514,6 +606,8 @@ def nccl_unique_id() -> bytes:
 # ---------------------------------------------------------------- POMDPs.jl verbs
 def solve(solver, pomdp, belief_mode=abi.BELIEF_UNWEIGHTED):
     """solve(solver, pomdp) -> POMCPPlanner (src/solver.jl:30-32)."""
+    if not isinstance(solver, POMCPSolver):
+        raise NotImplementedError(f"{type(solver).__name__} has no device path (POMCPDPWSolver: SURVEY.md §8f rank 3)")
     return POMCPPlanner(solver, pomdp, belief_mode)
 
 
@@ -690,6 +784,14 @@ test_solver.__test__ = False  # not a pytest test
 
 
 def create_json(policy):
+    if isinstance(policy, POMCPTreeVisualizer):
+        policy = policy.node.planner
+    elif isinstance(policy, BeliefNode):
+        policy = policy.planner
+    return _create_json(policy)
+
+
+def _create_json(policy):
     """create_json(POMCPTreeVisualizer(node)) (src/visualization.jl:12-72): the tree under the planner's root
     as the {id: {id, type, children_ids, tag, tt_tag, N[, V]}} dictionary MCTS.jl's D3 widget reads,
     serialised to JSON; returns (json, root_id) like the reference."""
@@ -720,3 +822,92 @@ def create_json(policy):
     sys.setrecursionlimit(max(sys.getrecursionlimit(), 10000))
     push_belief(policy.root_node(), "root", 0)
     return json.dumps(nd), 1
+
+
+# ---------------------------------------------------------------- remaining exported names (src/POMCP.jl:20-67)
+class POMCPDPWSolver(AbstractPOMCPSolver):
+    """POMCPDPWSolver (src/POMCP.jl:154-253, src/solver.jl:161-274): double progressive widening.  Out of scope
+    of the device path this round; constructing it records the parameters, solving
+    raises."""
+
+    def __init__(self, **kw):
+        self.params = kw
+
+
+class RandomActionGenerator:
+    """MCTS.RandomActionGenerator (next_action for the DPW solver, src/actions.jl:38-40)."""
+
+    def __init__(self, rng=0):
+        self.rng = rng
+
+
+class PORollout(RolloutEstimator):
+    """PORollout(solver, updater) (src/rollout.jl:12-16,48-51): partially observable rollout with an explicit
+    rollout updater.  On device the updater is implied by the policy (VoidUpdater for RandomSolver, the
+    previous-observation updater for FeedWhenCrying)."""
+
+    def __init__(self, solver=None, updater=None):
+        super().__init__(solver)
+        self.updater = updater
+
+
+PORolloutEstimator = PORollout  # deprecated alias, src/rollout.jl:17
+
+
+def create_policy(solver, pomdp):
+    """create_policy(solver, pomdp) (src/solver.jl:5-14)."""
+    return solve(solver, pomdp)
+
+
+def create_belief(up):
+    """create_belief(updater::RootUpdater) = RootNode(0, nothing, {}) (src/updater.jl:42-43)."""
+    return initialize_belief(up, initial_state_distribution(up.planner.problem))
+
+
+def init_V(initializer, problem=None, h=None, action=None):
+    """init_V(n::Number, ...) = Float64(n); callbacks are host functions (src/tree.jl:33-35)."""
+    return float(initializer(problem, h, action)) if callable(initializer) else float(initializer)
+
+
+def init_N(initializer, problem=None, h=None, action=None):
+    """init_N(n::Number, ...) = Int(n) (src/tree.jl:42-44)."""
+    return int(initializer(problem, h, action)) if callable(initializer) else int(initializer)
+
+
+def sparse_actions(pomcp, pomdp, h=None, num_actions=0):
+    """sparse_actions (src/actions.jl:10-33): the whole action space when num_actions <= 0 (the only branch
+    the device path implements)."""
+    if num_actions > 0:
+        raise NotImplementedError("random action sub-sampling (src/actions.jl:15-29) is not supported on device")
+    return list(range(pomdp.n_actions))
+
+
+def next_action(gen, pomdp, b=None, h=None):
+    """next_action(gen::RandomActionGenerator, ...) = rand(rng, actions(mdp, b)) (src/actions.jl:38-40)."""
+    rng = np.random.default_rng(gen.rng) if not isinstance(gen.rng, np.random.Generator) else gen.rng
+    return int(rng.integers(0, pomdp.n_actions))
+
+
+def add_N(a, b):
+    """add_N (src/solver.jl:287-288)."""
+    return (a if isinstance(a, int) else a.N) + b.N
+
+
+def convert_estimator(ev, solver, pomdp):
+    """convert_estimator (src/rollout.jl:41-61): on device the estimator is resolved to a kind code."""
+    s = POMCPSolver(estimate_value=ev)
+    return s.c_params(abi.BELIEF_UNWEIGHTED).estimator
+
+
+def extract_belief(rollout_updater, node):
+    """extract_belief (src/rollout.jl:101-108): nothing for a VoidUpdater, the node's label for the
+    previous-observation updater."""
+    return None if rollout_updater is None else node.label
+
+
+def estimate_value(estimator, pomdp, start_state, h=None, steps=0):
+    """estimate_value(n::Number, ...) = Float64(n) (src/rollout.jl:10); rollout estimators run inside the search
+    kernels (pomcp_rollout_batch evaluates them for given start states)."""
+    if isinstance(estimator, (int, float)):
+        return float(estimator)
+    raise NotImplementedError("rollout estimators are evaluated on the device (POMCPPlanner.rollout_batch)")

@@ -83,3 +83,37 @@ def test_create_json_tree_export(gpu_lib):
         if n["type"] == "action":
             assert n["N"] == sum(nd[c]["N"] for c in n["children_ids"])
     policy.close()
+
+
+def test_tree_navigation_like_the_reference(oracle, gpu_lib):
+    """b.children[a].children[o] walks the device tree like the reference's node objects (src/tree.jl:7-26; the
+    notebooks' `delete!(b.children[a].children, o)` idiom reads the same fields): N(h) = 1 + sum_a N(ha),
+    N(ha) = sum_o N(hao), and the values equal the oracle's for the same history (exact mode)."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    solver = pj.POMCPSolver(tree_queries=500, c=10.0, rng=3, search_mode="exact")
+    policy = pj.solve(solver, baby)
+    b = pj.initialize_belief(pj.updater(policy), pj.initial_state_distribution(baby))
+    a = pj.action(policy, b)
+    op = oracle.OraclePlanner(baby, solver.c_params(pj._abi.BELIEF_UNWEIGHTED))
+    op.set_belief_initial()
+    assert op.search(500)[1] == a
+    assert isinstance(b, pj.RootNode) and b.N == 500 and set(b.children) == {0, 1}
+    assert b.N == 1 + sum(n.N for n in b.children.values())
+    for act, an in b.children.items():
+        assert isinstance(an, pj.ActNode) and an.label == act
+        assert an.N == sum(c.N for c in an.children.values())
+        for o, hao in an.children.items():
+            assert isinstance(hao, pj.ObsNode) and hao.label == o
+            nN, npart, N_o, V_o = op.node_stats([(act, o)])
+            assert hao.N == nN
+            for a2, an2 in hao.children.items():
+                assert an2.N == N_o[a2] and an2.V == V_o[a2]
+    assert 5 not in b.children[0].children and b.children[0].children.get(5) is None
+    pj.update(pj.updater(policy), b, a, 0)
+    with pytest.raises(ValueError):
+        b.N  # stale after the re-root, like a dropped Julia reference
+    assert pj.convert_estimator(pj.PORollout(pj.RandomSolver(), None), solver, baby) == pj._abi.EST_RANDOM_ROLLOUT
+    assert pj.sparse_actions(policy, baby) == [0, 1] and pj.init_V(3, baby) == 3.0 and pj.init_N(2.0, baby) == 2
+    with pytest.raises(NotImplementedError):
+        pj.solve(pj.POMCPDPWSolver(tree_queries=100), baby)
+    policy.close()
