@@ -45,6 +45,15 @@ def _worker(rank, world, uid_path, out_dir, queries):
     a, N, V = pl.search_rootparallel(queries)
     rootN, ownN, ownV = pl.root_stats()
     np.save(os.path.join(out_dir, f"r{rank}.npy"), np.concatenate([[a, rootN], N, V, ownN, ownV]))
+    # belief update on every rank's own tree: the merged action and the real observation are
+    # the same everywhere; a rank whose tree lacks the child rebuilds its belief with the device-side
+    # reinvigorator instead of depleting, so the second decision merges complete searches again.
+    o = 0 if a >= 5 else 2
+    outcome = pl.update_reinvigorated(int(a), o, seed=500 + rank, n_min=4096)
+    n_bel = len(pl.belief_particles())
+    a2, N2, V2 = pl.search_rootparallel(queries)
+    rootN2, ownN2, _ = pl.root_stats()
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), np.concatenate([[a2, outcome, n_bel, rootN2], N2, V2, ownN2]))
     pl.close()
 
 
@@ -71,3 +80,11 @@ def test_rootparallel_nccl_merge(tmp_path):
         if v[i] >= v[best]:
             best = i
     assert int(r[0][0]) == best
+    # second decision after the per-rank belief update
+    s2 = [np.load(tmp_path / f"s{k}.npy") for k in range(world)]
+    assert s2[0][0] == s2[1][0] and np.array_equal(s2[0][4:4 + 2 * nA], s2[1][4:4 + 2 * nA])
+    for x in s2:
+        assert x[1] in (0, 1, 2) and x[2] >= 4096 or x[1] == 0
+        own = x[4 + 2 * nA:4 + 3 * nA]
+        assert own.sum() >= queries - 1  # tree reuse: the re-rooted child keeps its counts
+    assert np.array_equal(s2[0][4:4 + nA], s2[0][4 + 2 * nA:] + s2[1][4 + 2 * nA:])
