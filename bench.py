@@ -380,7 +380,7 @@ def run_gpu(args):
                 "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
                         "keep the tree no more than that many simulations stale",
             },
-            "solver": {"inflight_max": policy._sp.inflight_max or 1024, "inflight_ramp_div": policy._sp.inflight_ramp_div
+            "solver": {"inflight_max": policy._sp.inflight_max or "8 per SM (1184)", "inflight_ramp_div": policy._sp.inflight_ramp_div
                        or 32, "rollouts_per_leaf": policy._sp.rollouts_per_leaf or 64, "search_mode": "batched"},
             "rollouts_per_sec": cs["rollouts"] * n_gpus / (total_ms_max * 1e-3),
             "phase_ms_per_step": {"search": statistics.mean(search_ms), "worker_kernel": statistics.mean(rollout_ms),
