@@ -264,7 +264,11 @@ def run_gpu(args):
     sampler = ClockSampler(device)
     if rank == 0:
         sampler.start()
+    nodes_per_search = None
     for k in range(args.warmup):
+        if k == args.warmup - 1:  # untimed: how many belief nodes one decision allocates
+            decide()
+            nodes_per_search = policy.counters()["nodes"]
         resident_step(k)
     policy.reset_counters()
     barrier()
@@ -376,6 +380,12 @@ def run_gpu(args):
                 "frac": (steps_rank0 / roll_s) / (148 * 4 * 32 * sm_max * 1e6 / prof["rollout_thread_inst_per_step"])
                 if (prof.get("rollout_thread_inst_per_step") and roll_s > 0) else None,
                 "warp_efficiency": prof.get("rollout_warp_efficiency"),
+                "tree": {"avg_descent_depth": cs["tree_steps"] / max(cs["simulations"], 1),
+                         "nodes_per_sec": nodes_per_search / (statistics.mean(rollout_ms) * 1e-3)
+                         if (rollout_ms and nodes_per_search) else None,
+                         "rollout_steps_per_sim": cs["rollout_steps"] / max(cs["simulations"], 1),
+                         "dram_bytes_per_sim": (prof["workers_dram_bytes_per_launch"] / TREE_QUERIES)
+                         if prof.get("workers_dram_bytes_per_launch") else None},
                 "issue_active_pct": prof.get("workers_issue_active_pct"),
                 "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
                         "keep the tree no more than that many simulations stale",

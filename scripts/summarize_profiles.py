@@ -98,6 +98,10 @@ def main():
                 consts["workers_issue_active_pct"] = g("smsp__issue_active.avg.pct_of_peak_sustained_active")
                 consts["rollout_warp_efficiency"] = g("smsp__thread_inst_executed_per_inst_executed.ratio") / 32.0
                 consts["workers_thread_inst_per_launch"] = ti
+                sc = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                consts["workers_dram_bytes_per_launch"] = (
+                    g("dram__bytes_read.sum") * sc.get(units[hdr.index("dram__bytes_read.sum")], 1) +
+                    g("dram__bytes_write.sum") * sc.get(units[hdr.index("dram__bytes_write.sum")], 1))
                 if steps_per_decision:
                     consts["rollout_thread_inst_per_step"] = ti / steps_per_decision
                     consts["rollout_steps_per_profiled_launch"] = steps_per_decision
