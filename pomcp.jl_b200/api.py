@@ -606,8 +606,10 @@ def nccl_unique_id() -> bytes:
 # ---------------------------------------------------------------- POMDPs.jl verbs
 def solve(solver, pomdp, belief_mode=abi.BELIEF_UNWEIGHTED):
     """solve(solver, pomdp) -> POMCPPlanner (src/solver.jl:30-32)."""
+    if isinstance(solver, POMCPDPWSolver):
+        solver = solver.as_pomcp(pomdp)
     if not isinstance(solver, POMCPSolver):
-        raise NotImplementedError(f"{type(solver).__name__} has no device path (POMCPDPWSolver: SURVEY.md §8f rank 3)")
+        raise NotImplementedError(f"{type(solver).__name__} has no device path")
     return POMCPPlanner(solver, pomdp, belief_mode)
 
 
@@ -826,12 +828,32 @@ def _create_json(policy):
 
 # ---------------------------------------------------------------- remaining exported names (src/POMCP.jl:20-67)
 class POMCPDPWSolver(AbstractPOMCPSolver):
-    """POMCPDPWSolver (src/POMCP.jl:154-253, src/solver.jl:161-274): double progressive widening.  Out of scope
-    of the device path this round; constructing it records the parameters, solving
-    raises."""
+    """POMCPDPWSolver (src/POMCP.jl:154-253, src/constructor.jl:40-73, src/solver.jl:161-274): double progressive
+    widening.  The widening kernels are not built yet.  One configuration needs none:
+    with `enable_action_pw=false` every action is expanded at once (src/solver.jl:187-203), and on a problem
+    whose observation space has at most `k_observation` elements the test `length(children) <=
+    k_observation * N^alpha_observation` (src/solver.jl:223) is always true, so every step generates its
+    observation: the algorithm is POMCPSolver's, and solve() runs it on the POMCP kernels
+    (test/runtests.jl:49-54).  Everything else raises NotImplementedError."""
 
-    def __init__(self, **kw):
-        self.params = kw
+    def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0, node_belief_updater=None,
+                 estimate_value=None, enable_action_pw=True, alpha_observation=0.5, k_observation=10.0,
+                 alpha_action=0.5, k_action=10.0, init_V=0.0, init_N=0, next_action=None, default_action=None, **device_kw):
+        self.enable_action_pw = enable_action_pw
+        self.alpha_observation, self.k_observation = alpha_observation, k_observation
+        self.alpha_action, self.k_action = alpha_action, k_action
+        self.next_action = next_action
+        self._pomcp_kw = dict(eps=eps, max_depth=max_depth, c=c, tree_queries=tree_queries, rng=rng,
+                              node_belief_updater=node_belief_updater, estimate_value=estimate_value, init_V=init_V,
+                              init_N=init_N, default_action=default_action, **device_kw)
+
+    def as_pomcp(self, pomdp):
+        if self.enable_action_pw:
+            raise NotImplementedError("POMCPDPWSolver with action widening has no device path yet (SURVEY.md §8f rank 3)")
+        if pomdp.continuous_obs or pomdp.n_observations > self.k_observation or self.alpha_observation < 0:
+            raise NotImplementedError("POMCPDPWSolver observation widening has no device path yet: it would be active "
+                                      "on this problem (SURVEY.md §8f rank 3)")
+        return POMCPSolver(**self._pomcp_kw)
 
 
 class RandomActionGenerator:

@@ -115,5 +115,18 @@ def test_tree_navigation_like_the_reference(oracle, gpu_lib):
     assert pj.convert_estimator(pj.PORollout(pj.RandomSolver(), None), solver, baby) == pj._abi.EST_RANDOM_ROLLOUT
     assert pj.sparse_actions(policy, baby) == [0, 1] and pj.init_V(3, baby) == 3.0 and pj.init_N(2.0, baby) == 2
     with pytest.raises(NotImplementedError):
-        pj.solve(pj.POMCPDPWSolver(tree_queries=100), baby)
+        pj.solve(pj.POMCPDPWSolver(tree_queries=100), baby)  # action widening: no device path yet
+    with pytest.raises(NotImplementedError):
+        pj.solve(pj.POMCPDPWSolver(tree_queries=100, enable_action_pw=False), pj.LightDark1D())  # obs widening active
     policy.close()
+    # test/runtests.jl:49-54: DPW without action widening on Baby never widens (2 observations <= k_observation),
+    # i.e. it is POMCP: same tree as POMCPSolver with the same parameters
+    dpw = pj.POMCPDPWSolver(tree_queries=100, eps=0.01, c=10.0, enable_action_pw=False, rng=2, search_mode="exact")
+    r = pj.test_solver(dpw, baby)
+    assert np.isfinite(r)
+    p1, p2 = pj.solve(dpw, baby), pj.solve(pj.POMCPSolver(tree_queries=100, eps=0.01, c=10.0, rng=2, search_mode="exact"), baby)
+    for p_ in (p1, p2):
+        p_.set_belief_initial()
+    r1, r2 = p1.search(100), p2.search(100)
+    assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+    p1.close(); p2.close()
