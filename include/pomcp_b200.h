@@ -126,7 +126,14 @@ typedef struct pomcp_solver_params {
   int32_t rollouts_per_leaf; /* R rollouts averaged per leaf evaluation (0 = default: 1 exact, 64 batched).  Batched: 1..128, a
                               * worker is a team of ceil(R/32) warps that roll out together; exact: 1..64 on one warp */
   int32_t rank;              /* root-parallel rank, mixed into the Philox counter */
-  int32_t _pad1;
+  /* ---- observation progressive widening of POMCPDPWSolver with enable_action_pw = false
+   * (src/solver.jl:161-274, fields src/POMCP.jl:233-253, defaults src/constructor.jl:40-73).  At an action
+   * node a new observation is generated while #children <= k_observation * N^alpha_observation
+   * (src/solver.jl:223); otherwise one of the earlier generated (child, state) pairs is re-used, chosen with
+   * probability proportional to the child's N (src/solver.jl:249-255).  Device path: continuous observations. */
+  int32_t dpw_observation;   /* 0 = POMCPSolver (default) */
+  double k_observation;      /* 10.0 */
+  double alpha_observation;  /* 0.5 */
 } pomcp_solver_params;
 
 typedef struct pomcp_counters {

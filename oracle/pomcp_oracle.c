@@ -478,6 +478,8 @@ struct orc_planner {
   int32_t* child; /* discrete: [slot*nO + o] */
   /* continuous observations: open-addressed (slot, obs) -> node */
   int64_t ht_cap, ht_used; int32_t* ht;
+  /* DPW observation widening: per action node the generated (child, state) pairs in generation order */
+  int64_t* ev_n; int64_t* ev_cap; int64_t** ev_node; ostate** ev_state; int64_t* act_nc;
   /* particle log: linked per node, in push order */
   int64_t n_log, cap_log; ostate* log_state; int64_t* log_next;
   /* root */
@@ -506,6 +508,11 @@ static void grow_nodes(orc_planner* pl, int64_t need) {
   GROW(pl->node_parent_slot, int64_t, nc); GROW(pl->node_obs, uint64_t, nc);
   GROW(pl->act_N, int64_t, nc * pl->nA); GROW(pl->act_V, double, nc * pl->nA);
   if (pl->nO > 0) GROW(pl->child, int32_t, nc * pl->nA * pl->nO);
+  if (pl->sp.dpw_observation) {
+    GROW(pl->ev_n, int64_t, nc * pl->nA); GROW(pl->ev_cap, int64_t, nc * pl->nA); GROW(pl->act_nc, int64_t, nc * pl->nA);
+    GROW(pl->ev_node, int64_t*, nc * pl->nA); GROW(pl->ev_state, ostate*, nc * pl->nA);
+    for (int64_t k = pl->cap_nodes * pl->nA; k < nc * pl->nA; ++k) { pl->ev_n[k] = pl->ev_cap[k] = pl->act_nc[k] = 0; pl->ev_node[k] = NULL; pl->ev_state[k] = NULL; }
+  }
   pl->cap_nodes = nc;
 }
 
@@ -579,6 +586,11 @@ static void push_particle(orc_planner* pl, int64_t node, ostate s) {
 }
 
 static void free_tree(orc_planner* pl) {
+  if (pl->ev_node) {
+    for (int64_t k = 0; k < pl->cap_nodes * pl->nA; ++k) { free(pl->ev_node[k]); free(pl->ev_state[k]); }
+    free(pl->ev_n); free(pl->ev_cap); free(pl->ev_node); free(pl->ev_state); free(pl->act_nc);
+    pl->ev_n = pl->ev_cap = pl->act_nc = NULL; pl->ev_node = NULL; pl->ev_state = NULL;
+  }
   free(pl->node_N); free(pl->node_expanded); free(pl->node_phead); free(pl->node_ptail); free(pl->node_pcount);
   free(pl->node_parent_slot); free(pl->node_obs); free(pl->act_N); free(pl->act_V); free(pl->child); free(pl->ht);
   free(pl->log_state); free(pl->log_next);
@@ -600,6 +612,7 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   pl->sp = *sp;
   if (sp->num_sparse_actions > 0 || !(sp->eps > 0.0) || !(sp->eps < 1.0)) { free(pl); return NULL; }
   if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 64) { free(pl); return NULL; }
+  if (sp->dpw_observation && (!(sp->k_observation >= 0.0) || !(sp->alpha_observation >= 0.0))) { free(pl); return NULL; }
   if ((sp->estimator == POMCP_EST_FWC_ROLLOUT || sp->estimator == POMCP_EST_FO_FWC_ROLLOUT) &&
       p->problem_id != POMCP_BABY) { free(pl); return NULL; }
   if (sp->estimator == POMCP_EST_STATE_VALUE && p->problem_id == POMCP_LIGHTDARK1D) { free(pl); return NULL; }
@@ -786,7 +799,7 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
       int64_t nN = pl->act_N[h * pl->nA + a];
       double nV = pl->act_V[h * pl->nA + a];
       double crit;
-      if (nN == 0 && hN == 1) crit = nV;
+      if (nN == 0 && (sol->dpw_observation ? hN <= 1 : hN == 1)) crit = nV; /* src/solver.jl:112 / :210 */
       else if (nN == 0 && nV == -INFINITY) crit = INFINITY;
       else crit = nV + sol->c * sqrt(orc_det_log((double)hN) / (double)nN);
       if (crit >= best) { best = crit; best_a = a; }
@@ -799,9 +812,40 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
     model_step(m, s, best_a, u[0], u[2], u[3], 1, &sp, &o, &r);
     pl->ctr.tree_steps++;
     int64_t slot = h * pl->nA + best_a;
-    int64_t hao = find_child(pl, slot, o);
-    if (hao < 0) hao = insert_child(pl, slot, o); /* src/solver.jl:132-142 */
-    pl->path_slot[depth] = slot; pl->path_node[depth] = hao; pl->path_r[depth] = r; pl->path_sp[depth] = sp;
+    int64_t hao;
+    int generated = 1;
+    if (sol->dpw_observation) {
+      /* src/solver.jl:223: length(best_node.children) <= k_observation * best_node.N^alpha_observation */
+      int64_t bn = pl->act_N[slot];
+      double lim = bn <= 0 ? 0.0
+                 : sol->alpha_observation == 0.5 ? sol->k_observation * sqrt((double)bn)
+                 : sol->k_observation * orc_det_exp(sol->alpha_observation * orc_det_log((double)bn));
+      generated = (double)pl->act_nc[slot] <= lim;
+    }
+    if (generated) {
+      hao = find_child(pl, slot, o);
+      if (hao < 0) { hao = insert_child(pl, slot, o); if (sol->dpw_observation) pl->act_nc[slot]++; } /* src/solver.jl:132-142 */
+      if (sol->dpw_observation) {
+        /* state_was_generated: push!(hao.B, sp); hao.N += 1 BEFORE the recursive call (src/solver.jl:257-262) */
+        if (pl->ev_n[slot] == pl->ev_cap[slot]) {
+          int64_t ncap = pl->ev_cap[slot] ? pl->ev_cap[slot] * 2 : 4;
+          pl->ev_node[slot] = (int64_t*)realloc(pl->ev_node[slot], sizeof(int64_t) * (size_t)ncap);
+          pl->ev_state[slot] = (ostate*)realloc(pl->ev_state[slot], sizeof(ostate) * (size_t)ncap);
+          pl->ev_cap[slot] = ncap;
+        }
+        pl->ev_node[slot][pl->ev_n[slot]] = hao; pl->ev_state[slot][pl->ev_n[slot]] = sp; pl->ev_n[slot]++;
+        if (sol->belief_mode == POMCP_BELIEF_UNWEIGHTED) push_particle(pl, hao, sp);
+        pl->node_N[hao] += 1;
+      }
+    } else {
+      /* src/solver.jl:249-255: hao ~ children weighted by N, sp ~ hao.B, r = reward(s, a, sp).  Every generation
+       * event added one to its child's N and one state to its B, so a uniform draw over the events of this
+       * action node is that joint distribution. */
+      int64_t e = (int64_t)(u[1] * (double)pl->ev_n[slot]); /* word 1 of the level's block: unused by every model */
+      hao = pl->ev_node[slot][e];
+      sp = pl->ev_state[slot][e]; /* r of model_step above is reward(s, a, .): it does not depend on sp in these models */
+    }
+    pl->path_slot[depth] = slot; pl->path_node[depth] = generated ? hao : -hao - 1; pl->path_r[depth] = r; pl->path_sp[depth] = sp;
     h = hao; s = sp; ++depth;
   }
   if (depth > pl->ctr.max_depth_seen) pl->ctr.max_depth_seen = depth;
@@ -810,8 +854,10 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
   for (int64_t d = depth - 1; d >= 0; --d) {
     R = pl->path_r[d] + gamma * R;
     int64_t hao = pl->path_node[d], slot = pl->path_slot[d];
-    if (sol->belief_mode == POMCP_BELIEF_UNWEIGHTED) push_particle(pl, hao, pl->path_sp[d]);
-    pl->node_N[hao] += 1;
+    if (!sol->dpw_observation) { /* DPW did both before descending, and only for generated states */
+      if (sol->belief_mode == POMCP_BELIEF_UNWEIGHTED) push_particle(pl, hao, pl->path_sp[d]);
+      pl->node_N[hao] += 1;
+    }
     pl->act_N[slot] += 1;
     if (pl->act_V[slot] != -INFINITY) pl->act_V[slot] += (R - pl->act_V[slot]) / (double)pl->act_N[slot];
   }

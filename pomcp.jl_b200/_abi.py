@@ -59,7 +59,8 @@ class SolverParams(C.Structure):
         ("belief_mode", C.c_int32), ("search_mode", C.c_int32),
         ("max_nodes", C.c_int64), ("max_log", C.c_int64),
         ("inflight_min", C.c_int32), ("inflight_max", C.c_int32), ("inflight_ramp_div", C.c_int32),
-        ("rollouts_per_leaf", C.c_int32), ("rank", C.c_int32), ("_pad1", C.c_int32),
+        ("rollouts_per_leaf", C.c_int32), ("rank", C.c_int32), ("dpw_observation", C.c_int32),
+        ("k_observation", C.c_double), ("alpha_observation", C.c_double),
     ]
 
 

@@ -182,7 +182,7 @@ class POMCPSolver(AbstractPOMCPSolver):
                  node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
                  default_action=None, search_mode="batched", inflight_min=0, inflight_max=0, inflight_ramp_div=0, rollouts_per_leaf=0,
                  max_nodes=0,
-                 max_log=0, device=0, rank=0):
+                 max_log=0, device=0, rank=0, dpw_observation=None):
         self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
         self.rng = rng
         self.node_belief_updater = node_belief_updater if node_belief_updater is not None \
@@ -194,6 +194,7 @@ class POMCPSolver(AbstractPOMCPSolver):
         self.inflight_min, self.inflight_max, self.inflight_ramp_div = inflight_min, inflight_max, inflight_ramp_div
         self.rollouts_per_leaf = rollouts_per_leaf
         self.max_nodes, self.max_log, self.device, self.rank = max_nodes, max_log, device, rank
+        self.dpw_observation = dpw_observation  # (k_observation, alpha_observation) of POMCPDPWSolver, or None
 
     def c_params(self, belief_mode):
         sp = abi.SolverParams()
@@ -229,6 +230,9 @@ class POMCPSolver(AbstractPOMCPSolver):
         sp.inflight_min, sp.inflight_max = self.inflight_min, self.inflight_max
         sp.inflight_ramp_div, sp.rollouts_per_leaf = self.inflight_ramp_div, self.rollouts_per_leaf
         sp.rank = self.rank
+        if self.dpw_observation is not None:
+            sp.dpw_observation = 1
+            sp.k_observation, sp.alpha_observation = float(self.dpw_observation[0]), float(self.dpw_observation[1])
         return sp
 
 
@@ -608,6 +612,8 @@ def solve(solver, pomdp, belief_mode=abi.BELIEF_UNWEIGHTED):
     """solve(solver, pomdp) -> POMCPPlanner (src/solver.jl:30-32)."""
     if isinstance(solver, POMCPDPWSolver):
         solver = solver.as_pomcp(pomdp)
+        if solver.dpw_observation is not None:
+            belief_mode = abi.BELIEF_EXTERNAL  # continuous observations never re-root (SURVEY.md H4)
     if not isinstance(solver, POMCPSolver):
         raise NotImplementedError(f"{type(solver).__name__} has no device path")
     return POMCPPlanner(solver, pomdp, belief_mode)
@@ -834,7 +840,9 @@ class POMCPDPWSolver(AbstractPOMCPSolver):
     whose observation space has at most `k_observation` elements the test `length(children) <=
     k_observation * N^alpha_observation` (src/solver.jl:223) is always true, so every step generates its
     observation: the algorithm is POMCPSolver's, and solve() runs it on the POMCP kernels
-    (test/runtests.jl:49-54).  Everything else raises NotImplementedError."""
+    (test/runtests.jl:49-54).  With continuous observations (LightDark1D, test/runtests.jl:57) the observation
+    widening runs on the device (`dpw_observation`); it needs an external belief updater, as in the
+    reference's test.  Action widening raises NotImplementedError."""
 
     def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0, node_belief_updater=None,
                  estimate_value=None, enable_action_pw=True, alpha_observation=0.5, k_observation=10.0,
@@ -850,10 +858,12 @@ class POMCPDPWSolver(AbstractPOMCPSolver):
     def as_pomcp(self, pomdp):
         if self.enable_action_pw:
             raise NotImplementedError("POMCPDPWSolver with action widening has no device path yet (SURVEY.md §8f rank 3)")
-        if pomdp.continuous_obs or pomdp.n_observations > self.k_observation or self.alpha_observation < 0:
-            raise NotImplementedError("POMCPDPWSolver observation widening has no device path yet: it would be active "
-                                      "on this problem (SURVEY.md §8f rank 3)")
-        return POMCPSolver(**self._pomcp_kw)
+        if not pomdp.continuous_obs:
+            if pomdp.n_observations > self.k_observation:
+                raise NotImplementedError("observation widening on a discrete observation space larger than "
+                                          "k_observation has no device path yet")
+            return POMCPSolver(**self._pomcp_kw)  # never widens: it is POMCPSolver
+        return POMCPSolver(dpw_observation=(self.k_observation, self.alpha_observation), **self._pomcp_kw)
 
 
 class RandomActionGenerator:

@@ -97,7 +97,7 @@ struct pomcp_handle {
   double log_ratio = 0;
   double* d_gpow = nullptr;
   Pool pool{};
-  size_t ht_entries = 0;
+  size_t ht_entries = 0, ev_entries = 0;
   PathBuf pb{};
   int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32;
   void* d_bel[2] = {nullptr, nullptr};
@@ -220,6 +220,7 @@ int fresh_root(pomcp_handle* h) {
   int rc = pool_fill(h, std::min<unsigned long long>(h->nodes_used, h->pool.max_nodes));
   if (rc) return rc;
   if (h->hashed) CK(cudaMemsetAsync(h->pool.ht, 0, h->ht_entries * sizeof(uint32_t), h->stream));
+  if (h->pool.ev_key) CK(cudaMemsetAsync(h->pool.ev_key, 0, h->ev_entries * sizeof(unsigned long long), h->stream));
   DevCtr z{};
   z.node_count = 1;
   // keep cumulative counters: only the allocation cursors restart
@@ -259,6 +260,9 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.n_bel = h->n_bel;
   c.root = h->root;
   c.root_N0 = (uint32_t)h->root_visits;
+  c.dpw = h->sp.dpw_observation ? 1 : 0;
+  c.k_obs = h->sp.k_observation;
+  c.alpha_obs = h->sp.alpha_observation;
   c.rollouts = h->rollouts;
   c.team_warps = h->exact ? 1 : (h->rollouts > 64 ? 4 : (h->rollouts + 31) / 32);
   c.inflight_min = h->inflight_min;
@@ -585,6 +589,9 @@ void pomcp_default_solver_params(pomcp_solver_params* o) {  // src/constructor.j
   o->estimator = POMCP_EST_RANDOM_ROLLOUT;
   o->belief_mode = POMCP_BELIEF_UNWEIGHTED;
   o->search_mode = POMCP_MODE_BATCHED;
+  o->dpw_observation = 0;
+  o->k_observation = 10.0;  /* src/constructor.jl:48-49 */
+  o->alpha_observation = 0.5;
 }
 
 void pomcp_default_problem(int32_t pid, pomcp_problem* p) {
@@ -613,7 +620,8 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  void* ptrs[] = {h->d_eta, h->d_eta_thr, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
+  void* ptrs[] = {h->pool.act_nc, h->pool.act_ng, h->pool.ev_key, h->pool.ev_node, h->pool.ev_state,
+                  h->d_eta, h->d_eta_thr, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
@@ -649,6 +657,13 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     return fail(nullptr, POMCP_ERR_UNSUPPORTED,
                 "estimator (FeedWhenCrying rollouts exist for BabyPOMDP only, state-value tables for discrete states only)");
   if (sp->init_N < 0 || sp->max_depth < 0) return fail(nullptr, POMCP_ERR_INVALID_ARG, "init_N/max_depth < 0");
+  if (sp->dpw_observation) {
+    if (nO != 0 || sp->belief_mode != POMCP_BELIEF_EXTERNAL)
+      return fail(nullptr, POMCP_ERR_UNSUPPORTED,
+                  "observation widening runs on continuous-observation problems with an external belief updater");
+    if (!(sp->k_observation >= 0.0) || !(sp->alpha_observation >= 0.0))
+      return fail(nullptr, POMCP_ERR_INVALID_ARG, "k_observation / alpha_observation < 0");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, POMCP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
@@ -755,7 +770,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   size_t free_b = 0, total_b = 0;
   CKU(cudaMemGetInfo(&free_b, &total_b));
   long long Q = std::max<long long>(sp->tree_queries, 1);
-  size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4);
+  size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4) +
+                    (sp->dpw_observation ? (size_t)nA * 8 + 32 * (12 + (size_t)sb) : 0);
   // unweighted mode keeps the tree across decisions (re-rooting, no compaction yet): room for ~64 of them
   long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) + 65536;
   long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
@@ -777,6 +793,18 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     CKC(dev_alloc(h, &P.ht, e));
     CKC(dev_alloc(h, &P.node_obs, (size_t)want));
     CKU(cudaMemset(P.ht, 0, e * sizeof(uint32_t)));
+    if (sp->dpw_observation) {
+      // one event per generated tree step: room for 8 per node (POOL_EXHAUSTED beyond)
+      size_t ev = 1;
+      while (ev < (size_t)want * 16) ev <<= 1;
+      h->ev_entries = ev;
+      P.ev_mask = ev - 1;
+      CKC(dev_alloc(h, &P.act_nc, (size_t)want * nA));
+      CKC(dev_alloc(h, &P.act_ng, (size_t)want * nA));
+      CKC(dev_alloc(h, &P.ev_key, ev));
+      CKC(dev_alloc(h, &P.ev_node, ev));
+      CKU(cudaMalloc(&P.ev_state, ev * (size_t)sb));
+    }
   } else {
     CKC(dev_alloc(h, &P.child, (size_t)want * nA * nO));
   }

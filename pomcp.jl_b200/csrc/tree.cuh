@@ -45,6 +45,14 @@ struct Pool {
   unsigned long long* node_obs;
   uint32_t* log_node;
   void* log_state;
+  // observation progressive widening (POMCPDPWSolver, continuous observations): children / generation events of
+  // an action node, and the (slot, event) -> (child, state) table the widened step draws from
+  uint32_t* act_nc;
+  uint32_t* act_ng;
+  unsigned long long* ev_key;
+  uint32_t* ev_node;
+  void* ev_state;
+  unsigned long long ev_mask;
   DevCtr* ctr;
   unsigned long long ht_mask, log_cap;
   uint32_t max_nodes;
@@ -58,6 +66,8 @@ struct SearchCfg {
   long long n_state_values;
   int levels;          // first depth at which gamma^depth < eps (src/solver.jl:82), capped by max_depth
   int belief_unweighted, estimator;
+  int dpw;             // observation progressive widening on (src/solver.jl:223-262)
+  double k_obs, alpha_obs;
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
   int team_warps;      // batched mode: warps per worker; warp w runs rollouts 32 w .. 32 w + 31 of every leaf
   uint32_t key0, key1, rank, epoch;
@@ -106,6 +116,11 @@ struct SearchResult {
   long long ucur, rcur;
 };
 
+__device__ __forceinline__ unsigned long long ld_volatile_u64g(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
   return x;
@@ -437,6 +452,53 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
   }
 }
 
+// ---- observation progressive widening (src/solver.jl:223-262).  Every generated (child, state) pair of an
+// action node is an event e = 0, 1, ...; a widened step re-uses event floor(u * #events): the child with
+// probability N(child) / sum N and one of the states pushed into it, uniformly — what sample(os, WeightVec(N))
+// followed by rand(hao.B) draws.
+__device__ __forceinline__ bool dpw_generates(const SearchCfg& cfg, uint32_t act_n, uint32_t n_children) {
+  // length(best_node.children) <= k_observation * best_node.N^alpha_observation
+  const double lim = act_n == 0 ? 0.0
+                   : cfg.alpha_obs == 0.5 ? cfg.k_obs * sqrt((double)act_n)
+                   : cfg.k_obs * det_exp(cfg.alpha_obs * det_log((double)act_n));
+  return (double)n_children <= lim;
+}
+template <class State>
+__device__ __forceinline__ bool ev_insert(const Pool& P, uint32_t slot, uint32_t e, uint32_t node, const State& sp) {
+  const unsigned long long key = (((unsigned long long)slot << 32) | e) + 1ull;
+  unsigned long long h = mix64(key) & P.ev_mask;
+  for (unsigned probe = 0; probe < 4096; ++probe) {
+    const unsigned long long old = atomicCAS(&P.ev_key[h], 0ull, ~0ull);  // claim, fill, then publish the key
+    if (old == 0ull) {
+      P.ev_node[h] = node;
+      ((State*)P.ev_state)[h] = sp;
+      __threadfence();
+      atomicExch(&P.ev_key[h], key);
+      return true;
+    }
+    h = (h + 1) & P.ev_mask;
+  }
+  P.ctr->pool_overflow = 1;
+  return false;
+}
+template <class State>
+__device__ __forceinline__ bool ev_lookup(const Pool& P, uint32_t slot, uint32_t e, uint32_t& node, State& sp) {
+  const unsigned long long key = (((unsigned long long)slot << 32) | e) + 1ull;
+  unsigned long long h = mix64(key) & P.ev_mask;
+  for (unsigned probe = 0; probe < 4096; ++probe) {
+    const unsigned long long k = ld_volatile_u64g(&P.ev_key[h]);
+    if (k == key) {
+      __threadfence();
+      node = __ldcg(&P.ev_node[h]);
+      sp = ((const State*)P.ev_state)[h];
+      return true;
+    }
+    if (k == 0ull) return false;  // not (yet) published
+    h = (h + 1) & P.ev_mask;
+  }
+  return false;
+}
+
 // read-only lookup used by update / inspection
 template <int PID>
 __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m, uint32_t slot, uint64_t obs) {
@@ -457,6 +519,14 @@ __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m,
 
 __device__ __forceinline__ uint32_t baby_state(uint32_t s) { return s; }
 __device__ __forceinline__ uint32_t baby_state(const LDState&) { return 0u; }  // never called for LightDark
+
+__device__ __forceinline__ uint32_t shfl_state(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ LDState shfl_state(const LDState& v, int src) {
+  LDState o;
+  o.status = __shfl_sync(0xffffffffu, v.status, src);
+  o.y = __shfl_sync(0xffffffffu, v.y, src);
+  return o;
+}
 
 // fixed-shape butterfly sum over the warp: the oracle adds in the same binary tree
 __device__ __forceinline__ double warp_tree_sum(double x) {
@@ -593,7 +663,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       }
       if (!EXACT) v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
       uint32_t hn = EXACT ? hN : (hN < 1u ? 1u : hN);
-      if (n == 0 && hn == 1) crit = v;
+      if (n == 0 && (cfg.dpw ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
       else if (n == 0 && v == -INFINITY) crit = INFINITY;
       else crit = v + cfg.c * sqrt(det_log((double)hn) / (double)n);
       valid = (crit == crit);
@@ -628,7 +698,43 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       pre = __shfl_sync(0xffffffffu, mine, best_a);
     }
     uint32_t hao = 0, ticket = 0;
-    if (lane == 0) {
+    if (M::HASHED && cfg.dpw) {
+      // POMCPDPWSolver, enable_action_pw = false (exact mode only reaches here sequentially)
+      int reuse = 0;
+      if (lane == 0) {
+        const uint32_t bn = __ldcg(&P.act_N[slot]);  // best_node.N before this visit
+        const uint32_t nc = __ldcg(&P.act_nc[slot]), ng = __ldcg(&P.act_ng[slot]);
+        P.act_N[slot] = bn + 1u;
+        if (dpw_generates(cfg, bn, nc)) {
+          bool created_ = false;
+          hao = find_or_insert_child<PID>(P, m, slot, o, created_);
+          if (hao != 0) {
+            if (created_) P.act_nc[slot] = nc + 1u;
+            P.act_ng[slot] = ng + 1u;
+            if (!ev_insert<State>(P, slot, ng, hao, sp)) hao = 0;
+          }
+          if (hao != 0) {
+            ticket = __ldcg(&P.node_N[hao]) + 1u;  // hao.N += 1 before the recursive call (src/solver.jl:257-262)
+            P.node_N[hao] = ticket;
+          }
+        } else {
+          const uint32_t e = (uint32_t)(u[1] * (double)ng);  // word 1 of the level's block: unused by every model
+          reuse = 1;
+          if (!ev_lookup<State>(P, slot, e, hao, sp)) hao = 0;
+          if (hao != 0) ticket = __ldcg(&P.node_N[hao]);
+        }
+        if (hao != 0) {
+          fl = __ldcg(&P.node_flags[hao]);
+          size_t pi = (size_t)depth * pb.stride + slot_idx;
+          pb.path_slot[pi] = slot;
+          pb.path_node[pi] = hao;
+          pb.path_r[pi] = r;
+          path_state[pi] = sp;
+        }
+      }
+      reuse = __shfl_sync(0xffffffffu, reuse, 0);
+      if (reuse) sp = shfl_state(sp, 0);
+    } else if (lane == 0) {
       if (EXACT) P.act_N[slot] = __ldcg(&P.act_N[slot]) + 1u; else atomicAdd(&P.act_N[slot], 1u);
       bool created_;
       hao = pre ? pre : find_or_insert_child<PID>(P, m, slot, o, created_);
@@ -770,14 +876,6 @@ __device__ __forceinline__ void rs_tree_step(const DevModel& m, const RsTab* tb,
   sp = (st & ~0xffu) | (uint32_t)x | ((uint32_t)y << 4);
 }
 
-__device__ __forceinline__ uint32_t shfl_state(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ LDState shfl_state(const LDState& v, int src) {
-  LDState o;
-  o.status = __shfl_sync(0xffffffffu, v.status, src);
-  o.y = __shfl_sync(0xffffffffu, v.y, src);
-  return o;
-}
-
 template <class State>
 struct PathView {
   uint32_t* slot;
@@ -802,8 +900,9 @@ struct ActStats {
   uint32_t n, mm;
   double w;
   uint32_t kid[K];
-  __device__ __forceinline__ void load(const Pool& P, uint32_t h, int nA, int lane) {
-    n = 0; mm = 0; w = 0.0;
+  uint32_t nc, ng;  // observation widening (hashed models): children / generation events of the action node
+  __device__ __forceinline__ void load(const Pool& P, uint32_t h, int nA, int lane, bool dpw = false) {
+    n = 0; mm = 0; w = 0.0; nc = 0; ng = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) kid[k] = 0;
     if (lane < nA) {
@@ -811,6 +910,10 @@ struct ActStats {
       n = __ldcg(&P.act_N[sl]);
       w = __ldcg(&P.act_V[sl]);
       mm = __ldcg(&P.act_M[sl]);
+      if (ModelT<PID>::HASHED && dpw) {
+        nc = __ldcg(&P.act_nc[sl]);
+        ng = __ldcg(&P.act_ng[sl]);
+      }
       if (!ModelT<PID>::HASHED) {
 #pragma unroll
         for (int k = 0; k < ModelT<PID>::NO; ++k) kid[k] = __ldcg(&P.child[(size_t)sl * ModelT<PID>::NO + k]);
@@ -860,7 +963,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   uint32_t h = cfg.root;
   uint32_t hN = cfg.root_N0 + q;
   ActStats<PID> st;
-  st.load(P, h, nA, lane);
+  st.load(P, h, nA, lane, cfg.dpw != 0);
   uint32_t fl = 0;
   if (lane == 0) fl = __ldcg(&P.node_flags[h]);
   __syncwarp();
@@ -892,9 +995,11 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   // RockSample needs one word per level (the sensor draw), the other models two.
   constexpr int TW = (PID == POMCP_ROCKSAMPLE) ? 1 : 2, LV = 4 / TW;
   Philox4 ptb;
+  const bool dpw = M::HASHED && cfg.dpw;  // observation widening: one block per level (word 2 draws the event)
   auto spec_step = [&](int d) {
-    if (d % LV == 0) ptb = philox4x32_10((uint32_t)(d / LV), TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
-    const int k = d % LV;
+    if (dpw || d % LV == 0)
+      ptb = philox4x32_10((uint32_t)(dpw ? d : d / LV), TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+    const int k = dpw ? 0 : d % LV;
     uint32_t w0 = ptb.w[0], w1 = ptb.w[1];
     if (TW == 1) {
       w0 = k == 0 ? ptb.w[0] : k == 1 ? ptb.w[1] : k == 2 ? ptb.w[2] : ptb.w[3];
@@ -924,7 +1029,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       const float v = (st.mm > 0 && v_finite) ? (float)st.w * sfu_rcp((float)st.mm) : initV_f;
       const uint32_t hn = hN < 1u ? 1u : hN;
       float crit;
-      if (st.n == 0 && hn == 1) crit = v;
+      if (st.n == 0 && (dpw ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
       else if (st.n == 0 && v == -INFINITY) crit = INFINITY;
       else crit = v + c_f * sfu_sqrt(sfu_lg2((float)hn) * 0.69314718f * sfu_rcp((float)st.n));
       key = (crit == crit) ? f2ord(crit) : 0u;
@@ -942,9 +1047,30 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o_l == (uint64_t)k) ? st.kid[k] : mine;
     }
     uint32_t raw = __shfl_sync(0xffffffffu, mine, best_a);
-    const State sp = shfl_state(sp_l, best_a);
+    State sp = shfl_state(sp_l, best_a);
     const uint64_t o = __shfl_sync(0xffffffffu, o_l, best_a);
     const double r = __shfl_sync(0xffffffffu, r_l, best_a);
+    // observation progressive widening (src/solver.jl:223-262): re-use an earlier generated (child, state)
+    bool reuse = false;
+    if (dpw) {
+      const uint32_t bn = __shfl_sync(0xffffffffu, st.n, best_a);
+      const uint32_t nc = __shfl_sync(0xffffffffu, st.nc, best_a), ng = __shfl_sync(0xffffffffu, st.ng, best_a);
+      if (ng > 0 && !dpw_generates(cfg, bn, nc)) {
+        uint32_t node = 0;
+        State spe = sp;
+        int ok = 0;
+        if (lane == 0) {
+          const uint32_t e = __umulhi(ptb.w[2], ng);  // floor(u * #events)
+          ok = ev_lookup<State>(P, slot, e, node, spe) ? 1 : 0;  // a miss = the event is still being published
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (ok) {
+          reuse = true;
+          raw = __shfl_sync(0xffffffffu, node, 0);
+          sp = shfl_state(spe, 0);  // r = reward(s, a, sp) does not depend on sp in these models
+        }
+      }
+    }
     const bool cut_next = depth + 1 >= cfg.levels || M::terminal(m, sp);
 
     // src/solver.jl:132-142
@@ -971,7 +1097,11 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
     if (lane == 0) {
       atomicAdd(&P.act_N[slot], 1u);
-      atomicAdd(&P.node_N[hao], 1u);
+      if (!reuse) atomicAdd(&P.node_N[hao], 1u);  // hao.N counts generated arrivals only under widening
+      if (dpw && !reuse) {
+        if (created) atomicAdd(&P.act_nc[slot], 1u);
+        ev_insert<State>(P, slot, atomicAdd(&P.act_ng[slot], 1u), hao, sp);
+      }
       if (i_expand_child) {
         atomicOr(&P.node_flags[hao], 1u);  // nobody waits for it
       } else {
@@ -998,7 +1128,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       want_rollout = true;
       break;
     }
-    if (!try_claim) st.load(P, hao, nA, lane);
+    if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0);
     if (!cut_next) spec_step(depth);
     hN = __shfl_sync(0xffffffffu, seen, 0);
     fl = __shfl_sync(0xffffffffu, nfl, 0);
@@ -1007,7 +1137,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         want_rollout = true;
         break;
       }
-      st.load(P, hao, nA, lane);  // somebody else got there first (rare): descend through it
+      st.load(P, hao, nA, lane, cfg.dpw != 0);  // somebody else got there first (rare): descend through it
       fl = 1u;
     }
   }
@@ -1314,6 +1444,7 @@ __global__ void k_pool_fill(const __grid_constant__ Pool P, int nA, int nO, unsi
     P.act_N[k] = init_N;
     P.act_M[k] = init_N;
     P.act_V[k] = v0;
+    if (P.act_nc) { P.act_nc[k] = 0; P.act_ng[k] = 0; }
   }
   for (unsigned long long k = i; k < n_nodes; k += stride) {
     P.node_N[k] = 0;

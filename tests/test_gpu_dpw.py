@@ -1,0 +1,86 @@
+"""GPU tests of the observation progressive widening of POMCPDPWSolver (enable_action_pw = false) on continuous
+observations (src/solver.jl:161-274, test/runtests.jl:49-57): exact mode equals the
+oracle bit for bit, batched mode keeps the counting invariants and deepens the tree."""
+import numpy as np
+import pytest
+
+import pomcp_jl_b200 as pj
+from pomcp_jl_b200 import _abi as abi
+
+from helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.asarray(a, dtype=np.float64).view(np.uint64)
+
+
+@pytest.mark.parametrize("k,alpha,R", [(10.0, 0.5, 1), (2.0, 0.4, 1), (1.0, 0.25, 4), (3.0, 0.0, 1), (0.0, 0.5, 2)])
+def test_dpw_exact_bit_exact(oracle, gpu_lib, k, alpha, R):
+    ld = pj.LightDark1D()
+    rng = np.random.default_rng(5)
+    parts = np.zeros(3000, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, 3000)
+    for seed in (1, 2):
+        gp, op = make_pair(oracle, ld, 10.0, seed=seed, mode="exact", belief_mode=abi.BELIEF_EXTERNAL, tree_queries=2500,
+                           rollouts_per_leaf=R, dpw_observation=(k, alpha))
+        gp.set_belief_particles(parts)
+        op.set_belief_particles(parts)
+        for Q in (2500, 800):  # second search continues on the same tree
+            a_g, N_g, V_g = gp.search(Q)
+            rc, a_o, N_o, V_o = op.search(Q)
+            assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o), (N_g, N_o)
+            assert np.array_equal(_bits(V_g), _bits(V_o)), (V_g, V_o)
+            cg, co = gp.counters(), op.counters()
+            for key in ("simulations", "rollouts", "rollout_steps", "tree_steps", "nodes", "max_depth_seen"):
+                assert cg[key] == co[key], (key, cg[key], co[key])
+        gp.close()
+
+
+def test_dpw_batched_deepens_the_tree(oracle, gpu_lib):
+    ld = pj.LightDark1D()
+    rng = np.random.default_rng(6)
+    parts = np.zeros(20000, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, 20000)
+    Q = 100000
+    plain = pj.solve(pj.POMCPSolver(c=10.0, rng=4, tree_queries=Q), ld, belief_mode=abi.BELIEF_EXTERNAL)
+    plain.set_belief_particles(parts)
+    plain.search(Q)
+    assert plain.counters()["max_depth_seen"] == 1  # Float64 observations never repeat
+    plain.close()
+    acts, vals = [], []
+    for seed in range(3):
+        solver = pj.POMCPSolver(c=10.0, rng=4 + seed, tree_queries=Q, dpw_observation=(4.0, 0.4))
+        gp = pj.solve(solver, ld, belief_mode=abi.BELIEF_EXTERNAL)
+        gp.set_belief_particles(parts)
+        a, N, V = gp.search(Q)
+        cs = gp.counters()
+        assert gp.root_stats()[0] == Q and N.sum() == Q - 1 and cs["simulations"] == Q
+        assert cs["max_depth_seen"] >= 3 and cs["nodes"] < Q and cs["tree_steps"] > 2 * Q and np.isfinite(V).all()
+        acts.append(a); vals.append(V[a])
+        gp.close()
+        sp = solver.c_params(abi.BELIEF_EXTERNAL)
+        sp.search_mode, sp.rollouts_per_leaf = abi.MODE_EXACT, 1
+        op = oracle.OraclePlanner(ld, sp)
+        op.set_belief_particles(parts)
+        rc, a_o, N_o, V_o = op.search(Q)
+        assert rc == 0
+        # the chosen action's value agrees with the sequential oracle within 10% of the reward scale (10)
+        assert abs(V[a] - V_o[a_o]) < 1.0, (V, V_o)
+
+
+def test_dpw_solver_through_the_api(gpu_lib):
+    """test/runtests.jl:49-57: POMCPDPWSolver(enable_action_pw=false) on LightDark1D with SIRParticleFilter(…, 100)."""
+    ld = pj.LightDark1D()
+    solver = pj.POMCPDPWSolver(tree_queries=100, eps=0.01, c=10.0, enable_action_pw=False, rng=2)
+    policy = pj.solve(solver, ld)
+    rng = np.random.default_rng(0)
+    parts = np.zeros(100, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, 100)
+    sim = pj.RolloutSimulator(rng=9, max_steps=10)
+    r = pj.simulate(sim, ld, policy, pj.SIRParticleFilter(policy, 100, rng=1), pj.ParticleCollection(parts))
+    assert np.isfinite(r) and 1 <= len(sim.history) <= 10
+    policy.close()
+    with pytest.raises(NotImplementedError):
+        pj.solve(pj.POMCPDPWSolver(tree_queries=100), ld)  # action widening

@@ -347,3 +347,26 @@ def test_fo_rollout_and_fo_value_estimators(oracle):
             assert np.array_equal(np.array(V_t).view(np.uint64), V_o.view(np.uint64))
     with pytest.raises(ValueError):
         oracle.OraclePlanner(pj.LightDark1D(), oracle.default_params(estimator=abi.EST_STATE_VALUE))
+
+
+# ----------------------------------------------------------------------------- observation progressive widening
+def test_dpw_observation_widening_oracle(oracle):
+    """POMCPDPWSolver with enable_action_pw = false on LightDark1D (test/runtests.jl:49-57; src/solver.jl:161-274):
+    with Float64 observations plain POMCP never gets below depth 1 (one new child per simulation, SURVEY.md
+    H4); observation widening caps the children of an action node at k * N^alpha and re-uses generated
+    (child, state) pairs, so the tree deepens.  Invariants: Root.N = queries, sum_a N(a) = queries - 1,
+    #children(ha) <= k * N(ha)^alpha + 1, and N(ha) >= sum_o N(hao) (re-used visits do not count at the child)."""
+    ld = pj.LightDark1D()
+    Q = 6000
+    plain = oracle.OraclePlanner(ld, oracle.default_params(c=10.0, seed=3, tree_queries=Q))
+    plain.set_belief_initial()
+    assert plain.search(Q)[0] == 0 and plain.counters()["max_depth_seen"] == 1
+    k, alpha = 2.0, 0.4
+    pl = oracle.OraclePlanner(ld, oracle.default_params(c=10.0, seed=3, tree_queries=Q, dpw_observation=1,
+                                                        k_observation=k, alpha_observation=alpha))
+    pl.set_belief_initial()
+    rc, a, N, V = pl.search(Q)
+    assert rc == 0 and N.sum() == Q - 1 and pl.root_stats()[0] == Q
+    cs = pl.counters()
+    assert cs["max_depth_seen"] >= 3 and cs["nodes"] < Q and cs["tree_steps"] > 2 * Q
+    assert np.isfinite(V).all()
