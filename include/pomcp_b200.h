@@ -134,6 +134,14 @@ typedef struct pomcp_solver_params {
   int32_t dpw_observation;   /* 0 = POMCPSolver (default) */
   double k_observation;      /* 10.0 */
   double alpha_observation;  /* 0.5 */
+  /* ---- action progressive widening (enable_action_pw = true, src/solver.jl:172-186): while
+   * #children <= k_action * (sum of the children's N)^alpha_action a uniformly drawn action
+   * (RandomActionGenerator, src/actions.jl:38-40) is added; a node with at most one child after that step
+   * returns its leaf estimate; UCB runs over the existing children with total_N = sum of their N. */
+  int32_t dpw_action;        /* 0 = every action is expanded at once (default) */
+  int32_t _pad2;
+  double k_action;           /* 10.0 */
+  double alpha_action;       /* 0.5 */
 } pomcp_solver_params;
 
 typedef struct pomcp_counters {

@@ -471,6 +471,7 @@ struct orc_planner {
   int64_t n_nodes, cap_nodes;
   int64_t* node_N;
   uint8_t* node_expanded;
+  uint32_t* node_amask; /* action widening: bit a = ActNode a exists */
   int64_t* node_phead; int64_t* node_ptail; int64_t* node_pcount; /* ParticleCollection per node */
   int64_t* node_parent_slot; uint64_t* node_obs;                 /* label */
   /* action nodes: slot = node*nA + a */
@@ -503,7 +504,7 @@ static void grow_nodes(orc_planner* pl, int64_t need) {
   if (need <= pl->cap_nodes) return;
   int64_t nc = pl->cap_nodes ? pl->cap_nodes : 1024;
   while (nc < need) nc *= 2;
-  GROW(pl->node_N, int64_t, nc); GROW(pl->node_expanded, uint8_t, nc);
+  GROW(pl->node_N, int64_t, nc); GROW(pl->node_expanded, uint8_t, nc); GROW(pl->node_amask, uint32_t, nc);
   GROW(pl->node_phead, int64_t, nc); GROW(pl->node_ptail, int64_t, nc); GROW(pl->node_pcount, int64_t, nc);
   GROW(pl->node_parent_slot, int64_t, nc); GROW(pl->node_obs, uint64_t, nc);
   GROW(pl->act_N, int64_t, nc * pl->nA); GROW(pl->act_V, double, nc * pl->nA);
@@ -519,7 +520,7 @@ static void grow_nodes(orc_planner* pl, int64_t need) {
 static int64_t new_node(orc_planner* pl, int64_t parent_slot, uint64_t obs) {
   grow_nodes(pl, pl->n_nodes + 1);
   int64_t n = pl->n_nodes++;
-  pl->node_N[n] = 0; pl->node_expanded[n] = 0;
+  pl->node_N[n] = 0; pl->node_expanded[n] = 0; pl->node_amask[n] = 0;
   pl->node_phead[n] = -1; pl->node_ptail[n] = -1; pl->node_pcount[n] = 0;
   pl->node_parent_slot[n] = parent_slot; pl->node_obs[n] = obs;
   for (int a = 0; a < pl->nA; ++a) { pl->act_N[n * pl->nA + a] = 0; pl->act_V[n * pl->nA + a] = 0.0; }
@@ -591,7 +592,7 @@ static void free_tree(orc_planner* pl) {
     free(pl->ev_n); free(pl->ev_cap); free(pl->ev_node); free(pl->ev_state); free(pl->act_nc);
     pl->ev_n = pl->ev_cap = pl->act_nc = NULL; pl->ev_node = NULL; pl->ev_state = NULL;
   }
-  free(pl->node_N); free(pl->node_expanded); free(pl->node_phead); free(pl->node_ptail); free(pl->node_pcount);
+  free(pl->node_N); free(pl->node_expanded); free(pl->node_amask); pl->node_amask = NULL; free(pl->node_phead); free(pl->node_ptail); free(pl->node_pcount);
   free(pl->node_parent_slot); free(pl->node_obs); free(pl->act_N); free(pl->act_V); free(pl->child); free(pl->ht);
   free(pl->log_state); free(pl->log_next);
   pl->node_N = NULL; pl->node_expanded = NULL; pl->node_phead = pl->node_ptail = pl->node_pcount = NULL;
@@ -613,6 +614,7 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   if (sp->num_sparse_actions > 0 || !(sp->eps > 0.0) || !(sp->eps < 1.0)) { free(pl); return NULL; }
   if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > 64) { free(pl); return NULL; }
   if (sp->dpw_observation && (!(sp->k_observation >= 0.0) || !(sp->alpha_observation >= 0.0))) { free(pl); return NULL; }
+  if (sp->dpw_action && (!(sp->k_action >= 0.0) || !(sp->alpha_action >= 0.0) || pl->m.nA > 32)) { free(pl); return NULL; }
   if ((sp->estimator == POMCP_EST_FWC_ROLLOUT || sp->estimator == POMCP_EST_FO_FWC_ROLLOUT) &&
       p->problem_id != POMCP_BABY) { free(pl); return NULL; }
   if (sp->estimator == POMCP_EST_STATE_VALUE && p->problem_id == POMCP_LIGHTDARK1D) { free(pl); return NULL; }
@@ -743,10 +745,35 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
   for (;;) {
     /* src/solver.jl:82-86 */
     if (depth >= pl->horizon || is_terminal(m, s) || depth >= sol->max_depth) { leaf = 0.0; break; }
-    if (!pl->node_expanded[h]) {
+    int leaf_now = 0;
+    int64_t totalN = pl->node_N[h];
+    if (sol->dpw_action) {
+      /* src/solver.jl:172-186: action progressive widening */
+      uint32_t mask = pl->node_amask[h];
+      totalN = 0;
+      for (int a = 0; a < pl->nA; ++a) if ((mask >> a) & 1u) totalN += pl->act_N[h * pl->nA + a];
+      int nch = __builtin_popcount(mask);
+      double lim = totalN <= 0 ? 0.0
+                 : sol->alpha_action == 0.5 ? sol->k_action * sqrt((double)totalN)
+                 : sol->k_action * orc_det_exp(sol->alpha_action * orc_det_log((double)totalN));
+      if ((double)nch <= lim) {
+        double ua[1];
+        draws(g, TAG_TREE, (uint32_t)depth | 0x80000000u, q, 1, ua); /* next_action: rand(rng, actions(pomdp)) */
+        int an = (int)(ua[0] * (double)pl->nA);
+        if (!((mask >> an) & 1u)) {
+          pl->act_N[h * pl->nA + an] = sol->init_N; pl->act_V[h * pl->nA + an] = sol->init_V;
+          mask |= 1u << an;
+          pl->node_amask[h] = mask;
+        }
+        if (__builtin_popcount(mask) <= 1) leaf_now = 1; /* src/solver.jl:180-186 */
+      }
+    } else if (!pl->node_expanded[h]) {
       /* src/solver.jl:87-94: one ActNode per action, N=init_N, V=init_V */
       for (int a = 0; a < pl->nA; ++a) { pl->act_N[h * pl->nA + a] = sol->init_N; pl->act_V[h * pl->nA + a] = sol->init_V; }
       pl->node_expanded[h] = 1;
+      leaf_now = 1;
+    }
+    if (leaf_now) {
       if (depth > 0) {
         /* src/solver.jl:97-103 */
         int64_t steps_to_eps = (int64_t)ceil(pl->log_ratio - (double)depth);
@@ -794,12 +821,13 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
     /* UCB1, src/solver.jl:109-124 */
     double best = -INFINITY;
     int best_a = -1;
-    int64_t hN = pl->node_N[h];
+    int64_t hN = totalN; /* h.N, or the sum of the children's N under action widening (src/solver.jl:171) */
     for (int a = 0; a < pl->nA; ++a) {
+      if (sol->dpw_action && !((pl->node_amask[h] >> a) & 1u)) continue; /* only existing children */
       int64_t nN = pl->act_N[h * pl->nA + a];
       double nV = pl->act_V[h * pl->nA + a];
       double crit;
-      if (nN == 0 && (sol->dpw_observation ? hN <= 1 : hN == 1)) crit = nV; /* src/solver.jl:112 / :210 */
+      if (nN == 0 && ((sol->dpw_observation || sol->dpw_action) ? hN <= 1 : hN == 1)) crit = nV; /* src/solver.jl:112 / :210 */
       else if (nN == 0 && nV == -INFINITY) crit = INFINITY;
       else crit = nV + sol->c * sqrt(orc_det_log((double)hN) / (double)nN);
       if (crit >= best) { best = crit; best_a = a; }
@@ -921,7 +949,7 @@ int32_t orc_search_replay(orc_planner* pl, int64_t Q, const double* uniforms, in
 int32_t orc_update_unweighted(orc_planner* pl, int32_t a, uint64_t obs_bits) {
   if (a < 0 || a >= pl->nA) return POMCP_ERR_INVALID_ARG;
   if (pl->sp.belief_mode != POMCP_BELIEF_UNWEIGHTED) return POMCP_ERR_UNSUPPORTED;
-  if (!pl->node_expanded[pl->root]) return POMCP_ERR_INVALID_ARG; /* KeyError on b_old.children[a] */
+  if (!pl->node_expanded[pl->root] && !pl->node_amask[pl->root]) return POMCP_ERR_INVALID_ARG; /* KeyError on b_old.children[a] */
   int64_t hao = find_child(pl, pl->root * pl->nA + a, obs_bits);
   if (hao < 0) return POMCP_ERR_PARTICLE_DEPLETION;          /* handle_unseen_observation */
   if (pl->node_pcount[hao] == 0) return POMCP_ERR_PARTICLE_DEPLETION; /* reinvigorate! on empty collection */
@@ -1080,7 +1108,7 @@ int32_t orc_update_reinvigorated(orc_planner* pl, int32_t a, uint64_t obs, uint6
   if (pl->sp.belief_mode != POMCP_BELIEF_UNWEIGHTED) return POMCP_ERR_UNSUPPORTED;
   if (pl->belief_kind == 0) return POMCP_ERR_INVALID_ARG;
   const model* m = &pl->m;
-  int64_t hao = pl->node_expanded[pl->root] ? find_child(pl, pl->root * pl->nA + a, obs) : -1;
+  int64_t hao = (pl->node_expanded[pl->root] || pl->node_amask[pl->root]) ? find_child(pl, pl->root * pl->nA + a, obs) : -1;
   int64_t cnt = hao >= 0 ? pl->node_pcount[hao] : 0;
   int have = hao >= 0 && cnt > 0;
   if (outcome) *outcome = 0;

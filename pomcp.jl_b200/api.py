@@ -182,7 +182,7 @@ class POMCPSolver(AbstractPOMCPSolver):
                  node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
                  default_action=None, search_mode="batched", inflight_min=0, inflight_max=0, inflight_ramp_div=0, rollouts_per_leaf=0,
                  max_nodes=0,
-                 max_log=0, device=0, rank=0, dpw_observation=None):
+                 max_log=0, device=0, rank=0, dpw_observation=None, dpw_action=None):
         self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
         self.rng = rng
         self.node_belief_updater = node_belief_updater if node_belief_updater is not None \
@@ -195,6 +195,7 @@ class POMCPSolver(AbstractPOMCPSolver):
         self.rollouts_per_leaf = rollouts_per_leaf
         self.max_nodes, self.max_log, self.device, self.rank = max_nodes, max_log, device, rank
         self.dpw_observation = dpw_observation  # (k_observation, alpha_observation) of POMCPDPWSolver, or None
+        self.dpw_action = dpw_action  # (k_action, alpha_action) of POMCPDPWSolver with enable_action_pw, or None
 
     def c_params(self, belief_mode):
         sp = abi.SolverParams()
@@ -233,6 +234,9 @@ class POMCPSolver(AbstractPOMCPSolver):
         if self.dpw_observation is not None:
             sp.dpw_observation = 1
             sp.k_observation, sp.alpha_observation = float(self.dpw_observation[0]), float(self.dpw_observation[1])
+        if self.dpw_action is not None:
+            sp.dpw_action = 1
+            sp.k_action, sp.alpha_action = float(self.dpw_action[0]), float(self.dpw_action[1])
         return sp
 
 
@@ -835,14 +839,12 @@ def _create_json(policy):
 # ---------------------------------------------------------------- remaining exported names (src/POMCP.jl:20-67)
 class POMCPDPWSolver(AbstractPOMCPSolver):
     """POMCPDPWSolver (src/POMCP.jl:154-253, src/constructor.jl:40-73, src/solver.jl:161-274): double progressive
-    widening.  The widening kernels are not built yet.  One configuration needs none:
-    with `enable_action_pw=false` every action is expanded at once (src/solver.jl:187-203), and on a problem
-    whose observation space has at most `k_observation` elements the test `length(children) <=
-    k_observation * N^alpha_observation` (src/solver.jl:223) is always true, so every step generates its
-    observation: the algorithm is POMCPSolver's, and solve() runs it on the POMCP kernels
-    (test/runtests.jl:49-54).  With continuous observations (LightDark1D, test/runtests.jl:57) the observation
-    widening runs on the device (`dpw_observation`); it needs an external belief updater, as in the
-    reference's test.  Action widening raises NotImplementedError."""
+    widening, run on the device through POMCPSolver's kernels with the widening switches of the parameter block:
+    action widening (`enable_action_pw`, next_action = RandomActionGenerator) on every problem, observation
+    widening on continuous observations (LightDark1D, test/runtests.jl:57; needs an external belief updater, as
+    in the reference's test).  On a discrete observation space of at most `k_observation` elements the test
+    `length(children) <= k_observation * N^alpha_observation` (src/solver.jl:223) is always true, so no
+    observation widening is needed there (test/runtests.jl:44-54)."""
 
     def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0, node_belief_updater=None,
                  estimate_value=None, enable_action_pw=True, alpha_observation=0.5, k_observation=10.0,
@@ -856,14 +858,18 @@ class POMCPDPWSolver(AbstractPOMCPSolver):
                               init_N=init_N, default_action=default_action, **device_kw)
 
     def as_pomcp(self, pomdp):
+        kw = dict(self._pomcp_kw)
         if self.enable_action_pw:
-            raise NotImplementedError("POMCPDPWSolver with action widening has no device path yet (SURVEY.md §8f rank 3)")
-        if not pomdp.continuous_obs:
-            if pomdp.n_observations > self.k_observation:
-                raise NotImplementedError("observation widening on a discrete observation space larger than "
-                                          "k_observation has no device path yet")
-            return POMCPSolver(**self._pomcp_kw)  # never widens: it is POMCPSolver
-        return POMCPSolver(dpw_observation=(self.k_observation, self.alpha_observation), **self._pomcp_kw)
+            if self.next_action is not None and not isinstance(self.next_action, RandomActionGenerator):
+                raise NotImplementedError("next_action: only RandomActionGenerator runs on device (src/actions.jl:38-41)")
+            kw["dpw_action"] = (self.k_action, self.alpha_action)
+        if pomdp.continuous_obs:
+            kw["dpw_observation"] = (self.k_observation, self.alpha_observation)
+        elif pomdp.n_observations > self.k_observation:
+            raise NotImplementedError("observation widening on a discrete observation space larger than "
+                                      "k_observation has no device path yet")
+        # a discrete observation space of at most k_observation elements never widens (src/solver.jl:223)
+        return POMCPSolver(**kw)
 
 
 class RandomActionGenerator:

@@ -261,6 +261,9 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.root = h->root;
   c.root_N0 = (uint32_t)h->root_visits;
   c.dpw = h->sp.dpw_observation ? 1 : 0;
+  c.dpa = h->sp.dpw_action ? 1 : 0;
+  c.k_act = h->sp.k_action;
+  c.alpha_act = h->sp.alpha_action;
   c.k_obs = h->sp.k_observation;
   c.alpha_obs = h->sp.alpha_observation;
   c.rollouts = h->rollouts;
@@ -328,9 +331,15 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
         cfg.inflight_max = std::min<long long>(cfg.inflight_max, (long long)blocks * nteams);
         kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
       };
-      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1>);
-      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2>);
-      else launch(k_search_workers<PID, 1, 4>);
+      if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
+        if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, true>);
+        else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, true>);
+        else launch(k_search_workers<PID, 1, 4, true>);
+      } else {
+        if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, false>);
+        else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, false>);
+        else launch(k_search_workers<PID, 1, 4, false>);
+      }
     });
     rc = launch_check(h, "k_search_workers");
     if (rc) return rc;
@@ -592,6 +601,9 @@ void pomcp_default_solver_params(pomcp_solver_params* o) {  // src/constructor.j
   o->dpw_observation = 0;
   o->k_observation = 10.0;  /* src/constructor.jl:48-49 */
   o->alpha_observation = 0.5;
+  o->dpw_action = 0;
+  o->k_action = 10.0;  /* src/constructor.jl:50-51 */
+  o->alpha_action = 0.5;
 }
 
 void pomcp_default_problem(int32_t pid, pomcp_problem* p) {
@@ -620,7 +632,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-  void* ptrs[] = {h->pool.act_nc, h->pool.act_ng, h->pool.ev_key, h->pool.ev_node, h->pool.ev_state,
+  void* ptrs[] = {h->pool.node_amask, h->pool.act_nc, h->pool.act_ng, h->pool.ev_key, h->pool.ev_node, h->pool.ev_state,
                   h->d_eta, h->d_eta_thr, h->d_gpow, h->pool.node_N, h->pool.node_flags, h->pool.act_N, h->pool.act_M,
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
@@ -657,6 +669,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     return fail(nullptr, POMCP_ERR_UNSUPPORTED,
                 "estimator (FeedWhenCrying rollouts exist for BabyPOMDP only, state-value tables for discrete states only)");
   if (sp->init_N < 0 || sp->max_depth < 0) return fail(nullptr, POMCP_ERR_INVALID_ARG, "init_N/max_depth < 0");
+  if (sp->dpw_action && (!(sp->k_action >= 0.0) || !(sp->alpha_action >= 0.0)))
+    return fail(nullptr, POMCP_ERR_INVALID_ARG, "k_action / alpha_action < 0");
   if (sp->dpw_observation) {
     if (nO != 0 || sp->belief_mode != POMCP_BELIEF_EXTERNAL)
       return fail(nullptr, POMCP_ERR_UNSUPPORTED,
@@ -785,6 +799,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &P.act_M, (size_t)want * nA));
   CKC(dev_alloc(h, &P.act_V, (size_t)want * nA));
   CKC(dev_alloc(h, &P.node_pslot, (size_t)want));
+  if (sp->dpw_action) CKC(dev_alloc(h, &P.node_amask, (size_t)want));
   if (h->hashed) {
     size_t e = 1;
     while (e < (size_t)want * 2) e <<= 1;
@@ -1019,6 +1034,7 @@ static int gather_child_particles(pomcp_handle* h, uint32_t child, long long cnt
 }
 
 static int maybe_compact(pomcp_handle* h) {
+  if (h->sp.dpw_action) return POMCP_OK;  // the action masks are not compacted yet: the pool (64 x tree_queries) is the limit
   // reclaim the dead part of the pool / particle log once a quarter of either is used
   if (h->compact_always || h->nodes_used * 4 >= h->pool.max_nodes || h->log_used * 4 >= h->pool.log_cap)
     return compact_pool(h);

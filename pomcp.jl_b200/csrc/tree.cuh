@@ -47,6 +47,7 @@ struct Pool {
   void* log_state;
   // observation progressive widening (POMCPDPWSolver, continuous observations): children / generation events of
   // an action node, and the (slot, event) -> (child, state) table the widened step draws from
+  uint32_t* node_amask;  // action widening: bit a = ActNode a exists (NULL unless dpw_action)
   uint32_t* act_nc;
   uint32_t* act_ng;
   unsigned long long* ev_key;
@@ -68,6 +69,8 @@ struct SearchCfg {
   int belief_unweighted, estimator;
   int dpw;             // observation progressive widening on (src/solver.jl:223-262)
   double k_obs, alpha_obs;
+  int dpa;             // action progressive widening on (src/solver.jl:172-186)
+  double k_act, alpha_act;
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
   int team_warps;      // batched mode: warps per worker; warp w runs rollouts 32 w .. 32 w + 31 of every leaf
   uint32_t key0, key1, rank, epoch;
@@ -463,6 +466,13 @@ __device__ __forceinline__ bool dpw_generates(const SearchCfg& cfg, uint32_t act
                    : cfg.k_obs * det_exp(cfg.alpha_obs * det_log((double)act_n));
   return (double)n_children <= lim;
 }
+// length(h.children) <= k_action * total_N^alpha_action (src/solver.jl:173)
+__device__ __forceinline__ bool dpw_widens_actions(const SearchCfg& cfg, unsigned long long total_n, int n_children) {
+  const double lim = total_n == 0 ? 0.0
+                   : cfg.alpha_act == 0.5 ? cfg.k_act * sqrt((double)total_n)
+                   : cfg.k_act * det_exp(cfg.alpha_act * det_log((double)total_n));
+  return (double)n_children <= lim;
+}
 template <class State>
 __device__ __forceinline__ bool ev_insert(const Pool& P, uint32_t slot, uint32_t e, uint32_t node, const State& sp) {
   const unsigned long long key = (((unsigned long long)slot << 32) | e) + 1ull;
@@ -634,13 +644,33 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     // A per-lane load could return different values to different lanes of this warp (lanes are
     // not guaranteed to execute the load together) and split the warp across shuffle sites.
     int i_expand = 0;
-    if (lane == 0 && !(fl & 1u)) {
-      uint32_t old;
-      if (EXACT) { old = fl; P.node_flags[h] = fl | 1u; }
-      else old = atomicOr(&P.node_flags[h], 1u);
-      i_expand = !(old & 1u);
+    uint32_t amask = 0xffffffffu;  // existing ActNodes (all of them unless actions are widened progressively)
+    unsigned long long totalN = hN;
+    if (cfg.dpa) {
+      // src/solver.jl:172-186 (exact mode: sequential, plain loads / stores)
+      amask = __ldcg(&P.node_amask[h]);
+      const uint32_t nl = (lane < nA && ((amask >> lane) & 1u)) ? __ldcg(&P.act_N[h * (uint32_t)nA + (uint32_t)lane]) : 0u;
+      totalN = __reduce_add_sync(0xffffffffu, nl);
+      if (dpw_widens_actions(cfg, totalN, __popc(amask))) {
+        double ua[4];
+        get_draws<REPLAY>(cfg, rc, TAG_TREE, (uint32_t)depth | 0x80000000u, q, ua);
+        if (REPLAY) rc.ucur -= 3;  // next_action consumes one uniform
+        const uint32_t bit = 1u << (int)(ua[0] * (double)nA);
+        if (!(amask & bit)) {
+          amask |= bit;
+          if (lane == 0) P.node_amask[h] = amask;
+        }
+        i_expand = __popc(amask) <= 1;
+      }
+    } else {
+      if (lane == 0 && !(fl & 1u)) {
+        uint32_t old;
+        if (EXACT) { old = fl; P.node_flags[h] = fl | 1u; }
+        else old = atomicOr(&P.node_flags[h], 1u);
+        i_expand = !(old & 1u);
+      }
+      i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
     }
-    i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
     if (i_expand) {
       want_rollout = depth > 0;
       break;
@@ -662,11 +692,11 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
         for (int k = 0; k < M::NO; ++k) kid[k] = __ldcg(&P.child[(size_t)sl * M::NO + k]);
       }
       if (!EXACT) v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
-      uint32_t hn = EXACT ? hN : (hN < 1u ? 1u : hN);
-      if (n == 0 && (cfg.dpw ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
+      unsigned long long hn = cfg.dpa ? totalN : (EXACT ? hN : (hN < 1u ? 1u : hN));
+      if (n == 0 && ((cfg.dpw || cfg.dpa) ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
       else if (n == 0 && v == -INFINITY) crit = INFINITY;
       else crit = v + cfg.c * sqrt(det_log((double)hn) / (double)n);
-      valid = (crit == crit);
+      valid = (crit == crit) && ((amask >> lane) & 1u);
     }
     int best_a = lane;
 #pragma unroll
@@ -901,8 +931,10 @@ struct ActStats {
   double w;
   uint32_t kid[K];
   uint32_t nc, ng;  // observation widening (hashed models): children / generation events of the action node
-  __device__ __forceinline__ void load(const Pool& P, uint32_t h, int nA, int lane, bool dpw = false) {
+  uint32_t amask;   // action widening: existing ActNodes of the node (all ones otherwise)
+  __device__ __forceinline__ void load(const Pool& P, uint32_t h, int nA, int lane, bool dpw = false, bool dpa = false) {
     n = 0; mm = 0; w = 0.0; nc = 0; ng = 0;
+    amask = dpa ? __ldcg(&P.node_amask[h]) : 0xffffffffu;
 #pragma unroll
     for (int k = 0; k < K; ++k) kid[k] = 0;
     if (lane < nA) {
@@ -944,7 +976,7 @@ __device__ __forceinline__ void team_bar(int id, int nthreads) {
 
 // One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
 // (lane 0; requested early so its latency hides behind the rollouts).
-template <int PID>
+template <int PID, bool DPA>
 __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
                                                const uint32_t* eta_thr, const SearchCfg& cfg,
                                                const PathView<typename ModelT<PID>::State>& pv,
@@ -963,7 +995,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   uint32_t h = cfg.root;
   uint32_t hN = cfg.root_N0 + q;
   ActStats<PID> st;
-  st.load(P, h, nA, lane, cfg.dpw != 0);
+  st.load(P, h, nA, lane, cfg.dpw != 0, DPA);
   uint32_t fl = 0;
   if (lane == 0) fl = __ldcg(&P.node_flags[h]);
   __syncwarp();
@@ -995,6 +1027,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   // RockSample needs one word per level (the sensor draw), the other models two.
   constexpr int TW = (PID == POMCP_ROCKSAMPLE) ? 1 : 2, LV = 4 / TW;
   Philox4 ptb;
+  int a_new = 0;  // action widening: the action this level would add
   const bool dpw = M::HASHED && cfg.dpw;  // observation widening: one block per level (word 2 draws the event)
   auto spec_step = [&](int d) {
     if (dpw || d % LV == 0)
@@ -1007,6 +1040,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       w0 = ptb.w[2];
       w1 = ptb.w[3];
     }
+    if (DPA)  // next_action(RandomActionGenerator): rand(rng, actions(pomdp)), its own block per level
+      a_new = (int)__umulhi(philox4x32_10((uint32_t)d | 0x80000000u, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1).w[0],
+                            (uint32_t)nA);
     const int a_l = lane < nA ? lane : nA - 1;
     if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, w0, sp_l, o_l, r_l);
     else M::template step<true, double>(m, s, a_l, u01(w0), M::T_DRAW ? u01(w1) : u01(w0), u01(w1), sp_l, o_l, r_l);
@@ -1014,7 +1050,27 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   spec_step(0);
   for (;;) {
     if (depth >= cfg.levels || M::terminal(m, s)) break;  // src/solver.jl:82-86
-    if (!(fl & 1u)) {  // src/solver.jl:87-107: the first visitor that is not cut off expands the node
+    uint32_t amask = 0xffffffffu;
+    if (DPA) {
+      // action progressive widening, src/solver.jl:172-186: total_N = sum of the children's N (in-flight visits
+      // included), a uniformly drawn action is added while #children <= k * total_N^alpha, and a node left with at
+      // most one child returns its leaf estimate.  The mask read with the statistics may be a few additions
+      // behind; the bit is added with a fire-and-forget atomic.
+      amask = st.amask;
+      const uint32_t total = __reduce_add_sync(0xffffffffu, (lane < nA && ((amask >> lane) & 1u)) ? st.n : 0u);
+      hN = total;
+      if (dpw_widens_actions(cfg, total, __popc(amask))) {
+        const uint32_t bit = 1u << a_new;
+        if (!(amask & bit)) {
+          amask |= bit;
+          if (lane == 0) atomicOr(&P.node_amask[h], bit);
+        }
+        if (__popc(amask) <= 1) {
+          want_rollout = depth > 0;
+          break;
+        }
+      }
+    } else if (!(fl & 1u)) {  // src/solver.jl:87-107: the first visitor that is not cut off expands the node
       int i_expand = 0;
       if (lane == 0) i_expand = !(atomicOr(&P.node_flags[h], 1u) & 1u);
       i_expand = __shfl_sync(0xffffffffu, i_expand, 0);
@@ -1025,11 +1081,11 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
     // UCB1, src/solver.jl:109-124 (lanes = actions)
     uint32_t key = 0;
-    if (lane < nA) {
+    if (lane < nA && ((amask >> lane) & 1u)) {
       const float v = (st.mm > 0 && v_finite) ? (float)st.w * sfu_rcp((float)st.mm) : initV_f;
       const uint32_t hn = hN < 1u ? 1u : hN;
       float crit;
-      if (st.n == 0 && (dpw ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
+      if (st.n == 0 && ((dpw || DPA) ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
       else if (st.n == 0 && v == -INFINITY) crit = INFINITY;
       else crit = v + c_f * sfu_sqrt(sfu_lg2((float)hn) * 0.69314718f * sfu_rcp((float)st.n));
       key = (crit == crit) ? f2ord(crit) : 0u;
@@ -1079,7 +1135,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       const long long ti = clock64();
       if (lane == 0) {
         bool cr;
-        raw = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr, !M::HASHED && !cut_next);
+        raw = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr, !M::HASHED && !cut_next && !DPA);
         created = cr;
       }
       raw = __shfl_sync(0xffffffffu, raw, 0);
@@ -1089,7 +1145,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
     const uint32_t hao = raw & CHILD_ID_MASK;
     const bool i_expand_child = created && (raw & CHILD_EXPANDED);  // direct table: the creator expands
-    const bool try_claim = created && !i_expand_child && !cut_next;  // hashed table: claim now
+    const bool try_claim = created && !i_expand_child && !cut_next && !DPA;  // hashed table: claim now
     const bool flag_known = (raw & CHILD_EXPANDED) != 0;
     // Visit count, expansion flag and statistics of the child: one round trip.  The count is added
     // with a fire-and-forget reduction and read with a plain load (a load returns sooner than an
@@ -1128,7 +1184,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       want_rollout = true;
       break;
     }
-    if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0);
+    if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
     if (!cut_next) spec_step(depth);
     hN = __shfl_sync(0xffffffffu, seen, 0);
     fl = __shfl_sync(0xffffffffu, nfl, 0);
@@ -1137,7 +1193,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         want_rollout = true;
         break;
       }
-      st.load(P, hao, nA, lane, cfg.dpw != 0);  // somebody else got there first (rare): descend through it
+      st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);  // somebody else got there first (rare): descend through it
       fl = 1u;
     }
   }
@@ -1261,7 +1317,7 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
 // Measured oddity (scripts/cycle_probe.py, same rollout code as a __noinline__ function): the 32
 // rollouts of the tree warp take 18.4 k cycles when it rolls out alone (TEAM = 1) and 12.1 k when a
 // helper warp rolls out next to it (TEAM = 2), so R = 64 is not only free, it is faster per simulation.
-template <int PID, int TEAM, int NTEAMS>
+template <int PID, int TEAM, int NTEAMS, bool DPA>
 __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_search_workers(
     const __grid_constant__ Pool P, const __grid_constant__ DevModel m, const __grid_constant__ SearchCfg cfg,
     const __grid_constant__ PathBuf pb, long long queries) {
@@ -1345,7 +1401,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q);
+    simulate_async<PID, DPA>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q);
   }
   if (W > 1) {  // release the helpers
     if (lane == 0) job->cmd = 0;
@@ -1451,6 +1507,7 @@ __global__ void k_pool_fill(const __grid_constant__ Pool P, int nA, int nO, unsi
     P.node_flags[k] = 0;
     P.node_pslot[k] = 0;
     if (P.node_obs) P.node_obs[k] = 0;
+    if (P.node_amask) P.node_amask[k] = 0;
   }
   if (P.child)
     for (unsigned long long k = i; k < n_nodes * nA * nO; k += stride) P.child[k] = 0;
