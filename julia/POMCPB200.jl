@@ -36,7 +36,9 @@ struct CSolverParams
     belief_mode::Int32; search_mode::Int32
     max_nodes::Int64; max_log::Int64
     inflight_min::Int32; inflight_max::Int32; inflight_ramp_div::Int32; rollouts_per_leaf::Int32
-    rank::Int32; _pad1::Int32
+    rank::Int32
+    dpw_observation::Int32; k_observation::Float64; alpha_observation::Float64     # src/constructor.jl:40-73
+    dpw_action::Int32; _pad2::Int32; k_action::Float64; alpha_action::Float64
 end
 
 # ---- exceptions (src/exceptions.jl:1-26)
