@@ -101,7 +101,9 @@ function c_problem end
 function solve(solver::POMCPSolver, pomdp::POMDPs.POMDP)   # src/solver.jl:30-32
     sp = CSolverParams(solver.eps, solver.max_depth, solver.c, solver.tree_queries, solver.rng,
                        solver.init_V, solver.init_N, solver.num_sparse_actions, 0, 0.0,
-                       0, solver.search_mode == :exact ? 0 : 1, 0, 0, 0, 0, 0, 0, 0, 0)
+                       0, solver.search_mode == :exact ? 0 : 1, 0, 0, 0, 0, 0, 0, 0,
+                       0, 10.0, 0.5,            # dpw_observation off; k/alpha defaults of src/constructor.jl:60-63
+                       0, 0, 10.0, 0.5)         # dpw_action off
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:pomcp_create, LIB), Int32, (Ref{CProblem}, Ref{CSolverParams}, Int32, Ref{Ptr{Cvoid}}),
                c_problem(pomdp), sp, solver.device, h)
