@@ -107,7 +107,7 @@ struct ReplayCursor {
 struct LocalCtr {
   unsigned long long sims, skips, rollouts, rollout_steps, tree_steps, max_depth;
   // batched workers: SM cycles spent per phase (pomcp_worker_cycles): descent, insert, rollout, backup
-  unsigned long long cyc[4];
+  unsigned long long cyc[8];  // [4..7]: developer probes (-DPOMCP_PROBE)
 };
 
 struct SearchResult {
@@ -1050,6 +1050,12 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   spec_step(0);
   for (;;) {
     if (depth >= cfg.levels || M::terminal(m, s)) break;  // src/solver.jl:82-86
+#ifdef POMCP_PROBE
+    const long long tp0 = clock64();
+    asm volatile("" ::"r"(st.n), "d"(st.w), "r"(st.mm), "r"(st.kid[0]), "r"(st.kid[ActStats<PID>::K - 1]));
+    const long long tpw = clock64();
+    lc.cyc[4] += (unsigned long long)(tpw - tp0);  // waiting for the statistics
+#endif
     uint32_t amask = 0xffffffffu;
     if (DPA) {
       // action progressive widening, src/solver.jl:172-186: total_N = sum of the children's N (in-flight visits
@@ -1094,6 +1100,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     const unsigned tied = __ballot_sync(0xffffffffu, key == mx && lane < nA);
     const int best_a = mx ? 31 - __clz((int)tied) : nA - 1;  // ">=": the last maximal index wins
     const uint32_t slot = h * (uint32_t)nA + (uint32_t)best_a;
+#ifdef POMCP_PROBE
+    const long long tp1 = clock64();
+    lc.cyc[5] += (unsigned long long)(tp1 - tpw);  // UCB + arg-max
+#endif
 
     // outcome of the chosen action; child ids came with the statistics (ids never change once published)
     uint32_t mine = 0;
@@ -1176,6 +1186,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     // Re-converge here: without it lane 0 stays split from lanes 1..31 until the next shuffle and the
     // warp runs everything in between twice (measured: the whole rollout loop at 15.5 active lanes).
     __syncwarp();
+#ifdef POMCP_PROBE
+    const long long tp2 = clock64();
+    lc.cyc[6] += (unsigned long long)(tp2 - tp1);  // pick + publish
+#endif
     h = hao;
     s = sp;
     last_o = o;
@@ -1186,6 +1200,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
     if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
     if (!cut_next) spec_step(depth);
+#ifdef POMCP_PROBE
+    lc.cyc[7] += (unsigned long long)(clock64() - tp2);  // issue the child's loads + speculative step
+#endif
     hN = __shfl_sync(0xffffffffu, seen, 0);
     fl = __shfl_sync(0xffffffffu, nfl, 0);
     if (fl & 2u) {
@@ -1302,6 +1319,9 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
     atomicMax(&c->max_depth, lc.max_depth);
     for (int i = 0; i < 4; ++i)
       if (lc.cyc[i]) atomicAdd(&c->dbg[i], lc.cyc[i]);
+#ifdef POMCP_PROBE  // the probe build reports its four descent segments in dbg[4..7]
+    for (int i = 4; i < 8; ++i) atomicAdd(&c->dbg[i], lc.cyc[i]);
+#endif
   }
 }
 
@@ -1409,8 +1429,10 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   }
   if (lane == 0) {
     flush_counters(P, lc, false);
+#ifndef POMCP_PROBE
     atomicAdd(&c->dbg[4], (unsigned long long)(t_admitted - t_start));  // waiting for admission
     atomicAdd(&c->dbg[5], (unsigned long long)(clock64() - t_admitted));  // working
+#endif
   }
 }
 

@@ -28,7 +28,7 @@ for infl in inflights:
             cy = pl.worker_cycles().astype(np.float64)
             sims = max(cs["simulations"], 1)
             if it:
-                rows.append([ms, cs["rollout_steps"] / sims, cs["tree_steps"] / sims, cs["nodes"], V.max()] + list(cy[:6] / sims))
+                rows.append([ms, cs["rollout_steps"] / sims, cs["tree_steps"] / sims, cs["nodes"], V.max()] + list(cy[:8] / sims))
         r = np.array(rows)
         mean, lo, hi = r.mean(0), r.min(0), r.max(0)
         ms = mean[0]
@@ -38,4 +38,9 @@ for infl in inflights:
         print(f"   cycles/sim: descent {mean[5]:.0f} insert {mean[6]:.0f} rollout {mean[7]:.0f} backup {mean[8]:.0f} "
               f"| sum {mean[5:9].sum():.0f} | admitted-life/sim {mean[10]:.0f} | per level {mean[5] / mean[2]:.0f} "
               f"| rollout per lane-step {mean[7] / (mean[1] / R):.0f}")
+        if os.environ.get("POMCP_B200_LIB", "").endswith("_ab_probe.so"):  # -DPOMCP_PROBE: dbg[4..7] = descent segments
+            lv = mean[2]
+            seg = mean[9:13] / lv
+            print(f"   per level: wait statistics {seg[0]:.0f} | UCB+argmax {seg[1]:.0f} | pick+publish (insert included) {seg[2]:.0f} "
+                  f"| issue child loads + speculative step {seg[3]:.0f} | wait child N/flag {(mean[5] + mean[6]) / lv - seg.sum():.0f}")
         pl.close()
