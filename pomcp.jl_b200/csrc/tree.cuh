@@ -915,9 +915,11 @@ struct PathView {
   int stride;
 };
 
-__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sfu_rcp(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sfu_sqrt(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// .ftz: one MUFU each, no denormal pre/post-scaling (the arguments here are counts >= 1, their logarithms and ratios:
+// never denormal, so the results are those of the non-ftz forms)
+__device__ __forceinline__ float sfu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // order-preserving map float -> u32 (callers send NaN to 0)
 __device__ __forceinline__ uint32_t f2ord(float x) {
   uint32_t b = __float_as_uint(x);
@@ -1086,15 +1088,18 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       }
     }
     // UCB1, src/solver.jl:109-124 (lanes = actions)
-    uint32_t key = 0;
-    if (lane < nA && ((amask >> lane) & 1u)) {
-      const float v = (st.mm > 0 && v_finite) ? (float)st.w * sfu_rcp((float)st.mm) : initV_f;
+    // Straight-line on every lane (selects, no branches): rcp(0) = +inf makes an untried action's bonus +inf
+    // by itself; the two special cases of the reference are patched in afterwards.
+    uint32_t key;
+    {
       const uint32_t hn = hN < 1u ? 1u : hN;
-      float crit;
-      if (st.n == 0 && ((dpw || DPA) ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
-      else if (st.n == 0 && v == -INFINITY) crit = INFINITY;
-      else crit = v + c_f * sfu_sqrt(sfu_lg2((float)hn) * 0.69314718f * sfu_rcp((float)st.n));
-      key = (crit == crit) ? f2ord(crit) : 0u;
+      const float v = (st.mm > 0 && v_finite) ? (float)st.w * sfu_rcp((float)st.mm) : initV_f;
+      float crit = v + c_f * sfu_sqrt(sfu_lg2((float)hn) * 0.69314718f * sfu_rcp((float)st.n));
+      const bool n0 = st.n == 0;
+      crit = (n0 && v == -INFINITY) ? INFINITY : crit;
+      crit = (n0 && hn == 1u) ? v : crit;  // src/solver.jl:112 / :210
+      const bool valid = lane < nA && ((amask >> lane) & 1u);
+      key = (valid && crit == crit) ? f2ord(crit) : 0u;
     }
     const uint32_t mx = __reduce_max_sync(0xffffffffu, key);
     const unsigned tied = __ballot_sync(0xffffffffu, key == mx && lane < nA);
@@ -1157,24 +1162,39 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     const bool i_expand_child = created && (raw & CHILD_EXPANDED);  // direct table: the creator expands
     const bool try_claim = created && !i_expand_child && !cut_next && !DPA;  // hashed table: claim now
     const bool flag_known = (raw & CHILD_EXPANDED) != 0;
-    // Visit count, expansion flag and statistics of the child: one round trip.  The count is added
-    // with a fire-and-forget reduction and read with a plain load (a load returns sooner than an
-    // atomic; whether it sees this worker's own arrival does not matter to log(h.N)).
-    uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
+    // Arrival counts, then everything the next level waits for — the child's visit count, expansion flag
+    // and statistics — in one round trip, requested before any bookkeeping.  The count and the flag are read
+    // by every lane (one broadcast transaction, no shuffle, no divergence); whether the count includes this
+    // worker's own arrival does not matter to log(h.N).
     if (lane == 0) {
       atomicAdd(&P.act_N[slot], 1u);
       if (!reuse) atomicAdd(&P.node_N[hao], 1u);  // hao.N counts generated arrivals only under widening
+    }
+    __syncwarp();
+    uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
+    if (!i_expand_child) {
+      if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
+      seen = __ldcg(&P.node_N[hao]);
+      if (try_claim) {  // hashed table: bit1 = the claim was attempted here
+        if (lane == 0) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;
+        nfl = __shfl_sync(0xffffffffu, nfl, 0);
+      } else if (!flag_known) {
+        nfl = __ldcg(&P.node_flags[hao]);
+      }
+    }
+#ifdef POMCP_PROBE
+    const long long tp2 = clock64();
+    lc.cyc[6] += (unsigned long long)(tp2 - tp1);  // pick + request the child
+#endif
+    // speculative step of the next level, then the bookkeeping of this one: both run under the loads
+    s = sp;
+    if (!i_expand_child && !cut_next) spec_step(depth + 1);
+    if (lane == 0) {
       if (dpw && !reuse) {
         if (created) atomicAdd(&P.act_nc[slot], 1u);
         ev_insert<State>(P, slot, atomicAdd(&P.act_ng[slot], 1u), hao, sp);
       }
-      if (i_expand_child) {
-        atomicOr(&P.node_flags[hao], 1u);  // nobody waits for it
-      } else {
-        seen = __ldcg(&P.node_N[hao]);
-        if (try_claim) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;  // bit1: the claim was attempted here
-        else if (!flag_known) nfl = __ldcg(&P.node_flags[hao]);
-      }
+      if (i_expand_child) atomicOr(&P.node_flags[hao], 1u);  // nobody waits for it
       const int pi = depth * pv.stride;
       pv.slot[pi] = slot;
       pv.r[pi] = r;
@@ -1187,24 +1207,17 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     // warp runs everything in between twice (measured: the whole rollout loop at 15.5 active lanes).
     __syncwarp();
 #ifdef POMCP_PROBE
-    const long long tp2 = clock64();
-    lc.cyc[6] += (unsigned long long)(tp2 - tp1);  // pick + publish
+    lc.cyc[7] += (unsigned long long)(clock64() - tp2);  // speculative step + bookkeeping
 #endif
     h = hao;
-    s = sp;
     last_o = o;
     ++depth;
     if (i_expand_child) {  // expand + evaluate the leaf (src/solver.jl:87-103)
       want_rollout = true;
       break;
     }
-    if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
-    if (!cut_next) spec_step(depth);
-#ifdef POMCP_PROBE
-    lc.cyc[7] += (unsigned long long)(clock64() - tp2);  // issue the child's loads + speculative step
-#endif
-    hN = __shfl_sync(0xffffffffu, seen, 0);
-    fl = __shfl_sync(0xffffffffu, nfl, 0);
+    hN = seen;
+    fl = nfl;
     if (fl & 2u) {
       if (!(fl & 1u)) {  // claimed
         want_rollout = true;
