@@ -906,6 +906,27 @@ __device__ __forceinline__ void rs_tree_step(const DevModel& m, const RsTab* tb,
   sp = (st & ~0xffu) | (uint32_t)x | ((uint32_t)y << 4);
 }
 
+// Lane-predicated memory operations: "lane 0 publishes" without splitting the warp (a branch around one
+// instruction costs a BSSY / BSYNC pair, a re-convergence stall, and needs a __syncwarp() afterwards).
+__device__ __forceinline__ void red_add_u32_if(bool p, uint32_t* addr) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.global.add.u32 [%1], 1;\n\t}" ::"r"((uint32_t)p),
+               "l"(__cvta_generic_to_global(addr))
+               : "memory");
+}
+__device__ __forceinline__ void red_or_u32_if(bool p, uint32_t* addr, uint32_t v) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.global.or.b32 [%1], %2;\n\t}" ::"r"((uint32_t)p),
+               "l"(__cvta_generic_to_global(addr)), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ void st_u32_if(bool p, uint32_t* addr, uint32_t v) {  // generic address
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.u32 [%1], %2;\n\t}" ::"r"((uint32_t)p), "l"(addr), "r"(v)
+               : "memory");
+}
+__device__ __forceinline__ void st_f64_if(bool p, double* addr, double v) {  // generic address
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p st.f64 [%1], %2;\n\t}" ::"r"((uint32_t)p), "l"(addr), "d"(v)
+               : "memory");
+}
+
 template <class State>
 struct PathView {
   uint32_t* slot;
@@ -1166,11 +1187,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     // and statistics — in one round trip, requested before any bookkeeping.  The count and the flag are read
     // by every lane (one broadcast transaction, no shuffle, no divergence); whether the count includes this
     // worker's own arrival does not matter to log(h.N).
-    if (lane == 0) {
-      atomicAdd(&P.act_N[slot], 1u);
-      if (!reuse) atomicAdd(&P.node_N[hao], 1u);  // hao.N counts generated arrivals only under widening
-    }
-    __syncwarp();
+    const bool l0 = lane == 0;
+    red_add_u32_if(l0, &P.act_N[slot]);
+    red_add_u32_if(l0 && !reuse, &P.node_N[hao]);  // hao.N counts generated arrivals only under widening
     uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
     if (!i_expand_child) {
       if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
@@ -1189,23 +1208,26 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     // speculative step of the next level, then the bookkeeping of this one: both run under the loads
     s = sp;
     if (!i_expand_child && !cut_next) spec_step(depth + 1);
-    if (lane == 0) {
-      if (dpw && !reuse) {
+    if (dpw && !reuse) {
+      if (lane == 0) {
         if (created) atomicAdd(&P.act_nc[slot], 1u);
         ev_insert<State>(P, slot, atomicAdd(&P.act_ng[slot], 1u), hao, sp);
       }
-      if (i_expand_child) atomicOr(&P.node_flags[hao], 1u);  // nobody waits for it
-      const int pi = depth * pv.stride;
-      pv.slot[pi] = slot;
-      pv.r[pi] = r;
-      if (cfg.belief_unweighted) {
+      __syncwarp();
+    }
+    red_or_u32_if(l0 && i_expand_child, &P.node_flags[hao], 1u);  // nobody waits for it
+    const int pi = depth * pv.stride;
+    st_u32_if(l0, &pv.slot[pi], slot);
+    st_f64_if(l0, &pv.r[pi], r);
+    if (cfg.belief_unweighted) {
+      if (lane == 0) {
         pv.node[pi] = hao;
         pv.state[pi] = sp;
       }
+      // re-converge: a warp left split here runs everything up to the next shuffle twice (measured once: the
+      // whole rollout loop at 15.5 active lanes)
+      __syncwarp();
     }
-    // Re-converge here: without it lane 0 stays split from lanes 1..31 until the next shuffle and the
-    // warp runs everything in between twice (measured: the whole rollout loop at 15.5 active lanes).
-    __syncwarp();
 #ifdef POMCP_PROBE
     lc.cyc[7] += (unsigned long long)(clock64() - tp2);  // speculative step + bookkeeping
 #endif
@@ -1218,7 +1240,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
     hN = seen;
     fl = nfl;
-    if (fl & 2u) {
+    if (M::HASHED && (fl & 2u)) {  // (the direct table never claims here: its creator expands)
       if (!(fl & 1u)) {  // claimed
         want_rollout = true;
         break;
