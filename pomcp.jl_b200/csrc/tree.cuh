@@ -1052,16 +1052,36 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   Philox4 ptb;
   int a_new = 0;  // action widening: the action this level would add
   const bool dpw = M::HASHED && cfg.dpw;  // observation widening: one block per level (word 2 draws the event)
+  // The tree draws of a whole simulation in one lane-parallel Philox call: lane j holds block j (levels
+  // j * LV .. j * LV + LV - 1); a level fetches its words with a shuffle.  Same counters, same words as
+  // computing block d / LV at level d (which levels past the 32nd block still do).
+  Philox4 pall{};
+  if (!dpw) pall = philox4x32_10((uint32_t)lane, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
   auto spec_step = [&](int d) {
-    if (dpw || d % LV == 0)
-      ptb = philox4x32_10((uint32_t)(dpw ? d : d / LV), TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
-    const int k = dpw ? 0 : d % LV;
-    uint32_t w0 = ptb.w[0], w1 = ptb.w[1];
-    if (TW == 1) {
-      w0 = k == 0 ? ptb.w[0] : k == 1 ? ptb.w[1] : k == 2 ? ptb.w[2] : ptb.w[3];
-    } else if (k == 1) {
-      w0 = ptb.w[2];
-      w1 = ptb.w[3];
+    uint32_t w0, w1 = 0;
+    if (dpw) {
+      ptb = philox4x32_10((uint32_t)d, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+      w0 = ptb.w[0];
+      w1 = ptb.w[1];
+    } else {
+      const int blk = d / LV, k = d % LV;
+      if (blk < 32) {
+        if (TW == 1) {
+          const uint32_t lo = (k & 1) ? pall.w[1] : pall.w[0], hi = (k & 1) ? pall.w[3] : pall.w[2];
+          w0 = __shfl_sync(0xffffffffu, (k & 2) ? hi : lo, blk);
+        } else {
+          w0 = __shfl_sync(0xffffffffu, k ? pall.w[2] : pall.w[0], blk);
+          w1 = __shfl_sync(0xffffffffu, k ? pall.w[3] : pall.w[1], blk);
+        }
+      } else {
+        const Philox4 pb2 = philox4x32_10((uint32_t)blk, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+        if (TW == 1) {
+          w0 = k == 0 ? pb2.w[0] : k == 1 ? pb2.w[1] : k == 2 ? pb2.w[2] : pb2.w[3];
+        } else {
+          w0 = k ? pb2.w[2] : pb2.w[0];
+          w1 = k ? pb2.w[3] : pb2.w[1];
+        }
+      }
     }
     if (DPA)  // next_action(RandomActionGenerator): rand(rng, actions(pomdp)), its own block per level
       a_new = (int)__umulhi(philox4x32_10((uint32_t)d | 0x80000000u, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1).w[0],
