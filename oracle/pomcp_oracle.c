@@ -377,13 +377,17 @@ static double rollout_random(const model* m, ostate s, int64_t steps, const uint
   int64_t blk = -1;
   const int dps = m->draws_per_rollout_step;
   while (disc > 0.0 && !is_terminal(m, s) && step < steps) {
-    int64_t word = step * dps;
+    /* RockSample draws its action from 16 bits (8 steps per Philox block, low half of a word first):
+     * the rollout kernel is bound by instruction issue and the Philox rounds are a third of a step */
+    const int halves = m->p.problem_id == POMCP_ROCKSAMPLE;
+    int64_t word = halves ? step >> 1 : step * dps;
     if ((word >> 2) != blk) {
       blk = word >> 2;
       uint32_t ctr[4] = {(uint32_t)blk, tagword, q, epoch};
       orc_philox4x32_10(ctr, key, w);
     }
     uint32_t wa = w[word & 3];
+    if (halves) wa = (step & 1) ? (wa & 0xffff0000u) : (wa << 16);
     int a = (int)(((uint64_t)wa * (uint64_t)m->nA) >> 32); /* rand(rng, actions): floor(u*nA) */
     double ut0 = dps == 2 ? u01(w[(word & 3) + 1]) : 0.0;
     ostate sp; uint64_t o; double r;

@@ -260,10 +260,13 @@ __device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTa
     // Loop-carried chains per step are kept minimal: position (add + clamp), rock bits (one and-not
     // with a mask that comes from the position only), return (one add), discount (one multiply).
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
-        const uint32_t a = __umulhi(p[t].w[j], nA);  // rand(rng, actions): floor(u * nA)
+        // rand(rng, actions) = floor(u * nA) with a 16-bit u: a Philox block feeds 8 steps (low half of a
+        // word first).  P(a) is within nA / 2^16 (relative) of 1 / nA.
+        const uint32_t wj = p[t].w[j >> 1];
+        const uint32_t a = __umulhi((j & 1) ? (wj & 0xffff0000u) : (wj << 16), nA);
         // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
         const uint32_t mv = shr_clamped(0x3C14u, a * 4u);
         y[t] = min(max(y[t] + sbfe2(mv, 2), 0), nmax);
