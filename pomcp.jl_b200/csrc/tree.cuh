@@ -193,11 +193,37 @@ struct RsTab {
   double rtab[4];           // reward by event: 0 none, 1 exit, 2 sampled a bad rock, 3 sampled a good rock
   signed char rock_at[256]; // rock index at cell y*16+x, -1 none
   unsigned char rock_sh[256];  // the same as a shift amount: rock index, or 32 (-> empty mask) where there is no rock
+  // Rollout transition table, row = cell (y*16+x; row 255 = off the grid / finished, absorbing), column = min(a, 5):
+  // 0..3 the moves, 4 sample, 5 any sensing action.  Entry: bits 0-12 byte offset of the next row (cell * 32),
+  // bits 16-20 byte offset into rtab of the event without a good rock (0 none, 8 exit, 16 sampled),
+  // bits 24-29 shift of the rock the action samples (32 = none: the rock mask comes out empty).
+  uint32_t mv[256 * 8];
 };
+constexpr uint32_t RS_DEAD_ROW = 255u * 32u;
 __device__ __forceinline__ void rs_tab_init(RsTab* t, const DevModel& m) {
+  const int nmax = m.rs_n - 1;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     t->rock_at[i] = m.rock_at[i];
     t->rock_sh[i] = m.rock_at[i] >= 0 ? (unsigned char)m.rock_at[i] : (unsigned char)32;
+  }
+  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+    const int c = i >> 3, a = i & 7, x = c & 15, y = c >> 4;
+    uint32_t next = (uint32_t)c, ev = 0, sh = 32;
+    if (c == 255 || x > nmax || y > nmax) {
+      next = 255;  // absorbing
+    } else if (a == 0) {
+      next = (uint32_t)(min(y + 1, nmax) * 16 + x);
+    } else if (a == 1) {  // east: off the grid at the right edge
+      if (x + 1 > nmax) { next = 255; ev = 8; } else next = (uint32_t)(y * 16 + x + 1);
+    } else if (a == 2) {
+      next = (uint32_t)(max(y - 1, 0) * 16 + x);
+    } else if (a == 3) {
+      next = (uint32_t)(y * 16 + max(x - 1, 0));
+    } else if (a == 4 && m.rock_at[c] >= 0) {
+      ev = 16;
+      sh = (uint32_t)m.rock_at[c];
+    }
+    t->mv[i] = (next * 32u) | (ev << 16) | (sh << 24);
   }
   if (threadIdx.x < 4) t->rtab[threadIdx.x] = m.rs_rtab[threadIdx.x];
   __syncthreads();
@@ -221,10 +247,12 @@ __device__ __forceinline__ int sbfe2(uint32_t x, int pos) {  // signed 2-bit fie
 
 // RockSample rollouts: the same draws, transitions, rewards and fp64 operation order as
 // ModelT<ROCKSAMPLE>::step<false> (bit-identical returns, checked against the oracle through
-// pomcp_rollout_batch), arranged for the issue slots: position and rock bits stay unpacked in
-// registers, the move comes out of a nibble table, the rock lookup and the reward are
-// branch-free (32 lanes hold 32 different actions, so a branch would be taken by the warp on
-// almost every step anyway).
+// pomcp_rollout_batch), arranged for the issue slots (every pipe of a scheduler takes one warp
+// instruction per two cycles, and the search kernel is bound by exactly that): a step is one
+// shared-memory lookup of (next cell, event, rock shift) by (cell, action), one rock-bit extract /
+// clear, one reward lookup and three fp64 operations.  A trajectory that left the grid sits in an
+// absorbing row whose entries add +0.0, so there is no per-step "alive" select; the step limit and
+// the discount underflow are the same for every lane and are handled by the loop bounds.
 // NT trajectories per lane (1 or 2), interleaved (rollouts_per_leaf > 32 on a single warp).  Both start
 // at step 0, so they share the discount sequence; each accumulates exactly as it would alone.
 template <bool CHECK_DISC, int NT>
@@ -234,65 +262,72 @@ __device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTa
                                                    double (&total)[NT]) {
   const double gamma = m.gamma;
   const uint32_t nA = (uint32_t)m.nA;
-  const int nmax = m.rs_n - 1;
   const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
-  int x[NT], y[NT], step[NT];
+  const unsigned char* mvb = (const unsigned char*)tb->mv;
+  const unsigned char* rtb = (const unsigned char*)tb->rtab;
+  uint32_t row[NT];    // byte offset of the cell's row in tb->mv
   uint32_t rocks[NT];  // bit i: rock i is good
-  bool live[NT];
+  int step[NT];
   Philox4 p[NT];
   double disc = 1.0;
   bool any = false;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
-    x[t] = (int)(s & 15u);
-    y[t] = (int)((s >> 4) & 15u);
+    const bool live = enabled[t] && !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
+    row[t] = live ? (s & 0xffu) * 32u : RS_DEAD_ROW;
     rocks[t] = s >> 8;
     total[t] = 0.0;
     step[t] = 0;
-    live[t] = enabled[t] && !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
-    any = any || live[t];
+    any = any || live;
     p[t] = philox4x32_10(0u, tagword[t], q, epoch, k0, k1);
   }
+  // one step of trajectory t with the 16-bit draw j of its current block
+  auto one_step = [&](int t, int j) {
+    // rand(rng, actions) = floor(u * nA) with a 16-bit u: a Philox block feeds 8 steps (low half of a
+    // word first).  P(a) is within nA / 2^16 (relative) of 1 / nA.
+    const uint32_t wj = p[t].w[j >> 1];
+    const uint32_t a = __umulhi((j & 1) ? (wj & 0xffff0000u) : (wj << 16), nA);
+    step[t] += row[t] != RS_DEAD_ROW ? 1 : 0;
+    const uint32_t e = *(const uint32_t*)(mvb + row[t] + min(a, 5u) * 4u);
+    row[t] = e & 0x1fffu;
+    // sample on a rock: +good / -bad, and the rock is bad afterwards either way
+    const uint32_t sh = e >> 24;
+    const uint32_t good = shr_clamped(rocks[t], sh) & 1u;
+    rocks[t] &= ~shl_clamped(1u, sh);
+    total[t] += disc * *(const double*)(rtb + ((e >> 16) & 0x18u) + good * 8u);  // a finished trajectory adds +0.0
+  };
+  int base = 0;  // steps done by the lanes still on the grid
   for (uint32_t blk = 0; any; ++blk) {
     Philox4 pn[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) pn[t] = philox4x32_10(blk + 1u, tagword[t], q, epoch, k0, k1);
-    // Loop-carried chains per step are kept minimal: position (add + clamp), rock bits (one and-not
-    // with a mask that comes from the position only), return (one add), discount (one multiply).
+    bool stop = false;  // uniform: step limit reached or discount underflow
+    if (!CHECK_DISC && base + 8 <= nstep_max) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        // rand(rng, actions) = floor(u * nA) with a 16-bit u: a Philox block feeds 8 steps (low half of a
-        // word first).  P(a) is within nA / 2^16 (relative) of 1 / nA.
-        const uint32_t wj = p[t].w[j >> 1];
-        const uint32_t a = __umulhi((j & 1) ? (wj & 0xffff0000u) : (wj << 16), nA);
-        // nibble a: dx (2 bits, signed) | dy << 2;  0 north y+1, 1 east x+1, 2 south y-1, 3 west x-1
-        const uint32_t mv = shr_clamped(0x3C14u, a * 4u);
-        y[t] = min(max(y[t] + sbfe2(mv, 2), 0), nmax);
-        const int nx = x[t] + sbfe2(mv, 0);
-        const bool exits = nx > nmax;  // moving east off the grid
-        x[t] = min(max(nx, 0), nmax);
-        // sample (a == 4) on a rock: +good / -bad, and the rock is bad afterwards either way
-        const uint32_t mask = shl_clamped(a == 4u ? 1u : 0u, tb->rock_sh[y[t] * 16 + x[t]]);
-        const uint32_t goodbit = rocks[t] & mask;
-        rocks[t] &= ~mask;
-        const int ev = exits ? 1 : (mask ? (goodbit ? 3 : 2) : 0);
-        total[t] += disc * tb->rtab[live[t] ? ev : 0];  // a finished trajectory adds +0.0
-        step[t] += live[t] ? 1 : 0;
-        live[t] = live[t] && !exits && step[t] < nstep_max;
+        for (int t = 0; t < NT; ++t) one_step(t, j);
+        disc *= gamma;
       }
-      disc *= gamma;
-      if (CHECK_DISC && !(disc > 0.0)) {
+      base += 8;
+      stop = base >= nstep_max;
+    } else {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) live[t] = false;
+      for (int j = 0; j < 8; ++j) {
+        if (!stop) {
+#pragma unroll
+          for (int t = 0; t < NT; ++t) one_step(t, j);
+          disc *= gamma;
+          ++base;
+          stop = base >= nstep_max || (CHECK_DISC && !(disc > 0.0));
+        }
       }
     }
     any = false;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       p[t] = pn[t];
-      any = any || live[t];
+      any = any || (!stop && row[t] != RS_DEAD_ROW);
     }
   }
   nsteps = 0;
