@@ -100,6 +100,7 @@ struct pomcp_handle {
   size_t ht_entries = 0, ev_entries = 0;
   PathBuf pb{};
   int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32;
+  bool inflight_min_auto = true;  // no explicit inflight_min: max(8, tree_queries / 1024) per search
   void* d_bel[2] = {nullptr, nullptr};
   size_t bel_cap[2] = {0, 0};
   int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles
@@ -319,6 +320,10 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     cfg.eta_thr = h->d_eta_thr;
     smem += (size_t)h->eta_n * sizeof(uint32_t);
     long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
+    // Admission floor relative to the budget: the simulations started while the tree holds fewer than
+    // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
+    // nothing (measured, scripts/ramp_probe.py) and removes most of the ramp from a large search.
+    if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), h->inflight_max);
     int blocks = (int)((workers + nteams - 1) / nteams);
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
@@ -771,6 +776,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   // default: 8 simulations in flight per SM (1184 on a 148-SM B200) - whole CTAs on every SM
   h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096) : 8 * prop.multiProcessorCount;
   h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
+  h->inflight_min_auto = sp->inflight_min <= 0;
   h->inflight_min = std::max(1, std::min(h->inflight_min, h->inflight_max));
   h->ramp_div = sp->inflight_ramp_div > 0 ? sp->inflight_ramp_div : 32;
   if (sp->rollouts_per_leaf < 0 || sp->rollouts_per_leaf > (h->exact ? 64 : 128)) {
