@@ -22,8 +22,11 @@ struct SubtreeSrc {
   uint32_t nA;
   __device__ __forceinline__ unsigned long long operator()(long long i) const {
     uint32_t n = (uint32_t)i;
-    // ids grow along every root-to-leaf path (a child is allocated after its parent)
-    while (n > new_root) n = node_pslot[n] / nA;
+    // Walk the parent links until the new root or the pool's first node (id 0: its own parent, like every
+    // detached or never-used id).  Ids mostly grow along a path, so nodes older than the new root could stop
+    // at once, but the batched workers insert with ids allocated ahead of time and a child can be older than
+    // its parent.
+    while (n != new_root && n != 0u) n = node_pslot[n] / nA;
     return n == new_root ? 1ull : 0ull;
   }
 };

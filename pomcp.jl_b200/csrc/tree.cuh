@@ -493,6 +493,35 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
   }
 }
 
+// Batched workers, direct table: the same insertion with a node id the worker allocated ahead of time (`spare`,
+// 0 = none yet), so the critical path holds one round trip (the CAS) instead of two, and an id that loses
+// the race is kept for the next insertion instead of being dropped.  The replacement id is requested right
+// after a successful insertion and is not waited for until the next one.  Ids then no longer grow along every
+// root-to-leaf path (a spare can be older than the parent it ends up under); the pool compaction walks
+// parent links to the root instead of relying on that order.
+__device__ __forceinline__ uint32_t insert_child_spare(const Pool& P, int nO, uint32_t slot, uint64_t obs, bool& created,
+                                                       bool claim, uint32_t& spare) {
+  created = false;
+  uint32_t* cs = &P.child[(size_t)slot * nO + (uint32_t)obs];
+  uint32_t fresh = spare;
+  if (fresh == 0) fresh = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+  if (fresh >= P.max_nodes) {
+    P.ctr->pool_overflow = 1;
+    return 0;
+  }
+  P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
+  const uint32_t pub = claim ? (fresh | CHILD_EXPANDED) : fresh;
+  const uint32_t old = atomicCAS(cs, 0u, pub);
+  if (old == 0) {
+    created = true;
+    spare = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+    return pub;
+  }
+  P.node_pslot[fresh] = 0;  // lost the race: the id stays detached and is offered again next time
+  spare = fresh;
+  return old;
+}
+
 // ---- observation progressive widening (src/solver.jl:223-262).  Every generated (child, state) pair of an
 // action node is an event e = 0, 1, ...; a widened step re-uses event floor(u * #events): the child with
 // probability N(child) / sum N and one of the states pushed into it, uniformly — what sample(os, WeightVec(N))
@@ -1042,7 +1071,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
                                                const uint32_t* eta_thr, const SearchCfg& cfg,
                                                const PathView<typename ModelT<PID>::State>& pv,
                                                LeafJob<typename ModelT<PID>::State>* job, uint32_t q,
-                                               LocalCtr& lc, unsigned long long& next_q) {
+                                               LocalCtr& lc, unsigned long long& next_q, uint32_t& spare) {
   using M = ModelT<PID>;
   using State = typename M::State;
   const int lane = threadIdx.x & 31;
@@ -1229,7 +1258,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       const long long ti = clock64();
       if (lane == 0) {
         bool cr;
-        raw = find_or_insert_child<PID, !M::HASHED>(P, m, slot, o, cr, !M::HASHED && !cut_next && !DPA);
+        if constexpr (M::HASHED) raw = find_or_insert_child<PID, false>(P, m, slot, o, cr, false);
+        else raw = insert_child_spare(P, m.nO, slot, o, cr, !cut_next && !DPA, spare);
         created = cr;
       }
       raw = __shfl_sync(0xffffffffu, raw, 0);
@@ -1492,6 +1522,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   }
   LocalCtr lc{};
   unsigned long long next_q = ~0ull;
+  uint32_t spare = 0;  // lane 0: node id allocated ahead of the next insertion (direct child table)
   const long long t_start = clock64();
   if (lane == 0 && (long long)wid < (long long)cfg.inflight_max) {
     // admission: ramp the number of simulations in flight with the size of the tree
@@ -1514,7 +1545,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID, DPA>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q);
+    simulate_async<PID, DPA>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q, spare);
   }
   if (W > 1) {  // release the helpers
     if (lane == 0) job->cmd = 0;
