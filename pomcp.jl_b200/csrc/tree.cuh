@@ -1409,17 +1409,33 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       }
     }
   }
-  // backup, src/solver.jl:144-156: W += R, M += 1 (V = W / M)
-  if (lane == 0) {
-    double R = leaf;
-    for (int d = depth - 1; d >= 0; --d) {
-      const int pi = d * pv.stride;
-      R = pv.r[pi] + m.gamma * R;
-      const uint32_t slot = pv.slot[pi];
-      atomicAdd(&P.act_V[slot], R);
-      atomicAdd(&P.act_M[slot], 1u);
+  // backup, src/solver.jl:144-156: W += R, M += 1 (V = W / M) with R_d = r_d + gamma * R_{d+1}, R_depth = leaf.
+  // Lane-parallel: lane l of a 32-level chunk holds level lo + l; the discounted suffix sums come out of a
+  // five-step warp scan (v_d += gamma^k * v_{d+k}, k = 1, 2, 4, 8, 16) and every lane publishes its own level.
+  {
+    const double g1 = m.gamma, g2 = g1 * g1, g4 = g2 * g2, g8 = g4 * g4, g16 = g8 * g8;
+    double Rnext = leaf;
+    for (int hi = depth; hi > 0; hi -= 32) {  // deepest chunk first
+      const int lo = hi > 32 ? hi - 32 : 0, n = hi - lo;
+      const bool act = lane < n;
+      const int pi = (lo + lane) * pv.stride;
+      const double gtail = act ? cfg.gpow[n - lane] : 0.0;  // gamma^(levels between this one and R_hi)
+      double v = act ? pv.r[pi] : 0.0;
+      const uint32_t slot = act ? pv.slot[pi] : 0u;
+      double t;
+      t = __shfl_down_sync(0xffffffffu, v, 1);  if (lane + 1 < 32) v = v + g1 * t;
+      t = __shfl_down_sync(0xffffffffu, v, 2);  if (lane + 2 < 32) v = v + g2 * t;
+      t = __shfl_down_sync(0xffffffffu, v, 4);  if (lane + 4 < 32) v = v + g4 * t;
+      t = __shfl_down_sync(0xffffffffu, v, 8);  if (lane + 8 < 32) v = v + g8 * t;
+      t = __shfl_down_sync(0xffffffffu, v, 16); if (lane + 16 < 32) v = v + g16 * t;
+      const double R = v + gtail * Rnext;
+      if (act) {
+        atomicAdd(&P.act_V[slot], R);
+        atomicAdd(&P.act_M[slot], 1u);
+      }
+      Rnext = __shfl_sync(0xffffffffu, R, 0);
     }
-    atomicAdd(&P.node_N[cfg.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
+    if (lane == 0) atomicAdd(&P.node_N[cfg.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
   }
   __syncwarp();
   lc.cyc[3] += (unsigned long long)(clock64() - t2);

@@ -1,0 +1,34 @@
+"""Developer probe (GPU box): admission floor (inflight_min) against fidelity at 1e6 queries, 12 seeds."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pomcp_jl_b200 as pj
+from pomcp_jl_b200 import _abi as abi
+from oracle import oracle as O
+
+pomdp = pj.RockSamplePOMDP(7, 8, seed=7008)
+Q, seeds = 1000000, range(12)
+floors = [int(x) for x in sys.argv[1].split(",")]
+orc = []
+for seed in seeds:
+    solver = pj.POMCPSolver(c=20.0, rng=seed, tree_queries=Q, search_mode="exact")
+    op = O.OraclePlanner(pomdp, solver.c_params(abi.BELIEF_UNWEIGHTED))
+    op.set_belief_initial()
+    rc, a, N, V = op.search(Q)
+    orc.append((a, V))
+    op.close()
+vo = np.array([v[a] for a, v in orc])
+print(f"Q={Q}: oracle best-arm V {vo.mean():.2f} +- {vo.std() / np.sqrt(len(vo)):.2f}", flush=True)
+for fl in floors:
+    ag, vg, ms_l = [], [], []
+    for k, seed in enumerate(seeds):
+        solver = pj.POMCPSolver(c=20.0, rng=seed, tree_queries=Q, search_mode="batched", inflight_min=fl, max_nodes=4 * Q)
+        gp = pj.solve(solver, pomdp)
+        gp.set_belief_initial()
+        a, N, V = gp.search(Q)
+        ms_l.append(gp.phase_ms(abi.PHASE_SEARCH)[0])
+        gp.close()
+        ag.append(a == orc[k][0])
+        vg.append(V[a])
+    print(f"  inflight_min {fl:4d}: action = oracle's {sum(ag)}/{len(ag)}, best-arm V {np.mean(vg):.2f} +- "
+          f"{np.std(vg) / np.sqrt(len(vg)):.2f}, decision {np.mean(ms_l):.2f} ms", flush=True)
