@@ -15,8 +15,9 @@ policy = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
 parts, _ = bench.initial_particles(pomdp, bench.N_PARTICLES)
 policy.set_belief_particles(parts)
 for k in range(2):
+    policy.reset_counters()
     a, N, V = policy.search(Q)
+    cs = policy.counters()  # of this decision: ncu profiles the second one (-s 1)
     policy.pf_update_sir(5, k & 1, seed=k, n_out=bench.N_PARTICLES)
-cs = policy.counters()
 print("ok", a, cs["rollout_steps"], cs["waves"], cs["kernel_launches"])
 policy.close()

@@ -75,6 +75,12 @@ def ncu_raw(rep):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     steps_per_decision = float(sys.argv[2]) if len(sys.argv) > 2 else None
+    if steps_per_decision is None:  # rollout steps of the profiled decision, printed by scripts/profile_step.py
+        log = os.path.join(GP, "ncu_search.log")
+        if os.path.exists(log):
+            for ln in open(log):
+                if ln.startswith("ok "):
+                    steps_per_decision = float(ln.split()[2])
     os.makedirs(OUT, exist_ok=True)
     consts_path = os.path.join(OUT, "roofline_constants.json")
     consts = json.load(open(consts_path)) if os.path.exists(consts_path) else {}
