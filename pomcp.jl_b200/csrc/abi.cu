@@ -119,6 +119,8 @@ struct pomcp_handle {
   size_t cum_cap = 0;
   // one zero-initialised control block per scan / resample: [0..7] PfCtl, [8] ticket or barrier, [9..] tile status
   unsigned long long* d_scan_status = nullptr;
+  unsigned long long* d_pf_regions = nullptr;  // fused SIR: two control blocks, each zeroed by the launch that uses the other
+  int pf_flip = 0;
   size_t scan_cap = 0;
   void* d_tmp = nullptr;
   size_t tmp_cap = 0;
@@ -411,39 +413,47 @@ int ensure_scan(pomcp_handle* h, long long n) {
 // K6 -> K7 -> K8 on an arbitrary weight source
 template <class Src, class Out>
 int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long long n_out, Out* d_out) {
-  int rc = ensure_bytes(h, (void**)&h->d_cum, &h->cum_cap, (size_t)n * sizeof(unsigned long long));
-  if (rc) return rc;
-  rc = ensure_scan(h, n);
-  if (rc) return rc;
+  int rc;
   // fused single-launch path when the whole set fits one co-resident grid
   static int max_grid = -1;  // per <Src,Out> instantiation
   if (max_grid < 0) {
     int per_sm = 0, sms = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    max_grid = per_sm * sms;
+    max_grid = std::min(per_sm * sms, PF_MAX_GRID);
   }
-  // split the set evenly over the co-resident grid: rows of 32 particles per warp (<= PF_ITEMS)
+  // split the set evenly over the co-resident grid: `rows` consecutive particles per thread (<= PF_ITEMS)
   long long rows_ll = max_grid > 0 ? (n + (long long)max_grid * PF_THREADS - 1) / ((long long)max_grid * PF_THREADS) : 99;
   int rows = (int)std::max<long long>(rows_ll, 1);
   long long grid = (n + (long long)PF_THREADS * rows - 1) / ((long long)PF_THREADS * rows);
   if (rows <= PF_ITEMS && grid <= max_grid && !h->force_streaming_pf) {
+    // The control block (PfCtl, barrier counter, CTA totals) must start zeroed.  There are two; a launch uses
+    // one and zeroes the other for the next launch, so no memset sits between the caller and the kernel.
+    if (!h->d_pf_regions) {
+      CK(cudaMalloc((void**)&h->d_pf_regions, 2 * PF_CTRL_WORDS * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(h->d_pf_regions, 0, 2 * PF_CTRL_WORDS * sizeof(unsigned long long), h->stream));
+    }
+    unsigned long long* region = h->d_pf_regions + (size_t)h->pf_flip * PF_CTRL_WORDS;
+    unsigned long long* other = h->d_pf_regions + (size_t)(1 - h->pf_flip) * PF_CTRL_WORDS;
+    h->pf_flip ^= 1;
+    h->d_pfctl = (PfCtl*)region;
     PfCtl* ctl = h->d_pfctl;
-    unsigned long long* cta_tot = h->d_scan_status + 9;
-    unsigned int* bar = (unsigned int*)(h->d_scan_status + 8);
+    unsigned long long* cta_tot = region + 9;
+    unsigned int* bar = (unsigned int*)(region + 8);
     Src src_copy = src;
     void* args[] = {(void*)&src_copy, (void*)&n, (void*)&ctl, (void*)&ru, (void*)&n_out, (void*)&d_out,
-                    (void*)&cta_tot, (void*)&bar, (void*)&rows};
-    if (std::getenv("POMCP_PF_NONCOOP"))  // measurement only: plain launch (co-residency not guaranteed)
-      k_pf_fused<Src, Out><<<(unsigned)grid, PF_THREADS, 0, h->stream>>>(src_copy, n, ctl, ru, n_out, d_out, cta_tot, bar, rows);
-    else
-      CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
-                                     0, h->stream));
+                    (void*)&cta_tot, (void*)&bar, (void*)&rows, (void*)&other};
+    CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
+                                   0, h->stream));
     rc = launch_check(h, "k_pf_fused");
     if (rc) return rc;
     h->timers[POMCP_PHASE_PF].launches += 1;
     return POMCP_OK;
   }
+  rc = ensure_bytes(h, (void**)&h->d_cum, &h->cum_cap, (size_t)n * sizeof(unsigned long long));
+  if (rc) return rc;
+  rc = ensure_scan(h, n);
+  if (rc) return rc;
   // streaming path: weigh -> total -> scan + emit
   int blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
   k_pf_weigh<Src><<<blocks, 256, 0, h->stream>>>(src, n, (double*)h->d_cum, h->d_pfctl);
@@ -642,7 +652,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
-                  h->d_cum, h->d_scan_status, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values};
+                  h->d_cum, h->d_scan_status, h->d_pf_regions, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);

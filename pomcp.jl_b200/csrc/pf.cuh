@@ -147,6 +147,17 @@ struct ModelSrc {
     w = M::obs_weight(m, a, sp, obs);
     return true;
   }
+  // the same from a state that is already in registers
+  __device__ __forceinline__ bool eval_from(long long i, const State& s, State& sp, double& w) const {
+    if (M::terminal(m, s)) { sp = s; w = 0.0; return false; }
+    double ut0 = 0.0;
+    if (M::T_DRAW) ut0 = u01(philox4x32_10(0u, TAG_PF, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32), k0, k1).w[0]);
+    uint64_t o;
+    double r;
+    M::template step<false, double>(m, s, a, ut0, 0.0, 0.0, sp, o, r);
+    w = M::obs_weight(m, a, sp, obs);
+    return true;
+  }
   // generate_s only (the emit phase needs the state, not the weight, of the particles it copies)
   __device__ __forceinline__ void propagate(long long i, State& sp) const { propagate_from(i, states[i], sp); }
   __device__ __forceinline__ State load(long long i) const { return states[i]; }
@@ -169,7 +180,7 @@ struct ArraySrc {  // replayed weights (parity hook): payload is the index itsel
     sp = i;
     w = w_in[i];
     return true;
-  }
+  }  __device__ __forceinline__ bool eval_from(long long i, const State&, State& sp, double& w) const { return eval(i, sp, w); }
 };
 
 __device__ __forceinline__ int pf_scale(unsigned long long max_bits, long long n) {
@@ -449,16 +460,21 @@ __global__ void k_resample_seq_f64(const double* w, long long n, double r01, lon
 
 // ---- K6+K7+K8 fused: one persistent cooperative launch for particle sets that fit the grid
 // (n <= co-resident CTAs * 4096; 148 SMs x 2 CTAs x 4096 items = 1.2 M particles on B200).
-// The particles are split evenly over the grid (`rows` warp-rows of 32 per warp, <= 8); every CTA
-// owns 512*rows consecutive particles and keeps their fp64 weights in registers across two
-// grid-wide barriers, so HBM sees each input state once and each output state once:
-//   phase A  read s_i, propagate + weight          -> global max weight, first alive particle
-//   barrier  phase B  quantise, warp/CTA scan      -> per-CTA totals (gridDim values)
-//   barrier  phase C  offsets from the CTA totals, closed-form output ranges, write the copies
-// Same integers as the streaming path (k_pf_max / k_pf_scan / k_pf_emit), so the same indices.
+// The particles are split evenly over the grid, `items` (<= 8) consecutive particles per thread; a thread
+// keeps their states and fp64 weights in registers across two grid-wide barriers, so HBM sees each input
+// state once and each output state once:
+//   phase A  read s_i (all of a thread's loads in flight together), propagate + weight
+//                                               -> global max weight, first alive particle
+//   barrier  phase B  quantise, thread-local prefix, one u64 warp scan per thread, CTA scan
+//                                               -> per-CTA totals (gridDim values)
+//   barrier  phase C  offsets from the CTA totals; (quotient, remainder) of C * n_out / T carried from
+//                     particle to particle (PfDiv::Run), write the copies
+// Same integers as the streaming path, so the same indices.
 constexpr int PF_THREADS = 512;
 constexpr int PF_ITEMS = 8;
 constexpr int PF_CTA_ITEMS = PF_THREADS * PF_ITEMS;
+constexpr int PF_MAX_GRID = 1024;                 // CTA totals that fit a control block
+constexpr int PF_CTRL_WORDS = 9 + PF_MAX_GRID + 7;  // u64 words: PfCtl (8), barrier counter (1), CTA totals
 
 __device__ __forceinline__ void pf_grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
@@ -478,31 +494,46 @@ template <class Src, class Out>
 __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constant__ Src src, long long n, PfCtl* ctl,
                                                             uint32_t ru, long long n_out, Out* out,
                                                             unsigned long long* cta_tot, unsigned int* bar,
-                                                            int rows) {
+                                                            int items, unsigned long long* next_ctl) {
+  using State = typename Src::State;
   __shared__ unsigned long long s_a[PF_THREADS / 32];
   __shared__ unsigned long long s_b[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long base = ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * rows;
+  const long long base = ((long long)blockIdx.x * PF_THREADS + threadIdx.x) * items;
+  // the other control block, for the next launch (nobody uses it now); this launch's own lines are
+  // requested into L2 so that the first atomics on them do not pay a DRAM miss
+  if (blockIdx.x == gridDim.x - 1)
+    for (int k = threadIdx.x; k < PF_CTRL_WORDS; k += PF_THREADS) next_ctl[k] = 0ull;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(cta_tot + blockIdx.x));
+  }
 
-  // ---- phase A: propagate + weight
+  // ---- phase A: propagate + weight.  States of <= 8 bytes stay in registers for phase C.
+  constexpr bool KEEP = sizeof(State) <= 8;
+  State st[KEEP ? PF_ITEMS : 1];
+  if (KEEP) {
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k)
+      if (k < items && base + k < n) st[KEEP ? k : 0] = src.load(base + k);
+  }
   double w[PF_ITEMS];
   unsigned alive_mask = 0;
   unsigned long long mx = 0, first = ~0ull;
 #pragma unroll
-  for (int j = 0; j < PF_ITEMS; ++j) {
-    long long i = base + j * 32 + lane;
-    w[j] = 0.0;
-    if (j < rows && i < n) {
-      typename Src::State sp;
-      bool alive = src.eval(i, sp, w[j]);
+  for (int k = 0; k < PF_ITEMS; ++k) {
+    w[k] = 0.0;
+    if (k < items && base + k < n) {
+      State sp;
+      const bool alive = KEEP ? src.eval_from(base + k, st[KEEP ? k : 0], sp, w[k]) : src.eval(base + k, sp, w[k]);
       if (alive) {
-        alive_mask |= 1u << j;
-        if ((unsigned long long)i < first) first = (unsigned long long)i;
-        unsigned long long b = (w[j] > 0.0) ? d2u(w[j]) : 0ull;
+        alive_mask |= 1u << k;
+        if (first == ~0ull) first = (unsigned long long)(base + k);
+        const unsigned long long b = (w[k] > 0.0) ? d2u(w[k]) : 0ull;
         mx = b > mx ? b : mx;
       } else {
-        w[j] = 0.0;
+        w[k] = 0.0;
       }
     }
   }
@@ -527,33 +558,35 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   }
   pf_grid_barrier(bar, gridDim.x);
 
-  // ---- phase B: quantise and scan inside the CTA
+  // ---- phase B: quantise, prefix inside the thread, scan the thread totals in the warp and the CTA
   const unsigned long long max_bits = ld_volatile_u64(&ctl->max_bits);
   const int scale = pf_scale(max_bits, n);
   unsigned long long inc[PF_ITEMS];
-  unsigned long long carry = 0;
+  unsigned long long run = 0;
 #pragma unroll
-  for (int j = 0; j < PF_ITEMS; ++j) {
-    unsigned long long x = ((alive_mask >> j) & 1u) ? pf_quantise(w[j], scale) : 0ull;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
-      if (lane >= off) x += t;
-    }
-    inc[j] = x + carry;
-    carry += __shfl_sync(0xffffffffu, x, 31);
+  for (int k = 0; k < PF_ITEMS; ++k) {
+    run += ((alive_mask >> k) & 1u) ? pf_quantise(w[k], scale) : 0ull;
+    inc[k] = run;
   }
-  if (lane == 0) s_a[warp] = carry;
+  unsigned long long x = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += t;
+  }
+  const unsigned long long thread_excl = x - run;
+  __syncthreads();  // s_a is re-used
+  if (lane == 31) s_a[warp] = x;
   __syncthreads();
   if (warp == 0) {
-    unsigned long long v = (lane < PF_THREADS / 32) ? s_a[lane] : 0ull, x = v;
+    unsigned long long v = (lane < PF_THREADS / 32) ? s_a[lane] : 0ull, y = v;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
-      if (lane >= off) x += t;
+      unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+      if (lane >= off) y += t;
     }
-    if (lane < PF_THREADS / 32) s_a[lane] = x - v;  // exclusive over warps
-    if (lane == 31) atomicExch(&cta_tot[blockIdx.x], x);
+    if (lane < PF_THREADS / 32) s_a[lane] = y - v;  // exclusive over warps
+    if (lane == 31) atomicExch(&cta_tot[blockIdx.x], y);
   }
   pf_grid_barrier(bar, 2u * gridDim.x);
 
@@ -576,34 +609,42 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   const unsigned long long T = s_total;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->total = T;
-    int st = POMCP_OK;
-    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
-    else if (max_bits == 0 || T == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
-    ctl->status = st;
+    int stt = POMCP_OK;
+    if (!ctl->any_alive) stt = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+    else if (max_bits == 0 || T == 0) stt = POMCP_ERR_PARTICLE_DEPLETION;
+    ctl->status = stt;
   }
   if (T == 0) return;
 
   // ---- phase C: particle i owns outputs [M(C_{i-1}), M(C_i))
   const unsigned long long first_alive = ~ld_volatile_u64(&ctl->first_alive_inv);
-  const unsigned long long off0 = s_off + s_a[warp];
+  const unsigned long long off0 = s_off + s_a[warp] + thread_excl;  // C just before this thread's particles
   const PfDiv dv(T, ru, n_out);
-  long long prev_hi = dv.points_below(off0);  // M at the start of this warp's range
+  PfDiv::Run rn = dv.start(off0);
+  long long lo = dv.count(rn);
+  unsigned long long prev_inc = 0;
 #pragma unroll
-  for (int j = 0; j < PF_ITEMS; ++j) {
-    if (j >= rows) break;  // uniform
-    long long i = base + j * 32 + lane;
-    long long hi = dv.points_below(off0 + inc[j]);
-    long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
-    if (lane == 0) lo = prev_hi;
-    prev_hi = __shfl_sync(0xffffffffu, hi, 31);
-    if (j < rows && i < n && ((alive_mask >> j) & 1u)) {
+  for (int k = 0; k < PF_ITEMS; ++k) {
+    const long long i = base + k;
+    dv.advance(rn, inc[k] - prev_inc);
+    prev_inc = inc[k];
+    const long long hi = dv.count(rn);
+    if ((alive_mask >> k) & 1u) {
       if ((unsigned long long)i == first_alive) lo = 0;
-      if (lo < hi) {
-        typename Src::State sp;
-        src.propagate(i, sp);
-        for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+      const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
+      if (copies) {
+        State sp;
+        if (KEEP) src.propagate_from(i, st[KEEP ? k : 0], sp);
+        else src.propagate(i, sp);
+        Out* o = out + lo;
+        o[0] = (Out)sp;
+        if (copies > 1) {
+          o[1] = (Out)sp;
+          for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
+        }
       }
     }
+    lo = hi;
   }
 }
 
