@@ -418,7 +418,8 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   static int max_grid = -1;  // per <Src,Out> instantiation
   if (max_grid < 0) {
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
+    if (sizeof(typename Src::State) <= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused_striped<Src, Out>, PF_THREADS, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     max_grid = std::min(per_sm * sms, PF_MAX_GRID);
   }
@@ -443,8 +444,14 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     Src src_copy = src;
     void* args[] = {(void*)&src_copy, (void*)&n, (void*)&ctl, (void*)&ru, (void*)&n_out, (void*)&d_out,
                     (void*)&cta_tot, (void*)&bar, (void*)&rows, (void*)&other};
-    CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
-                                   0, h->stream));
+    if (sizeof(typename Src::State) <= 8) {
+      CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
+                                     0, h->stream));
+    } else {  // wide states: striped variant; its control block is zeroed here (it does not reset the other one)
+      CK(cudaMemsetAsync(other, 0, PF_CTRL_WORDS * sizeof(unsigned long long), h->stream));
+      CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused_striped<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS),
+                                     args, 0, h->stream));
+    }
     rc = launch_check(h, "k_pf_fused");
     if (rc) return rc;
     h->timers[POMCP_PHASE_PF].launches += 1;

@@ -648,6 +648,142 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   }
 }
 
+// The same three phases with the particles striped over the warp (particle = base + row * 32 + lane; one u64
+// warp scan per row, closed-form output range per particle): used for states wider than 8 bytes, whose
+// loads only coalesce this way (LightDark, 16 bytes: 44 us against 51 us at 2^20 particles).
+template <class Src, class Out>
+__global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid_constant__ Src src, long long n, PfCtl* ctl,
+                                                            uint32_t ru, long long n_out, Out* out,
+                                                            unsigned long long* cta_tot, unsigned int* bar,
+                                                            int rows) {
+  __shared__ unsigned long long s_a[PF_THREADS / 32];
+  __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_off, s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long base = ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * rows;
+
+  // ---- phase A: propagate + weight
+  double w[PF_ITEMS];
+  unsigned alive_mask = 0;
+  unsigned long long mx = 0, first = ~0ull;
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    long long i = base + j * 32 + lane;
+    w[j] = 0.0;
+    if (j < rows && i < n) {
+      typename Src::State sp;
+      bool alive = src.eval(i, sp, w[j]);
+      if (alive) {
+        alive_mask |= 1u << j;
+        if ((unsigned long long)i < first) first = (unsigned long long)i;
+        unsigned long long b = (w[j] > 0.0) ? d2u(w[j]) : 0ull;
+        mx = b > mx ? b : mx;
+      } else {
+        w[j] = 0.0;
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, off), of = __shfl_xor_sync(0xffffffffu, first, off);
+    mx = om > mx ? om : mx;
+    first = of < first ? of : first;
+  }
+  if (lane == 0) { s_a[warp] = mx; s_b[warp] = first; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < PF_THREADS / 32; ++k) {
+      mx = s_a[k] > mx ? s_a[k] : mx;
+      first = s_b[k] < first ? s_b[k] : first;
+    }
+    if (first != ~0ull) {
+      atomicMax(&ctl->max_bits, mx);
+      atomicMax(&ctl->first_alive_inv, ~first);
+      ctl->any_alive = 1;
+    }
+  }
+  pf_grid_barrier(bar, gridDim.x);
+
+  // ---- phase B: quantise and scan inside the CTA
+  const unsigned long long max_bits = ld_volatile_u64(&ctl->max_bits);
+  const int scale = pf_scale(max_bits, n);
+  unsigned long long inc[PF_ITEMS];
+  unsigned long long carry = 0;
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    unsigned long long x = ((alive_mask >> j) & 1u) ? pf_quantise(w[j], scale) : 0ull;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    inc[j] = x + carry;
+    carry += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) s_a[warp] = carry;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = (lane < PF_THREADS / 32) ? s_a[lane] : 0ull, x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    if (lane < PF_THREADS / 32) s_a[lane] = x - v;  // exclusive over warps
+    if (lane == 31) atomicExch(&cta_tot[blockIdx.x], x);
+  }
+  pf_grid_barrier(bar, 2u * gridDim.x);
+
+  // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
+  if (warp == 0) {
+    unsigned long long before = 0, all = 0;
+    for (int k = lane; k < (int)gridDim.x; k += 32) {
+      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
+      all += t;
+      if (k < (int)blockIdx.x) before += t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, off);
+      all += __shfl_xor_sync(0xffffffffu, all, off);
+    }
+    if (lane == 0) { s_off = before; s_total = all; }
+  }
+  __syncthreads();
+  const unsigned long long T = s_total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->total = T;
+    int st = POMCP_OK;
+    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+    else if (max_bits == 0 || T == 0) st = POMCP_ERR_PARTICLE_DEPLETION;
+    ctl->status = st;
+  }
+  if (T == 0) return;
+
+  // ---- phase C: particle i owns outputs [M(C_{i-1}), M(C_i))
+  const unsigned long long first_alive = ~ld_volatile_u64(&ctl->first_alive_inv);
+  const unsigned long long off0 = s_off + s_a[warp];
+  const PfDiv dv(T, ru, n_out);
+  long long prev_hi = dv.points_below(off0);  // M at the start of this warp's range
+#pragma unroll
+  for (int j = 0; j < PF_ITEMS; ++j) {
+    if (j >= rows) break;  // uniform
+    long long i = base + j * 32 + lane;
+    long long hi = dv.points_below(off0 + inc[j]);
+    long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
+    if (lane == 0) lo = prev_hi;
+    prev_hi = __shfl_sync(0xffffffffu, hi, 31);
+    if (j < rows && i < n && ((alive_mask >> j) & 1u)) {
+      if ((unsigned long long)i == first_alive) lo = 0;
+      if (lo < hi) {
+        typename Src::State sp;
+        src.propagate(i, sp);
+        for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+      }
+    }
+  }
+}
+
 // n draws from the problem's initial state distribution (the reinvigorator's stand-in for an old
 // belief that is still the distribution itself)
 template <int PID>
