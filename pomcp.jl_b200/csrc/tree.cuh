@@ -1060,13 +1060,40 @@ struct LeafJob {
   double partial[4];
   int psteps[4];
 };
-__device__ __forceinline__ void team_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// Named barrier with an immediate id: with the id in a register ptxas reserves all 16 barriers for the CTA,
+// and the SM's barrier pool then caps residency at four CTAs (the four-warp teams want seven).
+template <int ID>
+__device__ __forceinline__ void bar_imm(int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
+}
+template <int NTEAMS>
+__device__ __forceinline__ void team_bar(int id, int nthreads) {  // id in 1 .. 2 * NTEAMS (two per team)
+  if (NTEAMS == 1) {
+    if (id == 1) bar_imm<1>(nthreads); else bar_imm<2>(nthreads);
+  } else if (NTEAMS == 2) {
+    switch (id) {
+      case 1: bar_imm<1>(nthreads); break;
+      case 2: bar_imm<2>(nthreads); break;
+      case 3: bar_imm<3>(nthreads); break;
+      default: bar_imm<4>(nthreads); break;
+    }
+  } else {
+    switch (id) {
+      case 1: bar_imm<1>(nthreads); break;
+      case 2: bar_imm<2>(nthreads); break;
+      case 3: bar_imm<3>(nthreads); break;
+      case 4: bar_imm<4>(nthreads); break;
+      case 5: bar_imm<5>(nthreads); break;
+      case 6: bar_imm<6>(nthreads); break;
+      case 7: bar_imm<7>(nthreads); break;
+      default: bar_imm<8>(nthreads); break;
+    }
+  }
 }
 
 // One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
 // (lane 0; requested early so its latency hides behind the rollouts).
-template <int PID, bool DPA>
+template <int PID, bool DPA, int NTEAMS>
 __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
                                                const uint32_t* eta_thr, const SearchCfg& cfg,
                                                const PathView<typename ModelT<PID>::State>& pv,
@@ -1370,14 +1397,14 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
           job->q = q;
           job->cmd = 1;
         }
-        team_bar(job->bar, 32 * W);
+        team_bar<NTEAMS>(job->bar, 32 * W);
       }
       int nsteps = 0;
       const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
       double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       if (W > 1) {
-        team_bar(job->bar + 1, 32 * W);  // the helpers' partial sums are in shared memory
+        team_bar<NTEAMS>(job->bar + 1, 32 * W);  // the helpers' partial sums are in shared memory
         for (int w = 1; w < W; ++w) {
           sum += job->partial[w];
           nsteps += job->psteps[w];
@@ -1499,7 +1526,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   if (role > 0) {
     // helper warp of the rollout team: 32 rollouts of every leaf the tree warp posts
     for (;;) {
-      team_bar(bar, 32 * W);
+      team_bar<NTEAMS>(bar, 32 * W);
       if (job->cmd == 0) break;
       int nsteps = 0;
       const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, job->s, job->steps, job->last_o, job->q, lane, nsteps, 32 * role);
@@ -1509,7 +1536,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
         job->partial[role] = sum;
         job->psteps[role] = nsteps;
       }
-      team_bar(bar + 1, 32 * W);
+      team_bar<NTEAMS>(bar + 1, 32 * W);
     }
     return;
   }
@@ -1561,11 +1588,11 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID, DPA>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q, spare);
+    simulate_async<PID, DPA, NTEAMS>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q, spare);
   }
   if (W > 1) {  // release the helpers
     if (lane == 0) job->cmd = 0;
-    team_bar(bar, 32 * W);
+    team_bar<NTEAMS>(bar, 32 * W);
   }
   if (lane == 0) {
     flush_counters(P, lc, false);
