@@ -121,3 +121,44 @@ def test_long_episode_does_not_exhaust_the_pool(oracle, gpu_lib):
         pl.update_unweighted(a, int(o))
         assert pl.counters()["nodes"] <= 16 * Q
     pl.close()
+
+
+def test_batched_compaction_keeps_the_subtree(gpu_lib, monkeypatch):
+    """The batched workers insert with node ids allocated ahead of time, so a child can be older than its
+    parent; the compaction walks parent links instead of relying on id order.  After a compacting re-root the
+    kept sub-tree must be exactly the old one: same root visit count, same root statistics, N(ha) = sum_o N(hao)
+    everywhere, and no id lost to insertion races (ids in use <= nodes + one spare per worker)."""
+    monkeypatch.setenv("POMCP_COMPACT_ALWAYS", "1")
+    pomdp = pj.RockSamplePOMDP(7, 8, seed=7008)
+    Q = 200_000
+    pl = pj.solve(pj.POMCPSolver(c=20.0, rng=9, tree_queries=Q, search_mode="batched", max_nodes=4 * Q,
+                                 max_log=40 * Q), pomdp)
+    pl.set_belief_initial()
+    a, N, V = pl.search(Q)
+    cs = pl.counters()
+    assert cs["nodes"] <= cs["simulations"] + 1184 + 1
+    node_N, act_N, act_V, child = pl.dump_tree()
+    kid_N = np.where(child >= 0, node_N[np.maximum(child, 0)], 0).sum(axis=2)
+    assert np.array_equal(kid_N, act_N)
+    # the child ids are NOT monotone along paths any more (that is the point of the test)
+    parent_of = np.full(node_N.shape[0], -1, dtype=np.int64)
+    hs, as_, os_ = np.nonzero(child >= 0)
+    parent_of[child[hs, as_, os_]] = hs
+    linked = np.nonzero(parent_of >= 0)[0]
+    assert (parent_of[linked] > linked).any()
+    # re-root at the most visited child of the chosen action
+    o = int(np.argmax([pl.node_stats([(a, k)])[0] for k in range(pomdp.n_observations)]))
+    n_before, _, N_before, V_before = pl.node_stats([(a, o)])
+    sub_before = {(a2, o2): pl.node_stats([(a, o), (a2, o2)])[0] for a2 in range(pomdp.n_actions) for o2 in range(3)}
+    pl.update_unweighted(a, o)
+    rn, N1, V1 = pl.root_stats()
+    assert rn == n_before and np.array_equal(N1, N_before) and np.array_equal(_bits(V1), _bits(V_before))
+    for (a2, o2), n in sub_before.items():
+        assert pl.node_stats([(a2, o2)])[0] == n
+    node_N, act_N, act_V, child = pl.dump_tree()
+    kid_N = np.where(child >= 0, node_N[np.maximum(child, 0)], 0).sum(axis=2)
+    assert np.array_equal(kid_N, act_N)
+    assert pl.counters()["nodes"] < cs["nodes"]
+    a2, N2, V2 = pl.search(Q)  # and the tree keeps growing from there
+    assert pl.root_stats()[0] == rn + Q
+    pl.close()
