@@ -305,7 +305,12 @@ def run_gpu(args):
 
     # ---------------- end to end through the public API with host buffers
     sir = pj.SIRParticleFilter(policy, N_PARTICLES, rng=5)
-    belief = pj.ParticleCollection(parts)
+    # host buffers of the particle set: pinned, two of them (the new set is read back into the one the
+    # current set does not occupy)
+    pinned = [torch.empty(N_PARTICLES, dtype=torch.int32).pin_memory() for _ in range(2)]
+    host = [t.numpy().view(np.uint32) for t in pinned]
+    host[0][:] = parts
+    belief = pj.ParticleCollection(host[0])
 
     def e2e_step(k, b):
         if world > 1:
@@ -313,7 +318,8 @@ def run_gpu(args):
             a = policy.search_rootparallel(TREE_QUERIES)[0]
         else:
             a = pj.action(policy, b)                 # H2D particles, search, D2H action + root stats
-        return a, pj.update(sir, b, 5, k & 1)          # H2D particles, SIR on device, D2H new particles
+        # H2D particles, SIR on device, D2H new particles
+        return a, pj.update(sir, b, 5, k & 1, out=host[1] if b.particles.ctypes.data == host[0].ctypes.data else host[0])
 
     b = belief
     for k in range(max(1, args.warmup // 2)):

@@ -428,10 +428,17 @@ class POMCPPlanner:
         _check(lib().pomcp_set_belief_initial(self._h), self._h)
         self._generation += 1
 
-    def belief_particles(self):
+    def belief_particles(self, out=None):
+        """The belief's particles as a host array; `out` (same dtype, at least as long — e.g. a pinned buffer
+        the caller re-uses from step to step) receives them instead of a fresh array."""
         n = C.c_int64(0)
         _check(lib().pomcp_get_belief_particles(self._h, None, 0, C.byref(n)), self._h)
-        out = np.zeros(n.value, dtype=self.problem.state_dtype)
+        if out is not None:
+            if out.dtype != self.problem.state_dtype or out.ndim != 1 or len(out) < n.value or not out.flags.c_contiguous:
+                raise ValueError("out must be a contiguous 1-d array of the problem's state dtype, long enough")
+            out = out[:n.value]
+        else:
+            out = np.zeros(n.value, dtype=self.problem.state_dtype)
         if n.value:
             _check(lib().pomcp_get_belief_particles(self._h, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)),
                    self._h)
@@ -687,10 +694,11 @@ def initialize_belief(up, b):
     return _make_node(up.planner, b)
 
 
-def update(up, b_old, a, o):
-    """update(updater, b_old, a, o) (src/updater.jl:13-27 for RootUpdater; SIR filter otherwise)."""
+def update(up, b_old, a, o, out=None):
+    """update(updater, b_old, a, o) (src/updater.jl:13-27 for RootUpdater; SIR filter otherwise).
+    `out`: SIR filter only, host buffer that receives the new particle set (see belief_particles)."""
     if isinstance(up, SIRParticleFilter):
-        return up.update(b_old, a, o)
+        return up.update(b_old, a, o, out=out)
     pl = up.planner
     if not isinstance(b_old, BeliefNode):
         raise TypeError("RootUpdater.update needs the BeliefNode returned by initialize_belief/update")
@@ -730,13 +738,13 @@ class SIRParticleFilter:
             raise NotImplementedError("draw the initial particles on the host and pass a ParticleCollection")
         return b if isinstance(b, ParticleCollection) else ParticleCollection(b)
 
-    def update(self, b, a, o, on_device=False):
+    def update(self, b, a, o, on_device=False, out=None):
         pl = self.planner
         if not on_device:
             pl.set_belief_particles(b.particles)
         self._step += 1
         pl.pf_update_sir(a, o, (self.seed * 0x9E3779B97F4A7C15 + self._step) & (2 ** 64 - 1), self.n)
-        return ParticleCollection(pl.belief_particles())
+        return ParticleCollection(pl.belief_particles(out))
 
 
 def root_parallel_action(policy):
