@@ -355,6 +355,9 @@ def run_gpu(args):
         pj_path = os.path.join(ROOT, "profiles", "roofline_constants.json")
         if os.path.exists(pj_path):
             prof = json.load(open(pj_path))
+        n_search = max(len(rollout_ms), 1)
+        issue_frac = (prof["workers_thread_inst_per_launch"] * n_search / roll_s / (148 * 4 * 32 * sm_max * 1e6)
+                      if (prof.get("workers_thread_inst_per_launch") and roll_s > 0) else None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -381,10 +384,11 @@ def run_gpu(args):
                 "achieved": steps_rank0 / roll_s if roll_s > 0 else None, "unit": "rollout steps/s inside the kernel",
                 "share_of_step": roll_s * 1e3 / total_ms,
                 "thread_inst_per_step": prof.get("rollout_thread_inst_per_step"),
-                "peak": (148 * 4 * 32 * sm_max * 1e6 / prof["rollout_thread_inst_per_step"])
-                if prof.get("rollout_thread_inst_per_step") else None,
-                "frac": (steps_rank0 / roll_s) / (148 * 4 * 32 * sm_max * 1e6 / prof["rollout_thread_inst_per_step"])
-                if (prof.get("rollout_thread_inst_per_step") and roll_s > 0) else None,
+                # frac = thread instructions per launch (ncu, one pass; about constant from tree to tree, unlike
+                # the number of live rollout steps) / measured kernel time / (SMs x 4 schedulers x 32 lanes x f_clk):
+                # issue-slot utilisation x active lanes.  peak = achieved / frac.
+                "frac": issue_frac,
+                "peak": (steps_rank0 / roll_s / issue_frac) if (issue_frac and roll_s > 0) else None,
                 "warp_efficiency": prof.get("rollout_warp_efficiency"),
                 "tree": {"avg_descent_depth": cs["tree_steps"] / max(cs["simulations"], 1),
                          "nodes_per_sec": nodes_per_search / (statistics.mean(rollout_ms) * 1e-3)

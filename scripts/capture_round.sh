@@ -16,5 +16,11 @@ ncu --set full --clock-control none --import-source on -k regex:k_search_workers
   -o $out/prof_workers_$tag python scripts/profile_step.py > $out/ncu_search.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_pf_fused -s 1 -c 1 -f \
   -o $out/prof_pffused_$tag python scripts/profile_step.py > $out/ncu_pf.log 2>&1
+# instructions per rollout step: thread instructions and the step counter of the SAME kernel pass (the --set full
+# capture replays the kernel dozens of times, every pass grows a different tree, and the counter read afterwards
+# belongs to the last one) -- three SM counters fit one pass
+ncu --metrics smsp__thread_inst_executed.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active \
+  --clock-control none -k regex:k_search_workers -s 1 -c 1 --csv --log-file $out/workers_inst_$tag.csv \
+  python scripts/profile_step.py > $out/workers_inst_$tag.log 2>&1
 tail -n 2 $out/ncu_search.log; tail -n 2 $out/ncu_pf.log
 cat $out/bench_$tag.json

@@ -117,6 +117,25 @@ def main():
                 consts["pf_dram_bytes_per_update"] = (g("dram__bytes_read.sum") * scale.get(unit_r, 1) +
                                                       g("dram__bytes_write.sum") *
                                                       scale.get(units[hdr.index("dram__bytes_write.sum")], 1))
+    # single-pass instruction count + step counter of the same pass (capture_round.sh), when present
+    one = os.path.join(GP, f"workers_inst_{tag}.csv")
+    log1 = os.path.join(GP, f"workers_inst_{tag}.log")
+    if os.path.exists(one) and os.path.exists(log1):
+        steps1 = None
+        for ln in open(log1):
+            if ln.startswith("ok "):
+                steps1 = float(ln.split()[2])
+        vals = {}
+        for row in csv.DictReader([ln for ln in open(one) if not ln.startswith("==")]):
+            vals[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+        if steps1 and "smsp__thread_inst_executed.sum" in vals:
+            consts["rollout_thread_inst_per_step"] = vals["smsp__thread_inst_executed.sum"] / steps1
+            consts["rollout_steps_per_profiled_launch"] = steps1
+            consts["workers_thread_inst_per_launch"] = vals["smsp__thread_inst_executed.sum"]
+            consts["rollout_warp_efficiency"] = (vals["smsp__thread_inst_executed.sum"] /
+                                                 vals["smsp__inst_executed.sum"] / 32.0)
+            consts["workers_issue_active_pct"] = vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]
+            consts["inst_per_step_from"] = "one ncu pass (3 SM counters) + the step counter of that pass"
     consts["source"] = f"scripts/summarize_profiles.py {tag}"
     json.dump(consts, open(consts_path, "w"), indent=1)
     print(json.dumps(consts, indent=1))
