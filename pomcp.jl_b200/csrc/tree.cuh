@@ -493,6 +493,21 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
   }
 }
 
+// Value-returning atomic add whose result is NOT needed right away.  `atomicAdd` under `if (lane == 0)` is
+// compiled into the warp-aggregated form (vote, one ATOMG, shuffle of the result to the lanes), and that
+// shuffle waits for the round trip on the spot; the plain PTX instruction leaves the wait to the first use.
+__device__ __forceinline__ unsigned long long atom_add_u64_async(unsigned long long* addr, unsigned long long v,
+                                                                  unsigned any_runtime_value) {
+  // ptxas aggregates the PTX instruction as well when it can prove the address warp-uniform.  The callers are
+  // lane 0, so laneid * (anything it cannot fold) is an offset of zero that keeps the address lane-dependent.
+  unsigned laneid;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(laneid));
+  const unsigned long long off = (unsigned long long)laneid * (unsigned long long)any_runtime_value * 8ull;
+  unsigned long long r;
+  asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(r) : "l"(__cvta_generic_to_global(addr) + off), "l"(v) : "memory");
+  return r;
+}
+
 // Batched workers, direct table: the same insertion with a node id the worker allocated ahead of time (`spare`,
 // 0 = none yet), so the critical path holds one round trip (the CAS) instead of two, and an id that loses
 // the race is kept for the next insertion instead of being dropped.  The replacement id is requested right
@@ -514,7 +529,7 @@ __device__ __forceinline__ uint32_t insert_child_spare(const Pool& P, int nO, ui
   const uint32_t old = atomicCAS(cs, 0u, pub);
   if (old == 0) {
     created = true;
-    spare = (uint32_t)atomicAdd(&P.ctr->node_count, 1ull);
+    spare = (uint32_t)atom_add_u64_async(&P.ctr->node_count, 1ull, P.max_nodes);
     return pub;
   }
   P.node_pslot[fresh] = 0;  // lost the race: the id stays detached and is offered again next time
@@ -1366,7 +1381,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   }
   if (lane == 0) {
     if (aborted) atomicMax(&P.ctr->next_query, 1ull << 62);  // pool exhausted: stop every worker
-    next_q = atomicAdd(&P.ctr->next_query, 1ull);
+    next_q = atom_add_u64_async(&P.ctr->next_query, 1ull, P.max_nodes);
   }
   __syncwarp();  // lanes re-converge before the rollouts (see above)
   if (aborted) return;
