@@ -148,3 +148,46 @@ class Twin:
             if n.V >= best.V:
                 best = n
         return best.a, [n.N for n in nodes], [n.V for n in nodes]
+
+
+def rocksample_rollout(pomdp, state, steps, key, q, tagword=TAG_ROLLOUT, epoch=0):
+    """Random-policy rollout of RockSample written from the problem statement (Smith & Simmons 2004; moves
+    0 north y+1, 1 east x+1 (off the right edge = exit, terminal), 2 south, 3 west, 4 sample, 5+i check rock i),
+    on the rollout draw map of DESIGN.md §2: block = step // 8 of the (block, tag, query, epoch) Philox
+    stream, 16-bit uniform = low half of word (step % 8) // 2 for even steps, high half for odd ones,
+    a = floor(u16 * nA / 2^16).  Returns (discounted return, steps taken)."""
+    n, nA = pomdp.n, pomdp.n_actions
+    x, y, rocks = state & 15, (state >> 4) & 15, (state >> 8) & 0xFFFF
+    if state & 0x80000000:
+        return 0.0, 0
+    rock_at = {xy: i for i, xy in enumerate(pomdp.rocks)}
+    disc, total, step, blk, w = 1.0, 0.0, 0, -1, None
+    while disc > 0.0 and step < steps:
+        if step // 8 != blk:
+            blk = step // 8
+            w = philox4x32_10((blk, tagword, q, epoch), key)
+        word = w[(step % 8) // 2]
+        u16 = (word >> 16) if (step & 1) else (word & 0xFFFF)
+        a = (u16 * nA) >> 16
+        r, done = 0.0, False
+        if a == 0:
+            y = min(y + 1, n - 1)
+        elif a == 1:
+            if x + 1 > n - 1:
+                r, done = pomdp.r_exit, True
+            else:
+                x += 1
+        elif a == 2:
+            y = max(y - 1, 0)
+        elif a == 3:
+            x = max(x - 1, 0)
+        elif a == 4 and (x, y) in rock_at:
+            i = rock_at[(x, y)]
+            r = pomdp.r_good if (rocks >> i) & 1 else pomdp.r_bad
+            rocks &= ~(1 << i)
+        total += disc * r
+        disc *= pomdp.discount
+        step += 1
+        if done:
+            break
+    return total, step

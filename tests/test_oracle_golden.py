@@ -370,3 +370,24 @@ def test_dpw_observation_widening_oracle(oracle):
     cs = pl.counters()
     assert cs["max_depth_seen"] >= 3 and cs["nodes"] < Q and cs["tree_steps"] > 2 * Q
     assert np.isfinite(V).all()
+
+
+# ----------------------------------------------------------------------------- RockSample rollouts, independent twin
+@pytest.mark.parametrize("n,k,seed", [(7, 8, 7008), (4, 4, 4004), (11, 11, 11011)])
+def test_rocksample_rollouts_match_python_twin(oracle, n, k, seed):
+    """The oracle's RockSample rollout (16-bit action draws, 8 steps per Philox block) against a pure-Python
+    rollout written from the problem statement: returns bit-identical, step counts equal."""
+    from pytwin import rocksample_rollout
+    pomdp = pj.RockSamplePOMDP(n, k, seed=seed)
+    rng = np.random.default_rng(seed)
+    m = 48
+    states = np.array([pomdp.pack_state(int(rng.integers(0, n)), int(rng.integers(0, n)), int(rng.integers(0, 1 << k)))
+                       for _ in range(m)], dtype=np.uint32)
+    states[5] |= np.uint32(abi.RS_TERMINAL)
+    for steps, rseed in ((1, 3), (7, 4), (8, 5), (9, 6), (90, 7)):
+        ret, ns = oracle.rollout_batch(pomdp, states, steps, rseed)
+        key = (rseed & 0xFFFFFFFF, (rseed >> 32) & 0xFFFFFFFF)
+        for i in range(m):
+            want, took = rocksample_rollout(pomdp, int(states[i]), steps, key, i)
+            assert took == ns[i], (i, steps)
+            assert np.float64(want).view(np.uint64) == ret[i:i + 1].view(np.uint64)[0], (i, steps, want, ret[i])
