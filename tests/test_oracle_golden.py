@@ -391,3 +391,26 @@ def test_rocksample_rollouts_match_python_twin(oracle, n, k, seed):
             want, took = rocksample_rollout(pomdp, int(states[i]), steps, key, i)
             assert took == ns[i], (i, steps)
             assert np.float64(want).view(np.uint64) == ret[i:i + 1].view(np.uint64)[0], (i, steps, want, ret[i])
+
+
+def test_rocksample_sensor_model_matches_formula(oracle):
+    """Smith & Simmons' sensor written out in Python: check_i is correct with probability
+    eta = (1 + 2^(-d / d0)) / 2, d the Euclidean distance to rock i.  The oracle's observation weights equal
+    eta / 1 - eta (to 1 ulp: exp2 of the C library against Python's pow) and its generated observation is
+    `good` iff (rock good) == (u < eta) for draws away from the threshold."""
+    pomdp = pj.RockSamplePOMDP(7, 8, seed=7008)
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        x, y, bits = int(rng.integers(0, 7)), int(rng.integers(0, 7)), int(rng.integers(0, 256))
+        i = int(rng.integers(0, 8))
+        rx, ry = pomdp.rocks[i]
+        eta = 0.5 * (1.0 + 2.0 ** (-math.hypot(x - rx, y - ry) / pomdp.half_eff_dist))
+        s = pomdp.pack_state(x, y, bits)
+        good = (bits >> i) & 1
+        w_good, w_bad = oracle.obs_weight(pomdp, 5 + i, s, 0), oracle.obs_weight(pomdp, 5 + i, s, 1)
+        assert abs(w_good - (eta if good else 1.0 - eta)) < 4e-16 and abs(w_good + w_bad - 1.0) < 4e-16
+        assert oracle.obs_weight(pomdp, 5 + i, s, 2) == 0.0 and oracle.obs_weight(pomdp, 0, s, 2) == 1.0
+        u = float(rng.random())
+        if abs(u - eta) > 1e-9:
+            sp, o, r = oracle.model_step(pomdp, s, 5 + i, uo=(u, 0.0))
+            assert sp == s and r == 0.0 and o == (0 if good == (u < eta) else 1)
