@@ -395,7 +395,9 @@ def run_gpu(args):
                          if (rollout_ms and nodes_per_search) else None,
                          "rollout_steps_per_sim": cs["rollout_steps"] / max(cs["simulations"], 1),
                          "dram_bytes_per_sim": (prof["workers_dram_bytes_per_launch"] / TREE_QUERIES)
-                         if prof.get("workers_dram_bytes_per_launch") else None},
+                         if prof.get("workers_dram_bytes_per_launch") else None,
+                         "l2_atomic_sectors_per_sim": (prof["workers_l2_atomic_sectors_per_launch"] / TREE_QUERIES)
+                         if prof.get("workers_l2_atomic_sectors_per_launch") else None},
                 "issue_active_pct": prof.get("workers_issue_active_pct"),
                 "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
                         "keep the tree no more than that many simulations stale",

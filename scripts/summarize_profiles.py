@@ -108,6 +108,8 @@ def main():
                 consts["workers_dram_bytes_per_launch"] = (
                     g("dram__bytes_read.sum") * sc.get(units[hdr.index("dram__bytes_read.sum")], 1) +
                     g("dram__bytes_write.sum") * sc.get(units[hdr.index("dram__bytes_write.sum")], 1))
+                if "lts__t_sectors_op_atom.sum" in hdr and "lts__t_sectors_op_red.sum" in hdr:
+                    consts["workers_l2_atomic_sectors_per_launch"] = g("lts__t_sectors_op_atom.sum") + g("lts__t_sectors_op_red.sum")
                 if steps_per_decision:
                     consts["rollout_thread_inst_per_step"] = ti / steps_per_decision
                     consts["rollout_steps_per_profiled_launch"] = steps_per_decision
