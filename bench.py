@@ -396,8 +396,9 @@ def run_gpu(args):
                          "rollout_steps_per_sim": cs["rollout_steps"] / max(cs["simulations"], 1),
                          "dram_bytes_per_sim": (prof["workers_dram_bytes_per_launch"] / TREE_QUERIES)
                          if prof.get("workers_dram_bytes_per_launch") else None,
-                         "l2_atomic_sectors_per_sim": (prof["workers_l2_atomic_sectors_per_launch"] / TREE_QUERIES)
-                         if prof.get("workers_l2_atomic_sectors_per_launch") else None},
+                         # from the code path: per level two arrival counts (red) and two backup updates (red),
+                         # per simulation the root count, the next query id, the spare node id and the child CAS
+                         "atomic_ops_per_sim": 4.0 * cs["tree_steps"] / max(cs["simulations"], 1) + 4.0},
                 "issue_active_pct": prof.get("workers_issue_active_pct"),
                 "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
                         "keep the tree no more than that many simulations stale",
