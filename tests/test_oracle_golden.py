@@ -414,3 +414,27 @@ def test_rocksample_sensor_model_matches_formula(oracle):
         if abs(u - eta) > 1e-9:
             sp, o, r = oracle.model_step(pomdp, s, 5 + i, uo=(u, 0.0))
             assert sp == s and r == 0.0 and o == (0 if good == (u < eta) else 1)
+
+
+def test_lightdark_model_matches_notebook_formulas(oracle):
+    """LightDark1D as the reference's notebook defines it (notebooks/Minimal_Example.ipynb:68-146), written out
+    in Python: y' = y + a (a in {-1, 0, +1}); a = 0 stops the episode with +10 inside |y| < 1, -10 outside;
+    observation ~ N(y', sigma(y')), sigma(y) = |y - 5| / sqrt(2) + 0.01.  The oracle's transition, reward and
+    observation density agree (density to 2 ulp: its exp is the fdlibm algorithm in plain IEEE operations)."""
+    pomdp = pj.LightDark1D()
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        y = float(rng.normal(2.0, 3.0))
+        a = int(rng.integers(0, 3))
+        s = np.zeros((), dtype=pomdp.state_dtype)
+        s["y"] = y
+        sp, o, r = oracle.model_step(pomdp, s, a, uo=(float(rng.random()), float(rng.random())))
+        if a == 1:
+            assert sp["status"] != 0 and r == (pomdp.correct_r if abs(y) < 1.0 else pomdp.incorrect_r)
+        else:
+            assert sp["status"] == 0 and sp["y"] == y + (a - 1) and r == 0.0
+            sd = abs(sp["y"] - 5.0) / math.sqrt(2.0) + 1e-2
+            x = float(rng.normal(sp["y"], 2.0 * sd))
+            want = math.exp(-(x - sp["y"]) ** 2 / (2.0 * sd * sd)) / (sd * math.sqrt(2.0 * math.pi))
+            got = oracle.obs_weight(pomdp, a, sp, x)
+            assert abs(got - want) <= 4e-16 * max(want, 1e-300) + 1e-320, (got, want)
