@@ -355,9 +355,17 @@ def run_gpu(args):
         pj_path = os.path.join(ROOT, "profiles", "roofline_constants.json")
         if os.path.exists(pj_path):
             prof = json.load(open(pj_path))
+        # thread instructions of the timed launches = a * simulations + b * live rollout steps, (a, b) fitted to
+        # single-pass ncu counts of launches that grew different trees (scripts/summarize_profiles.py)
         n_search = max(len(rollout_ms), 1)
-        issue_frac = (prof["workers_thread_inst_per_launch"] * n_search / roll_s / (148 * 4 * 32 * sm_max * 1e6)
-                      if (prof.get("workers_thread_inst_per_launch") and roll_s > 0) else None)
+        if prof.get("workers_thread_inst_per_sim") and prof.get("workers_thread_inst_per_rollout_step"):
+            thread_inst = (prof["workers_thread_inst_per_sim"] * cs["simulations"] +
+                           prof["workers_thread_inst_per_rollout_step"] * steps_rank0)
+        elif prof.get("workers_thread_inst_per_launch"):
+            thread_inst = prof["workers_thread_inst_per_launch"] * n_search
+        else:
+            thread_inst = None
+        issue_frac = thread_inst / roll_s / (148 * 4 * 32 * sm_max * 1e6) if (thread_inst and roll_s > 0) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
@@ -383,7 +391,9 @@ def run_gpu(args):
                 "bound": "issue",
                 "achieved": steps_rank0 / roll_s if roll_s > 0 else None, "unit": "rollout steps/s inside the kernel",
                 "share_of_step": roll_s * 1e3 / total_ms,
-                "thread_inst_per_step": prof.get("rollout_thread_inst_per_step"),
+                "thread_inst_per_step": (thread_inst / steps_rank0) if (thread_inst and steps_rank0) else None,
+                "thread_inst_model": {"per_sim": prof.get("workers_thread_inst_per_sim"),
+                                      "per_rollout_step": prof.get("workers_thread_inst_per_rollout_step")},
                 # frac = thread instructions per launch (ncu, one pass; about constant from tree to tree, unlike
                 # the number of live rollout steps) / measured kernel time / (SMs x 4 schedulers x 32 lanes x f_clk):
                 # issue-slot utilisation x active lanes.  peak = achieved / frac.

@@ -138,6 +138,21 @@ def main():
                                                  vals["smsp__inst_executed.sum"] / 32.0)
             consts["workers_issue_active_pct"] = vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]
             consts["inst_per_step_from"] = "one ncu pass (3 SM counters) + the step counter of that pass"
+            # The instruction count of a launch depends on the tree it grows (how long its rollouts live):
+            # thread instructions = a * simulations + b * live rollout steps.  Keep the single-pass samples of the
+            # captures and fit (a, b); bench.py applies them to the simulations and steps it measures itself.
+            sims1 = 1.0e6  # scripts/profile_step.py profiles one decision of bench.TREE_QUERIES simulations
+            samples = [x for x in consts.get("workers_inst_samples", []) if x[:2] != [vals["smsp__thread_inst_executed.sum"], steps1]]
+            samples.append([vals["smsp__thread_inst_executed.sum"], steps1, sims1])
+            consts["workers_inst_samples"] = samples[-6:]
+            if len(samples) >= 2:
+                import numpy as np
+                A = np.array([[x[2], x[1]] for x in samples])
+                y = np.array([x[0] for x in samples])
+                (ca, cb), *_ = np.linalg.lstsq(A, y, rcond=None)
+                if ca > 0 and cb > 0:
+                    consts["workers_thread_inst_per_sim"] = float(ca)
+                    consts["workers_thread_inst_per_rollout_step"] = float(cb)
     consts["source"] = f"scripts/summarize_profiles.py {tag}"
     json.dump(consts, open(consts_path, "w"), indent=1)
     print(json.dumps(consts, indent=1))
