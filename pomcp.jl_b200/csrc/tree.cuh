@@ -436,8 +436,8 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
                                                 uint32_t q, int lane, int& nsteps_lane, int r_base = 0);
 
 // ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
-// race is not recycled (it stays an unreachable, zero-initialised slot): ids therefore grow along
-// every root-to-leaf path, which the pool compaction (reroot.cuh) relies on.
+// race here is not recycled (it stays an unreachable, zero-initialised slot whose parent link is 0, which
+// the pool compaction of reroot.cuh reads as "not in the tree").
 // SKIP_LOAD: the caller has just read the child slot as empty (direct table only), go straight to the insert.
 // `created` tells the caller that it published the node itself (then it is, like in the reference,
 // the natural first visitor of that node).
