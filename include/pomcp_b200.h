@@ -140,7 +140,10 @@ typedef struct pomcp_solver_params {
    * (RandomActionGenerator, src/actions.jl:38-40) is added; a node with at most one child after that step
    * returns its leaf estimate; UCB runs over the existing children with total_N = sum of their N. */
   int32_t dpw_action;        /* 0 = every action is expanded at once (default) */
-  int32_t _pad2;
+  int32_t dpw_solver;        /* 1 = simulate() of POMCPDPWSolver even where nothing widens: the leaf estimate runs
+                              * `depth` rollout steps (estimate_value(..., s, h, depth), src/solver.jl:182,199) and an
+                              * untried action scores its V while total_N <= 1 (:210).  Implied by dpw_observation /
+                              * dpw_action. */
   double k_action;           /* 10.0 */
   double alpha_action;       /* 0.5 */
 } pomcp_solver_params;

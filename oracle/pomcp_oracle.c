@@ -782,6 +782,8 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
         /* src/solver.jl:97-103 */
         int64_t steps_to_eps = (int64_t)ceil(pl->log_ratio - (double)depth);
         int64_t steps = sol->max_depth - depth < steps_to_eps ? sol->max_depth - depth : steps_to_eps;
+        /* POMCPDPWSolver hands `depth` to estimate_value as the step budget (src/solver.jl:182,199) */
+        if (sol->dpw_solver || sol->dpw_observation || sol->dpw_action) steps = depth;
         double est;
         if (g->replay) {
           if (g->rcur < g->nret) est = g->ret[g->rcur++]; else { est = 0.0; g->overflow = 1; }
@@ -831,7 +833,7 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
       int64_t nN = pl->act_N[h * pl->nA + a];
       double nV = pl->act_V[h * pl->nA + a];
       double crit;
-      if (nN == 0 && ((sol->dpw_observation || sol->dpw_action) ? hN <= 1 : hN == 1)) crit = nV; /* src/solver.jl:112 / :210 */
+      if (nN == 0 && ((sol->dpw_solver || sol->dpw_observation || sol->dpw_action) ? hN <= 1 : hN == 1)) crit = nV; /* src/solver.jl:112 / :210 */
       else if (nN == 0 && nV == -INFINITY) crit = INFINITY;
       else crit = nV + sol->c * sqrt(orc_det_log((double)hN) / (double)nN);
       if (crit >= best) { best = crit; best_a = a; }
@@ -896,17 +898,23 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
 }
 
 static int32_t root_argmax(orc_planner* pl, int32_t* action_out, int64_t* root_N_out, double* root_V_out, int32_t nA) {
-  /* src/solver.jl:60-70 */
+  /* src/solver.jl:60-70: `for node in values(b.children)` - only ActNodes that exist.  Under action
+   * widening a slot that was never added is not a child (its N / V are reported as 0 / init_V). */
   int64_t h = pl->root;
-  double best_V = pl->act_V[h * pl->nA + 0];
-  int best = 0;
-  if (best_V != best_V) return POMCP_ERR_NAN_VALUE;
-  for (int a = 1; a < pl->nA; ++a)
-    if (pl->act_V[h * pl->nA + a] >= best_V) { best_V = pl->act_V[h * pl->nA + a]; best = a; }
-  if (action_out) *action_out = best;
+  const uint32_t mask = pl->sp.dpw_action ? pl->node_amask[h] : 0xffffffffu;
+  double best_V = 0.0;
+  int best = -1;
+  for (int a = 0; a < pl->nA; ++a) {
+    if (!((mask >> a) & 1u)) continue;
+    double v = pl->act_V[h * pl->nA + a];
+    if (best < 0 && v != v) return POMCP_ERR_NAN_VALUE; /* @assert !isnan(best_V) on the first child, src/solver.jl:62 */
+    if (best < 0 || v >= best_V) { best_V = v; best = a; }
+  }
+  if (action_out) *action_out = best < 0 ? 0 : best;
   for (int a = 0; a < pl->nA && a < nA; ++a) {
-    if (root_N_out) root_N_out[a] = pl->act_N[h * pl->nA + a];
-    if (root_V_out) root_V_out[a] = pl->act_V[h * pl->nA + a];
+    const int exists = (mask >> a) & 1u;
+    if (root_N_out) root_N_out[a] = exists ? pl->act_N[h * pl->nA + a] : 0;
+    if (root_V_out) root_V_out[a] = exists ? pl->act_V[h * pl->nA + a] : pl->sp.init_V;
   }
   return POMCP_OK;
 }
@@ -1264,6 +1272,8 @@ int32_t orc_search_rootparallel(const pomcp_problem* p, const pomcp_solver_param
   pomcp_counters* cs = (pomcp_counters*)calloc((size_t)n_trees, sizeof(pomcp_counters));
   int64_t* tN = (int64_t*)calloc((size_t)n_trees * mA, sizeof(int64_t));
   double* tV = (double*)calloc((size_t)n_trees * mA, sizeof(double));
+  uint32_t* tE = (uint32_t*)calloc((size_t)n_trees, sizeof(uint32_t)); /* existing root ActNodes of tree t */
+  uint32_t anyE = 0;
 #ifdef _OPENMP
   if (n_threads > 0) omp_set_num_threads(n_threads);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -1277,6 +1287,7 @@ int32_t orc_search_rootparallel(const pomcp_problem* p, const pomcp_solver_param
     int32_t act;
     rcs[t] = orc_search(pl, Q, &act, tN + (size_t)t * mA, tV + (size_t)t * mA, mA);
     cs[t] = pl->ctr;
+    tE[t] = sp->dpw_action ? pl->node_amask[pl->root] : 0xffffffffu;
     orc_destroy(pl);
   }
   (void)n_threads;
@@ -1287,7 +1298,9 @@ int32_t orc_search_rootparallel(const pomcp_problem* p, const pomcp_solver_param
     if (rcs[t] == POMCP_ERR_ALL_SAMPLES_TERMINAL) continue;
     if (rcs[t] != POMCP_OK) { rc = rcs[t]; continue; }
     ++n_ok;
+    anyE |= tE[t];
     for (int a = 0; a < mA; ++a) {
+      if (!((tE[t] >> a) & 1u)) continue;
       cntN[a] += tN[(size_t)t * mA + a];
       sumN[a] += (double)tN[(size_t)t * mA + a];
       sumNV[a] += (double)tN[(size_t)t * mA + a] * tV[(size_t)t * mA + a];
@@ -1300,14 +1313,15 @@ int32_t orc_search_rootparallel(const pomcp_problem* p, const pomcp_solver_param
   }
   if (rc == POMCP_OK && n_ok == 0) rc = POMCP_ERR_ALL_SAMPLES_TERMINAL;
   if (rc == POMCP_OK) {
-    int best = 0; double bestV = 0.0;
+    int best = -1; double bestV = 0.0;
     for (int a = 0; a < mA; ++a) {
       double V = sumN[a] > 0.0 ? sumNV[a] / sumN[a] : sp->init_V;
-      if (a == 0 || V >= bestV) { bestV = V; best = a; }
       if (a < nA) { if (root_N_out) root_N_out[a] = cntN[a]; if (root_V_out) root_V_out[a] = V; }
+      if (!((anyE >> a) & 1u)) continue; /* no tree holds this ActNode (action widening) */
+      if (best < 0 || V >= bestV) { bestV = V; best = a; }
     }
-    if (action_out) *action_out = best;
+    if (action_out) *action_out = best < 0 ? 0 : best;
   }
-  free(sumN); free(sumNV); free(cntN); free(rcs); free(cs); free(tN); free(tV);
+  free(sumN); free(sumNV); free(cntN); free(rcs); free(cs); free(tN); free(tV); free(tE);
   return rc;
 }

@@ -61,7 +61,7 @@ class SolverParams(C.Structure):
         ("inflight_min", C.c_int32), ("inflight_max", C.c_int32), ("inflight_ramp_div", C.c_int32),
         ("rollouts_per_leaf", C.c_int32), ("rank", C.c_int32), ("dpw_observation", C.c_int32),
         ("k_observation", C.c_double), ("alpha_observation", C.c_double),
-        ("dpw_action", C.c_int32), ("_pad2", C.c_int32), ("k_action", C.c_double), ("alpha_action", C.c_double),
+        ("dpw_action", C.c_int32), ("dpw_solver", C.c_int32), ("k_action", C.c_double), ("alpha_action", C.c_double),
     ]
 
 

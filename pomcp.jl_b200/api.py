@@ -182,7 +182,7 @@ class POMCPSolver(AbstractPOMCPSolver):
                  node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
                  default_action=None, search_mode="batched", inflight_min=0, inflight_max=0, inflight_ramp_div=0, rollouts_per_leaf=0,
                  max_nodes=0,
-                 max_log=0, device=0, rank=0, dpw_observation=None, dpw_action=None):
+                 max_log=0, device=0, rank=0, dpw_observation=None, dpw_action=None, dpw_solver=False):
         self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
         self.rng = rng
         self.node_belief_updater = node_belief_updater if node_belief_updater is not None \
@@ -196,6 +196,7 @@ class POMCPSolver(AbstractPOMCPSolver):
         self.max_nodes, self.max_log, self.device, self.rank = max_nodes, max_log, device, rank
         self.dpw_observation = dpw_observation  # (k_observation, alpha_observation) of POMCPDPWSolver, or None
         self.dpw_action = dpw_action  # (k_action, alpha_action) of POMCPDPWSolver with enable_action_pw, or None
+        self.dpw_solver = dpw_solver  # simulate() of POMCPDPWSolver (its leaf step budget and untried-action rule)
 
     def c_params(self, belief_mode):
         sp = abi.SolverParams()
@@ -234,6 +235,7 @@ class POMCPSolver(AbstractPOMCPSolver):
         if self.dpw_observation is not None:
             sp.dpw_observation = 1
             sp.k_observation, sp.alpha_observation = float(self.dpw_observation[0]), float(self.dpw_observation[1])
+        sp.dpw_solver = 1 if self.dpw_solver else 0
         if self.dpw_action is not None:
             sp.dpw_action = 1
             sp.k_action, sp.alpha_action = float(self.dpw_action[0]), float(self.dpw_action[1])
@@ -867,6 +869,7 @@ class POMCPDPWSolver(AbstractPOMCPSolver):
 
     def as_pomcp(self, pomdp):
         kw = dict(self._pomcp_kw)
+        kw["dpw_solver"] = True  # src/solver.jl:161-274 is a different simulate() even where nothing widens
         if self.enable_action_pw:
             if self.next_action is not None and not isinstance(self.next_action, RandomActionGenerator):
                 raise NotImplementedError("next_action: only RandomActionGenerator runs on device (src/actions.jl:38-41)")

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libpomcp_b200.so")
 SOURCES = ["abi.cu"]
-HEADERS = ["philox.cuh", "detmath.cuh", "models.cuh", "tree.cuh", "pf.cuh"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh"))  # every header abi.cu can include
 
 
 def nvcc_path():

@@ -265,6 +265,7 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.root_N0 = (uint32_t)h->root_visits;
   c.dpw = h->sp.dpw_observation ? 1 : 0;
   c.dpa = h->sp.dpw_action ? 1 : 0;
+  c.dpw_solver = (h->sp.dpw_solver || h->sp.dpw_observation || h->sp.dpw_action) ? 1 : 0;
   c.k_act = h->sp.k_action;
   c.alpha_act = h->sp.alpha_action;
   c.k_obs = h->sp.k_observation;
@@ -812,7 +813,13 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   // unweighted mode keeps the tree across decisions (re-rooting, no compaction yet): room for ~64 of them
   long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) + 65536;
   long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
-  want = std::min<long long>(want, std::min<long long>(cap_mem, (1ll << 31) - 2));
+  // node ids carry a flag in bit 31, and action slots (id * nA + a) are 32-bit as well
+  const long long cap_ids = std::min<long long>((1ll << 31) - 2, ((1ll << 32) - 1) / std::max(nA, 1) - 1);
+  if (sp->max_nodes > cap_ids) {
+    h->err = "max_nodes * n_actions must stay below 2^32 (32-bit action slots)";
+    return bail(POMCP_ERR_INVALID_ARG);
+  }
+  want = std::min<long long>(want, std::min<long long>(cap_mem, cap_ids));
   if (want < 16) { h->err = "not enough device memory for the node pool"; return bail(POMCP_ERR_CUDA); }
   Pool& P = h->pool;
   P.max_nodes = (uint32_t)want;
@@ -1476,8 +1483,8 @@ int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t Q, int32_t* action_ou
   if (!h->comm) return fail(h, POMCP_ERR_INVALID_ARG, "pomcp_comm_init has not been called");
   int rc = enqueue_search(h, Q, nullptr, 0, nullptr, 0);
   if (rc) return rc;
-  // one fused all-reduce of [N_a ..., N_a*V_a ...] (2|A| doubles) before the arg-max of src/solver.jl:60-70
-  int nrc = g_nccl.AllReduce(h->d_res->merge, h->d_res->merge, (size_t)(2 * h->nA), NCCL_FLOAT64, NCCL_SUM, h->comm,
+  // one fused all-reduce of [N_a ..., N_a*V_a ..., exists_a ...] (3|A| doubles) before the arg-max of src/solver.jl:60-70
+  int nrc = g_nccl.AllReduce(h->d_res->merge, h->d_res->merge, (size_t)(3 * h->nA), NCCL_FLOAT64, NCCL_SUM, h->comm,
                              h->stream);
   if (nrc != 0) return fail(h, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce");
   k_root_merge_finish<<<1, 32, 0, h->stream>>>(h->nA, h->sp.init_V, h->d_res);

@@ -71,6 +71,8 @@ struct SearchCfg {
   double k_obs, alpha_obs;
   int dpa;             // action progressive widening on (src/solver.jl:172-186)
   double k_act, alpha_act;
+  int dpw_solver;      // simulate() of POMCPDPWSolver (src/solver.jl:161-274): the leaf estimate gets `depth` as its step
+                       // budget (:182,:199) and an untried action scores V while total_N <= 1 (:210)
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
   int team_warps;      // batched mode: warps per worker; warp w runs rollouts 32 w .. 32 w + 31 of every leaf
   uint32_t key0, key1, rank, epoch;
@@ -115,7 +117,7 @@ struct SearchResult {
   long long root_N;
   long long N[POMCP_MAX_ACTIONS];
   double V[POMCP_MAX_ACTIONS];
-  double merge[2 * POMCP_MAX_ACTIONS];  // [N_a..., N_a*V_a...] for the root-parallel all-reduce
+  double merge[3 * POMCP_MAX_ACTIONS];  // [N_a..., N_a*V_a..., exists_a...] for the root-parallel all-reduce
   long long ucur, rcur;
 };
 
@@ -775,7 +777,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       }
       if (!EXACT) v = (mm > 0 && fabs(cfg.init_V) != INFINITY) ? v / (double)mm : cfg.init_V;
       unsigned long long hn = cfg.dpa ? totalN : (EXACT ? hN : (hN < 1u ? 1u : hN));
-      if (n == 0 && ((cfg.dpw || cfg.dpa) ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
+      if (n == 0 && (cfg.dpw_solver ? hn <= 1 : hn == 1)) crit = v;  // src/solver.jl:112 / :210
       else if (n == 0 && v == -INFINITY) crit = INFINITY;
       else crit = v + cfg.c * sqrt(det_log((double)hn) / (double)n);
       valid = (crit == crit) && ((amask >> lane) & 1u);
@@ -877,6 +879,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
   if (want_rollout) {
     long long steps_to_eps = (long long)ceil(cfg.log_ratio - (double)depth);
     long long steps = min(cfg.max_depth - (long long)depth, steps_to_eps);
+    if (cfg.dpw_solver) steps = depth;  // estimate_value(..., s, h, depth), src/solver.jl:182,199
     double est;
     if (REPLAY) {
       est = (rc.rcur < cfg.n_rets) ? cfg.rets[rc.rcur] : 0.0;
@@ -1369,7 +1372,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       break;
     }
     hN = seen;
-    fl = nfl;
+    // The flag races with other workers' claims and steers control flow at the top of the next level: every lane
+    // must see the same value.  `flag_known` is warp-uniform (it comes out of a shuffle) and the claimed flag was
+    // broadcast above; only the per-lane load needs lane 0's copy.
+    fl = (flag_known || try_claim || i_expand_child) ? nfl : __shfl_sync(0xffffffffu, nfl, 0);
     if (M::HASHED && (fl & 2u)) {  // (the direct table never claims here: its creator expands)
       if (!(fl & 1u)) {  // claimed
         want_rollout = true;
@@ -1394,6 +1400,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   if (want_rollout) {
     long long steps_to_eps = (long long)ceil(cfg.log_ratio - (double)depth);
     long long steps = min(cfg.max_depth - (long long)depth, steps_to_eps);
+    if (cfg.dpw_solver) steps = depth;  // estimate_value(..., s, h, depth), src/solver.jl:182,199
     double est;
     if (cfg.estimator == POMCP_EST_CONSTANT) {
       est = cfg.est_value;  // src/rollout.jl:10
@@ -1647,14 +1654,19 @@ __global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Poo
 }
 
 // ---- K5: root statistics + arg-max V with ">=" (src/solver.jl:60-70); also packs the
-// [N_a, N_a*V_a] vector for the root-parallel merge (K10).
+// [N_a, N_a*V_a, exists_a] vector for the root-parallel merge (K10).  The reference iterates
+// values(b.children): under action widening only the ActNodes that were actually added take part
+// (a slot that was never added still holds the pool's prefill and must not win a ">=" against
+// negative values).
 __global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t root, int exact, double init_V,
                               SearchResult* res) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   DevCtr* c = P.ctr;
   res->root_N = P.node_N[root];
-  int best = 0;
+  const uint32_t amask = P.node_amask ? P.node_amask[root] : 0xffffffffu;
+  int best = -1;
   double best_V = 0.0;
+  bool nan_seen = false;
   for (int a = 0; a < nA; ++a) {
     uint32_t slot = root * (uint32_t)nA + a;
     double v = P.act_V[slot];
@@ -1663,15 +1675,19 @@ __global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t r
       uint32_t mm = P.act_M[slot];
       v = (mm > 0 && fabs(init_V) != INFINITY) ? v / (double)mm : init_V;
     }
-    res->N[a] = n;
+    const bool exists = (amask >> a) & 1u;
+    res->N[a] = exists ? n : 0;
     res->V[a] = v;
-    res->merge[a] = (double)n;
-    res->merge[nA + a] = (double)n * v;
-    if (a == 0 || v >= best_V) { best_V = v; best = a; }
+    res->merge[a] = exists ? (double)n : 0.0;
+    res->merge[nA + a] = exists ? (double)n * v : 0.0;
+    res->merge[2 * nA + a] = exists ? 1.0 : 0.0;
+    if (!exists) continue;
+    if (best < 0) nan_seen = v != v;  // best_V starts from the first child (src/solver.jl:61-62)
+    if (best < 0 || v >= best_V) { best_V = v; best = a; }
   }
-  res->action = best;
+  res->action = best < 0 ? 0 : best;
   int st = POMCP_OK;
-  if (res->V[0] != res->V[0]) st = POMCP_ERR_NAN_VALUE;           // @assert !isnan(best_V), src/solver.jl:62
+  if (nan_seen) st = POMCP_ERR_NAN_VALUE;                          // @assert !isnan(best_V), src/solver.jl:62
   if (!c->any_nonterminal) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;    // src/solver.jl:56-58
   if (c->pool_overflow || c->log_overflow) st = POMCP_ERR_POOL_EXHAUSTED;
   if (c->pool_overflow == 2) st = POMCP_ERR_CUDA;  // worker watchdog fired
@@ -1679,19 +1695,21 @@ __global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t r
   res->status = st;
 }
 
-// after the all-reduce: V_a = sum(N*V)/sum(N), then the reference's arg-max rule
+// after the all-reduce: V_a = sum(N*V)/sum(N) over the trees that hold ActNode a, then the reference's arg-max rule
 __global__ void k_root_merge_finish(int nA, double init_V, SearchResult* res) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int best = 0;
+  int best = -1;
   double best_V = 0.0;
   for (int a = 0; a < nA; ++a) {
     double n = res->merge[a], nv = res->merge[nA + a];
+    const bool exists = res->merge[2 * nA + a] > 0.0;
     double v = n > 0.0 ? nv / n : init_V;
     res->N[a] = (long long)n;
     res->V[a] = v;
-    if (a == 0 || v >= best_V) { best_V = v; best = a; }
+    if (!exists) continue;
+    if (best < 0 || v >= best_V) { best_V = v; best = a; }
   }
-  res->action = best;
+  res->action = best < 0 ? 0 : best;
 }
 
 // ---- pool (re)initialisation: ActNode(a, init_N, init_V, {}) for every slot (src/solver.jl:89-93)

@@ -142,3 +142,21 @@ def test_dpw_default_solver_smoke_and_batched(oracle, gpu_lib):
     # same decision; with randomly widened action sets the best arm's value moves by about +-1 from run to run
     # (batched runs: 4.2 .. 6.3 against the oracle's 5.26): tolerance 2.5 = a quarter of the reward scale
     assert rc == 0 and a == a_o and abs(V[a] - V_o[a_o]) < 2.5, (V, V_o)
+
+
+@pytest.mark.parametrize("mode", ["exact", "batched"])
+def test_action_widening_root_argmax_only_over_existing_children(oracle, gpu_lib, mode):
+    """src/solver.jl:60-70 iterates values(b.children): a root slot that was never added (pool prefill N = 0,
+    V = 0) must not win `>=` against the explored child's negative value.  Tiger, k_action = 0.1, 60 queries:
+    one ActNode exists, and it is the decision (exact mode: the oracle's, bit for bit)."""
+    tiger = pj.TigerPOMDP()
+    for seed in range(4):
+        gp, op = make_pair(oracle, tiger, 100.0, seed=seed, mode=mode, tree_queries=60, dpw_action=(0.1, 0.5))
+        gp.set_belief_initial()
+        op.set_belief_initial()
+        a, N, V = gp.search(60)
+        assert (N > 0).sum() == 1 and N[a] == 59 and V[a] < 0.0, (seed, a, N, V)
+        if mode == "exact":
+            rc, a_o, N_o, V_o = op.search(60)
+            assert rc == 0 and a == a_o and np.array_equal(N, N_o) and np.array_equal(_bits(V), _bits(V_o))
+        gp.close()

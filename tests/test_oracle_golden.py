@@ -438,3 +438,37 @@ def test_lightdark_model_matches_notebook_formulas(oracle):
             want = math.exp(-(x - sp["y"]) ** 2 / (2.0 * sd * sd)) / (sd * math.sqrt(2.0 * math.pi))
             got = oracle.obs_weight(pomdp, a, sp, x)
             assert abs(got - want) <= 4e-16 * max(want, 1e-300) + 1e-320, (got, want)
+
+
+# ----------------------------------------------------------------------------- action widening: root arg-max
+def test_action_widening_root_argmax_only_over_existing_children(oracle):
+    """src/solver.jl:60-70 iterates values(b.children).  Under action widening with a small k_action the root
+    holds a single ActNode; slots that were never added keep the pool prefill (N = init_N, V = init_V = 0) and
+    must not win the `>=` against the explored child's negative value (Tiger: every return is negative)."""
+    tiger = pj.TigerPOMDP()
+    for seed in range(4):
+        pl = oracle.OraclePlanner(tiger, oracle.default_params(c=100.0, seed=seed, tree_queries=60, dpw_action=1,
+                                                               k_action=0.1, alpha_action=0.5))
+        pl.set_belief_initial()
+        rc, a, N, V = pl.search(60)
+        assert rc == 0
+        assert (N > 0).sum() == 1 and N[a] == 59 and V[a] < 0.0, (seed, a, N, V)
+    # the root-parallel merge skips them as well
+    rc, a, N, V, _ = oracle.search_rootparallel(tiger, oracle.default_params(c=100.0, seed=1, tree_queries=60, dpw_action=1,
+                                                                            k_action=0.1, alpha_action=0.5), None, 3, 1, 60)
+    assert rc == 0 and N[a] > 0 and V[a] < 0.0, (a, N, V)
+
+
+def test_dpw_solver_leaf_budget_is_depth(oracle):
+    """estimate_value(pomcp.solved_estimate, pomcp.problem, s, h, depth) (src/solver.jl:182,199): POMCPDPWSolver's
+    leaf rollouts run `depth` steps, POMCPSolver's min(max_depth - depth, ceil(log(eps)/log(gamma) - depth))
+    (src/solver.jl:97-102).  On Baby with 300 queries the DPW trees therefore spend far fewer rollout steps."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    steps = {}
+    for flag in (0, 1):
+        pl = oracle.OraclePlanner(baby, oracle.default_params(c=10.0, seed=2, tree_queries=300, dpw_solver=flag))
+        pl.set_belief_initial()
+        assert pl.search(300)[0] == 0
+        cs = pl.counters()
+        steps[flag] = cs["rollout_steps"] / max(cs["rollouts"], 1)
+    assert steps[0] > 30 and steps[1] < 8, steps
