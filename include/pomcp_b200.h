@@ -24,9 +24,10 @@
 extern "C" {
 #endif
 
-#define POMCP_B200_ABI_VERSION 1
+#define POMCP_B200_ABI_VERSION 2
 #define POMCP_MAX_ROCKS 16
 #define POMCP_MAX_ACTIONS 32
+#define POMCP_MAX_TREES 128
 
 /* Status codes <-> reference exceptions (src/exceptions.jl:1-26,
  * src/particle_filter.jl:94-101, src/solver.jl:56-58,62). */
@@ -146,6 +147,13 @@ typedef struct pomcp_solver_params {
                               * dpw_action. */
   double k_action;           /* 10.0 */
   double alpha_action;       /* 0.5 */
+  /* ---- root parallelism inside one GPU: n_trees independent trees of tree_queries simulations each are searched
+   * side by side in ONE launch from the same belief (stream id of tree t: rank * n_trees + t), the workers and the
+   * in-flight cap are divided among them, and pomcp_search returns the merged decision: V_a = sum N_a V_a / sum N_a
+   * over the trees, then the arg-max of src/solver.jl:60-70 - the same merge pomcp_search_rootparallel then applies
+   * across GPUs.  Batched mode, external belief (0 / 1 = one tree). */
+  int32_t n_trees;
+  int32_t _pad3;
 } pomcp_solver_params;
 
 typedef struct pomcp_counters {
@@ -184,6 +192,9 @@ int32_t pomcp_destroy(pomcp_handle* h);
 int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t n);
 /* ... or over the problem's initial state distribution. */
 int32_t pomcp_set_belief_initial(pomcp_handle* h);
+/* The same for the belief already on the device: a fresh RootNode over it (what every action() call on a belief
+ * that is not a BeliefNode does, src/solver.jl:278-281), without sending the particles again. */
+int32_t pomcp_reset_tree(pomcp_handle* h);
 /* Table for POMCP_EST_STATE_VALUE: v[state_index(s)], state_index = s for Tiger/Baby (n = 2) and the packed
  * x | y<<4 | rocks<<8 for RockSample (n = 2^(8+k)); terminal states are worth 0. */
 int32_t pomcp_set_state_values(pomcp_handle* h, const double* values, int64_t n);
@@ -237,6 +248,10 @@ int32_t pomcp_pf_weights(pomcp_handle* h, const void* states, int64_t n, int32_t
 
 /* Tree inspection (replaces poking at BeliefNode fields; src/tree.jl:7-26). */
 int32_t pomcp_get_root_stats(pomcp_handle* h, int64_t* root_N, int64_t* act_N, double* act_V, int32_t n_actions);
+/* Tree t's own result of the last search, before the merge over trees (n_trees > 1) and ranks
+ * (pomcp_search_rootparallel); returns that tree's status. */
+int32_t pomcp_get_tree_result(pomcp_handle* h, int32_t tree, int32_t* action_out, int64_t* root_N, int64_t* act_N,
+                              double* act_V, int32_t n_actions);
 /* Children statistics of the belief node reached from the root by the given
  * (action, observation) history; *node_N = -1 if the node does not exist. */
 int32_t pomcp_get_node_stats(pomcp_handle* h, const int32_t* actions, const uint64_t* obs_bits, int32_t depth,
@@ -270,7 +285,9 @@ int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t tree_queries, int32_t
 /* Device-timer access for the bench harness: elapsed milliseconds spent in the
  * named phase by the last call (CUDA events on the handle's stream). */
 typedef enum pomcp_phase { POMCP_PHASE_SEARCH = 0, POMCP_PHASE_ROLLOUT = 1, POMCP_PHASE_PF = 2,
-                           POMCP_PHASE_REROOT = 3, POMCP_PHASE_COUNT = 4 } pomcp_phase;
+                           POMCP_PHASE_REROOT = 3,
+                           POMCP_PHASE_MERGE = 4, /* ncclAllReduce + finish of pomcp_search_rootparallel */
+                           POMCP_PHASE_COUNT = 5 } pomcp_phase;
 int32_t pomcp_last_phase_ms(pomcp_handle* h, int32_t phase, double* ms_out, int64_t* launches_out);
 /* Device-resident variants used by the bench's kernel-only timing: run on
  * whatever belief is already in HBM and leave results there. */

@@ -44,6 +44,7 @@ def lib():
     L.pomcp_destroy.argtypes = [vp]
     L.pomcp_set_belief_particles.argtypes = [vp, vp, i64]
     L.pomcp_set_belief_initial.argtypes = [vp]
+    L.pomcp_reset_tree.argtypes = [vp]
     L.pomcp_set_state_values.argtypes = [vp, vp, i64]
     L.pomcp_get_belief_particles.argtypes = [vp, vp, i64, P(i64)]
     L.pomcp_search.argtypes = [vp, i64, P(i32), vp, vp, i32]
@@ -55,6 +56,7 @@ def lib():
     L.pomcp_rollout_batch.argtypes = [vp, vp, i64, i32, u64, vp, vp]
     L.pomcp_pf_weights.argtypes = [vp, vp, i64, i32, u64, u64, vp, vp]
     L.pomcp_get_root_stats.argtypes = [vp, P(i64), vp, vp, i32]
+    L.pomcp_get_tree_result.argtypes = [vp, i32, P(i32), P(i64), vp, vp, i32]
     L.pomcp_get_node_stats.argtypes = [vp, vp, vp, i32, P(i64), P(i64), vp, vp, i32]
     L.pomcp_dump_tree.argtypes = [vp, i64, P(i64), vp, vp, vp, vp]
     L.pomcp_get_counters.argtypes = [vp, P(abi.Counters)]

@@ -176,13 +176,13 @@ class POMCPSolver(AbstractPOMCPSolver):
     """Keyword constructor with the reference defaults (src/constructor.jl:8-18; fields documented
     at src/POMCP.jl:75-136).  `rng` is an integer seed (Philox key) instead of an AbstractRNG.
     Device-only keywords: search_mode ("batched"|"exact"), inflight_min, inflight_max, inflight_ramp_div, rollouts_per_leaf,
-    max_nodes, max_log, device, rank."""
+    max_nodes, max_log, device, rank, n_trees."""
 
     def __init__(self, eps=0.01, max_depth=2 ** 63 - 1, c=1.0, tree_queries=100, rng=0,
                  node_belief_updater=None, estimate_value=None, init_V=0.0, init_N=0, num_sparse_actions=0,
                  default_action=None, search_mode="batched", inflight_min=0, inflight_max=0, inflight_ramp_div=0, rollouts_per_leaf=0,
                  max_nodes=0,
-                 max_log=0, device=0, rank=0, dpw_observation=None, dpw_action=None, dpw_solver=False):
+                 max_log=0, device=0, rank=0, dpw_observation=None, dpw_action=None, dpw_solver=False, n_trees=1):
         self.eps, self.max_depth, self.c, self.tree_queries = eps, max_depth, c, tree_queries
         self.rng = rng
         self.node_belief_updater = node_belief_updater if node_belief_updater is not None \
@@ -197,6 +197,7 @@ class POMCPSolver(AbstractPOMCPSolver):
         self.dpw_observation = dpw_observation  # (k_observation, alpha_observation) of POMCPDPWSolver, or None
         self.dpw_action = dpw_action  # (k_action, alpha_action) of POMCPDPWSolver with enable_action_pw, or None
         self.dpw_solver = dpw_solver  # simulate() of POMCPDPWSolver (its leaf step budget and untried-action rule)
+        self.n_trees = n_trees  # root parallelism inside the GPU: trees of tree_queries simulations each, merged
 
     def c_params(self, belief_mode):
         sp = abi.SolverParams()
@@ -236,6 +237,7 @@ class POMCPSolver(AbstractPOMCPSolver):
             sp.dpw_observation = 1
             sp.k_observation, sp.alpha_observation = float(self.dpw_observation[0]), float(self.dpw_observation[1])
         sp.dpw_solver = 1 if self.dpw_solver else 0
+        sp.n_trees = int(self.n_trees)
         if self.dpw_action is not None:
             sp.dpw_action = 1
             sp.k_action, sp.alpha_action = float(self.dpw_action[0]), float(self.dpw_action[1])
@@ -430,6 +432,11 @@ class POMCPPlanner:
         _check(lib().pomcp_set_belief_initial(self._h), self._h)
         self._generation += 1
 
+    def reset_tree(self):
+        """A fresh RootNode over the belief already on the device (make_node, src/solver.jl:278-281)."""
+        _check(lib().pomcp_reset_tree(self._h), self._h)
+        self._generation += 1
+
     def belief_particles(self, out=None):
         """The belief's particles as a host array; `out` (same dtype, at least as long — e.g. a pinned buffer
         the caller re-uses from step to step) receives them instead of a fresh array."""
@@ -501,6 +508,15 @@ class POMCPPlanner:
         _check(lib().pomcp_get_root_stats(self._h, C.byref(rn), N.ctypes.data_as(C.c_void_p),
                                           V.ctypes.data_as(C.c_void_p), self.nA), self._h)
         return rn.value, N, V
+
+    def tree_result(self, tree):
+        """(action, root N, N[a], V[a]) of tree `tree` of the last search, before the merge over trees / ranks."""
+        a, rn = C.c_int32(-1), C.c_int64(0)
+        N = np.zeros(self.nA, dtype=np.int64)
+        V = np.zeros(self.nA, dtype=np.float64)
+        _check(lib().pomcp_get_tree_result(self._h, int(tree), C.byref(a), C.byref(rn), N.ctypes.data_as(C.c_void_p),
+                                           V.ctypes.data_as(C.c_void_p), self.nA), self._h)
+        return a.value, rn.value, N, V
 
     def node_stats(self, history):
         acts = np.array([h[0] for h in history], dtype=np.int32)

@@ -105,8 +105,13 @@ struct pomcp_handle {
   size_t bel_cap[2] = {0, 0};
   int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles
   long long n_bel = 0;
-  uint32_t root = 0, epoch = 0;
+  uint32_t root = 0, epoch = 0;  // root / root_visits: tree 0's (the only tree unless n_trees > 1)
   long long root_visits = 0;
+  int n_trees = 1;               // trees searched side by side in one launch (root parallelism inside the GPU)
+  std::vector<uint32_t> roots;
+  std::vector<long long> tree_visits;
+  TreeCtl* d_trees = nullptr;
+  TreeCtl* h_trees = nullptr;    // pinned staging copy
   unsigned long long nodes_used = 1, log_used = 0;
   SearchResult* d_res = nullptr;
   SearchResult* h_res = nullptr;
@@ -224,19 +229,18 @@ int fresh_root(pomcp_handle* h) {
   if (rc) return rc;
   if (h->hashed) CK(cudaMemsetAsync(h->pool.ht, 0, h->ht_entries * sizeof(uint32_t), h->stream));
   if (h->pool.ev_key) CK(cudaMemsetAsync(h->pool.ev_key, 0, h->ev_entries * sizeof(unsigned long long), h->stream));
-  DevCtr z{};
-  z.node_count = 1;
   // keep cumulative counters: only the allocation cursors restart
   CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  h->h_ctr->node_count = 1;
+  h->h_ctr->node_count = (unsigned long long)h->n_trees;  // roots are nodes 0 .. n_trees - 1
   h->h_ctr->log_count = 0;
   h->h_ctr->pool_overflow = h->h_ctr->log_overflow = h->h_ctr->replay_overflow = 0;
   CK(cudaMemcpyAsync(h->pool.ctr, h->h_ctr, sizeof(DevCtr), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->root = 0;
   h->root_visits = 0;
-  h->nodes_used = 1;
+  for (int t = 0; t < h->n_trees; ++t) { h->roots[(size_t)t] = (uint32_t)t; h->tree_visits[(size_t)t] = 0; }
+  h->nodes_used = (unsigned long long)h->n_trees;
   h->log_used = 0;
   return POMCP_OK;
 }
@@ -257,8 +261,10 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.estimator = h->sp.estimator;
   c.key0 = (uint32_t)h->sp.seed;
   c.key1 = (uint32_t)(h->sp.seed >> 32);
-  c.rank = (uint32_t)h->sp.rank;
+  c.rank = (uint32_t)(h->sp.rank * h->n_trees);  // stream id of tree t: rank * n_trees + t
   c.epoch = h->epoch;
+  c.trees = h->d_trees;
+  c.n_trees = h->n_trees;
   c.bel = (h->bel_kind == 2) ? h->d_bel[h->bel_cur] : nullptr;
   c.n_bel = h->n_bel;
   c.root = h->root;
@@ -285,6 +291,8 @@ int reset_search_flags(pomcp_handle* h) {
   return POMCP_OK;
 }
 
+int finish_search(pomcp_handle* h);
+
 int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long n_uni, const double* d_rets,
                    long long n_rets) {
   if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
@@ -292,9 +300,30 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     return fail(h, POMCP_ERR_INVALID_ARG, "POMCP_EST_STATE_VALUE needs pomcp_set_state_values first");
   if (Q < 0) Q = h->sp.tree_queries;
   if (Q >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "tree_queries must be < 2^32");
-  int rc = reset_search_flags(h);
+  int rc;
+  if (h->pending) {  // the staging copy of the tree table is re-used: drain the previous search first
+    rc = finish_search(h);
+    if (rc != POMCP_OK && rc != POMCP_ERR_ALL_SAMPLES_TERMINAL && rc != POMCP_ERR_NAN_VALUE) return rc;
+  }
+  rc = reset_search_flags(h);
   if (rc) return rc;
   SearchCfg cfg = make_cfg(h);
+  h->roots[0] = h->root;
+  h->tree_visits[0] = h->root_visits;
+  for (int t = 0; t < h->n_trees; ++t) {
+    TreeCtl& tc = h->h_trees[t];
+    tc.next_query = 0;
+    tc.bel = cfg.bel;
+    tc.n_bel = cfg.n_bel;
+    tc.root = h->roots[(size_t)t];
+    tc.root_N0 = (uint32_t)h->tree_visits[(size_t)t];
+    tc.key0 = cfg.key0; tc.key1 = cfg.key1;
+    tc.rank = cfg.rank + (uint32_t)t;
+    tc.epoch = cfg.epoch;
+    tc.any_nonterminal = 0;
+    tc._pad = 0;
+  }
+  CK(cudaMemcpyAsync(h->d_trees, h->h_trees, sizeof(TreeCtl) * (size_t)h->n_trees, cudaMemcpyHostToDevice, h->stream));
   const bool replay = d_uni != nullptr;
   cfg.uni = d_uni; cfg.n_uni = n_uni; cfg.rets = d_rets; cfg.n_rets = n_rets;
   PhaseTimer& ts = h->timers[POMCP_PHASE_SEARCH];
@@ -322,11 +351,8 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     cfg.eta_n = h->eta_n;
     cfg.eta_thr = h->d_eta_thr;
     smem += (size_t)h->eta_n * sizeof(uint32_t);
-    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1));
-    // Admission floor relative to the budget: the simulations started while the tree holds fewer than
-    // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
-    // nothing (measured, scripts/ramp_probe.py) and removes most of the ramp from a large search.
-    if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), h->inflight_max);
+    const int T = h->n_trees;
+    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1) * T);
     int blocks = (int)((workers + nteams - 1) / nteams);
     CK(cudaEventRecord(tr.next(), h->stream));
     DISPATCH_PID(h->prob.problem_id, {
@@ -336,7 +362,13 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
-        cfg.inflight_max = std::min<long long>(cfg.inflight_max, (long long)blocks * nteams);
+        // workers are dealt to the trees round-robin: the in-flight cap, the admission floor and the ramp are per tree
+        cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cfg.inflight_max, (long long)blocks * nteams) / T);
+        // Admission floor relative to the budget: the simulations started while the tree holds fewer than
+        // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
+        // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
+        if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), cfg.inflight_max);
+        cfg.inflight_min = std::min(cfg.inflight_min, cfg.inflight_max);
         kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
       };
       if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
@@ -357,10 +389,16 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     h->last_waves = 1;
   }
   h->root_visits += Q;
-  k_root_result<<<1, 32, 0, h->stream>>>(h->pool, h->nA, h->root, h->exact ? 1 : 0, h->sp.init_V, h->d_res);
+  k_root_result<<<h->n_trees, 32, 0, h->stream>>>(h->pool, h->nA, h->d_trees, h->exact ? 1 : 0, h->sp.init_V, h->d_res);
   rc = launch_check(h, "k_root_result");
   if (rc) return rc;
   ts.launches++;
+  if (h->n_trees > 1) {  // merge the trees of this device like K10 merges the devices (src/solver.jl:60-70)
+    k_trees_merge<<<1, 32, 0, h->stream>>>(h->n_trees, h->nA, h->sp.init_V, h->d_res);
+    rc = launch_check(h, "k_trees_merge");
+    if (rc) return rc;
+    ts.launches++;
+  }
   CK(cudaEventRecord(ts.next(), h->stream));
   h->epoch++;
   h->pending = true;
@@ -369,13 +407,17 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
 
 // wait for the stream, pull result + counters back
 int finish_search(pomcp_handle* h) {
-  CK(cudaMemcpyAsync(h->h_res, h->d_res, sizeof(SearchResult), cudaMemcpyDeviceToHost, h->stream));
+  // h_res[0] = the decision (the merged result when several trees ran), h_res[1 + t] = tree t's own
+  const int T = h->n_trees;
+  CK(cudaMemcpyAsync(h->h_res, h->d_res + (T > 1 ? T : 0), sizeof(SearchResult), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_res + 1, h->d_res, sizeof(SearchResult) * (size_t)T, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->pending = false;
   h->nodes_used = std::max<unsigned long long>(h->h_ctr->node_count, 1);
   h->log_used = std::min<unsigned long long>(h->h_ctr->log_count, h->pool.log_cap);
-  h->root_visits = h->h_res->root_N;
+  for (int t = 0; t < T; ++t) h->tree_visits[(size_t)t] = h->h_res[1 + t].root_N;
+  h->root_visits = h->tree_visits[0];
   if (h->h_res->status == POMCP_ERR_POOL_EXHAUSTED)
     h->err = "node pool or particle log exhausted (raise max_nodes / max_log)";
   return h->h_res->status;
@@ -660,10 +702,12 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.act_V, h->pool.child, h->pool.ht, h->pool.node_pslot, h->pool.node_obs, h->pool.log_node,
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
-                  h->d_cum, h->d_scan_status, h->d_pf_regions, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values};
+                  h->d_cum, h->d_scan_status, h->d_pf_regions, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values,
+                  h->d_trees};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
+  if (h->h_trees) cudaFreeHost(h->h_trees);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->h_pfctl) cudaFreeHost(h->h_pfctl);
   if (h->h_ns) cudaFreeHost(h->h_ns);
@@ -701,6 +745,12 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     if (!(sp->k_observation >= 0.0) || !(sp->alpha_observation >= 0.0))
       return fail(nullptr, POMCP_ERR_INVALID_ARG, "k_observation / alpha_observation < 0");
   }
+  const int T = sp->n_trees > 1 ? sp->n_trees : 1;
+  if (T > POMCP_MAX_TREES) return fail(nullptr, POMCP_ERR_INVALID_ARG, "n_trees > POMCP_MAX_TREES");
+  if (T > 1 && sp->search_mode == POMCP_MODE_EXACT)
+    return fail(nullptr, POMCP_ERR_INVALID_ARG, "n_trees > 1 needs search_mode = batched (exact mode is one sequential tree)");
+  if (sp->rank < 0 || ((long long)sp->rank + 1) * T > 256)
+    return fail(nullptr, POMCP_ERR_INVALID_ARG, "(rank + 1) * n_trees must be <= 256 (8-bit Philox stream id)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, POMCP_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
@@ -723,6 +773,9 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->nA = nA; h->nO = nO; h->state_bytes = sb;
   h->hashed = (nO == 0);
   h->exact = sp->search_mode == POMCP_MODE_EXACT;
+  h->n_trees = T;
+  h->roots.assign((size_t)T, 0u);
+  h->tree_visits.assign((size_t)T, 0);
   h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
   h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
   h->compact_always = std::getenv("POMCP_COMPACT_ALWAYS") != nullptr;
@@ -811,7 +864,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4) +
                     (sp->dpw_observation ? (size_t)nA * 8 + 32 * (12 + (size_t)sb) : 0);
   // unweighted mode keeps the tree across decisions (re-rooting, no compaction yet): room for ~64 of them
-  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) + 65536;
+  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) * T + 65536;
   long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
   // node ids carry a flag in bit 31, and action slots (id * nA + a) are 32-bit as well
   const long long cap_ids = std::min<long long>((1ll << 31) - 2, ((1ll << 32) - 1) / std::max(nA, 1) - 1);
@@ -873,13 +926,15 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &h->pb.path_r, pw));
   CKU(cudaMalloc(&h->pb.path_state, pw * sb));
 
-  CKC(dev_alloc(h, &h->d_res, 1));
+  CKC(dev_alloc(h, &h->d_res, (size_t)T + 1));  // one per tree + the merged decision
   CKC(dev_alloc(h, &h->d_ns, 1));
-  CKU(cudaMallocHost((void**)&h->h_res, sizeof(SearchResult)));
+  CKC(dev_alloc(h, &h->d_trees, (size_t)T));
+  CKU(cudaMallocHost((void**)&h->h_trees, sizeof(TreeCtl) * (size_t)T));
+  CKU(cudaMallocHost((void**)&h->h_res, sizeof(SearchResult) * ((size_t)T + 1)));
   CKU(cudaMallocHost((void**)&h->h_ctr, sizeof(DevCtr)));
   CKU(cudaMallocHost((void**)&h->h_pfctl, sizeof(PfCtl)));
   CKU(cudaMallocHost((void**)&h->h_ns, sizeof(NodeStats)));
-  std::memset(h->h_res, 0, sizeof(SearchResult));
+  std::memset(h->h_res, 0, sizeof(SearchResult) * ((size_t)T + 1));
 
   CKC(ensure_scan(h, 1));
   h->nodes_used = want;  // first fill covers the whole pool
@@ -920,6 +975,15 @@ int32_t pomcp_set_belief_initial(pomcp_handle* h) {
   cudaSetDevice(h->device);
   h->bel_kind = 1;
   h->n_bel = 0;
+  return fresh_root(h);
+}
+
+// make_node for a belief that is not a BeliefNode (src/solver.jl:278-281): every action() on a particle
+// collection or a distribution starts from a new RootNode - here without sending the belief again.
+int32_t pomcp_reset_tree(pomcp_handle* h) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
   return fresh_root(h);
 }
 
@@ -1021,6 +1085,21 @@ int32_t pomcp_get_node_stats(pomcp_handle* h, const int32_t* actions, const uint
   return POMCP_OK;
 }
 
+// Tree t's own result of the last search (before the merge over trees / ranks).
+int32_t pomcp_get_tree_result(pomcp_handle* h, int32_t tree, int32_t* action_out, int64_t* root_N, int64_t* act_N,
+                              double* act_V, int32_t nA) {
+  if (!h || tree < 0 || tree >= h->n_trees) return fail(h, POMCP_ERR_INVALID_ARG, "bad tree index");
+  if (h->pending) return fail(h, POMCP_ERR_INVALID_ARG, "a search is still in flight (pomcp_sync first)");
+  const SearchResult& r = h->h_res[1 + tree];
+  if (action_out) *action_out = r.action;
+  if (root_N) *root_N = r.root_N;
+  for (int a = 0; a < h->nA && a < nA; ++a) {
+    if (act_N) act_N[a] = r.N[a];
+    if (act_V) act_V[a] = r.V[a];
+  }
+  return r.status;
+}
+
 int32_t pomcp_get_root_stats(pomcp_handle* h, int64_t* root_N, int64_t* act_N, double* act_V, int32_t nA) {
   return pomcp_get_node_stats(h, nullptr, nullptr, 0, root_N, nullptr, act_N, act_V, nA);
 }
@@ -1076,6 +1155,7 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
   if (!h) return POMCP_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
+  if (h->n_trees > 1) return fail(h, POMCP_ERR_UNSUPPORTED, "re-rooting needs n_trees = 1 (several trees share one external belief)");
   if (a < 0 || a >= h->nA) return fail(h, POMCP_ERR_INVALID_ARG, "bad action");
   PhaseTimer& t = h->timers[POMCP_PHASE_REROOT];
   t.reset();
@@ -1109,6 +1189,7 @@ int32_t pomcp_update_reinvigorated(pomcp_handle* h, int32_t a, uint64_t obs_bits
   if (!h) return POMCP_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (!h->unweighted) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was created with an external belief updater");
+  if (h->n_trees > 1) return fail(h, POMCP_ERR_UNSUPPORTED, "re-rooting needs n_trees = 1 (several trees share one external belief)");
   if (a < 0 || a >= h->nA || n_min <= 0 || n_min >= (1ll << 32)) return fail(h, POMCP_ERR_INVALID_ARG, "bad a / n_min");
   if (h->bel_kind == 0) return fail(h, POMCP_ERR_INVALID_ARG, "no belief set");
   if (outcome) *outcome = 0;
@@ -1472,6 +1553,7 @@ int32_t pomcp_comm_init(pomcp_handle* h, const void* uid, int32_t rank, int32_t 
   std::memcpy(&id, uid, sizeof(id));
   int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
   if (rc != 0) return fail(h, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclCommInitRank");
+  if (((long long)rank + 1) * h->n_trees > 256) return fail(h, POMCP_ERR_INVALID_ARG, "(rank + 1) * n_trees must be <= 256");
   h->nranks = nranks;
   h->sp.rank = rank;  // distinct Philox streams per tree
   return POMCP_OK;
@@ -1484,12 +1566,17 @@ int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t Q, int32_t* action_ou
   int rc = enqueue_search(h, Q, nullptr, 0, nullptr, 0);
   if (rc) return rc;
   // one fused all-reduce of [N_a ..., N_a*V_a ..., exists_a ...] (3|A| doubles) before the arg-max of src/solver.jl:60-70
-  int nrc = g_nccl.AllReduce(h->d_res->merge, h->d_res->merge, (size_t)(3 * h->nA), NCCL_FLOAT64, NCCL_SUM, h->comm,
-                             h->stream);
+  SearchResult* dec = h->d_res + (h->n_trees > 1 ? h->n_trees : 0);  // this device's (merged) result
+  PhaseTimer& tm = h->timers[POMCP_PHASE_MERGE];
+  tm.reset();
+  CK(cudaEventRecord(tm.next(), h->stream));
+  int nrc = g_nccl.AllReduce(dec->merge, dec->merge, (size_t)(3 * h->nA), NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
   if (nrc != 0) return fail(h, POMCP_ERR_NCCL, g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "ncclAllReduce");
-  k_root_merge_finish<<<1, 32, 0, h->stream>>>(h->nA, h->sp.init_V, h->d_res);
+  k_root_merge_finish<<<1, 32, 0, h->stream>>>(h->nA, h->sp.init_V, dec);
   rc = launch_check(h, "k_root_merge_finish");
   if (rc) return rc;
+  CK(cudaEventRecord(tm.next(), h->stream));
+  tm.launches = 2;
   rc = finish_search(h);
   if (rc == POMCP_OK) copy_out(h, action_out, N, V, nA);
   return rc;

@@ -59,6 +59,8 @@ struct Pool {
   uint32_t max_nodes;
 };
 
+struct TreeCtl;
+
 struct SearchCfg {
   double c, init_V, log_ratio, est_value;
   long long max_depth, init_N;
@@ -80,6 +82,8 @@ struct SearchCfg {
   long long n_bel;
   uint32_t root;
   uint32_t root_N0;  // root visits when the search started
+  TreeCtl* trees;    // batched mode: per-tree parameters (n_trees entries); key / rank / epoch / bel / root above are tree 0's
+  int n_trees;
   // asynchronous workers: in flight = clamp(root visits / ramp_div, inflight_min, inflight_max)
   int inflight_min, inflight_max, ramp_div;
   int path_smem;  // batched mode: the worker's recorded path lives in shared memory (else in PathBuf)
@@ -91,6 +95,30 @@ struct SearchCfg {
   long long n_uni;
   const double* rets;
   long long n_rets;
+};
+
+// Several trees in one launch (root-parallel replicas of one belief, or independent episodes): everything that
+// differs from tree to tree lives in one TreeCtl per tree in global memory; the rest of SearchCfg is shared.
+// A worker belongs to one tree for its whole life: tree = worker id % n_trees, and the admission ramp, the
+// query tickets and the in-flight cap are per tree.
+struct TreeCtl {
+  unsigned long long next_query;  // query ticket of this tree (zeroed by the host before every search)
+  const void* bel;                // root belief particles (NULL: the problem's initial distribution)
+  long long n_bel;
+  uint32_t root, root_N0;         // root node id, root visits when the search started
+  uint32_t key0, key1, rank, epoch;  // Philox key / stream id / epoch of this tree
+  uint32_t any_nonterminal;       // a query of this search ran a simulation (src/solver.jl:56-58)
+  uint32_t _pad;
+};
+// A worker's copy of its tree's parameters, in shared memory (one per team; the helper warps read the keys).
+struct TreeView {
+  const void* bel;
+  long long n_bel;
+  TreeCtl* ctl;
+  uint32_t root, root_N0, key0, key1, tagrank, epoch;
+};
+struct RngKey {
+  uint32_t key0, key1, tagrank, epoch;  // tagrank = rank << 8
 };
 
 // Per-worker scratch: path[level][slot], slot = worker index
@@ -434,8 +462,8 @@ __device__ __forceinline__ long long state_index(const LDState&) { return -1; }
 // butterfly, so the oracle reproduces the mean bit for bit.
 template <int PID>
 __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
-                                                typename ModelT<PID>::State s, long long steps, uint64_t last_o,
-                                                uint32_t q, int lane, int& nsteps_lane, int r_base = 0);
+                                                const RngKey& rk, typename ModelT<PID>::State s, long long steps,
+                                                uint64_t last_o, uint32_t q, int lane, int& nsteps_lane, int r_base = 0);
 
 // ---- child lookup / insert (src/solver.jl:132-142).  Lane 0 only.  A node id that loses an insertion
 // race here is not recycled (it stays an unreachable, zero-initialised slot whose parent link is 0, which
@@ -631,10 +659,10 @@ __device__ __forceinline__ double warp_tree_sum(double x) {
 
 template <int PID>
 __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* tb, const SearchCfg& cfg,
-                                                typename ModelT<PID>::State s, long long steps, uint64_t last_o,
-                                                uint32_t q, int lane, int& nsteps_lane, int r_base) {
+                                                const RngKey& rk, typename ModelT<PID>::State s, long long steps,
+                                                uint64_t last_o, uint32_t q, int lane, int& nsteps_lane, int r_base) {
   const int R = cfg.rollouts;
-  const uint32_t tag0 = TAG_ROLLOUT | (cfg.rank << 8);
+  const uint32_t tag0 = TAG_ROLLOUT | rk.tagrank;
   double ret = 0.0;
   nsteps_lane = 0;
   if (R > 32 && cfg.team_warps <= 1) {  // one warp, two trajectories per lane (warp-uniform)
@@ -642,7 +670,7 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
       const uint32_t tw[2] = {tag0 | ((uint32_t)lane << 16), tag0 | ((uint32_t)(lane + 32) << 16)};
       const bool en[2] = {true, lane + 32 < R};
       double tot[2];
-      rollout_rocksample<false, 2>(m, tb, s, steps, cfg.key0, cfg.key1, tw, en, q, cfg.epoch, nsteps_lane, tot);
+      rollout_rocksample<false, 2>(m, tb, s, steps, rk.key0, rk.key1, tw, en, q, rk.epoch, nsteps_lane, tot);
       ret = tot[0] + tot[1];
     } else {
       double tot[2] = {0.0, 0.0};
@@ -653,11 +681,11 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
         if (r < R) {
           const uint32_t tagword = tag0 | ((uint32_t)r << 16);
           if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
-            tot[t] = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+            tot[t] = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, rk.key0, rk.key1, tagword, q, rk.epoch, ns);
           else if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FO_FWC_ROLLOUT)
-            tot[t] = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+            tot[t] = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, rk.key0, rk.key1, tagword, q, rk.epoch, ns);
           else
-            tot[t] = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, ns);
+            tot[t] = rollout_random<PID, false>(m, tb, s, steps, rk.key0, rk.key1, tagword, q, rk.epoch, ns);
         }
         nsteps_lane += ns;
       }
@@ -666,11 +694,11 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
   } else if (r_base + lane < R) {  // rollout team: warp w of the worker runs rollouts 32 w .. 32 w + 31
     const uint32_t tagword = tag0 | ((uint32_t)(r_base + lane) << 16);
     if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FWC_ROLLOUT)
-      ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+      ret = rollout_fwc(m, (uint32_t)baby_state(s), steps, last_o, rk.key0, rk.key1, tagword, q, rk.epoch, nsteps_lane);
     else if (PID == POMCP_BABY && cfg.estimator == POMCP_EST_FO_FWC_ROLLOUT)
-      ret = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+      ret = rollout_fo_fwc(m, (uint32_t)baby_state(s), steps, rk.key0, rk.key1, tagword, q, rk.epoch, nsteps_lane);
     else
-      ret = rollout_random<PID, false>(m, tb, s, steps, cfg.key0, cfg.key1, tagword, q, cfg.epoch, nsteps_lane);
+      ret = rollout_random<PID, false>(m, tb, s, steps, rk.key0, rk.key1, tagword, q, rk.epoch, nsteps_lane);
   }
   return ret;
 }
@@ -894,7 +922,8 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       lc.rollouts++;
     } else {
       int nsteps = 0;
-      const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
+      const RngKey rk{cfg.key0, cfg.key1, cfg.rank << 8, cfg.epoch};
+      const double ret = leaf_rollouts<PID>(m, tb, cfg, rk, s, steps, last_o, q, lane, nsteps);
       est = warp_tree_sum(ret) / (double)cfg.rollouts;
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       lc.rollouts += cfg.rollouts;
@@ -1113,7 +1142,7 @@ __device__ __forceinline__ void team_bar(int id, int nthreads) {  // id in 1 .. 
 // (lane 0; requested early so its latency hides behind the rollouts).
 template <int PID, bool DPA, int NTEAMS>
 __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
-                                               const uint32_t* eta_thr, const SearchCfg& cfg,
+                                               const uint32_t* eta_thr, const SearchCfg& cfg, const TreeView& tv,
                                                const PathView<typename ModelT<PID>::State>& pv,
                                                LeafJob<typename ModelT<PID>::State>* job, uint32_t q,
                                                LocalCtr& lc, unsigned long long& next_q, uint32_t& spare) {
@@ -1121,14 +1150,14 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   using State = typename M::State;
   const int lane = threadIdx.x & 31;
   const int nA = m.nA;
-  const uint32_t tag_rank = cfg.rank << 8;
+  const uint32_t tag_rank = tv.tagrank;
   const float c_f = (float)cfg.c;
   const bool v_finite = fabs(cfg.init_V) != INFINITY;
   const float initV_f = (float)cfg.init_V;
 
   // root statistics are requested first: they do not depend on the draw
-  uint32_t h = cfg.root;
-  uint32_t hN = cfg.root_N0 + q;
+  uint32_t h = tv.root;
+  uint32_t hN = tv.root_N0 + q;
   ActStats<PID> st;
   st.load(P, h, nA, lane, cfg.dpw != 0, DPA);
   uint32_t fl = 0;
@@ -1136,15 +1165,15 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   __syncwarp();
 
   // rand(rng, b): src/solver.jl:48 -> src/updater.jl:53-55
-  Philox4 pr = philox4x32_10(0u, TAG_ROOT | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+  Philox4 pr = philox4x32_10(0u, TAG_ROOT | tag_rank, q, tv.epoch, tv.key0, tv.key1);
   const double u0 = u01(pr.w[0]), u1 = u01(pr.w[1]);
   State s;
-  if (cfg.bel != nullptr) s = ((const State*)cfg.bel)[(long long)(u0 * (double)cfg.n_bel)];
+  if (tv.bel != nullptr) s = ((const State*)tv.bel)[(long long)(u0 * (double)tv.n_bel)];
   else s = M::initial(m, u0, u1);
   fl = __shfl_sync(0xffffffffu, fl, 0);
   if (M::terminal(m, s)) {  // src/solver.jl:49: the query is consumed
     lc.skips++;
-    if (lane == 0) next_q = atomicAdd(&P.ctr->next_query, 1ull);
+    if (lane == 0) next_q = atomicAdd(&tv.ctl->next_query, 1ull);
     return;
   }
 
@@ -1168,11 +1197,11 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   // j * LV .. j * LV + LV - 1); a level fetches its words with a shuffle.  Same counters, same words as
   // computing block d / LV at level d (which levels past the 32nd block still do).
   Philox4 pall{};
-  if (!dpw) pall = philox4x32_10((uint32_t)lane, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+  if (!dpw) pall = philox4x32_10((uint32_t)lane, TAG_TREE | tag_rank, q, tv.epoch, tv.key0, tv.key1);
   auto spec_step = [&](int d) {
     uint32_t w0, w1 = 0;
     if (dpw) {
-      ptb = philox4x32_10((uint32_t)d, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+      ptb = philox4x32_10((uint32_t)d, TAG_TREE | tag_rank, q, tv.epoch, tv.key0, tv.key1);
       w0 = ptb.w[0];
       w1 = ptb.w[1];
     } else {
@@ -1186,7 +1215,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
           w1 = __shfl_sync(0xffffffffu, k ? pall.w[3] : pall.w[1], blk);
         }
       } else {
-        const Philox4 pb2 = philox4x32_10((uint32_t)blk, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1);
+        const Philox4 pb2 = philox4x32_10((uint32_t)blk, TAG_TREE | tag_rank, q, tv.epoch, tv.key0, tv.key1);
         if (TW == 1) {
           w0 = k == 0 ? pb2.w[0] : k == 1 ? pb2.w[1] : k == 2 ? pb2.w[2] : pb2.w[3];
         } else {
@@ -1196,7 +1225,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       }
     }
     if (DPA)  // next_action(RandomActionGenerator): rand(rng, actions(pomdp)), its own block per level
-      a_new = (int)__umulhi(philox4x32_10((uint32_t)d | 0x80000000u, TAG_TREE | tag_rank, q, cfg.epoch, cfg.key0, cfg.key1).w[0],
+      a_new = (int)__umulhi(philox4x32_10((uint32_t)d | 0x80000000u, TAG_TREE | tag_rank, q, tv.epoch, tv.key0, tv.key1).w[0],
                             (uint32_t)nA);
     const int a_l = lane < nA ? lane : nA - 1;
     if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, w0, sp_l, o_l, r_l);
@@ -1386,8 +1415,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     }
   }
   if (lane == 0) {
-    if (aborted) atomicMax(&P.ctr->next_query, 1ull << 62);  // pool exhausted: stop every worker
-    next_q = atom_add_u64_async(&P.ctr->next_query, 1ull, P.max_nodes);
+    if (aborted) atomicMax(&tv.ctl->next_query, 1ull << 62);  // pool exhausted: stop every worker of this tree
+    next_q = atom_add_u64_async(&tv.ctl->next_query, 1ull, P.max_nodes);
   }
   __syncwarp();  // lanes re-converge before the rollouts (see above)
   if (aborted) return;
@@ -1422,7 +1451,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         team_bar<NTEAMS>(job->bar, 32 * W);
       }
       int nsteps = 0;
-      const double ret = leaf_rollouts<PID>(m, tb, cfg, s, steps, last_o, q, lane, nsteps);
+      const RngKey rk{tv.key0, tv.key1, tv.tagrank, tv.epoch};
+      const double ret = leaf_rollouts<PID>(m, tb, cfg, rk, s, steps, last_o, q, lane, nsteps);
       double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       if (W > 1) {
@@ -1484,7 +1514,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       }
       Rnext = __shfl_sync(0xffffffffu, R, 0);
     }
-    if (lane == 0) atomicAdd(&P.node_N[cfg.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
+    if (lane == 0) atomicAdd(&P.node_N[tv.root], 1u);  // b.N += 1 after simulate (src/solver.jl:51)
   }
   __syncwarp();
   lc.cyc[3] += (unsigned long long)(clock64() - t2);
@@ -1533,6 +1563,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ RsTab rs_tab;
   __shared__ LeafJob<State> jobs[NTEAMS];
+  __shared__ TreeView tvs[NTEAMS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int team = warp / TEAM, role = warp % TEAM;
   constexpr int W = TEAM;
@@ -1544,6 +1575,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   }
   const uint32_t* eta_thr = (const uint32_t*)(dyn_smem + cfg.eta_off);
   LeafJob<State>* job = &jobs[team];
+  const TreeView& tv = tvs[team];
   const int bar = 1 + 2 * team;
   if (role > 0) {
     // helper warp of the rollout team: 32 rollouts of every leaf the tree warp posts
@@ -1551,7 +1583,8 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
       team_bar<NTEAMS>(bar, 32 * W);
       if (job->cmd == 0) break;
       int nsteps = 0;
-      const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, job->s, job->steps, job->last_o, job->q, lane, nsteps, 32 * role);
+      const RngKey rk{tv.key0, tv.key1, tv.tagrank, tv.epoch};  // written by the tree warp before its first barrier
+      const double ret = leaf_rollouts<PID>(m, &rs_tab, cfg, rk, job->s, job->steps, job->last_o, job->q, lane, nsteps, 32 * role);
       const double sum = warp_tree_sum(ret);
       nsteps = __reduce_add_sync(0xffffffffu, nsteps);
       if (lane == 0) {
@@ -1562,13 +1595,23 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
     }
     return;
   }
-  if (lane == 0) job->bar = bar;
-  __syncwarp();
   DevCtr* c = P.ctr;
   // worker ids are handed out in start order, so the admitted (lowest) ids are always resident
   unsigned wid = 0;
   if (lane == 0) wid = (unsigned)atomicAdd(&c->worker_ticket, 1ull);
   wid = __shfl_sync(0xffffffffu, wid, 0);
+  // the worker's tree: ids are dealt round-robin, wt = its index among the workers of that tree
+  const unsigned ntr = cfg.n_trees > 1 ? (unsigned)cfg.n_trees : 1u;
+  const unsigned ti = wid % ntr, wt = wid / ntr;
+  TreeCtl* const tc = cfg.trees + ti;
+  if (lane == 0) {
+    job->bar = bar;
+    TreeView& w = tvs[team];
+    w.bel = tc->bel; w.n_bel = tc->n_bel; w.ctl = tc;
+    w.root = tc->root; w.root_N0 = tc->root_N0;
+    w.key0 = tc->key0; w.key1 = tc->key1; w.tagrank = tc->rank << 8; w.epoch = tc->epoch;
+  }
+  __syncwarp();
   PathView<State> pv;
   if (cfg.path_smem) {
     const int L = cfg.levels > 0 ? cfg.levels : 1;
@@ -1589,14 +1632,15 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   unsigned long long next_q = ~0ull;
   uint32_t spare = 0;  // lane 0: node id allocated ahead of the next insertion (direct child table)
   const long long t_start = clock64();
-  if (lane == 0 && (long long)wid < (long long)cfg.inflight_max) {
-    // admission: ramp the number of simulations in flight with the size of the tree
+  if (lane == 0 && (long long)wt < (long long)cfg.inflight_max) {
+    // admission: ramp the number of simulations in flight with the size of the tree (cfg.inflight_* are per tree)
     const unsigned long long need =
-        (long long)wid < (long long)cfg.inflight_min ? 0ull : ((unsigned long long)wid + 1ull) * (unsigned long long)cfg.ramp_div;
+        (long long)wt < (long long)cfg.inflight_min ? 0ull : ((unsigned long long)wt + 1ull) * (unsigned long long)cfg.ramp_div;
     bool go = true;
     unsigned spins = 0;
-    while ((unsigned long long)__ldcg(&P.node_N[cfg.root]) < need) {
-      if (__ldcg((const unsigned long long*)&c->next_query) >= (unsigned long long)queries) { go = false; break; }
+    const uint32_t root = tc->root;
+    while ((unsigned long long)__ldcg(&P.node_N[root]) < need) {
+      if (__ldcg((const unsigned long long*)&tc->next_query) >= (unsigned long long)queries) { go = false; break; }
       if (++spins > (1u << 22)) {  // ~2 s without being admitted: give up instead of hanging the device
         c->pool_overflow = 2;
         go = false;
@@ -1604,13 +1648,13 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
       }
       __nanosleep(2000);
     }
-    if (go) next_q = atomicAdd(&c->next_query, 1ull);
+    if (go) next_q = atomicAdd(&tc->next_query, 1ull);
   }
   const long long t_admitted = clock64();
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID, DPA, NTEAMS>(P, m, &rs_tab, eta_thr, cfg, pv, job, (uint32_t)q, lc, next_q, spare);
+    simulate_async<PID, DPA, NTEAMS>(P, m, &rs_tab, eta_thr, cfg, tv, pv, job, (uint32_t)q, lc, next_q, spare);
   }
   if (W > 1) {  // release the helpers
     if (lane == 0) job->cmd = 0;
@@ -1618,6 +1662,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   }
   if (lane == 0) {
     flush_counters(P, lc, false);
+    if (lc.sims) tc->any_nonterminal = 1;
 #ifndef POMCP_PROBE
     atomicAdd(&c->dbg[4], (unsigned long long)(t_admitted - t_start));  // waiting for admission
     atomicAdd(&c->dbg[5], (unsigned long long)(clock64() - t_admitted));  // working
@@ -1658,9 +1703,12 @@ __global__ void __launch_bounds__(32) k_search_exact(const __grid_constant__ Poo
 // values(b.children): under action widening only the ActNodes that were actually added take part
 // (a slot that was never added still holds the pool's prefill and must not win a ">=" against
 // negative values).
-__global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t root, int exact, double init_V,
-                              SearchResult* res) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void k_root_result(const __grid_constant__ Pool P, int nA, const TreeCtl* trees, int exact, double init_V,
+                              SearchResult* res_all) {
+  if (threadIdx.x != 0) return;
+  const int t = blockIdx.x;  // one block per tree
+  SearchResult* res = res_all + t;
+  const uint32_t root = trees[t].root;
   DevCtr* c = P.ctr;
   res->root_N = P.node_N[root];
   const uint32_t amask = P.node_amask ? P.node_amask[root] : 0xffffffffu;
@@ -1688,11 +1736,44 @@ __global__ void k_root_result(const __grid_constant__ Pool P, int nA, uint32_t r
   res->action = best < 0 ? 0 : best;
   int st = POMCP_OK;
   if (nan_seen) st = POMCP_ERR_NAN_VALUE;                          // @assert !isnan(best_V), src/solver.jl:62
-  if (!c->any_nonterminal) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;    // src/solver.jl:56-58
+  if (!(exact ? c->any_nonterminal : trees[t].any_nonterminal)) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;  // src/solver.jl:56-58
   if (c->pool_overflow || c->log_overflow) st = POMCP_ERR_POOL_EXHAUSTED;
   if (c->pool_overflow == 2) st = POMCP_ERR_CUDA;  // worker watchdog fired
   if (c->replay_overflow) st = POMCP_ERR_INVALID_ARG;
   res->status = st;
+}
+
+// Several trees on one device (root parallelism inside a GPU): the same merge as K10, over the trees of this
+// handle.  res_all[0..T-1] are the trees' own results, res_all[T] receives the merged one; a tree whose samples
+// were all terminal contributes nothing (it has no children), any other failure is the merged status.
+__global__ void k_trees_merge(int T, int nA, double init_V, SearchResult* res_all) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  SearchResult* out = res_all + T;
+  int st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+  long long root_N = 0;
+  for (int i = 0; i < 3 * nA; ++i) out->merge[i] = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const SearchResult* r = res_all + t;
+    root_N += r->root_N;
+    if (r->status == POMCP_ERR_ALL_SAMPLES_TERMINAL) continue;
+    if (r->status != POMCP_OK) { st = r->status; break; }
+    if (st == POMCP_ERR_ALL_SAMPLES_TERMINAL) st = POMCP_OK;
+    for (int i = 0; i < 3 * nA; ++i) out->merge[i] += r->merge[i];  // fixed order: trees 0, 1, 2, ...
+  }
+  out->status = st;
+  out->root_N = root_N;
+  out->ucur = out->rcur = 0;
+  int best = -1;
+  double best_V = 0.0;
+  for (int a = 0; a < nA; ++a) {
+    const double n = out->merge[a], nv = out->merge[nA + a];
+    const double v = n > 0.0 ? nv / n : init_V;
+    out->N[a] = (long long)n;
+    out->V[a] = v;
+    if (!(out->merge[2 * nA + a] > 0.0)) continue;
+    if (best < 0 || v >= best_V) { best_V = v; best = a; }
+  }
+  out->action = best < 0 ? 0 : best;
 }
 
 // after the all-reduce: V_a = sum(N*V)/sum(N) over the trees that hold ActNode a, then the reference's arg-max rule

@@ -120,6 +120,47 @@ def test_c3_rocksample_7_8_1e6_queries(oracle, gpu_lib):
     gp.close()
 
 
+def test_c3_values_vs_oracle(oracle, gpu_lib):
+    """north_star criterion 2 at the headline size: RockSample(7,8), 10^6 queries, 6 seeds, the batched planner with
+    its defaults (8 simulations in flight per SM, 64 rollouts per leaf) against the sequential oracle on the same
+    seeds (one oracle tree per host thread).  Stated tolerance, the rule the 10^5-query test uses: the batched
+    planner picks the oracle's modal root action in >= 5 of 6 runs, and the mean value of that action differs
+    from the oracle's by no more than 3 standard errors of the difference + 3 % of the reward scale (10).
+    Measured (scripts/probe.py knob): the batched value is systematically lower (about -0.6 at 1184 in flight,
+    -0.1 at 64): simulations in flight cannot see each other's results, which costs the tree some exploitation."""
+    from concurrent.futures import ThreadPoolExecutor
+    pomdp = pj.RockSamplePOMDP(7, 8, seed=7008)
+    Q, seeds = 1_000_000, [60 + i for i in range(6)]
+
+    def orc(seed):
+        op = oracle.OraclePlanner(pomdp, oracle.default_params(c=20.0, seed=seed, tree_queries=Q))
+        op.set_belief_initial()
+        rc, a, N, V = op.search(Q)
+        op.close()
+        assert rc == 0
+        return a, V
+
+    with ThreadPoolExecutor(len(seeds)) as ex:
+        fut = [ex.submit(orc, s) for s in seeds]  # CPU: runs while the GPU searches below
+        res_g = []
+        for seed in seeds:
+            gp = pj.solve(pj.POMCPSolver(c=20.0, rng=seed, tree_queries=Q, search_mode="batched", max_nodes=3 * Q), pomdp)
+            gp.set_belief_initial()
+            a, N, V = gp.search(Q)
+            assert N.sum() == Q - 1
+            res_g.append((a, V))
+            gp.close()
+        res_o = [f.result() for f in fut]
+    modal = int(np.bincount([a for a, _ in res_o]).argmax())
+    assert sum(a == modal for a, _ in res_g) >= 5, ([a for a, _ in res_g], [a for a, _ in res_o])
+    vg = np.array([v[modal] for _, v in res_g])
+    vo = np.array([v[modal] for _, v in res_o])
+    se = np.sqrt(vg.var(ddof=1) / len(vg) + vo.var(ddof=1) / len(vo))
+    print(f"C3 values at 1e6: batched {vg.mean():.3f} +- {vg.std(ddof=1) / np.sqrt(len(vg)):.3f}, oracle {vo.mean():.3f} +- "
+          f"{vo.std(ddof=1) / np.sqrt(len(vo)):.3f}")
+    assert abs(vg.mean() - vo.mean()) <= 3 * se + 0.03 * 10.0, (vg, vo, se)
+
+
 # ----------------------------------------------------------------------------- C4
 @pytest.mark.parametrize("streaming", [False, True])
 def test_c4_lightdark_1e6_particles_sir(oracle, gpu_lib, streaming, monkeypatch):

@@ -527,11 +527,11 @@ def test_api_default_action_and_errors(gpu_lib):
 
 
 # ----------------------------------------------------------------------------- episode reward (criterion 3)
-def _run_episodes(oracle, pomdp, make_planner, n_episodes, max_steps, seed0, use_gpu, n_part=0):
+def _run_episodes(oracle, pomdp, make_planner, n_episodes, max_steps, seed0, use_gpu, n_part=0, first_ep=0):
     """RolloutSimulator outer loop: action -> environment step -> belief update.
     The environment is stepped by the oracle's generative model with a host RNG shared by both arms."""
     rewards = []
-    for ep in range(n_episodes):
+    for ep in range(first_ep, first_ep + n_episodes):
         env = np.random.default_rng(seed0 + ep)
         pl = make_planner(ep)
         if n_part:
