@@ -995,12 +995,21 @@ int32_t orc_resample_systematic_f64(const double* w, int64_t n, double r01, int6
 }
 
 static int ceil_log2_i64(int64_t n) { int L = 0; while (((int64_t)1 << L) < n) ++L; return L; }
+/* analytic ceiling of obs_weight(): weights < 2^(E + 1) */
+static int weight_ceil_exp(const model* m) { return m->p.problem_id == POMCP_LIGHTDARK1D ? 5 : 0; }
 
-/* Fixed-point restatement: q_i = trunc(w_i * 2^s) with s = 61 - ceil(log2 n) - floor(log2 max w);
- * output m takes the first i with  C_i * n_out * 2^32 >= (ru + m*2^32) * T  (ru = floor(r*2^32)).
- * Integer sums are associative, so a parallel scan gives the same indices in any order. */
+/* Fixed-point restatement: q_i = trunc(w_i * 2^s); output m takes the first i with
+ * C_i * n_out * 2^32 >= (ru + m*2^32) * T  (ru = floor(r*2^32)).  Integer sums are associative, so a parallel
+ * scan gives the same indices in any order.
+ * Scale rule: s = 61 - ceil(log2 n) - E keeps sum q < 2^62 when every weight is below 2^(E+1).
+ *   - weights of a model have an analytic ceiling (probabilities: E_ceil = 0; LightDark's Normal pdf with
+ *     sigma >= 0.01: at most 39.9 < 2^6, E_ceil = 5).  That a-priori scale is used when no weight exceeds the ceiling
+ *     and the total keeps at least 40 bits (sum q >= 2^40): the device then needs no pass over the data to find
+ *     the largest weight;
+ *   - otherwise (and for replayed weights, which have no ceiling) E = floor(log2 max w). */
+#define ORC_NO_CEIL (-100000)
 static int32_t resample_fixed(const double* w, const uint8_t* alive, int64_t n, uint32_t ru, int64_t n_out,
-                              int64_t* idx_out) {
+                              int64_t* idx_out, int e_ceil) {
   if (n <= 0 || n_out <= 0 || n_out >= ((int64_t)1 << 32) || n >= ((int64_t)1 << 32)) return POMCP_ERR_INVALID_ARG;
   double maxw = 0.0;
   for (int64_t i = 0; i < n; ++i) if ((!alive || alive[i]) && w[i] > maxw) maxw = w[i];
@@ -1008,7 +1017,14 @@ static int32_t resample_fixed(const double* w, const uint8_t* alive, int64_t n, 
   int e = (int)((d2u(maxw) >> 52) & 0x7ff) - 1023; /* floor(log2 maxw) for normal doubles */
   int s = 61 - ceil_log2_i64(n) - e;
   uint64_t T = 0;
-  for (int64_t i = 0; i < n; ++i) T += ((!alive || alive[i]) && w[i] > 0.0) ? (uint64_t)ldexp(w[i], s) : 0;
+  if (e_ceil != ORC_NO_CEIL && e <= e_ceil) {
+    int sc = 61 - ceil_log2_i64(n) - e_ceil;
+    uint64_t Tc = 0;
+    for (int64_t i = 0; i < n; ++i) Tc += ((!alive || alive[i]) && w[i] > 0.0) ? (uint64_t)ldexp(w[i], sc) : 0;
+    if (Tc >= ((uint64_t)1 << 40)) { s = sc; T = Tc; }
+  }
+  if (T == 0)
+    for (int64_t i = 0; i < n; ++i) T += ((!alive || alive[i]) && w[i] > 0.0) ? (uint64_t)ldexp(w[i], s) : 0;
   if (T == 0) return POMCP_ERR_PARTICLE_DEPLETION;
   int64_t i = -1;
   uint64_t C = 0;
@@ -1034,7 +1050,7 @@ static int32_t resample_fixed(const double* w, const uint8_t* alive, int64_t n, 
 
 int32_t orc_resample_systematic_fixed(const double* w, int64_t n, double r01, int64_t n_out, int64_t* idx_out) {
   if (!(r01 >= 0.0) || !(r01 < 1.0)) return POMCP_ERR_INVALID_ARG;
-  return resample_fixed(w, NULL, n, (uint32_t)(r01 * 4294967296.0), n_out, idx_out);
+  return resample_fixed(w, NULL, n, (uint32_t)(r01 * 4294967296.0), n_out, idx_out, ORC_NO_CEIL);
 }
 
 static void pf_propagate(const model* m, const void* states, int64_t n, int a, uint64_t obs, uint64_t seed,
@@ -1086,7 +1102,7 @@ int32_t orc_pf_update_sir(orc_planner* pl, int32_t a, uint64_t obs, uint64_t see
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {0, TAG_RESAMPLE, 0, 0}, wd[4];
     orc_philox4x32_10(ctr, key, wd);
-    if (mode == 0) rc = resample_fixed(w, alive, n, wd[0], n_out, idx);
+    if (mode == 0) rc = resample_fixed(w, alive, n, wd[0], n_out, idx, weight_ceil_exp(m));
     else {
       /* terminal particles are dropped before weighting: compact, resample, map back */
       int64_t na = 0;
@@ -1161,7 +1177,7 @@ int32_t orc_update_reinvigorated(orc_planner* pl, int32_t a, uint64_t obs, uint6
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t ctr[4] = {0, TAG_RESAMPLE, 0, 0}, wd[4];
     orc_philox4x32_10(ctr, key, wd);
-    rc = resample_fixed(w, alive, n_old, wd[0], extra, idx);
+    rc = resample_fixed(w, alive, n_old, wd[0], extra, idx, weight_ceil_exp(m));
   }
   if (rc == POMCP_OK) {
     if (have) {

@@ -147,6 +147,9 @@ struct pomcp_handle {
   bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
   long long compactions = 0;
   bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
+  bool pf_two_barriers = false;     // POMCP_PF_TWO_BARRIERS=1: never use the one-barrier (a-priori scale) kernel
+  bool pf_nocoop = false;           // POMCP_PF_NOCOOP=1: plain launch of the one-barrier kernel (developer timing)
+  long long pf_retries = 0;         // one-barrier launches that fell back to the max-scaled kernels
   nccl_comm comm = nullptr;
   int nranks = 1;
   std::string err;
@@ -453,18 +456,23 @@ int ensure_scan(pomcp_handle* h, long long n) {
   return POMCP_OK;
 }
 
-// K6 -> K7 -> K8 on an arbitrary weight source
+// K6 -> K7 -> K8 on an arbitrary weight source.  `allow_ceil`: try the one-barrier kernel with the a-priori
+// scale first (sources with a weight ceiling); it reports PF_RETRY_MAX_SCALE in the control block when that scale
+// does not fit, and the caller (run_resample_sync) then runs the max-scaled kernels.
 template <class Src, class Out>
-int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long long n_out, Out* d_out) {
+int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long long n_out, Out* d_out, bool allow_ceil) {
   int rc;
+  const bool ceil_ok = allow_ceil && Src::CEIL_EXP != PF_NO_CEIL && !h->pf_two_barriers;
+  constexpr bool blocked = sizeof(typename Src::State) <= 8;
   // fused single-launch path when the whole set fits one co-resident grid
   static int max_grid = -1;  // per <Src,Out> instantiation
   if (max_grid < 0) {
-    int per_sm = 0, sms = 0;
-    if (sizeof(typename Src::State) <= 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
+    int per_sm = 0, per_sm_c = 0, sms = 0;
+    if (blocked) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused<Src, Out>, PF_THREADS, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pf_fused_striped<Src, Out>, PF_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_pf_fused_ceil<Src, Out, blocked>, PF_THREADS, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    max_grid = std::min(per_sm * sms, PF_MAX_GRID);
+    max_grid = std::min(std::min(per_sm, per_sm_c) * sms, PF_MAX_GRID);
   }
   // split the set evenly over the co-resident grid: `rows` consecutive particles per thread (<= PF_ITEMS)
   long long rows_ll = max_grid > 0 ? (n + (long long)max_grid * PF_THREADS - 1) / ((long long)max_grid * PF_THREADS) : 99;
@@ -487,7 +495,17 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     Src src_copy = src;
     void* args[] = {(void*)&src_copy, (void*)&n, (void*)&ctl, (void*)&ru, (void*)&n_out, (void*)&d_out,
                     (void*)&cta_tot, (void*)&bar, (void*)&rows, (void*)&other};
-    if (sizeof(typename Src::State) <= 8) {
+    if (ceil_ok) {
+      // grid <= what the occupancy calculator says is co-resident; the cooperative launch makes the driver
+      // guarantee it (POMCP_PF_NOCOOP=1: plain launch, for timing the difference)
+      if (h->pf_nocoop) {
+        k_pf_fused_ceil<Src, Out, blocked><<<(unsigned)grid, PF_THREADS, 0, h->stream>>>(src_copy, n, ctl, ru, n_out, d_out,
+                                                                                         cta_tot, bar, rows, other);
+      } else {
+        CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused_ceil<Src, Out, blocked>, dim3((unsigned)grid),
+                                       dim3(PF_THREADS), args, 0, h->stream));
+      }
+    } else if (blocked) {
       CK(cudaLaunchCooperativeKernel((const void*)k_pf_fused<Src, Out>, dim3((unsigned)grid), dim3(PF_THREADS), args,
                                      0, h->stream));
     } else {  // wide states: striped variant; its control block is zeroed here (it does not reset the other one)
@@ -504,13 +522,13 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   if (rc) return rc;
   rc = ensure_scan(h, n);
   if (rc) return rc;
-  // streaming path: weigh -> total -> scan + emit
+  // streaming path: weigh -> total(s) -> scan + emit (picks the scale by the same rule)
   int blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
   k_pf_weigh<Src><<<blocks, 256, 0, h->stream>>>(src, n, (double*)h->d_cum, h->d_pfctl);
   rc = launch_check(h, "k_pf_weigh");
   if (rc) return rc;
   k_pf_total<<<(int)std::min<long long>((n + 2047) / 2048, 148 * 8), 256, 0, h->stream>>>((const double*)h->d_cum, n,
-                                                                                         h->d_pfctl);
+                                                                                         h->d_pfctl, Src::CEIL_EXP);
   rc = launch_check(h, "k_pf_total");
   if (rc) return rc;
   int tiles = (int)((n + PF2_TILE - 1) / PF2_TILE);
@@ -519,6 +537,26 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   rc = launch_check(h, "k_pf_scan_emit");
   if (rc) return rc;
   h->timers[POMCP_PHASE_PF].launches += 3;
+  return POMCP_OK;
+}
+
+// run_resample + the status read-back every caller needs; falls back to the max-scaled kernels when the
+// one-barrier kernel asks for it.  Leaves the stream synchronised and the status in h->h_pfctl->status.
+template <class Src, class Out>
+int run_resample_sync(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long long n_out, Out* d_out,
+                      cudaEvent_t done_event = nullptr) {
+  int rc = run_resample(h, src, n, ru, n_out, d_out, true);
+  if (rc) return rc;
+  if (done_event) CK(cudaEventRecord(done_event, h->stream));
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->h_pfctl->status != PF_RETRY_MAX_SCALE) return POMCP_OK;
+  h->pf_retries++;
+  rc = run_resample(h, src, n, ru, n_out, d_out, false);
+  if (rc) return rc;
+  if (done_event) CK(cudaEventRecord(done_event, h->stream));  // the phase timer then covers both attempts
+  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return POMCP_OK;
 }
 
@@ -540,6 +578,12 @@ int compact_pool(pomcp_handle* h) {
   if (rc) return rc;
   k_scan_total<<<1, 32, 0, h->stream>>>(h->d_scan_status + 9, tiles, &h->d_pfctl->total);
   rc = launch_check(h, "k_scan_total");
+  if (rc) return rc;
+  // the new root becomes node 0 (its rank is swapped with the rank-0 node's; the scratch word is PfCtl::_pad's neighbour)
+  uint32_t* d_root_rank = (uint32_t*)&h->d_pfctl->total_ceil;
+  k_root_rank<<<1, 32, 0, h->stream>>>(h->d_newid, h->root, d_root_rank);
+  k_root_first<<<(int)((n_nodes + 255) / 256), 256, 0, h->stream>>>(h->d_newid, n_nodes, h->root, d_root_rank);
+  rc = launch_check(h, "k_root_first");
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -778,6 +822,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->tree_visits.assign((size_t)T, 0);
   h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
   h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
+  h->pf_two_barriers = std::getenv("POMCP_PF_TWO_BARRIERS") != nullptr;
+  h->pf_nocoop = std::getenv("POMCP_PF_NOCOOP") != nullptr;
   h->compact_always = std::getenv("POMCP_COMPACT_ALWAYS") != nullptr;
   CKU(cudaSetDevice(device));
   CKU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -1232,11 +1278,9 @@ int32_t pomcp_update_reinvigorated(pomcp_handle* h, int32_t a, uint64_t obs_bits
   Philox4 pr = philox4x32_10(0u, TAG_RESAMPLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
   DISPATCH_PID(h->prob.problem_id, {
     auto src = make_src<PID>(h, old, a, obs_bits, seed);
-    rc = run_resample(h, src, n_old, pr.w[0], extra, (typename ModelT<PID>::State*)h->d_bel[nb] + cnt);
+    rc = run_resample_sync(h, src, n_old, pr.w[0], extra, (typename ModelT<PID>::State*)h->d_bel[nb] + cnt);
   });
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   const bool drew = h->h_pfctl->status == POMCP_OK;
   if (!drew && !have) return POMCP_ERR_PARTICLE_DEPLETION;  // nothing pushed by the planner and no posterior mass
   h->bel_cur = nb;
@@ -1267,14 +1311,12 @@ int32_t pomcp_pf_update_sir(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint6
   PhaseTimer& t = h->timers[POMCP_PHASE_PF];
   t.reset();
   CK(cudaEventRecord(t.next(), h->stream));
+  cudaEvent_t t_done = t.next();
   DISPATCH_PID(h->prob.problem_id, {
     auto src = make_src<PID>(h, h->d_bel[h->bel_cur], a, obs_bits, seed);
-    rc = run_resample(h, src, n, pr.w[0], n_out, (typename ModelT<PID>::State*)h->d_bel[nb]);
+    rc = run_resample_sync(h, src, n, pr.w[0], n_out, (typename ModelT<PID>::State*)h->d_bel[nb], t_done);
   });
   if (rc) return rc;
-  CK(cudaEventRecord(t.next(), h->stream));
-  CK(cudaMemcpyAsync(h->h_pfctl, h->d_pfctl, sizeof(PfCtl), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   if (h->h_pfctl->status != POMCP_OK) return h->h_pfctl->status;
   h->bel_cur = nb;
   h->n_bel = n_out;
@@ -1295,7 +1337,7 @@ int32_t pomcp_resample_systematic(pomcp_handle* h, const double* w, int64_t n, d
   CK(cudaMemsetAsync(h->d_tmp2, 0xff, (size_t)n_out * sizeof(long long), h->stream));
   if (mode == 0) {
     ArraySrc src{(const double*)h->d_tmp};
-    rc = run_resample(h, src, n, (uint32_t)(r * 4294967296.0), n_out, (long long*)h->d_tmp2);
+    rc = run_resample(h, src, n, (uint32_t)(r * 4294967296.0), n_out, (long long*)h->d_tmp2, false);
     if (rc) return rc;
   } else {
     rc = ensure_scan(h, 1);

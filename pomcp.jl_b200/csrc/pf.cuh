@@ -31,9 +31,21 @@ constexpr unsigned long long SCAN_VAL_MASK = (1ull << 62) - 1;
 struct PfCtl {
   unsigned long long max_bits;     // bits of the largest weight (weights >= 0: order-preserving)
   unsigned long long first_alive_inv;  // ~(index of the first non-terminal particle); 0 = none yet
-  unsigned long long total;        // T = sum q_i
+  unsigned long long total;        // T = sum q_i at the scale in use
   unsigned int any_alive, status;
+  unsigned long long total_ceil;   // streaming path: sum q_i at the a-priori scale (pf_scale_ceil)
+  unsigned int over_ceil, _pad;    // a weight above the model's analytic ceiling was seen: the a-priori scale is off
 };
+// Internal status of the one-barrier kernels: the a-priori scale does not resolve these weights (or a weight is
+// above the ceiling) - the caller runs the max-scaled kernels instead.  Never crosses the ABI.
+constexpr int PF_RETRY_MAX_SCALE = 100;
+// Scale rule (the oracle's resample_fixed states the same): weights of a model are bounded by an analytic
+// ceiling 2^(E+1) (probabilities: E = 0; LightDark's Normal pdf with sigma >= 0.01: 39.9 < 2^6, E = 5), so
+// s_ceil = 61 - ceil(log2 n) - E keeps sum q < 2^62 without looking at the data, and the max-weight pass with its
+// grid barrier goes away.  It is used when no weight exceeds the ceiling and the total keeps at least 40 bits
+// (sum q >= 2^40); otherwise the scale comes from the largest weight as before.
+constexpr unsigned long long PF_MIN_TOTAL_CEIL = 1ull << 40;
+constexpr int PF_NO_CEIL = -100000;
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -135,6 +147,7 @@ struct ModelSrc {
   int a;
   uint64_t obs;
   uint32_t k0, k1;
+  static constexpr int CEIL_EXP = (PID == POMCP_LIGHTDARK1D) ? 5 : 0;  // weights < 2^(CEIL_EXP + 1), see pf_scale rule
   // propagate + weight one particle: generate_s then pdf(observation(a, sp), o)
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
     State s = states[i];
@@ -172,6 +185,7 @@ struct ModelSrc {
 
 struct ArraySrc {  // replayed weights (parity hook): payload is the index itself
   using State = long long;
+  static constexpr int CEIL_EXP = PF_NO_CEIL;  // arbitrary weights: the scale always comes from the largest one
   const double* w_in;
   __device__ __forceinline__ void propagate(long long i, State& sp) const { sp = i; }
   __device__ __forceinline__ State load(long long i) const { return i; }
@@ -187,6 +201,13 @@ __device__ __forceinline__ int pf_scale(unsigned long long max_bits, long long n
   int e = (int)((max_bits >> 52) & 0x7ffull) - 1023;
   int L = (n <= 1) ? 0 : 64 - __clzll(n - 1);  // ceil(log2 n)
   return 61 - L - e;
+}
+__device__ __forceinline__ int pf_scale_ceil(int ceil_exp, long long n) {
+  int L = (n <= 1) ? 0 : 64 - __clzll(n - 1);
+  return 61 - L - ceil_exp;
+}
+__device__ __forceinline__ bool pf_over_ceil(double w, int ceil_exp) {  // w >= 2^(ceil_exp + 1), inf or NaN
+  return !(w < u2d((unsigned long long)(1023 + ceil_exp + 1) << 52));
 }
 // trunc(w * 2^s) like ldexp + conversion, without the library call: scaling by a power of two is exact
 // (s in [-994, 1135]; above 1000 in two exact steps, since 2^s itself would overflow), and wherever
@@ -248,20 +269,37 @@ __global__ void __launch_bounds__(256) k_pf_weigh(const __grid_constant__ Src sr
 }
 
 // T = sum_i trunc(w_i * 2^s): the output ranges of K8 need the total before the scan reaches the end.
-__global__ void __launch_bounds__(256) k_pf_total(const double* w, long long n, PfCtl* ctl) {
-  __shared__ unsigned long long s_sum[8];
+// With a weight ceiling (ceil_exp != PF_NO_CEIL) the total at the a-priori scale is summed in the same pass; the
+// scan picks one of the two (pf_pick_scale).
+__device__ __forceinline__ bool pf_use_ceil(const PfCtl* ctl, int ceil_exp) {
+  if (ceil_exp == PF_NO_CEIL) return false;
+  const int e = (int)((ctl->max_bits >> 52) & 0x7ffull) - 1023;
+  return e <= ceil_exp && ctl->total_ceil >= PF_MIN_TOTAL_CEIL;
+}
+__global__ void __launch_bounds__(256) k_pf_total(const double* w, long long n, PfCtl* ctl, int ceil_exp) {
+  __shared__ unsigned long long s_sum[8], s_sum2[8];
   const int scale = pf_scale(ctl->max_bits, n);
-  unsigned long long sum = 0;
+  const bool both = ceil_exp != PF_NO_CEIL && ((int)((ctl->max_bits >> 52) & 0x7ffull) - 1023) <= ceil_exp;
+  const int scale_c = pf_scale_ceil(both ? ceil_exp : 0, n);
+  unsigned long long sum = 0, sum_c = 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) sum += pf_quantise(w[i], scale);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double wi = w[i];
+    sum += pf_quantise(wi, scale);
+    if (both) sum_c += pf_quantise(wi, scale_c);
+  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  for (int off = 16; off > 0; off >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    sum_c += __shfl_xor_sync(0xffffffffu, sum_c, off);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_sum[warp] = sum;
+  if (lane == 0) { s_sum[warp] = sum; s_sum2[warp] = sum_c; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) sum += s_sum[k];
+    for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { sum += s_sum[k]; sum_c += s_sum2[k]; }
     if (sum) atomicAdd(&ctl->total, sum);
+    if (sum_c) atomicAdd(&ctl->total_ceil, sum_c);
   }
 }
 
@@ -342,7 +380,8 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_const
   __syncthreads();
   const int tile = (int)s_tile;
   const unsigned long long max_bits = ctl->max_bits;
-  const unsigned long long T = ctl->total;
+  const bool use_ceil = pf_use_ceil(ctl, Src::CEIL_EXP);
+  const unsigned long long T = use_ceil ? ctl->total_ceil : ctl->total;
   if (tile == 0 && threadIdx.x == 0) {
     int st = POMCP_OK;
     if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;  // "all states in the particle collection were terminal"
@@ -350,7 +389,7 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_const
     ctl->status = st;
   }
   if (T == 0) return;  // uniform: nothing to resample
-  const int scale = pf_scale(max_bits, n);
+  const int scale = use_ceil ? pf_scale_ceil(Src::CEIL_EXP, n) : pf_scale(max_bits, n);
   const long long base = (long long)tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
   double wv[PF2_ITEMS];
   if (base + PF2_ITEMS <= n) {
@@ -779,6 +818,203 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid
         typename Src::State sp;
         src.propagate(i, sp);
         for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+      }
+    }
+  }
+}
+
+// ---- K6+K7+K8 with ONE grid barrier: the a-priori scale (pf_scale_ceil) needs no max-weight pass, so phase A
+// goes straight from the weights to the quantised CTA totals; the only grid-wide dependency left is the total T
+// and the offsets of the CTAs, which every CTA derives from the <= 1024 CTA totals after the barrier.  When the
+// a-priori scale does not fit these weights the kernel says so (PF_RETRY_MAX_SCALE) and writes nothing.
+// BLOCKED: a thread owns `items` consecutive particles (states of <= 8 bytes: 16/32-byte vector-friendly, kept in
+// registers for the emit); otherwise particles are striped over the warp (particle = base + row * 32 + lane), the
+// only layout in which 16-byte states coalesce.
+template <class Src, class Out, bool BLOCKED>
+__global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_constant__ Src src, long long n, PfCtl* ctl,
+                                                                 uint32_t ru, long long n_out, Out* out,
+                                                                 unsigned long long* cta_tot, unsigned int* bar,
+                                                                 int items, unsigned long long* next_ctl) {
+  using State = typename Src::State;
+  __shared__ unsigned long long s_a[PF_THREADS / 32];
+  __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_off, s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the other control block, for the next launch (nobody uses it now)
+  if (blockIdx.x == gridDim.x - 1)
+    for (int k = threadIdx.x; k < PF_CTRL_WORDS; k += PF_THREADS) next_ctl[k] = 0ull;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(cta_tot + blockIdx.x));
+  }
+  const int scale = pf_scale_ceil(Src::CEIL_EXP, n);
+  const long long base = BLOCKED ? ((long long)blockIdx.x * PF_THREADS + threadIdx.x) * items
+                                 : ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * items;
+  auto index = [&](int k) { return BLOCKED ? base + k : base + (long long)k * 32 + lane; };
+
+  // ---- phase A: propagate, weight, quantise.  States of <= 8 bytes stay in registers for the emit.
+  constexpr bool KEEP = BLOCKED && sizeof(State) <= 8;
+  State st[KEEP ? PF_ITEMS : 1];
+  if (KEEP) {
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k)
+      if (k < items && index(k) < n) st[KEEP ? k : 0] = src.load(index(k));
+  }
+  unsigned long long q[PF_ITEMS];
+  unsigned alive_mask = 0;
+  unsigned long long first = ~0ull;
+  bool over = false;
+#pragma unroll
+  for (int k = 0; k < PF_ITEMS; ++k) {
+    q[k] = 0ull;
+    const long long i = index(k);
+    if (k < items && i < n) {
+      State sp;
+      double w;
+      const bool alive = KEEP ? src.eval_from(i, st[KEEP ? k : 0], sp, w) : src.eval(i, sp, w);
+      if (alive) {
+        alive_mask |= 1u << k;
+        if ((unsigned long long)i < first) first = (unsigned long long)i;
+        over = over || pf_over_ceil(w, Src::CEIL_EXP);
+        q[k] = pf_quantise(w, scale);
+      }
+    }
+  }
+  // inclusive cumulative sums in particle order inside the warp's range
+  unsigned long long inc[PF_ITEMS];
+  unsigned long long thread_excl = 0, warp_total;
+  if (BLOCKED) {
+    unsigned long long run = 0;
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) { run += q[k]; inc[k] = run; }
+    unsigned long long x = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    thread_excl = x - run;
+    warp_total = __shfl_sync(0xffffffffu, x, 31);
+  } else {
+    unsigned long long carry = 0;
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+      unsigned long long x = q[k];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += t;
+      }
+      inc[k] = x + carry;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    warp_total = carry;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long of = __shfl_xor_sync(0xffffffffu, first, off);
+    first = of < first ? of : first;
+  }
+  if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(&ctl->over_ceil, 1u);
+  if (lane == 0) { s_a[warp] = warp_total; s_b[warp] = first; }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = (lane < PF_THREADS / 32) ? s_a[lane] : 0ull, y = v;
+    unsigned long long f = (lane < PF_THREADS / 32) ? s_b[lane] : ~0ull;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+      if (lane >= off) y += t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      unsigned long long of = __shfl_xor_sync(0xffffffffu, f, off);
+      f = of < f ? of : f;
+    }
+    if (lane < PF_THREADS / 32) s_a[lane] = y - v;  // exclusive over warps
+    if (lane == 31) atomicExch(&cta_tot[blockIdx.x], y);
+    if (lane == 0 && f != ~0ull) {
+      atomicMax(&ctl->first_alive_inv, ~f);
+      ctl->any_alive = 1;
+    }
+  }
+  pf_grid_barrier(bar, gridDim.x);
+
+  // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
+  if (warp == 0) {
+    unsigned long long before = 0, all = 0;
+    for (int k = lane; k < (int)gridDim.x; k += 32) {
+      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
+      all += t;
+      if (k < (int)blockIdx.x) before += t;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, off);
+      all += __shfl_xor_sync(0xffffffffu, all, off);
+    }
+    if (lane == 0) { s_off = before; s_total = all; }
+  }
+  __syncthreads();
+  const unsigned long long T = s_total;
+  unsigned int over_any;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(over_any) : "l"(&ctl->over_ceil));
+  const bool retry = over_any != 0u || T < PF_MIN_TOTAL_CEIL;  // the same for every CTA
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->total = T;
+    ctl->status = retry ? PF_RETRY_MAX_SCALE : POMCP_OK;
+  }
+  if (retry) return;
+
+  // ---- emit: particle i owns outputs [M(C_{i-1}), M(C_i))
+  const unsigned long long first_alive = ~ld_volatile_u64(&ctl->first_alive_inv);
+  const PfDiv dv(T, ru, n_out);
+  if (BLOCKED) {
+    const unsigned long long off0 = s_off + s_a[warp] + thread_excl;  // C just before this thread's particles
+    PfDiv::Run rn = dv.start(off0);
+    long long lo = dv.count(rn);
+    unsigned long long prev_inc = 0;
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+      const long long i = base + k;
+      dv.advance(rn, inc[k] - prev_inc);
+      prev_inc = inc[k];
+      const long long hi = dv.count(rn);
+      if ((alive_mask >> k) & 1u) {
+        if ((unsigned long long)i == first_alive) lo = 0;
+        const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
+        if (copies) {
+          State sp;
+          if (KEEP) src.propagate_from(i, st[KEEP ? k : 0], sp);
+          else src.propagate(i, sp);
+          Out* o = out + lo;
+          o[0] = (Out)sp;
+          if (copies > 1) {
+            o[1] = (Out)sp;
+            for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
+          }
+        }
+      }
+      lo = hi;
+    }
+  } else {
+    const unsigned long long off0 = s_off + s_a[warp];
+    long long prev_hi = dv.points_below(off0);  // M at the start of this warp's range
+#pragma unroll
+    for (int k = 0; k < PF_ITEMS; ++k) {
+      if (k >= items) break;  // uniform
+      const long long i = base + (long long)k * 32 + lane;
+      const long long hi = dv.points_below(off0 + inc[k]);
+      long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
+      if (lane == 0) lo = prev_hi;
+      prev_hi = __shfl_sync(0xffffffffu, hi, 31);
+      if (i < n && ((alive_mask >> k) & 1u)) {
+        if ((unsigned long long)i == first_alive) lo = 0;
+        if (lo < hi) {
+          State sp;
+          src.propagate(i, sp);
+          for (long long mth = lo; mth < hi; ++mth) out[mth] = (Out)sp;
+        }
       }
     }
   }

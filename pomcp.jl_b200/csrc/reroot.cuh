@@ -2,8 +2,8 @@
 // new root alive and lets Julia's GC drop the rest (src/updater.jl:20-26); here the node pool and the
 // particle log are append-only, so a long episode needs the dead part reclaimed:
 //   1. mark + rank: a node is kept iff walking its parent links reaches the new root; the ranks of the
-//      kept nodes (stable: allocation order is preserved, the new root gets id 0) come out of the
-//      same single-pass scan that evaluates the marks;
+//      kept nodes (allocation order) come out of the same single-pass scan that evaluates the marks, and
+//      the new root then swaps ranks with whichever kept node got rank 0;
 //   2. copy the kept nodes' statistics, with child ids remapped, into a scratch block and back to the
 //      front of the pool; re-initialise the freed tail; rebuild the observation hash table (LightDark);
 //   3. filter the particle log the same way (stable, node ids remapped).
@@ -43,6 +43,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_rank_subtree(const uint32_t* n
   SubtreeSrc s{node_pslot, new_root, nA};
   NewIdSink k{newid};
   chained_scan(s, k, n_nodes, status, ticket);
+}
+
+// The new root must become node 0.  Ranks follow allocation order, and with the batched workers' pre-allocated
+// ids a descendant can be older than the new root and take rank 0: swap the two ranks.
+__global__ void k_root_rank(const uint32_t* newid, uint32_t new_root, uint32_t* root_rank) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *root_rank = newid[new_root];
+}
+__global__ void k_root_first(uint32_t* newid, long long n_nodes, uint32_t new_root, const uint32_t* root_rank) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const uint32_t r = *root_rank;
+  if (i >= n_nodes || r == 0u) return;
+  if ((uint32_t)i == new_root) newid[i] = 0u;
+  else if (newid[i] == 0u) newid[i] = r;
 }
 
 // scratch copy of the kept nodes (SoA mirrors of the pool arrays)

@@ -21,9 +21,15 @@ for stage in "$@"; do
               python scripts/episode_table.py --arm gpu --queries 1000000 --episodes 24 --inflight-max 256 --out $out/${tag}_episodes_gpu_1000000_infl256.json ;;
     rates)    python scripts/probe.py rates > $out/${tag}_rates.log 2>&1; cat $out/${tag}_rates.log
               python scripts/probe.py cycles > $out/${tag}_cycles.log 2>&1; cat $out/${tag}_cycles.log ;;
-    sir)      python scripts/probe.py sir --problem rs78 --log2 12,16,20,24,26 --out $out/${tag}_sir_rs78.json > $out/${tag}_sir.log 2>&1
-              python scripts/probe.py sir --problem lightdark --log2 1000000,20,24,26 --out $out/${tag}_sir_ld.json >> $out/${tag}_sir.log 2>&1
+    sir)      for variant in default POMCP_PF_NOCOOP POMCP_PF_TWO_BARRIERS; do
+                echo "--- $variant" >> $out/${tag}_sir.log
+                env $( [ $variant = default ] && echo X_UNUSED=1 || echo $variant=1 ) python scripts/probe.py sir --problem rs78 --log2 12,16,20,24,26 --out $out/${tag}_sir_rs78_$variant.json >> $out/${tag}_sir.log 2>&1
+                env $( [ $variant = default ] && echo X_UNUSED=1 || echo $variant=1 ) python scripts/probe.py sir --problem lightdark --log2 1000000,20,24,26 --out $out/${tag}_sir_ld_$variant.json >> $out/${tag}_sir.log 2>&1
+              done
               cat $out/${tag}_sir.log ;;
+    ncupf)    ncu --set full --clock-control none --import-source on -k regex:k_pf_ -s 1 -c 1 -f \
+                -o $out/prof_pf_$tag python scripts/probe.py step > $out/${tag}_ncu_pf.log 2>&1
+              tail -n 2 $out/${tag}_ncu_pf.log ;;
     ncu)      # launch list of the bench command (a number printed under ncu is never a bench value)
               ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
                 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $out/${tag}_ncu_launches.log 2>&1

@@ -341,6 +341,31 @@ def test_sir_update_bit_exact(oracle, gpu_lib, name, n, streaming, monkeypatch):
     gp.close()
 
 
+@pytest.mark.parametrize("path", ["fused", "two_barriers", "streaming"])
+def test_sir_scale_rule_small_weights(oracle, gpu_lib, path, monkeypatch):
+    """The fixed-point scale comes from the model's weight ceiling when that resolves the weights (one grid barrier
+    on the device) and from the largest weight otherwise.  An observation far in the tail (o = 40: weights around
+    1e-150) cannot be resolved at the a-priori scale: every path must fall back to the max-scaled integers and
+    still equal the oracle bit for bit; a plausible observation right after uses the a-priori scale again."""
+    if path == "streaming":
+        monkeypatch.setenv("POMCP_PF_STREAMING", "1")
+    if path == "two_barriers":
+        monkeypatch.setenv("POMCP_PF_TWO_BARRIERS", "1")
+    ld = pj.LightDark1D()
+    gp, op = make_pair(oracle, ld, 1.0, seed=4, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
+    n = 30000
+    rng = np.random.default_rng(21)
+    parts = np.zeros(n, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, n)
+    gp.set_belief_particles(parts)
+    op.set_belief_particles(parts)
+    for k, (a, o) in enumerate([(2, 100.0), (2, 14.0), (2, 40.0), (0, 13.5)]):
+        gp.pf_update_sir(a, o, seed=300 + k, n_out=n)
+        assert op.pf_update_sir(a, o, seed=300 + k, n_out=n, mode=0) == 0
+        assert gp.belief_particles().tobytes() == op.belief_particles().tobytes(), (path, k)
+    gp.close()
+
+
 def test_sir_baby_posterior_matches_golden_chain(oracle, gpu_lib):
     """D2: exact Baby belief chain 0 -> 0.0240964 -> 0.0298684 (notebooks/Display_Tree.ipynb:385):
     the 10^4-particle... here 2^20-particle SIR posterior mean must approach it within MC error."""
