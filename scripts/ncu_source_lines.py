@@ -65,8 +65,10 @@ def main():
     tot = sum(agg.values())
     src = {f: open(os.path.join(CSRC, f)).read().split("\n") for f in os.listdir(CSRC)}
     print(f"total samples {tot}, warp instructions {sum(inst.values())}")
+    tot_inst = sum(inst.values())
+    by_inst = "--by-inst" in sys.argv  # rank the lines by warp instructions executed instead of by stall samples
     for loc, n in sorted(agg.items(), key=lambda x: (x[0] or ("", 0))):
-        if n < tot * min_pct / 100:
+        if (inst[loc] < tot_inst * min_pct / 100) if by_inst else (n < tot * min_pct / 100):
             continue
         f, l = loc if loc else ("?", 0)
         text = src[f][l - 1].strip()[:88] if f in src and 0 < l <= len(src[f]) else ""

@@ -75,12 +75,12 @@ def ncu_raw(rep):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     steps_per_decision = float(sys.argv[2]) if len(sys.argv) > 2 else None
-    if steps_per_decision is None:  # rollout steps of the profiled decision, printed by scripts/profile_step.py
-        log = os.path.join(GP, "ncu_search.log")
+    if steps_per_decision is None:  # rollout steps of the profiled decision (-s 1: the second), printed by probe.py step
+        log = os.path.join(GP, f"{tag}_ncu_search.log")
         if os.path.exists(log):
-            for ln in open(log):
-                if ln.startswith("ok "):
-                    steps_per_decision = float(ln.split()[2])
+            dec = [json.loads(ln) for ln in open(log) if ln.startswith("{")]
+            if len(dec) >= 2:
+                steps_per_decision = float(dec[1]["rollout_steps"])
     os.makedirs(OUT, exist_ok=True)
     consts_path = os.path.join(OUT, "roofline_constants.json")
     consts = json.load(open(consts_path)) if os.path.exists(consts_path) else {}
@@ -113,46 +113,72 @@ def main():
                 if steps_per_decision:
                     consts["rollout_thread_inst_per_step"] = ti / steps_per_decision
                     consts["rollout_steps_per_profiled_launch"] = steps_per_decision
-            if "k_pf_fused" in kn:
+            if "k_pf_" in kn:
                 unit_r = units[hdr.index("dram__bytes_read.sum")]
                 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
                 consts["pf_dram_bytes_per_update"] = (g("dram__bytes_read.sum") * scale.get(unit_r, 1) +
                                                       g("dram__bytes_write.sum") *
                                                       scale.get(units[hdr.index("dram__bytes_write.sum")], 1))
-    # single-pass instruction count + step counter of the same pass (capture_round.sh), when present
+    # Single-pass instruction counts + the step counters of the SAME launches (scripts/gpu_session.sh ncu: three SM
+    # counters fit one pass; `probe.py step --repeat 8` prints one JSON line per decision).  The instruction count of a
+    # launch depends on the tree it grows (how long its rollouts live), so it is modelled as
+    #     thread instructions = a * simulations + b * live rollout steps
+    # fitted by least squares over all the launches of the run, residuals kept; bench.py applies (a, b) to the
+    # simulations and steps it counts itself.
     one = os.path.join(GP, f"workers_inst_{tag}.csv")
     log1 = os.path.join(GP, f"workers_inst_{tag}.log")
     if os.path.exists(one) and os.path.exists(log1):
-        steps1 = None
-        for ln in open(log1):
-            if ln.startswith("ok "):
-                steps1 = float(ln.split()[2])
-        vals = {}
+        import numpy as np
+        dec = [json.loads(ln) for ln in open(log1) if ln.startswith("{")]
+        per = collections.defaultdict(dict)
         for row in csv.DictReader([ln for ln in open(one) if not ln.startswith("==")]):
-            vals[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
-        if steps1 and "smsp__thread_inst_executed.sum" in vals:
-            consts["rollout_thread_inst_per_step"] = vals["smsp__thread_inst_executed.sum"] / steps1
-            consts["rollout_steps_per_profiled_launch"] = steps1
-            consts["workers_thread_inst_per_launch"] = vals["smsp__thread_inst_executed.sum"]
-            consts["rollout_warp_efficiency"] = (vals["smsp__thread_inst_executed.sum"] /
-                                                 vals["smsp__inst_executed.sum"] / 32.0)
-            consts["workers_issue_active_pct"] = vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]
-            consts["inst_per_step_from"] = "one ncu pass (3 SM counters) + the step counter of that pass"
-            # The instruction count of a launch depends on the tree it grows (how long its rollouts live):
-            # thread instructions = a * simulations + b * live rollout steps.  Keep the single-pass samples of the
-            # captures and fit (a, b); bench.py applies them to the simulations and steps it measures itself.
-            sims1 = 1.0e6  # scripts/profile_step.py profiles one decision of bench.TREE_QUERIES simulations
-            samples = [x for x in consts.get("workers_inst_samples", []) if x[:2] != [vals["smsp__thread_inst_executed.sum"], steps1]]
-            samples.append([vals["smsp__thread_inst_executed.sum"], steps1, sims1])
-            consts["workers_inst_samples"] = samples[-6:]
-            if len(samples) >= 2:
-                import numpy as np
-                A = np.array([[x[2], x[1]] for x in samples])
-                y = np.array([x[0] for x in samples])
-                (ca, cb), *_ = np.linalg.lstsq(A, y, rcond=None)
-                if ca > 0 and cb > 0:
-                    consts["workers_thread_inst_per_sim"] = float(ca)
-                    consts["workers_thread_inst_per_rollout_step"] = float(cb)
+            per[int(row["ID"])][row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+        ids = sorted(per)
+        if len(ids) == len(dec) and len(ids) >= 2:
+            ti = np.array([per[i]["smsp__thread_inst_executed.sum"] for i in ids])
+            wi = np.array([per[i]["smsp__inst_executed.sum"] for i in ids])
+            sims = np.array([d["simulations"] for d in dec], dtype=float)
+            steps = np.array([d["rollout_steps"] for d in dec], dtype=float)
+            A = np.stack([sims, steps], axis=1)
+            (ca, cb), *_ = np.linalg.lstsq(A, ti, rcond=None)
+            rel = (A @ np.array([ca, cb]) - ti) / ti
+            consts["workers_thread_inst_per_sim"] = float(ca)
+            consts["workers_thread_inst_per_rollout_step"] = float(cb)
+            consts["workers_inst_fit"] = {"launches": len(ids), "rms_rel_residual": float(np.sqrt((rel ** 2).mean())),
+                                          "max_rel_residual": float(np.abs(rel).max()),
+                                          "from": f"gpurun_out/workers_inst_{tag}.csv + .log (one ncu pass per launch)"}
+            consts["workers_inst_samples"] = [[float(t), float(st), float(sm)] for t, st, sm in zip(ti, steps, sims)]
+            consts["rollout_warp_efficiency"] = float((ti / wi / 32.0).mean())
+            consts["workers_issue_active_pct"] = float(np.mean([per[i]["smsp__issue_active.avg.pct_of_peak_sustained_active"]
+                                                                for i in ids]))
+            consts["workers_thread_inst_per_launch"] = float(ti.mean())
+            with open(os.path.join(OUT, f"{tag}_workers_inst_per_launch.csv"), "w") as f:
+                f.write("# ncu --metrics smsp__thread_inst_executed.sum,smsp__inst_executed.sum,smsp__issue_active... "
+                        "--clock-control none -k regex:k_search_workers -c 8 python scripts/probe.py step --repeat 8\n")
+                f.write("launch,thread_inst,warp_inst,issue_active_pct,simulations,rollout_steps,tree_steps,model_thread_inst,rel_residual\n")
+                for k, i in enumerate(ids):
+                    f.write(f"{i},{ti[k]:.0f},{wi[k]:.0f},{per[i]['smsp__issue_active.avg.pct_of_peak_sustained_active']},"
+                            f"{sims[k]:.0f},{steps[k]:.0f},{dec[k]['tree_steps']},{ca * sims[k] + cb * steps[k]:.0f},{rel[k]:.5f}\n")
+                f.write(f"# fit: thread_inst = {ca:.1f} * simulations + {cb:.3f} * rollout_steps; rms relative residual "
+                        f"{np.sqrt((rel ** 2).mean()):.4f}\n")
+    # pipe utilisation of the worker kernel (which pipe binds)
+    pp = os.path.join(GP, f"workers_pipes_{tag}.csv")
+    if os.path.exists(pp):
+        pipes = {}
+        for row in csv.DictReader([ln for ln in open(pp) if not ln.startswith("==")]):
+            m = row["Metric Name"]
+            if m.startswith("sm__inst_executed_pipe_"):
+                pipes[m[len("sm__inst_executed_pipe_"):].split(".")[0]] = float(row["Metric Value"])
+            elif m.startswith("sm__warps_active"):
+                pipes["warps_active"] = float(row["Metric Value"])
+            elif m.startswith("smsp__issue_active"):
+                pipes["issue_active"] = float(row["Metric Value"])
+        consts["workers_pipe_pct"] = pipes
+        with open(os.path.join(OUT, f"{tag}_workers_pipes.csv"), "w") as f:
+            f.write("# ncu --metrics sm__inst_executed_pipe_*.avg.pct_of_peak_sustained_active ... -k regex:k_search_workers -s 1 -c 1 "
+                    "python scripts/probe.py step\nmetric,pct_of_peak_sustained_active\n")
+            for k, v in sorted(pipes.items(), key=lambda kv: -kv[1]):
+                f.write(f"{k},{v}\n")
     consts["source"] = f"scripts/summarize_profiles.py {tag}"
     json.dump(consts, open(consts_path, "w"), indent=1)
     print(json.dumps(consts, indent=1))

@@ -147,15 +147,21 @@ def test_dpw_default_solver_smoke_and_batched(oracle, gpu_lib):
 @pytest.mark.parametrize("mode", ["exact", "batched"])
 def test_action_widening_root_argmax_only_over_existing_children(oracle, gpu_lib, mode):
     """src/solver.jl:60-70 iterates values(b.children): a root slot that was never added (pool prefill N = 0,
-    V = 0) must not win `>=` against the explored child's negative value.  Tiger, k_action = 0.1, 60 queries:
-    one ActNode exists, and it is the decision (exact mode: the oracle's, bit for bit)."""
+    V = 0) must not win `>=` against the explored children's negative values.  Tiger, k_action = 0.1, 60 queries:
+    in exact mode one ActNode exists and it is the decision (the oracle's, bit for bit)."""
     tiger = pj.TigerPOMDP()
     for seed in range(4):
         gp, op = make_pair(oracle, tiger, 100.0, seed=seed, mode=mode, tree_queries=60, dpw_action=(0.1, 0.5))
         gp.set_belief_initial()
         op.set_belief_initial()
         a, N, V = gp.search(60)
-        assert (N > 0).sum() == 1 and N[a] == 59 and V[a] < 0.0, (seed, a, N, V)
+        if mode == "batched":
+            # the first simulations run side by side and each adds the action it drew before seeing the others',
+            # so more than one ActNode can exist; the decision must still be one of them
+            assert N.sum() == 59 and N[a] > 0 and V[a] < 0.0, (seed, a, N, V)
+            assert a == max((i for i in range(3) if N[i] > 0), key=lambda i: (V[i], i)), (a, N, V)
+        else:
+            assert (N > 0).sum() == 1 and N[a] == 59 and V[a] < 0.0, (seed, a, N, V)
         if mode == "exact":
             rc, a_o, N_o, V_o = op.search(60)
             assert rc == 0 and a == a_o and np.array_equal(N, N_o) and np.array_equal(_bits(V), _bits(V_o))
