@@ -94,7 +94,10 @@ typedef enum pomcp_estimator {
 /* node_belief_updater kinds (src/solver.jl:135-139). */
 typedef enum pomcp_belief_mode {
   POMCP_BELIEF_UNWEIGHTED = 0, /* DeadReinvigorator: states pushed at visited nodes, src/solver.jl:146-148 */
-  POMCP_BELIEF_EXTERNAL = 1    /* belief maintained outside the tree (e.g. SIR filter): nothing stored */
+  POMCP_BELIEF_EXTERNAL = 1,   /* belief maintained outside the tree (e.g. SIR filter): nothing stored */
+  POMCP_BELIEF_EXACT2 = 2      /* node_belief_updater = the problem's exact discrete updater (`updater(problem)`,
+                                  notebooks/Sanity_Checks.ipynb:47,70; generic branch src/solver.jl:138 and
+                                  src/updater.jl:30-39): every node carries P(s = 1).  Two-state problems (Tiger, Baby). */
 } pomcp_belief_mode;
 
 typedef enum pomcp_search_mode {
@@ -192,6 +195,10 @@ int32_t pomcp_destroy(pomcp_handle* h);
 int32_t pomcp_set_belief_particles(pomcp_handle* h, const void* states, int64_t n);
 /* ... or over the problem's initial state distribution. */
 int32_t pomcp_set_belief_initial(pomcp_handle* h);
+/* ... or over BoolDistribution(p1) when the planner's node_belief_updater is the exact two-state updater
+ * (POMCP_BELIEF_EXACT2; p1 = P(s = 1): tiger behind the left door / baby hungry). */
+int32_t pomcp_set_belief_exact2(pomcp_handle* h, double p1);
+int32_t pomcp_get_belief_exact2(pomcp_handle* h, double* p1);
 /* The same for the belief already on the device: a fresh RootNode over it (what every action() call on a belief
  * that is not a BeliefNode does, src/solver.jl:278-281), without sending the particles again. */
 int32_t pomcp_reset_tree(pomcp_handle* h);
@@ -227,6 +234,11 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits);
  * outcome: 0 plain re-root, 1 topped up, 2 rebuilt.  PARTICLE_DEPLETION only if the posterior has no mass. */
 int32_t pomcp_update_reinvigorated(pomcp_handle* h, int32_t a, uint64_t obs_bits, uint64_t seed, int64_t n_min,
                                    int32_t* outcome);
+
+/* update(::RootUpdater, b_old, a, o) with a user-supplied belief updater (src/updater.jl:30-39), here the exact
+ * two-state updater of POMCP_BELIEF_EXACT2: re-roots at child (a,o); a child the tree does not hold is replaced by
+ * a new node carrying update(node_belief_updater, b_old.B, a, o) - no depletion with this updater. */
+int32_t pomcp_update_exact2(pomcp_handle* h, int32_t a, uint64_t obs_bits);
 
 /* update(::SIRParticleFilter, b::ParticleCollection, a, o) (call site test/runtests.jl:57):
  * propagate, weight by the observation density, systematic resample to n_out

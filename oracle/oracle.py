@@ -43,6 +43,11 @@ def lib():
         L.orc_set_belief_initial.argtypes = [vp]
         L.orc_set_state_values.argtypes = [vp, vp, i64]
         L.orc_get_belief_particles.argtypes = [vp, vp, i64, P(i64)]
+        L.orc_set_belief_exact2.argtypes = [vp, dbl]
+        L.orc_get_belief_exact2.argtypes = [vp, P(dbl)]
+        L.orc_update_exact2.argtypes = [vp, i32, u64]
+        L.orc_bayes2.argtypes = [P(abi.Problem), dbl, i32, u64]
+        L.orc_bayes2.restype = dbl
         L.orc_search.argtypes = [vp, i64, P(i32), vp, vp, i32]
         L.orc_search_replay.argtypes = [vp, i64, vp, i64, vp, i64, P(i32), vp, vp, i32, P(i64), P(i64)]
         L.orc_update_unweighted.argtypes = [vp, i32, u64]
@@ -114,6 +119,17 @@ class OraclePlanner:
 
     def set_belief_initial(self):
         return lib().orc_set_belief_initial(self._h)
+
+    def set_belief_exact2(self, p1):
+        return lib().orc_set_belief_exact2(self._h, float(p1))
+
+    def belief_exact2(self):
+        p = C.c_double(0.0)
+        assert lib().orc_get_belief_exact2(self._h, C.byref(p)) == 0
+        return p.value
+
+    def update_exact2(self, a, o):
+        return lib().orc_update_exact2(self._h, int(a), obs_bits(o))
 
     def set_state_values(self, values):
         values = np.ascontiguousarray(values, dtype=np.float64)
@@ -235,6 +251,11 @@ def obs_weight(pomdp, a, next_state, o):
     p = pomdp.c_struct()
     s = np.array([next_state], dtype=pomdp.state_dtype)
     return lib().orc_obs_weight(C.byref(p), a, _vp(s), obs_bits(o))
+
+
+def bayes2(pomdp, b, a, o):
+    p = pomdp.c_struct()
+    return lib().orc_bayes2(C.byref(p), float(b), int(a), obs_bits(o))
 
 
 def philox(ctr, key):

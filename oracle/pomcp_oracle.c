@@ -326,6 +326,24 @@ static double obs_weight(const model* m, int a, ostate sp, uint64_t obs) {
   return 0.0;
 }
 
+/* Exact Bayes filter of a two-state problem (POMDPModels' BabyBeliefUpdater / Tiger's discrete updater), the
+ * node_belief_updater of notebooks/Sanity_Checks.ipynb:47,70 (`updater(problem)`; src/solver.jl:138,
+ * src/updater.jl:33): b = P(s = 1), b' ~ O(o | a, s') * sum_s T(s' | s, a) b(s).  Reproduces the notebooks'
+ * belief chain (tests/golden D1, D2). */
+static double trans_p1(const model* m, int s, int a) {
+  if (m->p.problem_id == POMCP_TIGER) return a == 0 ? (s ? 1.0 : 0.0) : 0.5;
+  return a ? 0.0 : (s ? 1.0 : m->p.baby_p_become_hungry); /* Baby */
+}
+static double bayes2(const model* m, double b, int a, uint64_t obs) {
+  ostate s1; s1.i = 1; s1.y = 0.0;
+  ostate s0; s0.i = 0; s0.y = 0.0;
+  const double p1 = b * trans_p1(m, 1, a) + (1.0 - b) * trans_p1(m, 0, a);
+  const double n1 = obs_weight(m, a, s1, obs) * p1;
+  const double n0 = obs_weight(m, a, s0, obs) * (1.0 - p1);
+  const double den = n0 + n1;
+  return den > 0.0 ? n1 / den : p1;
+}
+
 static ostate load_state(const model* m, const void* arr, int64_t i) {
   ostate s;
   if (m->state_bytes == 4) { s.i = (int64_t)((const uint32_t*)arr)[i]; s.y = 0.0; }
@@ -355,6 +373,12 @@ double orc_obs_weight(const pomcp_problem* p, int32_t a, const void* next_state,
   double w = obs_weight(m, a, load_state(m, next_state, 0), obs_bits);
   free(m);
   return w;
+}
+double orc_bayes2(const pomcp_problem* p, double b, int32_t a, uint64_t obs_bits) {
+  model* m = (model*)malloc(sizeof(model));
+  double r = model_init(m, p) == POMCP_OK ? bayes2(m, b, a, obs_bits) : NAN;
+  free(m);
+  return r;
 }
 int32_t orc_is_terminal(const pomcp_problem* p, const void* state) {
   model* m = (model*)malloc(sizeof(model));
@@ -476,6 +500,7 @@ struct orc_planner {
   int64_t* node_N;
   uint8_t* node_expanded;
   uint32_t* node_amask; /* action widening: bit a = ActNode a exists */
+  double* node_bel;     /* POMCP_BELIEF_EXACT2: the node's exact two-state belief P(s = 1) */
   int64_t* node_phead; int64_t* node_ptail; int64_t* node_pcount; /* ParticleCollection per node */
   int64_t* node_parent_slot; uint64_t* node_obs;                 /* label */
   /* action nodes: slot = node*nA + a */
@@ -489,7 +514,7 @@ struct orc_planner {
   int64_t n_log, cap_log; ostate* log_state; int64_t* log_next;
   /* root */
   int64_t root;
-  int belief_kind; /* 0 none, 1 initial distribution, 2 explicit particles, 3 node particles */
+  int belief_kind; /* 0 none, 1 initial distribution, 2 explicit particles, 3 node particles, 4 exact two-state belief */
   int64_t n_bel; ostate* bel;
   /* horizon tables */
   int64_t horizon;    /* first depth with gamma^depth < eps */
@@ -509,6 +534,7 @@ static void grow_nodes(orc_planner* pl, int64_t need) {
   int64_t nc = pl->cap_nodes ? pl->cap_nodes : 1024;
   while (nc < need) nc *= 2;
   GROW(pl->node_N, int64_t, nc); GROW(pl->node_expanded, uint8_t, nc); GROW(pl->node_amask, uint32_t, nc);
+  GROW(pl->node_bel, double, nc);
   GROW(pl->node_phead, int64_t, nc); GROW(pl->node_ptail, int64_t, nc); GROW(pl->node_pcount, int64_t, nc);
   GROW(pl->node_parent_slot, int64_t, nc); GROW(pl->node_obs, uint64_t, nc);
   GROW(pl->act_N, int64_t, nc * pl->nA); GROW(pl->act_V, double, nc * pl->nA);
@@ -524,7 +550,7 @@ static void grow_nodes(orc_planner* pl, int64_t need) {
 static int64_t new_node(orc_planner* pl, int64_t parent_slot, uint64_t obs) {
   grow_nodes(pl, pl->n_nodes + 1);
   int64_t n = pl->n_nodes++;
-  pl->node_N[n] = 0; pl->node_expanded[n] = 0; pl->node_amask[n] = 0;
+  pl->node_N[n] = 0; pl->node_expanded[n] = 0; pl->node_amask[n] = 0; pl->node_bel[n] = 0.0;
   pl->node_phead[n] = -1; pl->node_ptail[n] = -1; pl->node_pcount[n] = 0;
   pl->node_parent_slot[n] = parent_slot; pl->node_obs[n] = obs;
   for (int a = 0; a < pl->nA; ++a) { pl->act_N[n * pl->nA + a] = 0; pl->act_V[n * pl->nA + a] = 0.0; }
@@ -596,7 +622,7 @@ static void free_tree(orc_planner* pl) {
     free(pl->ev_n); free(pl->ev_cap); free(pl->ev_node); free(pl->ev_state); free(pl->act_nc);
     pl->ev_n = pl->ev_cap = pl->act_nc = NULL; pl->ev_node = NULL; pl->ev_state = NULL;
   }
-  free(pl->node_N); free(pl->node_expanded); free(pl->node_amask); pl->node_amask = NULL; free(pl->node_phead); free(pl->node_ptail); free(pl->node_pcount);
+  free(pl->node_N); free(pl->node_expanded); free(pl->node_amask); pl->node_amask = NULL; free(pl->node_bel); pl->node_bel = NULL; free(pl->node_phead); free(pl->node_ptail); free(pl->node_pcount);
   free(pl->node_parent_slot); free(pl->node_obs); free(pl->act_N); free(pl->act_V); free(pl->child); free(pl->ht);
   free(pl->log_state); free(pl->log_next);
   pl->node_N = NULL; pl->node_expanded = NULL; pl->node_phead = pl->node_ptail = pl->node_pcount = NULL;
@@ -622,6 +648,7 @@ orc_planner* orc_create(const pomcp_problem* p, const pomcp_solver_params* sp) {
   if ((sp->estimator == POMCP_EST_FWC_ROLLOUT || sp->estimator == POMCP_EST_FO_FWC_ROLLOUT) &&
       p->problem_id != POMCP_BABY) { free(pl); return NULL; }
   if (sp->estimator == POMCP_EST_STATE_VALUE && p->problem_id == POMCP_LIGHTDARK1D) { free(pl); return NULL; }
+  if (sp->belief_mode == POMCP_BELIEF_EXACT2 && ((p->problem_id != POMCP_TIGER && p->problem_id != POMCP_BABY) || sp->dpw_action)) { free(pl); return NULL; }
   pl->nA = pl->m.nA; pl->nO = pl->m.nO;
   /* cut-off gamma^depth < eps (src/solver.jl:82) and steps_to_eps (src/solver.jl:100) */
   pl->log_ratio = log(sp->eps) / log(p->discount);
@@ -669,6 +696,33 @@ int32_t orc_set_belief_initial(orc_planner* pl) {
   free(pl->bel); pl->bel = NULL; pl->n_bel = 0; pl->belief_kind = 1;
   return POMCP_OK;
 }
+/* initialize_belief(up, BoolDistribution(p)) = RootNode(0, b, {}) (src/updater.jl:45-47) */
+int32_t orc_set_belief_exact2(orc_planner* pl, double p1) {
+  if (pl->sp.belief_mode != POMCP_BELIEF_EXACT2) return POMCP_ERR_UNSUPPORTED;
+  if (!(p1 >= 0.0) || !(p1 <= 1.0)) return POMCP_ERR_INVALID_ARG;
+  fresh_root(pl);
+  free(pl->bel); pl->bel = NULL; pl->n_bel = 0; pl->belief_kind = 4;
+  pl->node_bel[pl->root] = p1;
+  return POMCP_OK;
+}
+int32_t orc_get_belief_exact2(orc_planner* pl, double* p1) {
+  if (pl->belief_kind != 4) return POMCP_ERR_INVALID_ARG;
+  *p1 = pl->node_bel[pl->root];
+  return POMCP_OK;
+}
+static int64_t find_child(orc_planner* pl, int64_t slot, uint64_t obs);
+/* update(::RootUpdater, b_old, a, o) with a user-supplied belief updater, src/updater.jl:30-39 */
+int32_t orc_update_exact2(orc_planner* pl, int32_t a, uint64_t obs) {
+  if (pl->belief_kind != 4) return POMCP_ERR_UNSUPPORTED;
+  if (a < 0 || a >= pl->nA || obs >= (uint64_t)pl->nO) return POMCP_ERR_INVALID_ARG;
+  int64_t hao = pl->node_expanded[pl->root] ? find_child(pl, pl->root * pl->nA + a, obs) : -1;
+  if (hao >= 0) { pl->root = hao; return POMCP_OK; } /* the child with its subtree */
+  const double nb = bayes2(&pl->m, pl->node_bel[pl->root], a, obs);
+  fresh_root(pl); /* ObsNode(o, 0, new_belief, {}) */
+  pl->node_bel[pl->root] = nb;
+  return POMCP_OK;
+}
+
 int32_t orc_get_belief_particles(orc_planner* pl, void* out, int64_t cap, int64_t* n) {
   if (pl->belief_kind == 2) {
     *n = pl->n_bel;
@@ -728,6 +782,9 @@ static ostate sample_root(orc_planner* pl, orng* g, uint32_t q) {
   const pomcp_problem* p = &pl->m.p;
   if (pl->belief_kind == 2) {
     return pl->bel[(int64_t)(u[0] * (double)pl->n_bel)];
+  } else if (pl->belief_kind == 4) { /* rand(rng, BoolDistribution(p)) */
+    ostate s; s.i = u[0] < pl->node_bel[pl->root] ? 1 : 0; s.y = 0.0;
+    return s;
   } else if (pl->belief_kind == 3) {
     int64_t k = (int64_t)(u[0] * (double)pl->node_pcount[pl->root]);
     int64_t e = pl->node_phead[pl->root];
@@ -858,7 +915,13 @@ static void simulate(orc_planner* pl, orng* g, ostate s, uint32_t q) {
     }
     if (generated) {
       hao = find_child(pl, slot, o);
-      if (hao < 0) { hao = insert_child(pl, slot, o); if (sol->dpw_observation) pl->act_nc[slot]++; } /* src/solver.jl:132-142 */
+      if (hao < 0) { /* src/solver.jl:132-142 */
+        /* new_belief = update(pomcp.node_belief_updater, h.B, a, o) (src/solver.jl:138) */
+        const double nb = sol->belief_mode == POMCP_BELIEF_EXACT2 ? bayes2(m, pl->node_bel[h], best_a, o) : 0.0;
+        hao = insert_child(pl, slot, o);
+        pl->node_bel[hao] = nb;
+        if (sol->dpw_observation) pl->act_nc[slot]++;
+      }
       if (sol->dpw_observation) {
         /* state_was_generated: push!(hao.B, sp); hao.N += 1 BEFORE the recursive call (src/solver.jl:257-262) */
         if (pl->ev_n[slot] == pl->ev_cap[slot]) {

@@ -24,7 +24,7 @@ TIGER, BABY, ROCKSAMPLE, LIGHTDARK1D = 0, 1, 2, 3
 RS_TERMINAL = 0x80000000
 
 EST_RANDOM_ROLLOUT, EST_CONSTANT, EST_FWC_ROLLOUT, EST_FO_FWC_ROLLOUT, EST_STATE_VALUE = 0, 1, 2, 3, 4
-BELIEF_UNWEIGHTED, BELIEF_EXTERNAL = 0, 1
+BELIEF_UNWEIGHTED, BELIEF_EXTERNAL, BELIEF_EXACT2 = 0, 1, 2
 MODE_EXACT, MODE_BATCHED = 0, 1
 PHASE_SEARCH, PHASE_ROLLOUT, PHASE_PF, PHASE_REROOT, PHASE_MERGE = 0, 1, 2, 3, 4
 
@@ -85,7 +85,7 @@ STATUS_NAMES = {
 EXPORTS = [
     "pomcp_abi_version", "pomcp_status_string", "pomcp_last_error", "pomcp_default_solver_params",
     "pomcp_default_problem", "pomcp_num_actions", "pomcp_state_bytes", "pomcp_create", "pomcp_destroy",
-    "pomcp_set_belief_particles", "pomcp_set_belief_initial", "pomcp_reset_tree", "pomcp_set_state_values", "pomcp_get_belief_particles", "pomcp_search",
+    "pomcp_set_belief_particles", "pomcp_set_belief_initial", "pomcp_set_belief_exact2", "pomcp_get_belief_exact2", "pomcp_update_exact2", "pomcp_reset_tree", "pomcp_set_state_values", "pomcp_get_belief_particles", "pomcp_search",
     "pomcp_search_replay", "pomcp_update_unweighted", "pomcp_update_reinvigorated", "pomcp_pf_update_sir", "pomcp_resample_systematic",
     "pomcp_rollout_batch", "pomcp_pf_weights", "pomcp_get_root_stats", "pomcp_get_tree_result", "pomcp_get_node_stats", "pomcp_dump_tree",
     "pomcp_generate_sor", "pomcp_initial_state", "pomcp_root_node", "pomcp_get_counters", "pomcp_reset_counters", "pomcp_worker_cycles", "pomcp_nccl_unique_id", "pomcp_comm_init",

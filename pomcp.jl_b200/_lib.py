@@ -45,6 +45,9 @@ def lib():
     L.pomcp_set_belief_particles.argtypes = [vp, vp, i64]
     L.pomcp_set_belief_initial.argtypes = [vp]
     L.pomcp_reset_tree.argtypes = [vp]
+    L.pomcp_set_belief_exact2.argtypes = [vp, dbl]
+    L.pomcp_get_belief_exact2.argtypes = [vp, P(dbl)]
+    L.pomcp_update_exact2.argtypes = [vp, i32, u64]
     L.pomcp_set_state_values.argtypes = [vp, vp, i64]
     L.pomcp_get_belief_particles.argtypes = [vp, vp, i64, P(i64)]
     L.pomcp_search.argtypes = [vp, i64, P(i32), vp, vp, i32]

@@ -21,7 +21,7 @@ __all__ = [
     "POMCPSolver", "POMCPPlanner", "RolloutEstimator", "FORollout", "FOValue", "RandomSolver", "FeedWhenCrying", "DefaultReinvigoratorStub",
     "DeadReinvigorator", "ParticleReinvigorator", "SIRReinvigorator", "ExceptionRethrow", "NoDecision", "AllSamplesTerminal",
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
-    "InitialStateDistribution", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
+    "InitialStateDistribution", "BoolDistribution", "DiscreteBeliefUpdater", "BabyBeliefUpdater", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
     "RolloutSimulator", "simulate", "test_solver", "create_json", "ObsNode", "ActNode", "AbstractActNode",
     "POMCPTreeVisualizer", "AbstractPOMCPSolver", "POMCPDPWSolver", "RandomActionGenerator", "PORollout",
@@ -166,6 +166,30 @@ class SIRReinvigorator(ParticleReinvigorator):
     def next_seed(self):
         self._step += 1
         return (self.seed * 0x9E3779B97F4A7C15 + self._step) & (2 ** 64 - 1)
+
+
+class DiscreteBeliefUpdater:
+    """The problem's own exact belief updater (`updater(problem)`: POMDPModels.BabyBeliefUpdater, the
+    DiscreteUpdater of Tiger) used as node_belief_updater (notebooks/Sanity_Checks.ipynb:47,70;
+    test/Belief_and_Particle_Filter_Options.jl:63-77): every tree node then carries the exact belief
+    (src/solver.jl:138) and update() never depletes (src/updater.jl:30-39).  On device for the two-state
+    problems (Tiger, Baby), where the belief is the single number P(s = 1)."""
+
+    def __init__(self, pomdp=None):
+        self.pomdp = pomdp
+
+
+BabyBeliefUpdater = DiscreteBeliefUpdater
+
+
+class BoolDistribution:
+    """POMDPModels.BoolDistribution(p): P(true) = p (hungry / tiger behind the left door)."""
+
+    def __init__(self, p):
+        self.p = float(p)
+
+    def __repr__(self):
+        return f"BoolDistribution({self.p})"
 
 
 class DefaultReinvigoratorStub:
@@ -394,9 +418,13 @@ class POMCPPlanner:
         nbu = solver.node_belief_updater
         if isinstance(nbu, DefaultReinvigoratorStub):
             nbu = DeadReinvigorator()  # src/solver.jl:6-10
-        if not isinstance(nbu, ParticleReinvigorator):
-            raise NotImplementedError("node_belief_updater: only ParticleReinvigorators are supported on device")
+        if isinstance(nbu, DiscreteBeliefUpdater):
+            belief_mode = abi.BELIEF_EXACT2  # the generic branch of src/solver.jl:138 / src/updater.jl:30-39
+        elif not isinstance(nbu, ParticleReinvigorator):
+            raise NotImplementedError("node_belief_updater: ParticleReinvigorators and the exact updater of the two-state "
+                                      "problems (DiscreteBeliefUpdater) are supported on device")
         self.node_belief_updater = nbu
+        self.belief_mode = belief_mode
         self._p = pomdp.c_struct()
         self._sp = solver.c_params(belief_mode)
         self.nA = pomdp.n_actions
@@ -430,6 +458,19 @@ class POMCPPlanner:
 
     def set_belief_initial(self):
         _check(lib().pomcp_set_belief_initial(self._h), self._h)
+        self._generation += 1
+
+    def set_belief_exact2(self, p1):
+        _check(lib().pomcp_set_belief_exact2(self._h, float(p1)), self._h)
+        self._generation += 1
+
+    def belief_exact2(self):
+        p = C.c_double(0.0)
+        _check(lib().pomcp_get_belief_exact2(self._h, C.byref(p)), self._h)
+        return p.value
+
+    def update_exact2(self, a, o):
+        _check(lib().pomcp_update_exact2(self._h, int(a), obs_bits(o)), self._h)
         self._generation += 1
 
     def reset_tree(self):
@@ -669,6 +710,10 @@ def _make_node(planner, belief):
         return belief
     if isinstance(belief, ParticleCollection):
         planner.set_belief_particles(belief.particles)
+    elif isinstance(belief, BoolDistribution):
+        planner.set_belief_exact2(belief.p)
+    elif isinstance(belief, InitialStateDistribution) and planner.belief_mode == abi.BELIEF_EXACT2:
+        planner.set_belief_exact2(belief.pomdp.initial_p1)  # the distribution itself, not samples of it
     elif isinstance(belief, InitialStateDistribution):
         planner.set_belief_initial()
     elif isinstance(belief, np.ndarray):
@@ -699,7 +744,10 @@ class RootUpdater:
 
 
 def updater(policy):
-    """updater(policy::POMCPPlanner) (src/updater.jl:41)."""
+    """updater(policy::POMCPPlanner) = RootUpdater (src/updater.jl:41); updater(problem) = the problem's exact
+    belief updater (the node_belief_updater of notebooks/Sanity_Checks.ipynb:47)."""
+    if isinstance(policy, POMDP):
+        return DiscreteBeliefUpdater(policy)
     return RootUpdater(policy)
 
 
@@ -721,6 +769,11 @@ def update(up, b_old, a, o, out=None):
     if not isinstance(b_old, BeliefNode):
         raise TypeError("RootUpdater.update needs the BeliefNode returned by initialize_belief/update")
     b_old._live()
+    if isinstance(up.node_belief_updater, DiscreteBeliefUpdater):  # src/updater.jl:30-39
+        pl.update_exact2(a, o)
+        node = BeliefNode(pl, pl._generation)
+        node.B = BoolDistribution(pl.belief_exact2())
+        return node
     if isinstance(up.node_belief_updater, SIRReinvigorator):  # both hooks run on the device
         r = up.node_belief_updater
         r.last_outcome = pl.update_reinvigorated(a, o, r.next_seed(), r.n)

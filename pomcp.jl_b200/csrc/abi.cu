@@ -103,7 +103,10 @@ struct pomcp_handle {
   bool inflight_min_auto = true;  // no explicit inflight_min: max(8, tree_queries / 1024) per search
   void* d_bel[2] = {nullptr, nullptr};
   size_t bel_cap[2] = {0, 0};
-  int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles
+  int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles, 3 exact two-state belief (EXACT2)
+  bool exact2 = false;            // belief_mode = EXACT2: nodes carry P(s = 1)
+  double root_p = 0.0;            // EXACT2: belief of a fresh root (written to node_bel by fresh_root)
+  double* d_scalar = nullptr;     // one double of scratch
   long long n_bel = 0;
   uint32_t root = 0, epoch = 0;  // root / root_visits: tree 0's (the only tree unless n_trees > 1)
   long long root_visits = 0;
@@ -240,6 +243,11 @@ int fresh_root(pomcp_handle* h) {
   h->h_ctr->pool_overflow = h->h_ctr->log_overflow = h->h_ctr->replay_overflow = 0;
   CK(cudaMemcpyAsync(h->pool.ctr, h->h_ctr, sizeof(DevCtr), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->exact2 && h->bel_kind == 3) {
+    for (int t = 0; t < h->n_trees; ++t) k_set_node_bel<<<1, 32, 0, h->stream>>>(h->pool.node_bel, (uint32_t)t, nullptr, h->root_p);
+    rc = launch_check(h, "k_set_node_bel");
+    if (rc) return rc;
+  }
   h->root = 0;
   h->root_visits = 0;
   for (int t = 0; t < h->n_trees; ++t) { h->roots[(size_t)t] = (uint32_t)t; h->tree_visits[(size_t)t] = 0; }
@@ -275,6 +283,7 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.dpw = h->sp.dpw_observation ? 1 : 0;
   c.dpa = h->sp.dpw_action ? 1 : 0;
   c.dpw_solver = (h->sp.dpw_solver || h->sp.dpw_observation || h->sp.dpw_action) ? 1 : 0;
+  c.exact2 = (h->exact2 && h->bel_kind == 3) ? 1 : 0;
   c.k_act = h->sp.k_action;
   c.alpha_act = h->sp.alpha_action;
   c.k_obs = h->sp.k_observation;
@@ -592,7 +601,7 @@ int compact_pool(pomcp_handle* h) {
   // 2. copy the kept nodes through a scratch block
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_N = 0, o_fl = o_N + al((size_t)kept * 4), o_ps = o_fl + al((size_t)kept * 4),
-         o_obs = o_ps + al((size_t)kept * 4), o_aN = o_obs + al(h->hashed ? (size_t)kept * 8 : 0),
+         o_obs = o_ps + al((size_t)kept * 4), o_aN = o_obs + al((h->hashed || h->exact2) ? (size_t)kept * 8 : 0),
          o_aM = o_aN + al((size_t)kept * nA * 4), o_aV = o_aM + al((size_t)kept * nA * 4),
          o_ch = o_aV + al((size_t)kept * nA * 8), total = o_ch + al((size_t)kept * nA * nO * 4);
   rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, total);
@@ -611,6 +620,7 @@ int compact_pool(pomcp_handle* h) {
   CK(d2d(P.node_flags, T.node_flags, (size_t)kept * 4));
   CK(d2d(P.node_pslot, T.node_pslot, (size_t)kept * 4));
   if (h->hashed) CK(d2d(P.node_obs, T.node_obs, (size_t)kept * 8));
+  if (h->exact2) CK(d2d(P.node_bel, T.node_obs, (size_t)kept * 8));  // the scratch column is shared: never both
   CK(d2d(P.act_N, T.act_N, (size_t)kept * nA * 4));
   CK(d2d(P.act_M, T.act_M, (size_t)kept * nA * 4));
   CK(d2d(P.act_V, T.act_V, (size_t)kept * nA * 8));
@@ -747,7 +757,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
                   h->d_cum, h->d_scan_status, h->d_pf_regions, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values,
-                  h->d_trees};
+                  h->d_trees, h->pool.node_bel, h->d_scalar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
@@ -821,6 +831,12 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->roots.assign((size_t)T, 0u);
   h->tree_visits.assign((size_t)T, 0);
   h->unweighted = sp->belief_mode == POMCP_BELIEF_UNWEIGHTED;
+  h->exact2 = sp->belief_mode == POMCP_BELIEF_EXACT2;
+  if (h->exact2 && p->problem_id != POMCP_TIGER && p->problem_id != POMCP_BABY) {
+    h->err = "belief_mode EXACT2 (the problem's exact discrete updater as node_belief_updater) exists for the two-state problems";
+    return bail(POMCP_ERR_UNSUPPORTED);
+  }
+  if (h->exact2 && sp->dpw_action) { h->err = "EXACT2 with action widening is not supported"; return bail(POMCP_ERR_UNSUPPORTED); }
   h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
   h->pf_two_barriers = std::getenv("POMCP_PF_TWO_BARRIERS") != nullptr;
   h->pf_nocoop = std::getenv("POMCP_PF_NOCOOP") != nullptr;
@@ -910,7 +926,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   size_t per_node = 8 + (size_t)nA * 16 + (h->hashed ? 12 + 8 : (size_t)nA * nO * 4) +
                     (sp->dpw_observation ? (size_t)nA * 8 + 32 * (12 + (size_t)sb) : 0);
   // unweighted mode keeps the tree across decisions (re-rooting, no compaction yet): room for ~64 of them
-  long long want = sp->max_nodes > 0 ? sp->max_nodes : (h->unweighted ? 64 * Q : 2 * Q) * T + 65536;
+  long long want = sp->max_nodes > 0 ? sp->max_nodes : ((h->unweighted || h->exact2) ? 64 * Q : 2 * Q) * T + 65536;
   long long cap_mem = (long long)((free_b * 4 / 10) / per_node);
   // node ids carry a flag in bit 31, and action slots (id * nA + a) are 32-bit as well
   const long long cap_ids = std::min<long long>((1ll << 31) - 2, ((1ll << 32) - 1) / std::max(nA, 1) - 1);
@@ -929,6 +945,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &P.act_V, (size_t)want * nA));
   CKC(dev_alloc(h, &P.node_pslot, (size_t)want));
   if (sp->dpw_action) CKC(dev_alloc(h, &P.node_amask, (size_t)want));
+  if (h->exact2) CKC(dev_alloc(h, &P.node_bel, (size_t)want));
+  CKC(dev_alloc(h, &h->d_scalar, 1));
   if (h->hashed) {
     size_t e = 1;
     while (e < (size_t)want * 2) e <<= 1;
@@ -1022,6 +1040,27 @@ int32_t pomcp_set_belief_initial(pomcp_handle* h) {
   h->bel_kind = 1;
   h->n_bel = 0;
   return fresh_root(h);
+}
+
+// initialize_belief(up, BoolDistribution(p)) for a planner whose node_belief_updater is the problem's exact
+// two-state updater: RootNode(0, b, {}) with b = P(s = 1) (src/updater.jl:45-47).
+int32_t pomcp_set_belief_exact2(pomcp_handle* h, double p1) {
+  if (!h || !(p1 >= 0.0) || !(p1 <= 1.0)) return fail(h, POMCP_ERR_INVALID_ARG, "belief must be a probability");
+  cudaSetDevice(h->device);
+  if (!h->exact2) return fail(h, POMCP_ERR_UNSUPPORTED, "planner was not created with belief_mode = EXACT2");
+  h->bel_kind = 3;
+  h->n_bel = 0;
+  h->root_p = p1;
+  return fresh_root(h);
+}
+
+int32_t pomcp_get_belief_exact2(pomcp_handle* h, double* p1) {
+  if (!h || !p1) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->exact2 || h->bel_kind != 3) return fail(h, POMCP_ERR_INVALID_ARG, "no exact belief set");
+  CK(cudaMemcpyAsync(p1, h->pool.node_bel + h->root, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return POMCP_OK;
 }
 
 // make_node for a belief that is not a BeliefNode (src/solver.jl:278-281): every action() on a particle
@@ -1223,6 +1262,34 @@ int32_t pomcp_update_unweighted(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
   h->root = child;
   h->root_visits = cnt;
   return maybe_compact(h);
+}
+
+// update(::RootUpdater, b_old, a, o) with a user-supplied (here: the problem's exact two-state) belief updater,
+// src/updater.jl:30-39: the child (a, o) becomes the root with its subtree; if the tree does not hold it, a new
+// node with update(node_belief_updater, b_old.B, a, o) takes its place - this updater never depletes.
+int32_t pomcp_update_exact2(pomcp_handle* h, int32_t a, uint64_t obs_bits) {
+  if (!h) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  if (!h->exact2 || h->bel_kind != 3) return fail(h, POMCP_ERR_UNSUPPORTED, "planner holds no exact two-state belief");
+  if (h->n_trees > 1) return fail(h, POMCP_ERR_UNSUPPORTED, "re-rooting needs n_trees = 1");
+  if (a < 0 || a >= h->nA || obs_bits >= (uint64_t)h->nO) return fail(h, POMCP_ERR_INVALID_ARG, "bad action / observation");
+  int32_t acts[1] = {a};
+  uint64_t obs[1] = {obs_bits};
+  int rc = node_stats_impl(h, acts, obs, 1);
+  if (rc) return rc;
+  if (h->h_ns->node >= 0) {
+    h->root = (uint32_t)h->h_ns->node;
+    h->root_visits = h->h_ns->N;
+    return maybe_compact(h);
+  }
+  DISPATCH_PID(h->prob.problem_id, {
+    k_bayes2<PID><<<1, 32, 0, h->stream>>>(h->dm, h->pool.node_bel, h->root, a, obs_bits, h->d_scalar);
+  });
+  rc = launch_check(h, "k_bayes2");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(&h->root_p, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return fresh_root(h);  // ObsNode(o, 0, new_belief, {}): an empty tree under the new belief
 }
 
 // update(::RootUpdater{R}, b_old, a, o) with the device-side reinvigorator R = SIRReinvigorator(n_min)

@@ -56,6 +56,9 @@ struct ModelT<POMCP_TIGER> {
   static constexpr bool HASHED = false;
   static constexpr int NO = 2;
   static constexpr bool T_DRAW = true;  // the transition consumes a uniform
+  static constexpr bool TWO_STATE = true;
+  // P(s' = 1 | s, a): listening keeps the tiger where it is, opening a door resets it uniformly
+  __device__ __forceinline__ static double trans_p1(const DevModel&, State s, int a) { return a == 0 ? (s ? 1.0 : 0.0) : 0.5; }
   __device__ __forceinline__ static bool terminal(const DevModel&, State) { return false; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State s, int a, U ut0, double uo0, double,
@@ -87,6 +90,11 @@ struct ModelT<POMCP_BABY> {
   static constexpr bool HASHED = false;
   static constexpr int NO = 2;
   static constexpr bool T_DRAW = true;  // the transition consumes a uniform
+  static constexpr bool TWO_STATE = true;
+  // P(hungry' | s, a): feeding sates, a hungry baby stays hungry, otherwise it becomes hungry w.p. p_become_hungry
+  __device__ __forceinline__ static double trans_p1(const DevModel& m, State s, int a) {
+    return a ? 0.0 : (s ? 1.0 : m.b_p_hungry);
+  }
   __device__ __forceinline__ static bool terminal(const DevModel&, State) { return false; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State s, int a, U ut0, double uo0, double,
@@ -116,6 +124,7 @@ struct ModelT<POMCP_ROCKSAMPLE> {
   static constexpr bool HASHED = false;
   static constexpr int NO = 3;
   static constexpr bool T_DRAW = false;  // deterministic transitions
+  static constexpr bool TWO_STATE = false;
   __device__ __forceinline__ static bool terminal(const DevModel&, State s) { return (s & POMCP_RS_TERMINAL) != 0; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, State st, int a, U, double uo0, double, State& sp,
@@ -174,6 +183,7 @@ struct ModelT<POMCP_LIGHTDARK1D> {
   static constexpr bool HASHED = true;  // Float64 observations: children live in a hash table
   static constexpr int NO = 0;
   static constexpr bool T_DRAW = false;  // deterministic transitions
+  static constexpr bool TWO_STATE = false;
   __device__ __forceinline__ static bool terminal(const DevModel&, const State& s) { return s.status < 0; }
   template <bool OBS, class U>
   __device__ __forceinline__ static void step(const DevModel& m, const State& s, int a, U, double uo0, double uo1,
@@ -206,5 +216,23 @@ struct ModelT<POMCP_LIGHTDARK1D> {
     return s;
   }
 };
+
+// Exact Bayes filter of a two-state problem (POMDPModels' BabyBeliefUpdater / the DiscreteUpdater of Tiger), the
+// node_belief_updater of notebooks/Sanity_Checks.ipynb:47,70 (`updater(problem)`; used at src/solver.jl:138 and
+// src/updater.jl:33): b = P(s = 1), b' proportional to O(o | a, s') * sum_s T(s' | s, a) b(s).  The operation order
+// is part of the spec (the oracle evaluates the same expression; Baby reproduces the notebooks' belief chain).
+template <int PID>
+__device__ __forceinline__ double bayes2(const DevModel& m, double b, int a, uint64_t obs) {
+  using M = ModelT<PID>;
+  if constexpr (M::TWO_STATE) {
+    const double p1 = b * M::trans_p1(m, 1u, a) + (1.0 - b) * M::trans_p1(m, 0u, a);
+    const double n1 = M::obs_weight(m, a, 1u, obs) * p1;
+    const double n0 = M::obs_weight(m, a, 0u, obs) * (1.0 - p1);
+    const double den = n0 + n1;
+    return den > 0.0 ? n1 / den : p1;
+  } else {
+    return b;
+  }
+}
 
 }  // namespace pomcp

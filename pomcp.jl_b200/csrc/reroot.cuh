@@ -82,6 +82,7 @@ __global__ void k_copy_kept(const __grid_constant__ Pool P, const __grid_constan
   // parent slot -> (new parent id, same action); the new root has no parent
   T.node_pslot[m] = ((uint32_t)n == new_root) ? 0u : newid[ps / (uint32_t)nA] * (uint32_t)nA + ps % (uint32_t)nA;
   if (P.node_obs) T.node_obs[m] = P.node_obs[n];
+  else if (P.node_bel) T.node_obs[m] = (unsigned long long)__double_as_longlong(P.node_bel[n]);  // same scratch column
   for (int a = 0; a < nA; ++a) {
     size_t so = (size_t)n * nA + a, sn = (size_t)m * nA + a;
     T.act_N[sn] = P.act_N[so];

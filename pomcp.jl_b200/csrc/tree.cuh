@@ -47,6 +47,7 @@ struct Pool {
   void* log_state;
   // observation progressive widening (POMCPDPWSolver, continuous observations): children / generation events of
   // an action node, and the (slot, event) -> (child, state) table the widened step draws from
+  double* node_bel;      // exact two-state node beliefs P(s = 1) (NULL unless belief_mode = EXACT2; src/solver.jl:138)
   uint32_t* node_amask;  // action widening: bit a = ActNode a exists (NULL unless dpw_action)
   uint32_t* act_nc;
   uint32_t* act_ng;
@@ -73,6 +74,7 @@ struct SearchCfg {
   double k_obs, alpha_obs;
   int dpa;             // action progressive widening on (src/solver.jl:172-186)
   double k_act, alpha_act;
+  int exact2;          // node beliefs are exact two-state distributions (Pool::node_bel), roots are sampled from them
   int dpw_solver;      // simulate() of POMCPDPWSolver (src/solver.jl:161-274): the leaf estimate gets `depth` as its step
                        // budget (:182,:199) and an untried action scores V while total_N <= 1 (:210)
   int rollouts;        // R rollouts averaged per leaf, lane r runs rollout r
@@ -474,7 +476,8 @@ __device__ __forceinline__ double leaf_rollouts(const DevModel& m, const RsTab* 
 // `claim` (direct table only): publish the id with CHILD_EXPANDED; the returned value keeps that bit.
 template <int PID, bool SKIP_LOAD = false>
 __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const DevModel& m, uint32_t slot,
-                                                         uint64_t obs, bool& created, bool claim = false) {
+                                                         uint64_t obs, bool& created, bool claim = false,
+                                                         double bel = 0.0) {
   using M = ModelT<PID>;
   created = false;
   if (!M::HASHED) {
@@ -489,6 +492,7 @@ __device__ __forceinline__ uint32_t find_or_insert_child(const Pool& P, const De
       return 0;
     }
     P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
+    if (P.node_bel) { P.node_bel[fresh] = bel; __threadfence(); }  // new_belief = update(node_belief_updater, h.B, a, o)
     const uint32_t pub = claim ? (fresh | CHILD_EXPANDED) : fresh;
     uint32_t old = atomicCAS(cs, 0u, pub);
     if (old == 0) { created = true; return pub; }
@@ -545,7 +549,7 @@ __device__ __forceinline__ unsigned long long atom_add_u64_async(unsigned long l
 // root-to-leaf path (a spare can be older than the parent it ends up under); the pool compaction walks
 // parent links to the root instead of relying on that order.
 __device__ __forceinline__ uint32_t insert_child_spare(const Pool& P, int nO, uint32_t slot, uint64_t obs, bool& created,
-                                                       bool claim, uint32_t& spare) {
+                                                       bool claim, uint32_t& spare, double bel = 0.0) {
   created = false;
   uint32_t* cs = &P.child[(size_t)slot * nO + (uint32_t)obs];
   uint32_t fresh = spare;
@@ -555,6 +559,7 @@ __device__ __forceinline__ uint32_t insert_child_spare(const Pool& P, int nO, ui
     return 0;
   }
   P.node_pslot[fresh] = slot;  // parent link, used by the pool compaction (reroot.cuh)
+  if (P.node_bel) { P.node_bel[fresh] = bel; __threadfence(); }  // the node's belief is in place before its id is visible
   const uint32_t pub = claim ? (fresh | CHILD_EXPANDED) : fresh;
   const uint32_t old = atomicCAS(cs, 0u, pub);
   if (old == 0) {
@@ -639,6 +644,8 @@ __device__ __forceinline__ uint32_t find_child(const Pool& P, const DevModel& m,
   }
 }
 
+__device__ __forceinline__ uint32_t two_state(uint32_t, bool one) { return one ? 1u : 0u; }
+__device__ __forceinline__ LDState two_state(const LDState& s, bool) { return s; }  // never called for LightDark
 __device__ __forceinline__ uint32_t baby_state(uint32_t s) { return s; }
 __device__ __forceinline__ uint32_t baby_state(const LDState&) { return 0u; }  // never called for LightDark
 
@@ -731,6 +738,8 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
   if (cfg.bel != nullptr) {
     long long idx = (long long)(u[0] * (double)cfg.n_bel);
     s = ((const State*)cfg.bel)[idx];
+  } else if (M::TWO_STATE && cfg.exact2) {
+    s = two_state(State{}, u[0] < __ldcg(&P.node_bel[cfg.root]));  // rand(rng, BoolDistribution(p))
   } else {
     s = M::initial(m, u[0], u[1]);
   }
@@ -879,7 +888,9 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
     } else if (lane == 0) {
       if (EXACT) P.act_N[slot] = __ldcg(&P.act_N[slot]) + 1u; else atomicAdd(&P.act_N[slot], 1u);
       bool created_;
-      hao = pre ? pre : find_or_insert_child<PID>(P, m, slot, o, created_);
+      if (pre) hao = pre;
+      else hao = find_or_insert_child<PID>(P, m, slot, o, created_, false,
+                                           (M::TWO_STATE && cfg.exact2) ? bayes2<PID>(m, P.node_bel[h], best_a, o) : 0.0);
       if (hao != 0) {
         if (EXACT) { ticket = __ldcg(&P.node_N[hao]); P.node_N[hao] = ticket + 1u; }
         else ticket = atomicAdd(&P.node_N[hao], 1u);
@@ -1169,6 +1180,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   const double u0 = u01(pr.w[0]), u1 = u01(pr.w[1]);
   State s;
   if (tv.bel != nullptr) s = ((const State*)tv.bel)[(long long)(u0 * (double)tv.n_bel)];
+  else if (M::TWO_STATE && cfg.exact2) s = two_state(State{}, u0 < __ldcg(&P.node_bel[tv.root]));  // rand(rng, BoolDistribution(p))
   else s = M::initial(m, u0, u1);
   fl = __shfl_sync(0xffffffffu, fl, 0);
   if (M::terminal(m, s)) {  // src/solver.jl:49: the query is consumed
@@ -1333,7 +1345,8 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       if (lane == 0) {
         bool cr;
         if constexpr (M::HASHED) raw = find_or_insert_child<PID, false>(P, m, slot, o, cr, false);
-        else raw = insert_child_spare(P, m.nO, slot, o, cr, !cut_next && !DPA, spare);
+        else raw = insert_child_spare(P, m.nO, slot, o, cr, !cut_next && !DPA, spare,
+                                      (M::TWO_STATE && cfg.exact2) ? bayes2<PID>(m, __ldcg(&P.node_bel[h]), best_a, o) : 0.0);
         created = cr;
       }
       raw = __shfl_sync(0xffffffffu, raw, 0);
@@ -1815,6 +1828,15 @@ __global__ void k_pool_fill(const __grid_constant__ Pool P, int nA, int nO, unsi
   if (P.child)
     for (unsigned long long k = i; k < n_nodes * nA * nO; k += stride) P.child[k] = 0;
 }
+__global__ void k_set_node_bel(double* node_bel, uint32_t node, const double* src, double value) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) node_bel[node] = src ? *src : value;
+}
+// update(node_belief_updater, b_old.B, a, o) for a child the tree does not hold (src/updater.jl:33)
+template <int PID>
+__global__ void k_bayes2(const __grid_constant__ DevModel m, const double* node_bel, uint32_t node, int a,
+                         unsigned long long obs, double* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *out = bayes2<PID>(m, node_bel[node], a, obs);
+}
 
 // ---- inspection / update helpers (single thread)
 struct NodeQuery {
@@ -1824,6 +1846,7 @@ struct NodeQuery {
 };
 struct NodeStats {
   long long node;  // -1: absent
+  double bel;      // exact two-state belief of the node (EXACT2)
   long long N, n_particles;
   long long act_N[POMCP_MAX_ACTIONS];
   double act_V[POMCP_MAX_ACTIONS];
@@ -1841,6 +1864,7 @@ __global__ void k_node_stats(const __grid_constant__ Pool P, const __grid_consta
     h = c;
   }
   out->node = h;
+  out->bel = P.node_bel ? P.node_bel[h] : 0.0;
   out->N = P.node_N[h];
   out->n_particles = (h == root) ? n_bel : (unweighted ? (long long)P.node_N[h] : 0);
   for (int a = 0; a < m.nA; ++a) {

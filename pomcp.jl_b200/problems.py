@@ -72,6 +72,7 @@ class TigerPOMDP(POMDP):
 
     n_actions = 3
     n_observations = 2
+    initial_p1 = 0.5  # initial_state_distribution: the tiger is behind either door
 
     def c_struct(self):
         p = _abi.Problem()
@@ -95,6 +96,7 @@ class BabyPOMDP(POMDP):
 
     n_actions = 2
     n_observations = 2
+    initial_p1 = 0.0  # initial_state_distribution = BoolDistribution(0.0): not hungry
 
     def c_struct(self):
         p = _abi.Problem()

@@ -157,8 +157,9 @@ def test_action_widening_root_argmax_only_over_existing_children(oracle, gpu_lib
         a, N, V = gp.search(60)
         if mode == "batched":
             # the first simulations run side by side and each adds the action it drew before seeing the others',
-            # so more than one ActNode can exist; the decision must still be one of them
-            assert N.sum() == 59 and N[a] > 0 and V[a] < 0.0, (seed, a, N, V)
+            # so more than one ActNode can exist (and the queries that found the root with a single child return at
+            # once, src/solver.jl:180-186); the decision must still be one of the existing children
+            assert 0 < N.sum() <= 59 and N[a] > 0 and V[a] < 0.0, (seed, a, N, V)
             assert a == max((i for i in range(3) if N[i] > 0), key=lambda i: (V[i], i)), (a, N, V)
         else:
             assert (N > 0).sum() == 1 and N[a] == 59 and V[a] < 0.0, (seed, a, N, V)

@@ -117,16 +117,21 @@ def test_tree_navigation_like_the_reference(oracle, gpu_lib):
     with pytest.raises(NotImplementedError):  # widening would be active on a discrete space larger than k_observation
         pj.solve(pj.POMCPDPWSolver(tree_queries=100, enable_action_pw=False, k_observation=1.0), baby)
     policy.close()
-    # test/runtests.jl:49-54: DPW without action widening on Baby never widens (2 observations <= k_observation),
-    # i.e. it is POMCP: same tree as POMCPSolver with the same parameters
+    # test/runtests.jl:49-54: DPW without action widening on Baby never widens (2 observations <= k_observation), but it
+    # is still POMCPDPWSolver's simulate(): its leaf rollouts get `depth` as their step budget (src/solver.jl:199)
+    # where POMCPSolver's run to the horizon (src/solver.jl:97-102).  Bit-identical to the oracle with dpw_solver = 1,
+    # and not the tree POMCPSolver builds with the same parameters.
     dpw = pj.POMCPDPWSolver(tree_queries=100, eps=0.01, c=10.0, enable_action_pw=False, rng=2, search_mode="exact")
     r = pj.test_solver(dpw, baby)
     assert np.isfinite(r)
     p1, p2 = pj.solve(dpw, baby), pj.solve(pj.POMCPSolver(tree_queries=100, eps=0.01, c=10.0, rng=2, search_mode="exact"), baby)
-    for p_ in (p1, p2):
+    op = oracle.OraclePlanner(baby, oracle.default_params(tree_queries=100, eps=0.01, c=10.0, seed=2, dpw_solver=1))
+    for p_ in (p1, p2, op):
         p_.set_belief_initial()
     r1, r2 = p1.search(100), p2.search(100)
-    assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+    rc, a_o, N_o, V_o = op.search(100)
+    assert rc == 0 and r1[0] == a_o and np.array_equal(r1[1], N_o) and np.array_equal(r1[2].view(np.uint64), V_o.view(np.uint64))
+    assert p1.counters()["rollout_steps"] < p2.counters()["rollout_steps"] / 3
     p1.close(); p2.close()
 
 
