@@ -303,6 +303,51 @@ int reset_search_flags(pomcp_handle* h) {
   return POMCP_OK;
 }
 
+// One persistent launch of the batched workers: four-warp CTAs, 4 / team_warps workers per CTA, workers dealt to
+// the cfg.n_trees trees round-robin, admission ramped on the device.  The per-tree table (cfg.trees) must be in
+// place on the stream.
+int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
+  const int nteams = 4 / cfg.team_warps;
+  size_t path_bytes = ((size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes) + 15) & ~(size_t)15;
+  cfg.path_smem = path_bytes * nteams <= 40 * 1024 ? 1 : 0;
+  cfg.path_bytes = (int)path_bytes;
+  size_t smem = cfg.path_smem ? path_bytes * nteams : 0;
+  cfg.eta_off = (int)smem;
+  cfg.eta_n = h->eta_n;
+  cfg.eta_thr = h->d_eta_thr;
+  smem += (size_t)h->eta_n * sizeof(uint32_t);
+  const int T = std::max(cfg.n_trees, 1);
+  long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1) * T);
+  int blocks = (int)((workers + nteams - 1) / nteams);
+  DISPATCH_PID(h->prob.problem_id, {
+    // no more workers than can be co-resident: a worker that is not resident does not search
+    auto launch = [&](auto kern) {
+      int per_sm = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+      if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
+      // workers are dealt to the trees round-robin: the in-flight cap, the admission floor and the ramp are per tree
+      cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cfg.inflight_max, (long long)blocks * nteams) / T);
+      // Admission floor relative to the budget: the simulations started while the tree holds fewer than
+      // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
+      // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
+      if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), cfg.inflight_max);
+      cfg.inflight_min = std::min(cfg.inflight_min, cfg.inflight_max);
+      kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
+    };
+    if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
+      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, true>);
+      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, true>);
+      else launch(k_search_workers<PID, 1, 4, true>);
+    } else {
+      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, false>);
+      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, false>);
+      else launch(k_search_workers<PID, 1, 4, false>);
+    }
+  });
+  return launch_check(h, "k_search_workers");
+}
+
 int finish_search(pomcp_handle* h);
 
 int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long n_uni, const double* d_rets,
@@ -353,47 +398,8 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     if (rc) return rc;
     ts.launches++;
   } else {
-    // one persistent launch of four-warp CTAs: 4 / team_warps workers per CTA, admission ramped on the device
-    const int nteams = 4 / cfg.team_warps;
-    size_t path_bytes = ((size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes) + 15) & ~(size_t)15;
-    cfg.path_smem = path_bytes * nteams <= 40 * 1024 ? 1 : 0;
-    cfg.path_bytes = (int)path_bytes;
-    size_t smem = cfg.path_smem ? path_bytes * nteams : 0;
-    cfg.eta_off = (int)smem;
-    cfg.eta_n = h->eta_n;
-    cfg.eta_thr = h->d_eta_thr;
-    smem += (size_t)h->eta_n * sizeof(uint32_t);
-    const int T = h->n_trees;
-    long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1) * T);
-    int blocks = (int)((workers + nteams - 1) / nteams);
     CK(cudaEventRecord(tr.next(), h->stream));
-    DISPATCH_PID(h->prob.problem_id, {
-      // no more workers than can be co-resident: a worker that is not resident does not search
-      auto launch = [&](auto kern) {
-        int per_sm = 0, sms = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
-        // workers are dealt to the trees round-robin: the in-flight cap, the admission floor and the ramp are per tree
-        cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cfg.inflight_max, (long long)blocks * nteams) / T);
-        // Admission floor relative to the budget: the simulations started while the tree holds fewer than
-        // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
-        // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
-        if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), cfg.inflight_max);
-        cfg.inflight_min = std::min(cfg.inflight_min, cfg.inflight_max);
-        kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
-      };
-      if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
-        if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, true>);
-        else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, true>);
-        else launch(k_search_workers<PID, 1, 4, true>);
-      } else {
-        if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, false>);
-        else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, false>);
-        else launch(k_search_workers<PID, 1, 4, false>);
-      }
-    });
-    rc = launch_check(h, "k_search_workers");
+    rc = launch_batched_workers(h, cfg, Q);
     if (rc) return rc;
     CK(cudaEventRecord(tr.next(), h->stream));
     tr.launches++;

