@@ -278,6 +278,27 @@ int32_t pomcp_dump_tree(pomcp_handle* h, int64_t cap_nodes, int64_t* n_nodes, in
 int32_t pomcp_generate_sor(pomcp_handle* h, const void* state, int32_t a, uint64_t seed, uint32_t step,
                            void* next_state, uint64_t* obs_bits, double* reward, int32_t* terminal);
 int32_t pomcp_initial_state(pomcp_handle* h, uint64_t seed, void* state_out);
+/* E independent episodes of the outer simulation loop entirely on the device: POMDPToolbox.RolloutSimulator.simulate
+ * as test_solver (test/runtests.jl:19) and est_reward (notebooks/Sanity_Checks.ipynb:47-77, 100 episodes spread
+ * over processes) run it -
+ *     while disc > eps && !isterminal(s) && step <= max_steps:
+ *         a = action(policy, b); (sp, o, r) = generate_sor(pomdp, s, a); total += disc * r; b = update(up, b, a, o)
+ * One search tree per episode (the planner must have been created with n_trees >= n_episodes and search_mode
+ * batched), all trees searched side by side in one launch per step, environment step and belief update on the
+ * device, no host round trip inside an episode.  The belief updater follows the planner's belief_mode:
+ * UNWEIGHTED = RootUpdater with the DeadReinvigorator (tree reuse; an episode that depletes ends with status
+ * PARTICLE_DEPLETION, where the reference throws), EXACT2 = RootUpdater over the exact two-state updater
+ * (src/updater.jl:30-39), EXTERNAL = SIRParticleFilter(model, sir_particles) with a fresh root every step. */
+typedef struct pomcp_episode_params {
+  int32_t max_steps;      /* RolloutSimulator max_steps */
+  int32_t initial_state;  /* < 0: s0 ~ initial_state_distribution; >= 0: that state (two-state problems; Sanity_Checks: false) */
+  double sim_eps;         /* RolloutSimulator eps: an episode runs while disc > eps (0: max_steps / terminal states only) */
+  uint64_t env_seed;      /* episode e draws its environment from Philox(env_seed + e) */
+  int64_t sir_particles;  /* EXTERNAL: particles per belief */
+  double initial_p1;      /* EXACT2: initial belief BoolDistribution(initial_p1) */
+} pomcp_episode_params;
+int32_t pomcp_run_episodes(pomcp_handle* h, const pomcp_episode_params* ep, int32_t n_episodes, double* rewards_out,
+                           int32_t* steps_out, int32_t* status_out);
 /* Index of the current root in the arrays pomcp_dump_tree returns (0 after a fresh root or a compaction). */
 int32_t pomcp_root_node(pomcp_handle* h, int64_t* node_id);
 int32_t pomcp_get_counters(pomcp_handle* h, pomcp_counters* out);

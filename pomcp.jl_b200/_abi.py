@@ -66,6 +66,11 @@ class SolverParams(C.Structure):
     ]
 
 
+class EpisodeParams(C.Structure):
+    _fields_ = [("max_steps", C.c_int32), ("initial_state", C.c_int32), ("sim_eps", C.c_double),
+                ("env_seed", C.c_uint64), ("sir_particles", C.c_int64), ("initial_p1", C.c_double)]
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "simulations", "terminal_skips", "rollouts", "rollout_steps", "tree_steps", "nodes", "log_entries",
@@ -88,6 +93,6 @@ EXPORTS = [
     "pomcp_set_belief_particles", "pomcp_set_belief_initial", "pomcp_set_belief_exact2", "pomcp_get_belief_exact2", "pomcp_update_exact2", "pomcp_reset_tree", "pomcp_set_state_values", "pomcp_get_belief_particles", "pomcp_search",
     "pomcp_search_replay", "pomcp_update_unweighted", "pomcp_update_reinvigorated", "pomcp_pf_update_sir", "pomcp_resample_systematic",
     "pomcp_rollout_batch", "pomcp_pf_weights", "pomcp_get_root_stats", "pomcp_get_tree_result", "pomcp_get_node_stats", "pomcp_dump_tree",
-    "pomcp_generate_sor", "pomcp_initial_state", "pomcp_root_node", "pomcp_get_counters", "pomcp_reset_counters", "pomcp_worker_cycles", "pomcp_nccl_unique_id", "pomcp_comm_init",
+    "pomcp_generate_sor", "pomcp_initial_state", "pomcp_run_episodes", "pomcp_root_node", "pomcp_get_counters", "pomcp_reset_counters", "pomcp_worker_cycles", "pomcp_nccl_unique_id", "pomcp_comm_init",
     "pomcp_search_rootparallel", "pomcp_last_phase_ms", "pomcp_event_record", "pomcp_event_elapsed_ms", "pomcp_search_async", "pomcp_sync", "pomcp_flush_l2",
 ]

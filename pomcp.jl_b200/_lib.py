@@ -65,6 +65,7 @@ def lib():
     L.pomcp_get_counters.argtypes = [vp, P(abi.Counters)]
     L.pomcp_generate_sor.argtypes = [vp, vp, i32, u64, C.c_uint32, vp, P(u64), P(dbl), P(i32)]
     L.pomcp_initial_state.argtypes = [vp, u64, vp]
+    L.pomcp_run_episodes.argtypes = [vp, P(abi.EpisodeParams), i32, vp, vp, vp]
     L.pomcp_root_node.argtypes = [vp, P(i64)]
     L.pomcp_reset_counters.argtypes = [vp]
     L.pomcp_worker_cycles.argtypes = [vp, vp]

@@ -23,7 +23,7 @@ __all__ = [
     "ParticleDepletion", "PoolExhausted", "POMCPError", "BeliefNode", "RootNode", "ParticleCollection",
     "InitialStateDistribution", "BoolDistribution", "DiscreteBeliefUpdater", "BabyBeliefUpdater", "RootUpdater", "SIRParticleFilter", "solve", "action", "updater", "update",
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
-    "RolloutSimulator", "simulate", "test_solver", "create_json", "ObsNode", "ActNode", "AbstractActNode",
+    "RolloutSimulator", "simulate", "simulate_episodes", "test_solver", "create_json", "ObsNode", "ActNode", "AbstractActNode",
     "POMCPTreeVisualizer", "AbstractPOMCPSolver", "POMCPDPWSolver", "RandomActionGenerator", "PORollout",
     "PORolloutEstimator", "create_policy", "create_belief", "init_V", "init_N", "sparse_actions", "next_action", "add_N",
     "convert_estimator", "extract_belief", "estimate_value",
@@ -599,6 +599,20 @@ class POMCPPlanner:
                                         sp.ctypes.data_as(C.c_void_p), C.byref(o), C.byref(r), C.byref(t)), self._h)
         return sp[0], obs_from_bits(self.problem, o.value), r.value, bool(t.value)
 
+    def run_episodes(self, n_episodes, max_steps, env_seed=0, initial_state=-1, sim_eps=0.0, sir_particles=0,
+                     initial_p1=0.0):
+        """n_episodes runs of the outer simulation loop on the device, one tree per episode, no host round trip
+        inside an episode (pomcp_run_episodes).  Returns (discounted rewards, steps taken, status per episode)."""
+        ep = abi.EpisodeParams(int(max_steps), int(initial_state), float(sim_eps), int(env_seed) & (2 ** 64 - 1),
+                               int(sir_particles), float(initial_p1))
+        r = np.zeros(n_episodes, dtype=np.float64)
+        st = np.zeros(n_episodes, dtype=np.int32)
+        status = np.zeros(n_episodes, dtype=np.int32)
+        _check(lib().pomcp_run_episodes(self._h, C.byref(ep), int(n_episodes), r.ctypes.data_as(C.c_void_p),
+                                        st.ctypes.data_as(C.c_void_p), status.ctypes.data_as(C.c_void_p)), self._h)
+        self._generation += 1
+        return r, st, status
+
     def initial_state(self, seed):
         s = np.zeros(1, dtype=self.problem.state_dtype)
         _check(lib().pomcp_initial_state(self._h, int(seed), s.ctypes.data_as(C.c_void_p)), self._h)
@@ -859,6 +873,33 @@ def simulate(sim, pomdp, policy, up=None, initial_belief=None):
         disc *= pomdp.discount
         step += 1
     return total
+
+
+def simulate_episodes(sim, pomdp, policy, n_episodes, up=None, initial_belief=None):
+    """n_episodes independent runs of simulate(sim, pomdp, policy, updater, initial_belief) - what est_reward of
+    notebooks/Sanity_Checks.ipynb:47-77 spreads over worker processes - in ONE device call: one tree per episode
+    (the planner needs n_trees >= n_episodes), no host round trip inside an episode.  Episode e draws its
+    environment from Philox(sim.rng + e).  Returns (discounted rewards, steps, status codes)."""
+    import math
+    if policy.problem is not pomdp:
+        raise ValueError("the planner was solved for another problem instance")
+    eps = 0.0 if sim.eps is None else float(sim.eps)
+    if sim.max_steps is not None:
+        max_steps = int(sim.max_steps)
+    elif eps > 0.0:
+        max_steps = int(math.ceil(math.log(eps) / math.log(pomdp.discount)))  # disc > eps fails after that many steps
+    else:
+        raise ValueError("RolloutSimulator needs max_steps or eps for a device-resident episode loop")
+    kw = {}
+    if isinstance(up, SIRParticleFilter):
+        if policy.belief_mode != abi.BELIEF_EXTERNAL:
+            raise ValueError("a SIR particle filter needs a planner solved with belief_mode = EXTERNAL")
+        kw["sir_particles"] = up.n
+    elif policy.belief_mode == abi.BELIEF_EXACT2:
+        b0 = initial_belief if initial_belief is not None else initial_state_distribution(pomdp)
+        kw["initial_p1"] = b0.p if isinstance(b0, BoolDistribution) else pomdp.initial_p1
+    s0 = -1 if sim.initial_state is None else int(sim.initial_state)
+    return policy.run_episodes(n_episodes, max_steps, env_seed=sim.rng, initial_state=s0, sim_eps=eps, **kw)
 
 
 def test_solver(solver, pomdp, max_steps=10, updater=None, rng=0):

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/pomcp_b200.h"
+#include "episode.cuh"
 #include "pf.cuh"
 #include "reroot.cuh"
 #include "tree.cuh"
@@ -153,6 +154,11 @@ struct pomcp_handle {
   bool pf_two_barriers = false;     // POMCP_PF_TWO_BARRIERS=1: never use the one-barrier (a-priori scale) kernel
   bool pf_nocoop = false;           // POMCP_PF_NOCOOP=1: plain launch of the one-barrier kernel (developer timing)
   long long pf_retries = 0;         // one-barrier launches that fell back to the max-scaled kernels
+  // device-resident episodes
+  EpisodeCtl* d_eps = nullptr;
+  unsigned long long* d_ep_logctr = nullptr;
+  void* d_ep_bel[2] = {nullptr, nullptr};
+  size_t ep_bel_cap[2] = {0, 0};
   nccl_comm comm = nullptr;
   int nranks = 1;
   std::string err;
@@ -379,6 +385,9 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     tc.epoch = cfg.epoch;
     tc.any_nonterminal = 0;
     tc._pad = 0;
+    tc.log_ctr = &h->pool.ctr->log_count;  // device address: one log, one cursor (several trees share both)
+    tc.log_base = 0;
+    tc.log_cap = h->pool.log_cap;
   }
   CK(cudaMemcpyAsync(h->d_trees, h->h_trees, sizeof(TreeCtl) * (size_t)h->n_trees, cudaMemcpyHostToDevice, h->stream));
   const bool replay = d_uni != nullptr;
@@ -763,7 +772,7 @@ int32_t pomcp_destroy(pomcp_handle* h) {
                   h->pool.log_state, h->pool.ctr, h->pb.path_slot, h->pb.path_node, h->pb.path_r, h->pb.path_state,
                   h->d_bel[0], h->d_bel[1], h->d_res, h->d_ns,
                   h->d_cum, h->d_scan_status, h->d_pf_regions, h->d_tmp, h->d_tmp2, h->d_flush, h->d_newid, h->d_init, h->d_state_values,
-                  h->d_trees, h->pool.node_bel, h->d_scalar};
+                  h->d_trees, h->pool.node_bel, h->d_scalar, h->d_eps, h->d_ep_logctr, h->d_ep_bel[0], h->d_ep_bel[1]};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (h->h_res) cudaFreeHost(h->h_res);
@@ -1646,6 +1655,135 @@ int32_t pomcp_flush_l2(pomcp_handle* h) {
   }
   k_flush_l2<<<148 * 8, 256, 0, h->stream>>>(h->d_flush, h->flush_n);
   return launch_check(h, "k_flush_l2");
+}
+
+// ---- device-resident batched episodes (episode.cuh)
+__global__ void k_ep_sir_done_one(TreeCtl* tc, EpisodeCtl* ec, const PfCtl* ctl, const void* new_bel, long long n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0 || !ec->update_pending) return;
+  const int st = (int)ctl->status;
+  if (st != POMCP_OK) { ec->status = st; ec->active = 0; return; }
+  tc->bel = new_bel;
+  tc->n_bel = n;
+}
+
+int32_t pomcp_run_episodes(pomcp_handle* h, const pomcp_episode_params* ep, int32_t n_episodes, double* rewards_out,
+                           int32_t* steps_out, int32_t* status_out) {
+  if (!h || !ep || !rewards_out) return fail(h, POMCP_ERR_INVALID_ARG, "null argument");
+  cudaSetDevice(h->device);
+  if (h->exact) return fail(h, POMCP_ERR_UNSUPPORTED, "episodes run on the batched workers (search_mode = batched)");
+  if (n_episodes < 1 || n_episodes > h->n_trees)
+    return fail(h, POMCP_ERR_INVALID_ARG, "n_episodes must be in 1..n_trees (one tree per episode; create the planner with n_trees >= n_episodes)");
+  if (ep->max_steps < 1 || !(ep->sim_eps >= 0.0)) return fail(h, POMCP_ERR_INVALID_ARG, "bad max_steps / sim_eps");
+  if (h->sp.dpw_action || h->sp.dpw_observation)
+    return fail(h, POMCP_ERR_UNSUPPORTED, "device episodes with progressive widening are not supported");
+  const int T = n_episodes;
+  const int mode = h->exact2 ? POMCP_BELIEF_EXACT2 : (h->unweighted ? POMCP_BELIEF_UNWEIGHTED : POMCP_BELIEF_EXTERNAL);
+  const long long Q = h->sp.tree_queries;
+  const long long sir_n = mode == POMCP_BELIEF_EXTERNAL ? ep->sir_particles : 0;
+  if (mode == POMCP_BELIEF_EXTERNAL && (sir_n < 1 || sir_n > (1ll << 20)))
+    return fail(h, POMCP_ERR_INVALID_ARG, "sir_particles must be in 1..2^20 per episode");
+  if (mode == POMCP_BELIEF_EXACT2 && (!(ep->initial_p1 >= 0.0) || !(ep->initial_p1 <= 1.0)))
+    return fail(h, POMCP_ERR_INVALID_ARG, "initial_p1 must be a probability");
+  int rc;
+  if (h->pending) { rc = finish_search(h); (void)rc; }
+  if (!h->d_eps) {
+    CK(cudaMalloc((void**)&h->d_eps, sizeof(EpisodeCtl) * (size_t)h->n_trees));
+    CK(cudaMalloc((void**)&h->d_ep_logctr, sizeof(unsigned long long) * (size_t)h->n_trees));
+  }
+  // belief buffers: SIR ping-pong sets of sir_n particles per episode; unweighted: room for the particles of a root
+  long long bel_cap = 0;
+  if (mode == POMCP_BELIEF_EXTERNAL) bel_cap = sir_n;
+  if (mode == POMCP_BELIEF_UNWEIGHTED) bel_cap = std::min<long long>(Q * (long long)ep->max_steps, (long long)(h->pool.log_cap / (unsigned long long)T));
+  for (int k = 0; k < (mode == POMCP_BELIEF_EXTERNAL ? 2 : (mode == POMCP_BELIEF_UNWEIGHTED ? 1 : 0)); ++k) {
+    rc = ensure_bytes(h, &h->d_ep_bel[k], &h->ep_bel_cap[k], (size_t)bel_cap * (size_t)T * (size_t)h->state_bytes);
+    if (rc) return rc;
+  }
+  h->bel_kind = 1;
+  rc = fresh_root(h);  // wipes what earlier trees used; roots = nodes 0 .. n_trees - 1
+  if (rc) return rc;
+  EpisodeCfg ec{};
+  ec.n = T; ec.max_steps = ep->max_steps; ec.initial_state = ep->initial_state; ec.updater = mode;
+  ec.sim_eps = ep->sim_eps; ec.initial_p1 = ep->initial_p1;
+  ec.env_k0 = (uint32_t)ep->env_seed; ec.env_k1 = (uint32_t)(ep->env_seed >> 32);
+  ec.key0 = (uint32_t)h->sp.seed; ec.key1 = (uint32_t)(h->sp.seed >> 32);
+  ec.rank0 = (uint32_t)(h->sp.rank * h->n_trees);
+  ec.sir_n = sir_n;
+  ec.log_seg = h->pool.log_cap / (unsigned long long)T;
+  const int eb = (T + 127) / 128;
+  DISPATCH_PID(h->prob.problem_id, {
+    k_ep_init<PID><<<eb, 128, 0, h->stream>>>(h->pool, h->dm, ec, h->d_trees, h->d_eps, h->d_ep_logctr, h->d_ep_bel[0]);
+    if (mode == POMCP_BELIEF_EXTERNAL)
+      k_ep_init_particles<PID><<<(int)(((long long)T * sir_n + 255) / 256), 256, 0, h->stream>>>(
+          h->dm, ec, (typename ModelT<PID>::State*)h->d_ep_bel[0]);
+  });
+  rc = launch_check(h, "k_ep_init");
+  if (rc) return rc;
+  PhaseTimer& ts = h->timers[POMCP_PHASE_SEARCH];
+  ts.reset();
+  CK(cudaEventRecord(ts.next(), h->stream));
+  int cur = 0;
+  for (int step = 1; step <= ep->max_steps; ++step) {
+    k_ep_prepare<<<eb, 128, 0, h->stream>>>(h->d_trees, h->d_eps, T, h->epoch + (uint32_t)step);
+    rc = reset_search_flags(h);
+    if (rc) return rc;
+    SearchCfg cfg = make_cfg(h);
+    cfg.n_trees = T;
+    cfg.bel = nullptr; cfg.n_bel = 0;
+    cfg.exact2 = mode == POMCP_BELIEF_EXACT2 ? 1 : 0;
+    rc = launch_batched_workers(h, cfg, Q);
+    if (rc) return rc;
+    k_root_result<<<T, 32, 0, h->stream>>>(h->pool, h->nA, h->d_trees, 0, h->sp.init_V, h->d_res);
+    DISPATCH_PID(h->prob.problem_id, {
+      k_ep_step<PID><<<eb, 128, 0, h->stream>>>(h->pool, h->dm, ec, h->d_trees, h->d_eps, h->d_res, (uint32_t)step);
+    });
+    rc = launch_check(h, "k_ep_step");
+    if (rc) return rc;
+    ts.launches += 4;
+    if (mode == POMCP_BELIEF_UNWEIGHTED) {
+      if (h->state_bytes == 4) k_ep_gather<uint32_t><<<T, 256, 0, h->stream>>>(h->pool, h->d_trees, h->d_eps, (uint32_t*)h->d_ep_bel[0], bel_cap);
+      else k_ep_gather<LDState><<<T, 256, 0, h->stream>>>(h->pool, h->d_trees, h->d_eps, (LDState*)h->d_ep_bel[0], bel_cap);
+      rc = launch_check(h, "k_ep_gather");
+      if (rc) return rc;
+    } else if (mode == POMCP_BELIEF_EXTERNAL) {
+      // update(::SIRParticleFilter, b, a, o) per episode, action and observation read on the device
+      for (int e = 0; e < T; ++e) {
+        const uint64_t seed = ep->env_seed * 0x9E3779B97F4A7C15ull + ((uint64_t)e << 20) + (uint64_t)step;
+        const Philox4 pr = philox4x32_10(0u, TAG_RESAMPLE, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        DISPATCH_PID(h->prob.problem_id, {
+          using State = typename ModelT<PID>::State;
+          EpisodeSrc<PID> src;
+          src.states = (const State*)h->d_ep_bel[cur] + (size_t)e * (size_t)sir_n;
+          src.m = h->dm; src.ep = h->d_eps + e; src.k0 = (uint32_t)seed; src.k1 = (uint32_t)(seed >> 32);
+          State* dst = (State*)h->d_ep_bel[1 - cur] + (size_t)e * (size_t)sir_n;
+          rc = run_resample(h, src, sir_n, pr.w[0], sir_n, dst, false);
+          if (rc == POMCP_OK) k_ep_sir_done_one<<<1, 32, 0, h->stream>>>(h->d_trees + e, h->d_eps + e, h->d_pfctl, dst, sir_n);
+        });
+        if (rc) return rc;
+      }
+      cur ^= 1;
+      // every tree is discarded after its decision (src/solver.jl:278-281): recycle the pool
+      k_ep_pool_wipe<<<148 * 8, 256, 0, h->stream>>>(h->pool, h->nA, h->nO, (uint32_t)h->sp.init_N, h->sp.init_V);
+      k_ep_pool_restart<<<eb, 128, 0, h->stream>>>(h->pool, h->d_trees, T);
+      rc = launch_check(h, "k_ep_pool_wipe");
+      if (rc) return rc;
+    }
+  }
+  CK(cudaEventRecord(ts.next(), h->stream));
+  std::vector<EpisodeCtl> host((size_t)T);
+  CK(cudaMemcpyAsync(host.data(), h->d_eps, sizeof(EpisodeCtl) * (size_t)T, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int e = 0; e < T; ++e) {
+    rewards_out[e] = host[(size_t)e].total;
+    if (steps_out) steps_out[e] = host[(size_t)e].steps;
+    if (status_out) status_out[e] = host[(size_t)e].status;
+  }
+  h->epoch += (uint32_t)ep->max_steps + 1u;
+  h->nodes_used = std::max<unsigned long long>(h->h_ctr->node_count, (unsigned long long)h->n_trees);
+  h->log_used = 0;
+  h->bel_kind = 0;  // the trees and beliefs of the episodes are gone: set a belief before the next search
+  if (h->h_ctr->pool_overflow == 2) return fail(h, POMCP_ERR_CUDA, "worker watchdog fired");
+  return POMCP_OK;
 }
 
 // ---- K10: root-parallel merge over NCCL

@@ -148,6 +148,7 @@ struct ModelSrc {
   uint64_t obs;
   uint32_t k0, k1;
   static constexpr int CEIL_EXP = (PID == POMCP_LIGHTDARK1D) ? 5 : 0;  // weights < 2^(CEIL_EXP + 1), see pf_scale rule
+  __device__ __forceinline__ bool skip() const { return false; }
   // propagate + weight one particle: generate_s then pdf(observation(a, sp), o)
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
     State s = states[i];
@@ -186,6 +187,7 @@ struct ModelSrc {
 struct ArraySrc {  // replayed weights (parity hook): payload is the index itself
   using State = long long;
   static constexpr int CEIL_EXP = PF_NO_CEIL;  // arbitrary weights: the scale always comes from the largest one
+  __device__ __forceinline__ bool skip() const { return false; }
   const double* w_in;
   __device__ __forceinline__ void propagate(long long i, State& sp) const { sp = i; }
   __device__ __forceinline__ State load(long long i) const { return i; }
@@ -544,6 +546,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   // requested into L2 so that the first atomics on them do not pay a DRAM miss
   if (blockIdx.x == gridDim.x - 1)
     for (int k = threadIdx.x; k < PF_CTRL_WORDS; k += PF_THREADS) next_ctl[k] = 0ull;
+  if (src.skip()) return;  // (episodes: no update pending for this belief) - the same for every CTA
   if (threadIdx.x == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(cta_tot + blockIdx.x));
@@ -700,6 +703,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long base = ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * rows;
+  if (src.skip()) return;  // (episodes: no update pending for this belief) - the same for every CTA
 
   // ---- phase A: propagate + weight
   double w[PF_ITEMS];
@@ -843,6 +847,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   // the other control block, for the next launch (nobody uses it now)
   if (blockIdx.x == gridDim.x - 1)
     for (int k = threadIdx.x; k < PF_CTRL_WORDS; k += PF_THREADS) next_ctl[k] = 0ull;
+  if (src.skip()) return;
   if (threadIdx.x == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(cta_tot + blockIdx.x));

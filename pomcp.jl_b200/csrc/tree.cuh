@@ -111,12 +111,18 @@ struct TreeCtl {
   uint32_t key0, key1, rank, epoch;  // Philox key / stream id / epoch of this tree
   uint32_t any_nonterminal;       // a query of this search ran a simulation (src/solver.jl:56-58)
   uint32_t _pad;
+  // particle log of this tree (unweighted mode): entries [log_base, log_base + log_cap) of Pool::log_*, cursor *log_ctr
+  // (one tree: the whole log and DevCtr::log_count; episodes: one segment and one cursor per tree)
+  unsigned long long* log_ctr;
+  unsigned long long log_base, log_cap;
 };
 // A worker's copy of its tree's parameters, in shared memory (one per team; the helper warps read the keys).
 struct TreeView {
   const void* bel;
   long long n_bel;
   TreeCtl* ctl;
+  unsigned long long* log_ctr;
+  unsigned long long log_base, log_cap;
   uint32_t root, root_N0, key0, key1, tagrank, epoch;
 };
 struct RngKey {
@@ -1488,8 +1494,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   if (cfg.belief_unweighted && depth > 0) {
     unsigned long long log_base = 0;
     if (lane == 0) {
-      log_base = atomicAdd(&P.ctr->log_count, (unsigned long long)depth);
-      if (log_base + depth > P.log_cap) { P.ctr->log_overflow = 1; log_base = ~0ull; }
+      log_base = atomicAdd(tv.log_ctr, (unsigned long long)depth);
+      if (log_base + depth > tv.log_cap) { P.ctr->log_overflow = 1; log_base = ~0ull; }
+      else log_base += tv.log_base;
     }
     log_base = __shfl_sync(0xffffffffu, log_base, 0);
     if (log_base != ~0ull) {
@@ -1623,6 +1630,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
     w.bel = tc->bel; w.n_bel = tc->n_bel; w.ctl = tc;
     w.root = tc->root; w.root_N0 = tc->root_N0;
     w.key0 = tc->key0; w.key1 = tc->key1; w.tagrank = tc->rank << 8; w.epoch = tc->epoch;
+    w.log_ctr = tc->log_ctr; w.log_base = tc->log_base; w.log_cap = tc->log_cap;
   }
   __syncwarp();
   PathView<State> pv;
