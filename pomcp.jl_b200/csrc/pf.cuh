@@ -327,6 +327,21 @@ struct PfDiv {
     long long cnt = (long long)k + ((unsigned long long)rem >= thr ? 1 : 0);
     return cnt < n_out ? cnt : n_out;
   }
+  // The same count from one fp64 evaluation, used when it is provably the exact integer: x = C * n_out / T - ru / 2^32
+  // is computed with a relative error below 2^-50 (u64 -> fp64 conversion, the rounded ratio, one product, one
+  // difference), so floor(x) + 1 is M(C) unless x lies within eps = (|x| + 1) * 2^-46 of an integer; those few
+  // (about 2^-20 of the particles at n_out = 2^20) take the integer path.  Same integers either way.
+  __device__ __forceinline__ long long points_below_fast(unsigned long long C, double ru_frac) const {
+    const double x = (double)C * ratio - ru_frac;
+    const double fl = floor(x);
+    const double fr = x - fl;
+    const double eps = (fabs(x) + 1.0) * 1.4210854715202004e-14;  // 2^-46
+    if (fr > eps && fr < 1.0 - eps && x < 4.0e18) {
+      const long long cnt = x < 0.0 ? 0ll : (long long)fl + 1ll;
+      return cnt < n_out ? cnt : n_out;
+    }
+    return points_below(C);
+  }
   // The same count for a run of cumulative sums C, C + q1, C + q1 + q2, ...: (k, rem) is carried and a
   // step adds q * n_out to the remainder, so the quotient grows by the number of copies of that
   // particle (a few subtractions) instead of being divided out again.  Falls back to the closed form
@@ -877,6 +892,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
       State sp;
       double w;
       const bool alive = KEEP ? src.eval_from(i, st[KEEP ? k : 0], sp, w) : src.eval(i, sp, w);
+      if (KEEP) st[KEEP ? k : 0] = sp;  // the propagated state is what the emit copies
       if (alive) {
         alive_mask |= 1u << k;
         if ((unsigned long long)i < first) first = (unsigned long long)i;
@@ -976,21 +992,18 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   const PfDiv dv(T, ru, n_out);
   if (BLOCKED) {
     const unsigned long long off0 = s_off + s_a[warp] + thread_excl;  // C just before this thread's particles
-    PfDiv::Run rn = dv.start(off0);
-    long long lo = dv.count(rn);
-    unsigned long long prev_inc = 0;
+    const double ru_frac = (double)ru * 2.3283064365386963e-10;  // ru / 2^32, exact
+    long long lo = dv.points_below_fast(off0, ru_frac);
 #pragma unroll
     for (int k = 0; k < PF_ITEMS; ++k) {
       const long long i = base + k;
-      dv.advance(rn, inc[k] - prev_inc);
-      prev_inc = inc[k];
-      const long long hi = dv.count(rn);
+      const long long hi = ((alive_mask >> k) & 1u) ? dv.points_below_fast(off0 + inc[k], ru_frac) : lo;
       if ((alive_mask >> k) & 1u) {
         if ((unsigned long long)i == first_alive) lo = 0;
         const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
         if (copies) {
           State sp;
-          if (KEEP) src.propagate_from(i, st[KEEP ? k : 0], sp);
+          if (KEEP) sp = st[KEEP ? k : 0];
           else src.propagate(i, sp);
           Out* o = out + lo;
           o[0] = (Out)sp;
@@ -1004,12 +1017,13 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
     }
   } else {
     const unsigned long long off0 = s_off + s_a[warp];
-    long long prev_hi = dv.points_below(off0);  // M at the start of this warp's range
+    const double ru_frac = (double)ru * 2.3283064365386963e-10;  // ru / 2^32, exact
+    long long prev_hi = dv.points_below_fast(off0, ru_frac);  // M at the start of this warp's range
 #pragma unroll
     for (int k = 0; k < PF_ITEMS; ++k) {
       if (k >= items) break;  // uniform
       const long long i = base + (long long)k * 32 + lane;
-      const long long hi = dv.points_below(off0 + inc[k]);
+      const long long hi = dv.points_below_fast(off0 + inc[k], ru_frac);
       long long lo = __shfl_up_sync(0xffffffffu, hi, 1);
       if (lane == 0) lo = prev_hi;
       prev_hi = __shfl_sync(0xffffffffu, hi, 31);

@@ -37,35 +37,43 @@ def test_sanity_checks_experiment_in_one_call(oracle, gpu_lib):
     RolloutSimulator(initial_state = false, eps = 0.01) from BoolDistribution(0.0) - here one device call.
     The notebook prints -15.92 for it, -15.06 for FeedWhenCrying and -14.69 for the optimal policy on ITS 100
     environment seeds; on ours the three are compared on common random numbers (the Python side replays the
-    device's environment draws): the gaps POMCP - optimal (-1.23) and POMCP - FeedWhenCrying (-0.86) must agree within
-    3 standard errors of the paired difference on either side."""
+    device's environment draws).  With one rollout per leaf - the reference's estimator - the gaps POMCP - optimal
+    (-1.23 in the notebook) and POMCP - FeedWhenCrying (-0.86) agree within 3 standard errors of the paired difference
+    on either side; with the batched default of 64 rollouts per leaf the planner is not worse than that (it is
+    better: the leaf estimates of a 300-query tree are much less noisy)."""
     baby = pj.BabyPOMDP(-5.0, -10.0)
     E = 100
-    solver = pj.POMCPSolver(eps=0.01, c=10.0, tree_queries=300, rng=2, node_belief_updater=pj.updater(baby), n_trees=E)
-    policy = pj.solve(solver, baby)
-    sim = pj.RolloutSimulator(rng=777, initial_state=0, eps=0.01)
-    r, steps, status = pj.simulate_episodes(sim, baby, policy, E, pj.updater(policy), pj.BoolDistribution(0.0))
-    ms = policy.phase_ms(abi.PHASE_SEARCH)[0]
-    cs = policy.counters()
-    assert (status == 0).all() and (steps == 44).all()
-    assert cs["simulations"] == E * 44 * 300
+    nb_opt, nb_fwc = -15.919206742702293 + 14.686851194997828, -15.919206742702293 + 15.061634270536405
     fwc = np.array([_baby_policy_reward(oracle, baby, "fwc", 777, e, 44) for e in range(E)])
     opt = np.array([_baby_policy_reward(oracle, baby, "opt", 777, e, 44) for e in range(E)])
-    print(f"100 Baby episodes x 44 steps x 300 queries on the device: {ms:.1f} ms; POMCP {r.mean():.2f}, FeedWhenCrying "
-          f"{fwc.mean():.2f}, optimal {opt.mean():.2f}")
-    for other, nb_gap in ((opt, -15.919206742702293 + 14.686851194997828), (fwc, -15.919206742702293 + 15.061634270536405)):
-        d = r - other
-        se = d.std(ddof=1) / np.sqrt(E)
-        assert abs(d.mean() - nb_gap) <= 3 * np.sqrt(2.0) * se + 0.05, (d.mean(), se, nb_gap)
-    assert opt.mean() > r.mean() > -25.0
-    # a second call on the same planner starts over (other environment seeds)
-    r2, steps2, status2 = policy.run_episodes(10, 5, env_seed=9, initial_state=0, initial_p1=0.0)
-    assert (status2 == 0).all() and (steps2 == 5).all() and np.isfinite(r2).all()
-    # ... and ordinary searches still work afterwards
-    policy.set_belief_exact2(0.3)
-    a, N, V = policy.search(300)
-    assert N.sum() == E * 299
-    policy.close()
+    for R in (1, 0):
+        solver = pj.POMCPSolver(eps=0.01, c=10.0, tree_queries=300, rng=2, node_belief_updater=pj.updater(baby), n_trees=E,
+                                rollouts_per_leaf=R)
+        policy = pj.solve(solver, baby)
+        sim = pj.RolloutSimulator(rng=777, initial_state=0, eps=0.01)
+        r, steps, status = pj.simulate_episodes(sim, baby, policy, E, pj.updater(policy), pj.BoolDistribution(0.0))
+        ms = policy.phase_ms(abi.PHASE_SEARCH)[0]
+        cs = policy.counters()
+        assert (status == 0).all() and (steps == 44).all()
+        assert cs["simulations"] == E * 44 * 300
+        print(f"100 Baby episodes x 44 steps x 300 queries on the device, {R or 64} rollout(s) per leaf: {ms:.1f} ms; POMCP "
+              f"{r.mean():.2f}, FeedWhenCrying {fwc.mean():.2f}, optimal {opt.mean():.2f}")
+        for other, nb_gap in ((opt, nb_opt), (fwc, nb_fwc)):
+            d = r - other
+            se = d.std(ddof=1) / np.sqrt(E)
+            assert d.mean() >= nb_gap - 3 * np.sqrt(2.0) * se - 0.05, (R, d.mean(), se, nb_gap)
+            if R == 1:
+                assert d.mean() <= nb_gap + 3 * np.sqrt(2.0) * se + 0.05, (R, d.mean(), se, nb_gap)
+        assert opt.mean() + 0.3 > r.mean() > -25.0
+        if R == 0:
+            # a second call on the same planner starts over (other environment seeds)
+            r2, steps2, status2 = policy.run_episodes(10, 5, env_seed=9, initial_state=0, initial_p1=0.0)
+            assert (status2 == 0).all() and (steps2 == 5).all() and np.isfinite(r2).all()
+            # ... and ordinary searches still work afterwards
+            policy.set_belief_exact2(0.3)
+            a, N, V = policy.search(300)
+            assert N.sum() == E * 299
+        policy.close()
 
 
 def test_unweighted_episodes_deplete_like_the_reference(gpu_lib):
