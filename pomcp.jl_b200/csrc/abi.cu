@@ -1786,6 +1786,17 @@ int32_t pomcp_run_episodes(pomcp_handle* h, const pomcp_episode_params* ep, int3
   return POMCP_OK;
 }
 
+#ifdef POMCP_PROBE
+// developer probe build only (scripts/build_variant.sh probe -DPOMCP_PROBE): per-CTA timestamps of the last one-barrier SIR launch
+int32_t pomcp_debug_pf_probe(pomcp_handle* h, unsigned long long* out, int32_t n_words) {
+  if (!h || !out) return POMCP_ERR_INVALID_ARG;
+  cudaSetDevice(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpyFromSymbol(out, g_pf_probe, sizeof(unsigned long long) * (size_t)std::min(n_words, PF_MAX_GRID * 4)));
+  return POMCP_OK;
+}
+#endif
+
 // ---- K10: root-parallel merge over NCCL
 int32_t pomcp_nccl_unique_id(void* id_out) {
   std::string err;

@@ -532,19 +532,58 @@ constexpr int PF_CTA_ITEMS = PF_THREADS * PF_ITEMS;
 constexpr int PF_MAX_GRID = 1024;                 // CTA totals that fit a control block
 constexpr int PF_CTRL_WORDS = 9 + PF_MAX_GRID + 7;  // u64 words: PfCtl (8), barrier counter (1), CTA totals
 
+// Grid barrier of a co-resident grid.  One release (fence + add) on the way in, relaxed polling - an acquire load per
+// poll from ~300 CTAs on one address took the barrier 2 - 6 us after its last arrival (scripts/pf_barrier_probe.py) -
+// and one fence on the way out.
 __device__ __forceinline__ void pf_grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
     unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar));
-    } while (v < target);
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      __nanosleep(64);
+    }
     __threadfence();
   }
   __syncthreads();
 }
+// Sum of the CTA totals before this CTA and the grand total, by the whole CTA: every thread loads one total (two
+// past 512 CTAs), so the phase costs one L2 round trip - a volatile load per loop iteration of one warp, each waited
+// for, cost the emit phase ten of them (scripts/pf_barrier_probe.py).  Ends with __syncthreads(); the results are
+// in s_off / s_total.
+__device__ __forceinline__ void pf_cta_offsets(const unsigned long long* cta_tot, unsigned long long* s_part_before,
+                                               unsigned long long* s_part_all, unsigned long long& s_off,
+                                               unsigned long long& s_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = (int)gridDim.x, i0 = (int)threadIdx.x, i1 = (int)threadIdx.x + PF_THREADS;
+  const unsigned long long t0 = i0 < g ? __ldcg(&cta_tot[i0]) : 0ull;
+  const unsigned long long t1 = i1 < g ? __ldcg(&cta_tot[i1]) : 0ull;
+  unsigned long long all = t0 + t1;
+  unsigned long long before = (i0 < (int)blockIdx.x ? t0 : 0ull) + (i1 < (int)blockIdx.x ? t1 : 0ull);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, off);
+    all += __shfl_xor_sync(0xffffffffu, all, off);
+  }
+  if (lane == 0) { s_part_before[warp] = before; s_part_all[warp] = all; }
+  __syncthreads();
+  if (warp == 0) {
+    before = lane < PF_THREADS / 32 ? s_part_before[lane] : 0ull;
+    all = lane < PF_THREADS / 32 ? s_part_all[lane] : 0ull;
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, off);
+      all += __shfl_xor_sync(0xffffffffu, all, off);
+    }
+    if (lane == 0) { s_off = before; s_total = all; }
+  }
+  __syncthreads();
+}
+static_assert(PF_MAX_GRID <= 2 * PF_THREADS, "pf_cta_offsets loads two totals per thread");
+static_assert(PF_THREADS / 32 <= 16, "second-level reduction covers 16 warps");
 
 template <class Src, class Out>
 __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constant__ Src src, long long n, PfCtl* ctl,
@@ -554,6 +593,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   using State = typename Src::State;
   __shared__ unsigned long long s_a[PF_THREADS / 32];
   __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_c[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long base = ((long long)blockIdx.x * PF_THREADS + threadIdx.x) * items;
@@ -648,21 +688,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused(const __grid_constan
   pf_grid_barrier(bar, 2u * gridDim.x);
 
   // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
-  if (warp == 0) {
-    unsigned long long before = 0, all = 0;
-    for (int k = lane; k < (int)gridDim.x; k += 32) {
-      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
-      all += t;
-      if (k < (int)blockIdx.x) before += t;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      before += __shfl_xor_sync(0xffffffffu, before, off);
-      all += __shfl_xor_sync(0xffffffffu, all, off);
-    }
-    if (lane == 0) { s_off = before; s_total = all; }
-  }
-  __syncthreads();
+  pf_cta_offsets(cta_tot, s_b, s_c, s_off, s_total);
   const unsigned long long T = s_total;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->total = T;
@@ -715,6 +741,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid
                                                             int rows) {
   __shared__ unsigned long long s_a[PF_THREADS / 32];
   __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_c[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long base = ((long long)blockIdx.x * PF_THREADS + (long long)warp * 32) * rows;
@@ -793,21 +820,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid
   pf_grid_barrier(bar, 2u * gridDim.x);
 
   // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
-  if (warp == 0) {
-    unsigned long long before = 0, all = 0;
-    for (int k = lane; k < (int)gridDim.x; k += 32) {
-      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
-      all += t;
-      if (k < (int)blockIdx.x) before += t;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      before += __shfl_xor_sync(0xffffffffu, before, off);
-      all += __shfl_xor_sync(0xffffffffu, all, off);
-    }
-    if (lane == 0) { s_off = before; s_total = all; }
-  }
-  __syncthreads();
+  pf_cta_offsets(cta_tot, s_b, s_c, s_off, s_total);
   const unsigned long long T = s_total;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->total = T;
@@ -842,6 +855,19 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_striped(const __grid
   }
 }
 
+#ifdef POMCP_PROBE  // developer probe: %globaltimer of every CTA at start / barrier arrival / barrier exit / end
+__device__ unsigned long long g_pf_probe[PF_MAX_GRID * 4];
+__device__ __forceinline__ void pf_probe(int slot) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pf_probe[blockIdx.x * 4 + slot] = t;
+  }
+}
+#else
+__device__ __forceinline__ void pf_probe(int) {}
+#endif
+
 // ---- K6+K7+K8 with ONE grid barrier: the a-priori scale (pf_scale_ceil) needs no max-weight pass, so phase A
 // goes straight from the weights to the quantised CTA totals; the only grid-wide dependency left is the total T
 // and the offsets of the CTAs, which every CTA derives from the <= 1024 CTA totals after the barrier.  When the
@@ -857,12 +883,14 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   using State = typename Src::State;
   __shared__ unsigned long long s_a[PF_THREADS / 32];
   __shared__ unsigned long long s_b[PF_THREADS / 32];
+  __shared__ unsigned long long s_c[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // the other control block, for the next launch (nobody uses it now)
   if (blockIdx.x == gridDim.x - 1)
     for (int k = threadIdx.x; k < PF_CTRL_WORDS; k += PF_THREADS) next_ctl[k] = 0ull;
   if (src.skip()) return;
+  pf_probe(0);
   if (threadIdx.x == 0) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(cta_tot + blockIdx.x));
@@ -959,24 +987,12 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
       ctl->any_alive = 1;
     }
   }
+  pf_probe(1);
   pf_grid_barrier(bar, gridDim.x);
+  pf_probe(2);
 
   // ---- offsets: sum of the CTA totals before this CTA, and the grand total T
-  if (warp == 0) {
-    unsigned long long before = 0, all = 0;
-    for (int k = lane; k < (int)gridDim.x; k += 32) {
-      unsigned long long t = ld_volatile_u64(&cta_tot[k]);
-      all += t;
-      if (k < (int)blockIdx.x) before += t;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      before += __shfl_xor_sync(0xffffffffu, before, off);
-      all += __shfl_xor_sync(0xffffffffu, all, off);
-    }
-    if (lane == 0) { s_off = before; s_total = all; }
-  }
-  __syncthreads();
+  pf_cta_offsets(cta_tot, s_b, s_c, s_off, s_total);
   const unsigned long long T = s_total;
   unsigned int over_any;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(over_any) : "l"(&ctl->over_ceil));
@@ -1037,6 +1053,8 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
       }
     }
   }
+  __syncthreads();
+  pf_probe(3);
 }
 
 // n draws from the problem's initial state distribution (the reinvigorator's stand-in for an old
