@@ -27,6 +27,14 @@ for stage in "$@"; do
                 env $( [ $variant = default ] && echo X_UNUSED=1 || echo $variant=1 ) python scripts/probe.py sir --problem lightdark --log2 1000000,20,24,26 --out $out/${tag}_sir_ld_$variant.json >> $out/${tag}_sir.log 2>&1
               done
               cat $out/${tag}_sir.log ;;
+    multi)    # needs gpurun --gpus N; N from $NGPU (default 2)
+              N=${NGPU:-2}
+              TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+              python -m pytest tests/test_gpu_multirank.py -m gpu -q > $out/${tag}_pytest_multirank.log 2>&1; tail -n 3 $out/${tag}_pytest_multirank.log
+              $TR bench.py --gpus $N --steps 10 --warmup 3 > $out/${tag}_bench_n$N.json 2> $out/${tag}_bench_n$N.err; tail -c 400 $out/${tag}_bench_n$N.err; head -c 300 $out/${tag}_bench_n$N.json; echo
+              $TR bench.py --gpus $N --config c5 --steps 3 --warmup 3 > $out/${tag}_bench_c5_n$N.json 2> $out/${tag}_bench_c5_n$N.err; tail -c 400 $out/${tag}_bench_c5_n$N.err; head -c 300 $out/${tag}_bench_c5_n$N.json; echo
+              python scripts/probe.py c4 > $out/${tag}_c4_n1.json 2>&1; cat $out/${tag}_c4_n1.json
+              $TR scripts/probe.py c4 > $out/${tag}_c4_n$N.json 2> $out/${tag}_c4_n$N.err; tail -n 1 $out/${tag}_c4_n$N.json ;;
     ncupf)    ncu --set full --clock-control none --import-source on -k regex:k_pf_ -s 1 -c 1 -f \
                 -o $out/prof_pf_$tag python scripts/probe.py step > $out/${tag}_ncu_pf.log 2>&1
               tail -n 2 $out/${tag}_ncu_pf.log ;;

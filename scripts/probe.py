@@ -13,6 +13,8 @@
         SIR update time and algorithmic GB/s per particle count and path
     python scripts/probe.py rates
         batched search rates of the concrete problems with the library defaults
+    python scripts/probe.py c4      (or: python -m torch.distributed.run --nproc-per-node 2 ... scripts/probe.py c4)
+        BASELINE configs[3] (LightDark1D, 1e6 particles) on 1 / 2 GPUs: what the second GPU buys
     python scripts/probe.py step [--queries Q] [--rollouts R] [--trees T]
         one warmed-up decision (search + SIR 2^20) on the bench workload: the ncu target
 """
@@ -269,9 +271,60 @@ def cmd_step(a):
     policy.close()
 
 
+def cmd_c4(a):
+    """BASELINE configs[3] on 1 or 2 GPUs (run under torchrun for 2): LightDark1D, 10^6 particles, SIR update +
+    plain POMCP (10^5 queries per GPU, root-parallel: the second GPU doubles the simulations behind a decision; the
+    particle set is replicated and every rank runs the same SIR update with the same seed - no exchange)."""
+    import torch
+    import pomcp_jl_b200 as pj
+    from pomcp_jl_b200 import _abi as abi
+    from pomcp_jl_b200.api import nccl_unique_id
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ld = pj.LightDark1D()
+    n, Q = 1_000_000, 100_000
+    pl = pj.solve(pj.POMCPSolver(c=1.0, rng=4, tree_queries=Q, search_mode="batched", device=local, rank=rank), ld,
+                  belief_mode=abi.BELIEF_EXTERNAL)
+    if world > 1:
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        pl.comm_init(uid[0], rank, world)
+    parts = np.zeros(n, dtype=ld.state_dtype)
+    parts["y"] = np.random.default_rng(11).normal(2.0, 3.0, n)
+    pl.set_belief_particles(parts)
+    rows = []
+    for k in range(a.repeat + 3):
+        pl.flush_l2()
+        pl.sync()
+        pl.event_record(0)
+        act, N, V = pl.search_rootparallel(Q) if world > 1 else pl.search(Q)
+        pl.pf_update_sir(2 if k % 2 == 0 else 0, 3.0 if k % 2 == 0 else 2.0, seed=100 + k, n_out=n)
+        pl.event_record(1)
+        rows.append((pl.event_elapsed_ms(0, 1), pl.phase_ms(abi.PHASE_SEARCH)[0], pl.phase_ms(abi.PHASE_PF)[0],
+                     pl.phase_ms(abi.PHASE_MERGE)[0] if world > 1 else 0.0, int(N.sum())))
+    r = np.array(rows[3:])
+    t = torch.tensor(r.mean(0), dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        m = t.cpu().numpy()
+        print(json.dumps({"config": "C4 LightDark1D, 1e6 particles SIR + plain POMCP 1e5 queries per GPU", "gpus": world,
+                          "decision_ms": m[0], "search_ms": m[1], "sir_us": m[2] * 1e3, "merge_us": m[3] * 1e3,
+                          "simulations_behind_a_decision": int(m[4]) + world,
+                          "sir_alg_GBs": n * 48 / (m[2] * 1e-3) / 1e9}), flush=True)
+    pl.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("cmd", choices=["oracle-values", "knob", "equal-time", "cycles", "sir", "rates", "step"])
+    ap.add_argument("cmd", choices=["oracle-values", "knob", "equal-time", "cycles", "sir", "rates", "step", "c4"])
     ap.add_argument("--queries", type=int, default=1_000_000)
     ap.add_argument("--seeds", type=int, default=12)
     ap.add_argument("--knob", default="inflight_max")
@@ -288,7 +341,7 @@ def main():
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     {"oracle-values": cmd_oracle_values, "knob": cmd_knob, "equal-time": cmd_equal_time, "cycles": cmd_cycles,
-     "sir": cmd_sir, "rates": cmd_rates, "step": cmd_step}[a.cmd](a)
+     "sir": cmd_sir, "rates": cmd_rates, "step": cmd_step, "c4": cmd_c4}[a.cmd](a)
 
 
 if __name__ == "__main__":
