@@ -112,6 +112,8 @@ struct pomcp_handle {
   uint32_t root = 0, epoch = 0;  // root / root_visits: tree 0's (the only tree unless n_trees > 1)
   long long root_visits = 0;
   int n_trees = 1;               // trees searched side by side in one launch (root parallelism inside the GPU)
+  int res_index = 0;             // slot of d_res that holds the decision of the search in flight: a tree's own (0),
+                                 // the merge over this device's trees (n_trees) or over the ranks (n_trees + 1)
   std::vector<uint32_t> roots;
   std::vector<long long> tree_visits;
   TreeCtl* d_trees = nullptr;
@@ -429,6 +431,7 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
   CK(cudaEventRecord(ts.next(), h->stream));
   h->epoch++;
   h->pending = true;
+  h->res_index = h->n_trees > 1 ? h->n_trees : 0;
   return POMCP_OK;
 }
 
@@ -436,7 +439,7 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
 int finish_search(pomcp_handle* h) {
   // h_res[0] = the decision (the merged result when several trees ran), h_res[1 + t] = tree t's own
   const int T = h->n_trees;
-  CK(cudaMemcpyAsync(h->h_res, h->d_res + (T > 1 ? T : 0), sizeof(SearchResult), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->h_res, h->d_res + h->res_index, sizeof(SearchResult), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_res + 1, h->d_res, sizeof(SearchResult) * (size_t)T, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(h->h_ctr, h->pool.ctr, sizeof(DevCtr), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -1005,7 +1008,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   CKC(dev_alloc(h, &h->pb.path_r, pw));
   CKU(cudaMalloc(&h->pb.path_state, pw * sb));
 
-  CKC(dev_alloc(h, &h->d_res, (size_t)T + 1));  // one per tree + the merged decision
+  CKC(dev_alloc(h, &h->d_res, (size_t)T + 2));  // one per tree + the merge over the trees + the merge over the ranks
   CKC(dev_alloc(h, &h->d_ns, 1));
   CKC(dev_alloc(h, &h->d_trees, (size_t)T));
   CKU(cudaMallocHost((void**)&h->h_trees, sizeof(TreeCtl) * (size_t)T));
@@ -1830,7 +1833,10 @@ int32_t pomcp_search_rootparallel(pomcp_handle* h, int64_t Q, int32_t* action_ou
   int rc = enqueue_search(h, Q, nullptr, 0, nullptr, 0);
   if (rc) return rc;
   // one fused all-reduce of [N_a ..., N_a*V_a ..., exists_a ...] (3|A| doubles) before the arg-max of src/solver.jl:60-70
-  SearchResult* dec = h->d_res + (h->n_trees > 1 ? h->n_trees : 0);  // this device's (merged) result
+  // the cross-rank merge gets its own slot: the trees' own results stay readable (pomcp_get_tree_result)
+  SearchResult* dec = h->d_res + h->n_trees + 1;
+  CK(cudaMemcpyAsync(dec, h->d_res + h->res_index, sizeof(SearchResult), cudaMemcpyDeviceToDevice, h->stream));
+  h->res_index = h->n_trees + 1;
   PhaseTimer& tm = h->timers[POMCP_PHASE_MERGE];
   tm.reset();
   CK(cudaEventRecord(tm.next(), h->stream));
