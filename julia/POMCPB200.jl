@@ -38,7 +38,13 @@ struct CSolverParams
     inflight_min::Int32; inflight_max::Int32; inflight_ramp_div::Int32; rollouts_per_leaf::Int32
     rank::Int32
     dpw_observation::Int32; k_observation::Float64; alpha_observation::Float64     # src/constructor.jl:40-73
-    dpw_action::Int32; _pad2::Int32; k_action::Float64; alpha_action::Float64
+    dpw_action::Int32; dpw_solver::Int32; k_action::Float64; alpha_action::Float64
+    n_trees::Int32; _pad3::Int32                                                    # ABI version 2
+end
+
+struct CEpisodeParams                                                               # pomcp_run_episodes
+    max_steps::Int32; initial_state::Int32; sim_eps::Float64; env_seed::UInt64
+    sir_particles::Int64; initial_p1::Float64
 end
 
 # ---- exceptions (src/exceptions.jl:1-26)
@@ -103,7 +109,8 @@ function solve(solver::POMCPSolver, pomdp::POMDPs.POMDP)   # src/solver.jl:30-32
                        solver.init_V, solver.init_N, solver.num_sparse_actions, 0, 0.0,
                        0, solver.search_mode == :exact ? 0 : 1, 0, 0, 0, 0, 0, 0, 0,
                        0, 10.0, 0.5,            # dpw_observation off; k/alpha defaults of src/constructor.jl:60-63
-                       0, 0, 10.0, 0.5)         # dpw_action off
+                       0, 0, 10.0, 0.5,         # dpw_action off, dpw_solver off
+                       1, 0)                    # n_trees (ABI version 2)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:pomcp_create, LIB), Int32, (Ref{CProblem}, Ref{CSolverParams}, Int32, Ref{Ptr{Cvoid}}),
                c_problem(pomdp), sp, solver.device, h)
