@@ -25,8 +25,7 @@ __all__ = [
     "initialize_belief", "initial_state_distribution", "default_action", "root_parallel_action",
     "RolloutSimulator", "simulate", "simulate_episodes", "test_solver", "create_json", "ObsNode", "ActNode", "AbstractActNode",
     "POMCPTreeVisualizer", "AbstractPOMCPSolver", "POMCPDPWSolver", "RandomActionGenerator", "PORollout",
-    "PORolloutEstimator", "create_policy", "create_belief", "init_V", "init_N", "sparse_actions", "next_action", "add_N",
-    "convert_estimator", "extract_belief", "estimate_value",
+    "PORolloutEstimator", "init_V", "init_N", "sparse_actions", "convert_estimator", "extract_belief", "estimate_value",
 ]
 
 
@@ -956,7 +955,7 @@ def _create_json(policy):
     return json.dumps(nd), 1
 
 
-# ---------------------------------------------------------------- remaining exported names (src/POMCP.jl:20-67)
+# ---------------------------------------------------------------- POMCPDPWSolver and the small exported helpers the tests call
 class POMCPDPWSolver(AbstractPOMCPSolver):
     """POMCPDPWSolver (src/POMCP.jl:154-253, src/constructor.jl:40-73, src/solver.jl:161-274): double progressive
     widening, run on the device through POMCPSolver's kernels with the widening switches of the parameter block:
@@ -1013,14 +1012,8 @@ class PORollout(RolloutEstimator):
 PORolloutEstimator = PORollout  # deprecated alias, src/rollout.jl:17
 
 
-def create_policy(solver, pomdp):
-    """create_policy(solver, pomdp) (src/solver.jl:5-14)."""
-    return solve(solver, pomdp)
 
 
-def create_belief(up):
-    """create_belief(updater::RootUpdater) = RootNode(0, nothing, {}) (src/updater.jl:42-43)."""
-    return initialize_belief(up, initial_state_distribution(up.planner.problem))
 
 
 def init_V(initializer, problem=None, h=None, action=None):
@@ -1041,15 +1034,8 @@ def sparse_actions(pomcp, pomdp, h=None, num_actions=0):
     return list(range(pomdp.n_actions))
 
 
-def next_action(gen, pomdp, b=None, h=None):
-    """next_action(gen::RandomActionGenerator, ...) = rand(rng, actions(mdp, b)) (src/actions.jl:38-40)."""
-    rng = np.random.default_rng(gen.rng) if not isinstance(gen.rng, np.random.Generator) else gen.rng
-    return int(rng.integers(0, pomdp.n_actions))
 
 
-def add_N(a, b):
-    """add_N (src/solver.jl:287-288)."""
-    return (a if isinstance(a, int) else a.N) + b.N
 
 
 def convert_estimator(ev, solver, pomdp):

@@ -36,16 +36,18 @@ def test_library_exports_every_declared_symbol(gpu_lib):
 def test_struct_layout_matches_header(tmp_path):
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pomcp_b200.h"\n'
-                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pomcp_problem), '
+                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(pomcp_problem), '
                     'sizeof(pomcp_solver_params), sizeof(pomcp_counters), sizeof(pomcp_lightdark_state), '
                     'offsetof(pomcp_problem, rs_half_eff_dist), offsetof(pomcp_solver_params, max_nodes), '
-                    'offsetof(pomcp_problem, ld_correct_r));return 0;}\n')
+                    'offsetof(pomcp_problem, ld_correct_r), offsetof(pomcp_solver_params, n_trees), '
+                    'offsetof(pomcp_solver_params, dpw_solver), sizeof(pomcp_episode_params));return 0;}\n')
     exe = tmp_path / "sz"
     gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(abi.Problem), C.sizeof(abi.SolverParams), C.sizeof(abi.Counters), C.sizeof(abi.LightDarkState),
-            abi.Problem.rs_half_eff_dist.offset, abi.SolverParams.max_nodes.offset, abi.Problem.ld_correct_r.offset]
+            abi.Problem.rs_half_eff_dist.offset, abi.SolverParams.max_nodes.offset, abi.Problem.ld_correct_r.offset,
+            abi.SolverParams.n_trees.offset, abi.SolverParams.dpw_solver.offset, C.sizeof(abi.EpisodeParams)]
     assert got == want
 
 
