@@ -183,7 +183,7 @@ __global__ void k_ep_step(const __grid_constant__ Pool P, const __grid_constant_
 // unweighted update: the new root's particle collection = the states pushed at it, gathered from the episode's
 // segment of the particle log (order is not preserved: rand(b) is uniform over the collection)
 template <class State>
-__global__ void __launch_bounds__(256) k_ep_gather(const __grid_constant__ Pool P, TreeCtl* trees, const EpisodeCtl* eps,
+__global__ void __launch_bounds__(256) k_ep_gather(const __grid_constant__ Pool P, TreeCtl* trees, EpisodeCtl* eps,
                                                    State* bel_buf, long long cap) {
   const int e = blockIdx.x;
   if (!eps[e].update_pending) return;
@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(256) k_ep_gather(const __grid_constant__ Pool 
   if (threadIdx.x == 0) {
     tc.bel = out;
     tc.n_bel = min((long long)s_count, cap);
+    if (s_count == 0) {  // an empty collection is a depleted belief (src/particle_filter.jl:85-92)
+      eps[e].status = POMCP_ERR_PARTICLE_DEPLETION;
+      eps[e].active = 0;
+    }
   }
 }
 
