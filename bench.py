@@ -364,6 +364,34 @@ def config_latencies():
     return out
 
 
+def wide_preset(cfg_name, parts, device):
+    """The throughput preset next to the headline: one-warp workers (32 rollouts per leaf), every
+    resident warp a tree walker (16 per SM in flight).  Same decision, same belief, 6 timed decisions."""
+    import pomcp_jl_b200 as pj
+    from pomcp_jl_b200 import _abi as abi
+    cfg = CONFIGS[cfg_name]
+    Q = cfg["tree_queries"]
+    pomdp = make_pomdp(cfg_name)
+    solver = pj.POMCPSolver(c=UCB_C, rng=SOLVER_SEED, tree_queries=Q, search_mode="batched", device=device, max_nodes=3 * Q,
+                            rollouts_per_leaf=32, inflight_max=4096)
+    pl = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
+    pl.set_belief_particles(parts)
+    ms, steps = [], []
+    for k in range(8):
+        pl.reset_tree()
+        pl.reset_counters()
+        pl.flush_l2()
+        pl.search(Q)
+        ms.append(pl.phase_ms(abi.PHASE_SEARCH)[0])
+        steps.append(pl.counters()["rollout_steps"])
+    pl.close()
+    m, st = statistics.mean(ms[2:]), statistics.mean(steps[2:])
+    return {"rollouts_per_leaf": 32, "inflight_max": "16 per SM", "ms_per_decision": m, "tree_sims_per_sec": Q / m * 1e3,
+            "rollout_steps_per_sec": st / m * 1e3,
+            "note": "value estimates sit further from the sequential algorithm's at equal queries (-2.1 of 10 against -1.2) "
+                    "and further above them at equal time: DESIGN.md 4.1"}
+
+
 def run_gpu(args):
     import torch
     import pomcp_jl_b200 as pj
@@ -646,6 +674,8 @@ def run_gpu(args):
         if n_gpus == 1 and not args.no_extras:
             try:
                 line["config_latencies_us"] = config_latencies()
+                if cfg["sir"]:
+                    line["presets"] = {"wide": wide_preset(args.config, np.array(parts), device)}
             except Exception as ex:  # an extra must not take the headline down with it
                 line["config_latencies_us"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)

@@ -122,25 +122,35 @@ def cmd_knob(a):
             q = a.queries // int(v)
             rows.append(report(f"n_trees={v} x Q={q}", gpu_runs(q, seeds, n_trees=int(v)), orc))
         else:
-            rows.append(report(f"{a.knob}={v} Q={a.queries}", gpu_runs(a.queries, seeds, **{a.knob: int(v)}), orc))
+            kw = {a.knob: int(v)}
+            R = int(a.rollouts.split(",")[0])
+            if R and a.knob != "rollouts_per_leaf":
+                kw["rollouts_per_leaf"] = R
+            rows.append(report(f"{a.knob}={v} Q={a.queries}" + (f" rollouts_per_leaf={R}" if R else ""),
+                               gpu_runs(a.queries, seeds, **kw), orc))
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)
 
 
 def cmd_equal_time(a):
-    """Which in-flight cap gives the best decision in the same wall time?  The query budget of every cap is what
-    fits `budget_ms` at that cap's own rate (measured on a first run); the yardstick is the 1e6-query oracle."""
+    """Which setting gives the best decision in the same wall time?  The query budget of every in-flight cap (and,
+    with --rollouts, of every rollouts-per-leaf setting) is what fits `budget_ms` at that setting's own rate
+    (measured on a first run); the yardstick is the 1e6-query oracle."""
     seeds = range(a.seeds)
     orc = oracle_values(1_000_000, seeds, a.oracle_cache)
     rows = []
-    for v in a.values.split(","):
-        infl = int(v)
-        trial = gpu_runs(200_000, [99], inflight_max=infl)[0]
-        q = int(200_000 * a.budget_ms / trial[2])
-        for _ in range(2):  # the rate grows with the tree: one refinement
-            t2 = gpu_runs(q, [98], inflight_max=infl)[0]
-            q = int(q * a.budget_ms / t2[2])
-        rows.append(report(f"inflight_max={infl} Q={q} (budget {a.budget_ms} ms)", gpu_runs(q, seeds, inflight_max=infl), orc))
+    for R in [int(x) for x in a.rollouts.split(",")]:
+        for v in a.values.split(","):
+            kw = {"inflight_max": int(v)}
+            if R:
+                kw["rollouts_per_leaf"] = R
+            trial = gpu_runs(200_000, [99], **kw)[0]
+            q = int(200_000 * a.budget_ms / trial[2])
+            for _ in range(2):  # the rate grows with the tree: refine
+                t2 = gpu_runs(q, [98], **kw)[0]
+                q = int(q * a.budget_ms / t2[2])
+            rows.append(report(f"inflight_max={v} rollouts_per_leaf={R or 64} Q={q} (budget {a.budget_ms} ms)",
+                               gpu_runs(q, seeds, **kw), orc))
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)
 
