@@ -130,3 +130,32 @@ def test_run_episodes_rejects_what_it_cannot_do(gpu_lib):
     with pytest.raises(NotImplementedError):
         policy.run_episodes(1, 10)
     policy.close()
+
+
+def test_episode_edge_cases(gpu_lib):
+    """One episode, one step, one particle, continuous observations, the largest tree count."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    policy = pj.solve(pj.POMCPSolver(tree_queries=1, n_trees=1, rng=1), baby)
+    r, steps, status = policy.run_episodes(1, 1, env_seed=1)
+    assert status[0] == 0 and steps[0] == 1 and r[0] in (0.0, -5.0, -10.0, -15.0)
+    policy.close()
+    # 128 trees (POMCP_MAX_TREES), two queries each: every episode still advances
+    policy = pj.solve(pj.POMCPSolver(tree_queries=2, n_trees=128, rng=1, node_belief_updater=pj.updater(baby)), baby)
+    r, steps, status = policy.run_episodes(128, 3, env_seed=2, initial_p1=0.5)
+    assert (status == 0).all() and (steps == 3).all()
+    policy.close()
+    # LightDark1D: continuous observations (hashed children shared by the trees), SIR beliefs of 1 and of 500 particles
+    ld = pj.LightDark1D()
+    for n_part in (1, 500):
+        policy = pj.solve(pj.POMCPSolver(c=10.0, tree_queries=500, n_trees=16, rng=3), ld, belief_mode=abi.BELIEF_EXTERNAL)
+        r, steps, status = policy.run_episodes(16, 12, env_seed=7, sir_particles=n_part)
+        # an episode ends when the agent stops (terminal), at the step limit, or when its SIR update has no weight left
+        assert set(status) <= {0, abi.ERR_PARTICLE_DEPLETION, abi.ERR_ALL_SAMPLES_TERMINAL} and (steps >= 1).all()
+        assert np.isfinite(r).all() and (np.abs(r) <= 10.0 + 1e-9).all()
+        policy.close()
+    # Tiger with the particle updater: the default RootUpdater on 8 trees
+    tiger = pj.TigerPOMDP()
+    policy = pj.solve(pj.POMCPSolver(c=100.0, tree_queries=2000, n_trees=8, rng=5), tiger)
+    r, steps, status = policy.run_episodes(8, 20, env_seed=11)
+    assert set(status) <= {0, abi.ERR_PARTICLE_DEPLETION} and (steps >= 1).all() and np.isfinite(r).all()
+    policy.close()

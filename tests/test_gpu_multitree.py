@@ -105,3 +105,25 @@ def test_c5_eight_trees_one_gpu_reduced(gpu_lib):
     print(f"C5/10: 8 trees x 1e6: {ms:.1f} ms, {T * Q / ms * 1e3:.3e} sims/s, {cs['rollout_steps'] / ms * 1e3:.3e} rollout "
           f"steps/s, {cs['nodes']} nodes")
     gp.close()
+
+
+def test_multitree_edge_cases(gpu_lib):
+    """Fewer queries than workers, the largest tree count, continuous observations."""
+    baby = pj.BabyPOMDP(-5.0, -10.0)
+    for T, Q in ((128, 1), (128, 3), (7, 50), (3, 1000)):
+        gp = pj.solve(pj.POMCPSolver(c=10.0, rng=1, tree_queries=Q, n_trees=T), baby, belief_mode=abi.BELIEF_EXTERNAL)
+        gp.set_belief_initial()
+        a, N, V = gp.search(Q)
+        assert N.sum() == T * (Q - 1), (T, Q, N)
+        for t in (0, T - 1):
+            assert gp.tree_result(t)[1] == Q
+        gp.close()
+    ld = pj.LightDark1D()
+    gp = pj.solve(pj.POMCPSolver(c=10.0, rng=2, tree_queries=20000, n_trees=4), ld, belief_mode=abi.BELIEF_EXTERNAL)
+    rng = np.random.default_rng(3)
+    parts = np.zeros(5000, dtype=ld.state_dtype)
+    parts["y"] = rng.normal(2.0, 3.0, 5000)
+    gp.set_belief_particles(parts)
+    a, N, V = gp.search(20000)
+    assert N.sum() == 4 * 19999 and np.isfinite(V).all()
+    gp.close()
