@@ -126,6 +126,8 @@ def cmd_knob(a):
             R = int(a.rollouts.split(",")[0])
             if R and a.knob != "rollouts_per_leaf":
                 kw["rollouts_per_leaf"] = R
+            if a.inflight != "1184" and a.knob != "inflight_max":  # a second fixed knob: --inflight N
+                kw["inflight_max"] = int(a.inflight)
             rows.append(report(f"{a.knob}={v} Q={a.queries}" + (f" rollouts_per_leaf={R}" if R else ""),
                                gpu_runs(a.queries, seeds, **kw), orc))
     if a.out:
