@@ -229,41 +229,49 @@ __device__ __forceinline__ double rollout_generic(const DevModel& m, typename Mo
 // which the constant cache would serialise (one address per access) and shared memory does not.
 struct RsTab {
   double rtab[4];           // reward by event: 0 none, 1 exit, 2 sampled a bad rock, 3 sampled a good rock
+  double rtab2[6];          // the same by the rollout table's event field (byte offset 0 none, 16 exit, 32 bad, 40 good)
   signed char rock_at[256]; // rock index at cell y*16+x, -1 none
-  unsigned char rock_sh[256];  // the same as a shift amount: rock index, or 32 (-> empty mask) where there is no rock
-  // Rollout transition table, row = cell (y*16+x; row 255 = off the grid / finished, absorbing), column = min(a, 5):
-  // 0..3 the moves, 4 sample, 5 any sensing action.  Entry: bits 0-12 byte offset of the next row (cell * 32),
-  // bits 16-20 byte offset into rtab of the event without a good rock (0 none, 8 exit, 16 sampled),
-  // bits 24-29 shift of the rock the action samples (32 = none: the rock mask comes out empty).
-  uint32_t mv[256 * 8];
+  // Rollout transition table: row = cell (y*16+x; row 255 = off the grid / finished, absorbing), 64 bytes per row,
+  // column = action (16 columns; actions >= 15 share column 15: from 5 on every action is a sensing action, which
+  // neither moves nor pays).  Entry, laid out so that a rollout step needs no field extraction at all:
+  //   bits 0-1   zero                 bits 6-13  next row, i.e. bits 6-13 of the next entry's byte offset
+  //   bits 2-3   zero                 bits 14-29 mask of the rock the action samples (bit 14 + i), 0 = none
+  //   bits 4-5   event: byte offset / 16 into rtab2 (0 none, 1 exit, 2 sampled)
+  //   bit 31     the row this entry belongs to is on the grid (counts live steps)
+  // The next lookup address is (entry & RS_ROW_MASK) | (4 * action): one LOP3, since 4 * action < 64 fits bits 2-5.
+  uint32_t mv[256 * 16];
 };
-constexpr uint32_t RS_DEAD_ROW = 255u * 32u;
+constexpr uint32_t RS_ROW_MASK = 0x3fc3u;      // row field + the two always-zero low bits
+constexpr uint32_t RS_DEAD_ROW = 255u * 64u;
+constexpr int RS_ROCK_SHIFT = 14;
 __device__ __forceinline__ void rs_tab_init(RsTab* t, const DevModel& m) {
   const int nmax = m.rs_n - 1;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    t->rock_at[i] = m.rock_at[i];
-    t->rock_sh[i] = m.rock_at[i] >= 0 ? (unsigned char)m.rock_at[i] : (unsigned char)32;
-  }
-  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-    const int c = i >> 3, a = i & 7, x = c & 15, y = c >> 4;
-    uint32_t next = (uint32_t)c, ev = 0, sh = 32;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t->rock_at[i] = m.rock_at[i];
+  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+    const int c = i >> 4, a = i & 15, x = c & 15, y = c >> 4;
+    uint32_t next = (uint32_t)c, ev = 0, mask = 0, alive = 1;
     if (c == 255 || x > nmax || y > nmax) {
       next = 255;  // absorbing
+      alive = 0;
     } else if (a == 0) {
       next = (uint32_t)(min(y + 1, nmax) * 16 + x);
     } else if (a == 1) {  // east: off the grid at the right edge
-      if (x + 1 > nmax) { next = 255; ev = 8; } else next = (uint32_t)(y * 16 + x + 1);
+      if (x + 1 > nmax) { next = 255; ev = 1; } else next = (uint32_t)(y * 16 + x + 1);
     } else if (a == 2) {
       next = (uint32_t)(max(y - 1, 0) * 16 + x);
     } else if (a == 3) {
       next = (uint32_t)(y * 16 + max(x - 1, 0));
     } else if (a == 4 && m.rock_at[c] >= 0) {
-      ev = 16;
-      sh = (uint32_t)m.rock_at[c];
+      ev = 2;
+      mask = 1u << m.rock_at[c];
     }
-    t->mv[i] = (next * 32u) | (ev << 16) | (sh << 24);
+    t->mv[i] = (next << 6) | (ev << 4) | (mask << RS_ROCK_SHIFT) | (alive << 31);
   }
   if (threadIdx.x < 4) t->rtab[threadIdx.x] = m.rs_rtab[threadIdx.x];
+  if (threadIdx.x < 6) {
+    const int k = threadIdx.x;
+    t->rtab2[k] = k == 2 ? m.rs_rtab[1] : k == 4 ? m.rs_rtab[2] : k == 5 ? m.rs_rtab[3] : 0.0;
+  }
   __syncthreads();
 }
 
@@ -286,34 +294,37 @@ __device__ __forceinline__ int sbfe2(uint32_t x, int pos) {  // signed 2-bit fie
 // RockSample rollouts: the same draws, transitions, rewards and fp64 operation order as
 // ModelT<ROCKSAMPLE>::step<false> (bit-identical returns, checked against the oracle through
 // pomcp_rollout_batch), arranged for the issue slots (every pipe of a scheduler takes one warp
-// instruction per two cycles, and the search kernel is bound by exactly that): a step is one
-// shared-memory lookup of (next cell, event, rock shift) by (cell, action), one rock-bit extract /
-// clear, one reward lookup and three fp64 operations.  A trajectory that left the grid sits in an
-// absorbing row whose entries add +0.0, so there is no per-step "alive" select; the step limit and
-// the discount underflow are the same for every lane and are handled by the loop bounds.
+// instruction per two cycles, and the search kernel is bound by exactly that).  A step is: 16 bits of a Philox
+// word -> 4 * action (one IMAD.HI: floor(4 u nA) with the low two bits dropped is 4 floor(u nA)), one LOP3 that
+// joins it with the row field of the previous table entry, one shared-memory load of the new entry, two LOP3 on
+// the rock bits (good? / the rock is bad afterwards), the reward address, its load, and three fp64 operations;
+// the live-step counter adds the entry's top bit.  A trajectory that left the grid sits in an absorbing row whose
+// entries add +0.0, so there is no per-step "alive" select; the step limit and the discount underflow are the same
+// for every lane and are handled by the loop bounds.
 // NT trajectories per lane (1 or 2), interleaved (rollouts_per_leaf > 32 on a single warp).  Both start
 // at step 0, so they share the discount sequence; each accumulates exactly as it would alone.
-template <bool CHECK_DISC, int NT>
-__device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
-                                                   uint32_t k0, uint32_t k1, const uint32_t (&tagword)[NT],
-                                                   const bool (&enabled)[NT], uint32_t q, uint32_t epoch, int& nsteps,
-                                                   double (&total)[NT]) {
+// WIDE: more than 16 actions (k > 11 rocks); actions from 15 on are clamped into column 15.
+template <bool CHECK_DISC, int NT, bool WIDE>
+__device__ __forceinline__ void rollout_rocksample_impl(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
+                                                        uint32_t k0, uint32_t k1, const uint32_t (&tagword)[NT],
+                                                        const bool (&enabled)[NT], uint32_t q, uint32_t epoch,
+                                                        int& nsteps, double (&total)[NT]) {
   const double gamma = m.gamma;
-  const uint32_t nA = (uint32_t)m.nA;
+  const uint32_t nA4 = 4u * (uint32_t)m.nA;
   const int nstep_max = (int)(steps < 0x7fffffffll ? steps : 0x7fffffffll);
   const unsigned char* mvb = (const unsigned char*)tb->mv;
-  const unsigned char* rtb = (const unsigned char*)tb->rtab;
-  uint32_t row[NT];    // byte offset of the cell's row in tb->mv
-  uint32_t rocks[NT];  // bit i: rock i is good
-  int step[NT];
+  const unsigned char* rtb = (const unsigned char*)tb->rtab2;
+  uint32_t ent[NT];    // the table entry of the last step: its row field is where the trajectory is now
+  uint32_t rocks[NT];  // bit 14 + i: rock i is good
+  uint32_t step[NT];
   Philox4 p[NT];
   double disc = 1.0;
   bool any = false;
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     const bool live = enabled[t] && !(s & POMCP_RS_TERMINAL) && nstep_max > 0;
-    row[t] = live ? (s & 0xffu) * 32u : RS_DEAD_ROW;
-    rocks[t] = s >> 8;
+    ent[t] = live ? (s & 0xffu) * 64u : RS_DEAD_ROW;
+    rocks[t] = ((s >> 8) & 0xffffu) << RS_ROCK_SHIFT;
     total[t] = 0.0;
     step[t] = 0;
     any = any || live;
@@ -324,15 +335,17 @@ __device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTa
     // rand(rng, actions) = floor(u * nA) with a 16-bit u: a Philox block feeds 8 steps (low half of a
     // word first).  P(a) is within nA / 2^16 (relative) of 1 / nA.
     const uint32_t wj = p[t].w[j >> 1];
-    const uint32_t a = __umulhi((j & 1) ? (wj & 0xffff0000u) : (wj << 16), nA);
-    step[t] += row[t] != RS_DEAD_ROW ? 1 : 0;
-    const uint32_t e = *(const uint32_t*)(mvb + row[t] + min(a, 5u) * 4u);
-    row[t] = e & 0x1fffu;
+    uint32_t a4 = __umulhi((j & 1) ? (wj & 0xffff0000u) : (wj << 16), nA4);  // 4 a + two junk bits
+    if (WIDE) a4 = min(a4, 63u);
+    uint32_t off;  // (ent & RS_ROW_MASK) | (a4 & ~RS_ROW_MASK) as ONE LOP3 (the compiler splits the two masks)
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(off) : "r"(ent[t]), "r"(a4), "n"(RS_ROW_MASK));
+    const uint32_t e = *(const uint32_t*)(mvb + off);
+    step[t] += e >> 31;
     // sample on a rock: +good / -bad, and the rock is bad afterwards either way
-    const uint32_t sh = e >> 24;
-    const uint32_t good = shr_clamped(rocks[t], sh) & 1u;
-    rocks[t] &= ~shl_clamped(1u, sh);
-    total[t] += disc * *(const double*)(rtb + ((e >> 16) & 0x18u) + good * 8u);  // a finished trajectory adds +0.0
+    const uint32_t good = rocks[t] & e;
+    rocks[t] &= ~e;
+    total[t] += disc * *(const double*)(rtb + (e & 0x30u) + (good ? 8u : 0u));  // a finished trajectory adds +0.0
+    ent[t] = e;
   };
   int base = 0;  // steps done by the lanes still on the grid
   for (uint32_t blk = 0; any; ++blk) {
@@ -365,12 +378,20 @@ __device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTa
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       p[t] = pn[t];
-      any = any || (!stop && row[t] != RS_DEAD_ROW);
+      any = any || (!stop && (ent[t] & 0x3fc0u) != RS_DEAD_ROW);
     }
   }
   nsteps = 0;
 #pragma unroll
-  for (int t = 0; t < NT; ++t) nsteps += step[t];
+  for (int t = 0; t < NT; ++t) nsteps += (int)step[t];
+}
+template <bool CHECK_DISC, int NT>
+__device__ __forceinline__ void rollout_rocksample(const DevModel& m, const RsTab* tb, uint32_t s, long long steps,
+                                                   uint32_t k0, uint32_t k1, const uint32_t (&tagword)[NT],
+                                                   const bool (&enabled)[NT], uint32_t q, uint32_t epoch, int& nsteps,
+                                                   double (&total)[NT]) {
+  if (m.nA > 16) rollout_rocksample_impl<CHECK_DISC, NT, true>(m, tb, s, steps, k0, k1, tagword, enabled, q, epoch, nsteps, total);
+  else rollout_rocksample_impl<CHECK_DISC, NT, false>(m, tb, s, steps, k0, k1, tagword, enabled, q, epoch, nsteps, total);
 }
 
 template <bool CHECK_DISC>

@@ -61,9 +61,12 @@ def test_sanity_checks_experiment_in_one_call(oracle, gpu_lib):
         for other, nb_gap in ((opt, nb_opt), (fwc, nb_fwc)):
             d = r - other
             se = d.std(ddof=1) / np.sqrt(E)
-            assert d.mean() >= nb_gap - 3 * np.sqrt(2.0) * se - 0.05, (R, d.mean(), se, nb_gap)
+            # the notebook's gap is itself one draw of 100 episodes: its standard error is taken from the sequential
+            # oracle's paired measurement of the same experiment (0.29, tests/test_oracle_golden.py), ours from the data
+            tol = 3 * np.sqrt(se * se + 0.29 * 0.29) + 0.05
+            assert d.mean() >= nb_gap - tol, (R, d.mean(), se, nb_gap)
             if R == 1:
-                assert d.mean() <= nb_gap + 3 * np.sqrt(2.0) * se + 0.05, (R, d.mean(), se, nb_gap)
+                assert d.mean() <= nb_gap + tol, (R, d.mean(), se, nb_gap)
         assert opt.mean() + 0.3 > r.mean() > -25.0
         if R == 0:
             # a second call on the same planner starts over (other environment seeds)
