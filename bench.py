@@ -364,16 +364,18 @@ def config_latencies():
     return out
 
 
-def wide_preset(cfg_name, parts, device):
-    """The throughput preset next to the headline: one-warp workers (32 rollouts per leaf), every
-    resident warp a tree walker (16 per SM in flight).  Same decision, same belief, 6 timed decisions."""
+def narrow_preset(cfg_name, parts, device):
+    """The round-1 setting next to the headline: 8 two-warp workers per SM in flight instead of 16
+    one-warp workers (same 64 rollouts per leaf).  Same decision, same belief, 6 timed decisions."""
     import pomcp_jl_b200 as pj
     from pomcp_jl_b200 import _abi as abi
     cfg = CONFIGS[cfg_name]
     Q = cfg["tree_queries"]
     pomdp = make_pomdp(cfg_name)
+    import torch
+    n_sm = torch.cuda.get_device_properties(device).multi_processor_count
     solver = pj.POMCPSolver(c=UCB_C, rng=SOLVER_SEED, tree_queries=Q, search_mode="batched", device=device, max_nodes=3 * Q,
-                            rollouts_per_leaf=32, inflight_max=4096)
+                            inflight_max=8 * n_sm)
     pl = pj.solve(solver, pomdp, belief_mode=abi.BELIEF_EXTERNAL)
     pl.set_belief_particles(parts)
     ms, steps = [], []
@@ -386,10 +388,10 @@ def wide_preset(cfg_name, parts, device):
         steps.append(pl.counters()["rollout_steps"])
     pl.close()
     m, st = statistics.mean(ms[2:]), statistics.mean(steps[2:])
-    return {"rollouts_per_leaf": 32, "inflight_max": "16 per SM", "ms_per_decision": m, "tree_sims_per_sec": Q / m * 1e3,
-            "rollout_steps_per_sec": st / m * 1e3,
-            "note": "value estimates sit further from the sequential algorithm's at equal queries (-2.1 of 10 against -1.2) "
-                    "and further above them at equal time: DESIGN.md 4.1"}
+    return {"rollouts_per_leaf": 64, "inflight_max": f"8 per SM ({8 * n_sm})", "ms_per_decision": m,
+            "tree_sims_per_sec": Q / m * 1e3, "rollout_steps_per_sec": st / m * 1e3,
+            "note": "value estimates sit closer to the sequential algorithm's at equal queries (-1.1 of 10 against -1.6) "
+                    "and below the default's at equal time (8.8 against 10.5 in 13 ms): DESIGN.md 4.1"}
 
 
 def run_gpu(args):
@@ -638,7 +640,7 @@ def run_gpu(args):
                 "note": "latency-bound by design: the number of simulations in flight is capped (inflight_max) to "
                         "keep the tree no more than that many simulations stale",
             },
-            "solver": {"inflight_max": policy._sp.inflight_max or f"8 per SM ({8 * n_sm})",
+            "solver": {"inflight_max": policy._sp.inflight_max or f"16 per SM ({16 * n_sm}), one-warp workers",
                        "inflight_ramp_div": policy._sp.inflight_ramp_div or 32,
                        "rollouts_per_leaf": policy._sp.rollouts_per_leaf or GPU_ROLLOUTS_PER_LEAF, "search_mode": "batched",
                        "trees_per_gpu": T},
@@ -675,7 +677,7 @@ def run_gpu(args):
             try:
                 line["config_latencies_us"] = config_latencies()
                 if cfg["sir"]:
-                    line["presets"] = {"wide": wide_preset(args.config, np.array(parts), device)}
+                    line["presets"] = {"narrow": narrow_preset(args.config, np.array(parts), device)}
             except Exception as ex:  # an extra must not take the headline down with it
                 line["config_latencies_us"] = {"error": repr(ex)}
         print(json.dumps(line), flush=True)

@@ -100,7 +100,7 @@ struct pomcp_handle {
   Pool pool{};
   size_t ht_entries = 0, ev_entries = 0;
   PathBuf pb{};
-  int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32;
+  int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32, sm_count = 148;
   bool inflight_min_auto = true;  // no explicit inflight_min: max(8, tree_queries / 1024) per search
   void* d_bel[2] = {nullptr, nullptr};
   size_t bel_cap[2] = {0, 0};
@@ -297,7 +297,12 @@ SearchCfg make_cfg(pomcp_handle* h) {
   c.k_obs = h->sp.k_observation;
   c.alpha_obs = h->sp.alpha_observation;
   c.rollouts = h->rollouts;
+  // Warps per worker: one per 32 rollouts.  33..64 rollouts also run on ONE warp, two trajectories per lane (1.3x the
+  // time of 32, tree.cuh), and that is what the library does when the caller asks for more simulations in flight
+  // than two-warp teams can keep co-resident (8 per SM at 16 warps per SM): the request can only be met by workers
+  // of one warp, 16 per SM.
   c.team_warps = h->exact ? 1 : (h->rollouts > 64 ? 4 : (h->rollouts + 31) / 32);
+  if (c.team_warps == 2 && h->inflight_max > 8 * h->sm_count) c.team_warps = 1;
   c.inflight_min = h->inflight_min;
   c.inflight_max = h->inflight_max;
   c.ramp_div = h->ramp_div;
@@ -924,8 +929,13 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   }
 
   // simulations in flight (batched mode) and rollouts per leaf
-  // default: 8 simulations in flight per SM (1184 on a 148-SM B200) - whole CTAs on every SM
-  h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096) : 8 * prop.multiProcessorCount;
+  // default: every resident warp a tree walker on RockSample (16 per SM, 2368 on a 148-SM B200: its rollouts run two
+  // trajectories per lane, so a worker of 64 rollouts per leaf is one warp), 8 two-warp teams per SM (1184) elsewhere.
+  // Measured at equal wall time the wider setting gives the better decision; inflight_max = 8 per SM
+  // restores the narrower one (value estimates closer to the sequential algorithm's at equal queries).
+  h->sm_count = prop.multiProcessorCount;
+  h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096)
+                                         : (p->problem_id == POMCP_ROCKSAMPLE ? 16 : 8) * prop.multiProcessorCount;
   h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
   h->inflight_min_auto = sp->inflight_min <= 0;
   h->inflight_min = std::max(1, std::min(h->inflight_min, h->inflight_max));

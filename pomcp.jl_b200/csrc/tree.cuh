@@ -349,11 +349,14 @@ __device__ __forceinline__ void rollout_rocksample_impl(const DevModel& m, const
   };
   int base = 0;  // steps done by the lanes still on the grid
   for (uint32_t blk = 0; any; ++blk) {
+    // The next block's Philox rounds are written INSIDE each arm: they have to sit in the same basic block as the
+    // steps to be scheduled next to them (in front of the branch they ran first, and the look-up chain started 110
+    // cycles late in every block).
     Philox4 pn[NT];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) pn[t] = philox4x32_10(blk + 1u, tagword[t], q, epoch, k0, k1);
     bool stop = false;  // uniform: step limit reached or discount underflow
     if (!CHECK_DISC && base + 8 <= nstep_max) {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) pn[t] = philox4x32_10(blk + 1u, tagword[t], q, epoch, k0, k1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -363,6 +366,8 @@ __device__ __forceinline__ void rollout_rocksample_impl(const DevModel& m, const
       base += 8;
       stop = base >= nstep_max;
     } else {
+#pragma unroll
+      for (int t = 0; t < NT; ++t) pn[t] = philox4x32_10(blk + 1u, tagword[t], q, epoch, k0, k1);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (!stop) {

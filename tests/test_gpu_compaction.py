@@ -136,7 +136,7 @@ def test_batched_compaction_keeps_the_subtree(gpu_lib, monkeypatch):
     pl.set_belief_initial()
     a, N, V = pl.search(Q)
     cs = pl.counters()
-    assert cs["nodes"] <= cs["simulations"] + 1184 + 1
+    assert cs["nodes"] <= cs["simulations"] + 2368 + 1
     node_N, act_N, act_V, child = pl.dump_tree()
     kid_N = np.where(child >= 0, node_N[np.maximum(child, 0)], 0).sum(axis=2)
     assert np.array_equal(kid_N, act_N)
