@@ -153,6 +153,7 @@ struct pomcp_handle {
   bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
   long long compactions = 0;
   bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
+  bool pf_legacy_streaming = false;  // POMCP_PF_LEGACY_STREAMING=1: the max-scaled (look-back) kernels even where the tiled ones apply
   bool pf_two_barriers = false;     // POMCP_PF_TWO_BARRIERS=1: never use the one-barrier (a-priori scale) kernel
   bool pf_nocoop = false;           // POMCP_PF_NOCOOP=1: plain launch of the one-barrier kernel (developer timing)
   long long pf_retries = 0;         // one-barrier launches that fell back to the max-scaled kernels
@@ -554,7 +555,25 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   if (rc) return rc;
   rc = ensure_scan(h, n);
   if (rc) return rc;
-  // streaming path: weigh -> total(s) -> scan + emit (picks the scale by the same rule)
+  if (ceil_ok && !h->pf_legacy_streaming) {
+    // tiled streaming path at the a-priori scale: weigh + quantise + tile sums -> tile prefix -> scan + emit per tile
+    const long long ntiles = (n + PF2_TILE - 1) / PF2_TILE;
+    unsigned long long* tile_sum = h->d_scan_status + 9;
+    k_pf_weigh_q<Src><<<(unsigned)ntiles, PF2_THREADS, 0, h->stream>>>(src, n, (unsigned long long*)h->d_cum, tile_sum,
+                                                                      h->d_pfctl);
+    rc = launch_check(h, "k_pf_weigh_q");
+    if (rc) return rc;
+    k_pf_tile_prefix<<<1, 1024, 0, h->stream>>>(tile_sum, ntiles, h->d_pfctl);
+    rc = launch_check(h, "k_pf_tile_prefix");
+    if (rc) return rc;
+    k_pf_emit_tiled<Src, Out><<<(unsigned)ntiles, PF2_THREADS, 0, h->stream>>>(src, n, (const unsigned long long*)h->d_cum,
+                                                                              tile_sum, h->d_pfctl, ru, n_out, d_out);
+    rc = launch_check(h, "k_pf_emit_tiled");
+    if (rc) return rc;
+    h->timers[POMCP_PHASE_PF].launches += 3;
+    return POMCP_OK;
+  }
+  // max-scaled streaming path: weigh -> total(s) -> scan + emit (picks the scale by the same rule)
   int blocks = (int)std::min<long long>((n + 1023) / 1024, 148 * 8);
   k_pf_weigh<Src><<<blocks, 256, 0, h->stream>>>(src, n, (double*)h->d_cum, h->d_pfctl);
   rc = launch_check(h, "k_pf_weigh");
@@ -861,6 +880,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   }
   if (h->exact2 && sp->dpw_action) { h->err = "EXACT2 with action widening is not supported"; return bail(POMCP_ERR_UNSUPPORTED); }
   h->force_streaming_pf = std::getenv("POMCP_PF_STREAMING") != nullptr;
+  h->pf_legacy_streaming = std::getenv("POMCP_PF_LEGACY_STREAMING") != nullptr;
   h->pf_two_barriers = std::getenv("POMCP_PF_TWO_BARRIERS") != nullptr;
   h->pf_nocoop = std::getenv("POMCP_PF_NOCOOP") != nullptr;
   h->compact_always = std::getenv("POMCP_COMPACT_ALWAYS") != nullptr;

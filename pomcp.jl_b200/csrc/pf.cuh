@@ -491,6 +491,196 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_const
   }
 }
 
+// ---- Tiled streaming path (round 2): the a-priori scale (pf_scale_ceil) needs no look at the data, so the weights
+// are quantised where they are computed and the scan needs no look-back:
+//   K6  k_pf_weigh_q      read s_i, propagate + weight, q_i = trunc(w_i * 2^s_ceil) -> write q_i, one sum per tile of
+//                         2048 particles (flags: alive particles, first alive particle, a weight above the ceiling)
+//       k_pf_tile_prefix  one CTA: exclusive prefix of the tile sums, T, the status word (or PF_RETRY_MAX_SCALE when
+//                         the a-priori scale does not resolve these weights: the caller then runs the max-scaled path)
+//   K7+K8 k_pf_emit_tiled read q_i (and s_i), scan inside the tile, output range [M(C_{i-1}), M(C_i)) of every
+//                         particle from the fp64 form of M (exact, integer fall-back), write the copies
+// 3S + 16 bytes per particle (max-scaled path: 3S + 24), every tile independent of every other.  Same integers as
+// every other path, so the same indices.
+template <class Src>
+__global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constant__ Src src, long long n,
+                                                            unsigned long long* __restrict__ q_out,
+                                                            unsigned long long* __restrict__ tile_sum, PfCtl* ctl) {
+  __shared__ unsigned long long s_sum[PF2_THREADS / 32];
+  __shared__ unsigned s_first[PF2_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int scale = pf_scale_ceil(Src::CEIL_EXP, n);
+  const long long base = (long long)blockIdx.x * PF2_TILE;
+  unsigned long long sum = 0;
+  unsigned first = 0xffffffffu;  // offset inside the tile of the first alive particle this thread met
+  bool over = false;
+  // striped over the CTA: every load and store instruction of a warp covers consecutive particles
+#pragma unroll
+  for (int k = 0; k < PF2_ITEMS; ++k) {
+    const long long i = base + (long long)k * PF2_THREADS + threadIdx.x;
+    if (i < n) {
+      typename Src::State sp;
+      double wk;
+      const bool alive = src.eval(i, sp, wk);
+      unsigned long long q = 0;
+      if (alive) {
+        first = min(first, (unsigned)(k * PF2_THREADS + (int)threadIdx.x));
+        over = over || pf_over_ceil(wk, Src::CEIL_EXP);
+        q = pf_quantise(wk, scale);
+      }
+      q_out[i] = q;
+      sum += q;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+  }
+  over = __any_sync(0xffffffffu, over);
+  if (lane == 0) {
+    s_sum[warp] = sum;
+    s_first[warp] = first;
+    if (over) ctl->over_ceil = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < PF2_THREADS / 32; ++k) {
+      sum += s_sum[k];
+      first = min(first, s_first[k]);
+    }
+    tile_sum[blockIdx.x] = sum;
+    if (first != 0xffffffffu) {
+      atomicMax(&ctl->first_alive_inv, ~(unsigned long long)(base + first));
+      ctl->any_alive = 1;
+    }
+  }
+}
+
+// Exclusive prefix of the tile sums in place (one CTA; a thread owns a contiguous chunk), grand total and status.
+__global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* tile_sum, long long ntiles, PfCtl* ctl) {
+  __shared__ unsigned long long s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long chunk = (ntiles + 1023) / 1024;
+  const long long lo = (long long)threadIdx.x * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
+  unsigned long long mine = 0;
+  for (long long t = lo; t < hi; ++t) mine += tile_sum[t];
+  unsigned long long x = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += t;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long v = s_warp[lane];
+    unsigned long long y = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
+      if (lane >= off) y += t;
+    }
+    s_warp[lane] = y - v;
+    if (lane == 31) {
+      const unsigned long long T = y;
+      ctl->total_ceil = T;
+      ctl->total = T;
+      int st = POMCP_OK;
+      if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+      else if (ctl->over_ceil || T < PF_MIN_TOTAL_CEIL) st = PF_RETRY_MAX_SCALE;
+      ctl->status = (unsigned)st;
+    }
+  }
+  __syncthreads();
+  unsigned long long run = s_warp[warp] + (x - mine);
+  for (long long t = lo; t < hi; ++t) {
+    const unsigned long long v = tile_sum[t];
+    tile_sum[t] = run;
+    run += v;
+  }
+}
+
+template <class Src, class Out>
+__global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_constant__ Src src, long long n,
+                                                               const unsigned long long* __restrict__ q,
+                                                               const unsigned long long* __restrict__ tile_off,
+                                                               const PfCtl* __restrict__ ctl, uint32_t ru, long long n_out,
+                                                               Out* out) {
+  __shared__ unsigned long long s_warp[PF2_THREADS / 32];
+  if (ctl->status != POMCP_OK) return;  // uniform: all terminal, or the max-scaled path takes over
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long T = ctl->total_ceil;
+  const long long base = (long long)blockIdx.x * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
+  unsigned long long qv[PF2_ITEMS];
+  if (base + PF2_ITEMS <= n) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(q + base);  // 64-byte aligned
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS / 2; ++k) {
+      const ulonglong2 a = p[k];
+      qv[2 * k] = a.x;
+      qv[2 * k + 1] = a.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k) qv[k] = (base + k < n) ? q[base + k] : 0ull;
+  }
+  // small states are requested now and used after the scan (16-byte states would cost 32 registers)
+  constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;
+  typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];
+  if (PRELOAD) {
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k)
+      if (base + k < n) st_in[PRELOAD ? k : 0] = src.load(base + k);
+  }
+  unsigned long long run = 0;
+#pragma unroll
+  for (int k = 0; k < PF2_ITEMS; ++k) {
+    run += qv[k];
+    qv[k] = run;  // inclusive inside the thread
+  }
+  unsigned long long x = run;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= off) x += t;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  unsigned long long warp_excl = 0;
+#pragma unroll
+  for (int k = 0; k < PF2_THREADS / 32; ++k) warp_excl += (k < warp) ? s_warp[k] : 0ull;
+  const unsigned long long off0 = tile_off[blockIdx.x] + warp_excl + (x - run);  // C just before this thread's particles
+  const unsigned long long first_alive = ~ctl->first_alive_inv;
+  // nothing of this thread's is copied (terminal or zero-weight particles only; the first alive particle owns output 0)
+  if (run == 0ull && first_alive - (unsigned long long)base >= (unsigned long long)PF2_ITEMS) return;
+  const PfDiv dv(T, ru, n_out);
+  const double ru_frac = (double)ru * 2.3283064365386963e-10;
+  long long lo = dv.points_below_fast(off0, ru_frac);
+  unsigned long long prev = 0;
+#pragma unroll
+  for (int k = 0; k < PF2_ITEMS; ++k) {
+    const long long i = base + k;
+    if (qv[k] != prev || (unsigned long long)i == first_alive) {  // q_i > 0 (or the particle that owns output 0)
+      const long long hi = dv.points_below_fast(off0 + qv[k], ru_frac);
+      if ((unsigned long long)i == first_alive) lo = 0;
+      const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
+      if (copies) {
+        typename Src::State sp;
+        if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
+        else src.propagate(i, sp);
+        Out* o = out + lo;
+        o[0] = (Out)sp;
+        if (copies > 1) {
+          o[1] = (Out)sp;
+          for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
+        }
+      }
+      lo = hi;
+      prev = qv[k];
+    }
+  }
+}
+
 // Upstream running-sum semantics on one thread (verification mode of pomcp_resample_systematic).
 __global__ void k_resample_seq_f64(const double* w, long long n, double r01, long long n_out, long long* idx,
                                    PfCtl* ctl) {

@@ -317,12 +317,15 @@ def test_unweighted_update_depletion(oracle, gpu_lib):
 
 
 # ----------------------------------------------------------------------------- SIR update
-@pytest.mark.parametrize("streaming", [False, True])
+@pytest.mark.parametrize("streaming", [False, True, "legacy"])
 @pytest.mark.parametrize("name,n", [("baby", 10000), ("tiger", 4096), ("rs78", 50000), ("lightdark", 100000),
                                     ("lightdark", 1000000), ("rs78", 1 << 20)])
 def test_sir_update_bit_exact(oracle, gpu_lib, name, n, streaming, monkeypatch):
+    """fused kernel / tiled streaming kernels at the a-priori scale / max-scaled look-back kernels (legacy)"""
     if streaming:
         monkeypatch.setenv("POMCP_PF_STREAMING", "1")
+    if streaming == "legacy":
+        monkeypatch.setenv("POMCP_PF_LEGACY_STREAMING", "1")
     pomdp, c = PROBS[name]
     gp, op = make_pair(oracle, pomdp, c, seed=4, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
     rng = np.random.default_rng(9)
@@ -341,14 +344,16 @@ def test_sir_update_bit_exact(oracle, gpu_lib, name, n, streaming, monkeypatch):
     gp.close()
 
 
-@pytest.mark.parametrize("path", ["fused", "two_barriers", "streaming"])
+@pytest.mark.parametrize("path", ["fused", "two_barriers", "streaming", "streaming_legacy"])
 def test_sir_scale_rule_small_weights(oracle, gpu_lib, path, monkeypatch):
     """The fixed-point scale comes from the model's weight ceiling when that resolves the weights (one grid barrier
     on the device) and from the largest weight otherwise.  An observation far in the tail (o = 40: weights around
     1e-150) cannot be resolved at the a-priori scale: every path must fall back to the max-scaled integers and
     still equal the oracle bit for bit; a plausible observation right after uses the a-priori scale again."""
-    if path == "streaming":
+    if path.startswith("streaming"):  # tiled kernels at the a-priori scale (they hand over to the max-scaled ones)
         monkeypatch.setenv("POMCP_PF_STREAMING", "1")
+    if path == "streaming_legacy":
+        monkeypatch.setenv("POMCP_PF_LEGACY_STREAMING", "1")
     if path == "two_barriers":
         monkeypatch.setenv("POMCP_PF_TWO_BARRIERS", "1")
     ld = pj.LightDark1D()
