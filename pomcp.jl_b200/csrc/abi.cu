@@ -559,15 +559,17 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     // tiled streaming path at the a-priori scale: weigh + quantise + tile sums -> tile prefix -> scan + emit per tile
     const long long ntiles = (n + PF2_TILE - 1) / PF2_TILE;
     unsigned long long* tile_sum = h->d_scan_status + 9;
-    k_pf_weigh_q<Src><<<(unsigned)ntiles, PF2_THREADS, 0, h->stream>>>(src, n, (unsigned long long*)h->d_cum, tile_sum,
-                                                                      h->d_pfctl);
+    // CTAs walk several tiles when the model has a weight-class table (built once per CTA)
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, Src::NCLASS > 0 ? (long long)h->sm_count * 8 : ntiles);
+    k_pf_weigh_q<Src><<<grid, PF2_THREADS, 0, h->stream>>>(src, n, ntiles, (unsigned long long*)h->d_cum, tile_sum,
+                                                           h->d_pfctl);
     rc = launch_check(h, "k_pf_weigh_q");
     if (rc) return rc;
     k_pf_tile_prefix<<<1, 1024, 0, h->stream>>>(tile_sum, ntiles, h->d_pfctl);
     rc = launch_check(h, "k_pf_tile_prefix");
     if (rc) return rc;
-    k_pf_emit_tiled<Src, Out><<<(unsigned)ntiles, PF2_THREADS, 0, h->stream>>>(src, n, (const unsigned long long*)h->d_cum,
-                                                                              tile_sum, h->d_pfctl, ru, n_out, d_out);
+    k_pf_emit_tiled<Src, Out><<<grid, PF2_THREADS, 0, h->stream>>>(src, n, ntiles, (const unsigned long long*)h->d_cum,
+                                                                   tile_sum, h->d_pfctl, ru, n_out, d_out);
     rc = launch_check(h, "k_pf_emit_tiled");
     if (rc) return rc;
     h->timers[POMCP_PHASE_PF].launches += 3;

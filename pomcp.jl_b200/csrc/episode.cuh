@@ -253,6 +253,11 @@ struct EpisodeSrc {
   const EpisodeCtl* ep;
   uint32_t k0, k1;
   static constexpr int CEIL_EXP = ModelSrc<PID>::CEIL_EXP;
+  static constexpr int NCLASS = ModelSrc<PID>::NCLASS;
+  static constexpr bool CLASS_IN = ModelSrc<PID>::CLASS_IN;
+  __device__ __forceinline__ bool identity() const { return src().identity(); }
+  __device__ __forceinline__ int wclass(const State& sp) const { return src().wclass(sp); }
+  __device__ __forceinline__ double class_weight(int c) const { return src().class_weight(c); }
   __device__ __forceinline__ bool skip() const { return ep->update_pending == 0; }
   __device__ __forceinline__ ModelSrc<PID> src() const {
     ModelSrc<PID> s;

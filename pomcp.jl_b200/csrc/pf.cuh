@@ -148,6 +148,40 @@ struct ModelSrc {
   uint64_t obs;
   uint32_t k0, k1;
   static constexpr int CEIL_EXP = (PID == POMCP_LIGHTDARK1D) ? 5 : 0;  // weights < 2^(CEIL_EXP + 1), see pf_scale rule
+  // Weight classes (tiled streaming path): for a fixed (a, o) the weight of a discrete problem depends on a few bits of
+  // the propagated state only - the state itself (Tiger, Baby), the cell and the sensed rock's bit (RockSample) - so the
+  // QUANTISED weights live in a small shared-memory table built per launch and a particle's q is one look-up: nothing
+  // is stored per particle between the two passes.  0 = no such table (continuous observations).
+  static constexpr int NCLASS = (PID == POMCP_TIGER || PID == POMCP_BABY) ? 2 : (PID == POMCP_ROCKSAMPLE ? 512 : 0);
+  // The class can be read off the INPUT state: RockSample's sensing actions leave the state alone and every other
+  // action's weight is the same for all states; Tiger's listening likewise, and an opened door weighs 0.5 whatever the
+  // state.  (Baby's next state is drawn: its class needs the propagated particle.)
+  static constexpr bool CLASS_IN = PID == POMCP_ROCKSAMPLE || PID == POMCP_TIGER;
+  // the action leaves every (non-terminal) state as it is: RockSample's sensing actions, Tiger's listening
+  __device__ __forceinline__ bool identity() const {
+    return (PID == POMCP_ROCKSAMPLE && a >= 5) || (PID == POMCP_TIGER && a == 0);
+  }
+  __device__ __forceinline__ int wclass(const State& sp) const {
+    if constexpr (PID == POMCP_ROCKSAMPLE) {
+      const int ri = a >= 5 ? a - 5 : 0;
+      return (int)((sp & 0xffu) | (((sp >> (8 + ri)) & 1u) << 8));
+    } else if constexpr (PID == POMCP_TIGER || PID == POMCP_BABY) {
+      return (int)(sp & 1u);
+    } else {
+      return 0;
+    }
+  }
+  __device__ __forceinline__ double class_weight(int c) const {  // obs_weight of any state of class c
+    if constexpr (PID == POMCP_ROCKSAMPLE) {
+      const int ri = a >= 5 ? a - 5 : 0;
+      const uint32_t sp = (uint32_t)(c & 0xff) | ((uint32_t)((c >> 8) & 1) << (8 + ri));
+      return M::obs_weight(m, a, sp, obs);
+    } else if constexpr (PID == POMCP_TIGER || PID == POMCP_BABY) {
+      return M::obs_weight(m, a, (uint32_t)c, obs);
+    } else {
+      return 0.0;
+    }
+  }
   __device__ __forceinline__ bool skip() const { return false; }
   // propagate + weight one particle: generate_s then pdf(observation(a, sp), o)
   __device__ __forceinline__ bool eval(long long i, State& sp, double& w) const {
@@ -187,6 +221,11 @@ struct ModelSrc {
 struct ArraySrc {  // replayed weights (parity hook): payload is the index itself
   using State = long long;
   static constexpr int CEIL_EXP = PF_NO_CEIL;  // arbitrary weights: the scale always comes from the largest one
+  static constexpr int NCLASS = 0;
+  static constexpr bool CLASS_IN = false;
+  __device__ __forceinline__ bool identity() const { return false; }
+  __device__ __forceinline__ int wclass(const State&) const { return 0; }
+  __device__ __forceinline__ double class_weight(int) const { return 0.0; }
   __device__ __forceinline__ bool skip() const { return false; }
   const double* w_in;
   __device__ __forceinline__ void propagate(long long i, State& sp) const { sp = i; }
@@ -339,6 +378,30 @@ struct PfDiv {
     if (fr > eps && fr < 1.0 - eps && x < 4.0e18) {
       const long long cnt = x < 0.0 ? 0ll : (long long)fl + 1ll;
       return cnt < n_out ? cnt : n_out;
+    }
+    return points_below(C);
+  }
+  // The same test with ONE tolerance for the whole launch: |x| <= n_out + 1, so eps = (n_out + 2) * 2^-46 covers every
+  // particle, and "x is further than eps from an integer" is floor(x - eps) == floor(x + eps) - two conversions with
+  // round-down instead of floor, a difference, a product and three comparisons.  Counts fit 32 bits (n_out < 2^32).
+  struct Fast {
+    double sub_lo, sub_hi;  // ru / 2^32 + eps, ru / 2^32 - eps
+  };
+  __device__ __forceinline__ Fast fast(uint32_t ru) const {
+    const double f = (double)ru * 2.3283064365386963e-10, eps = ((double)n_out + 2.0) * 1.4210854715202004e-14;
+    return Fast{f + eps, f - eps};
+  }
+  __device__ __forceinline__ long long points_below_fast2(unsigned long long C, const Fast& f) const {
+    const double y = (double)C * ratio;  // <= n_out < 2^32 (plus rounding)
+    const double a = y - f.sub_lo, b = y - f.sub_hi;  // x - eps, x + eps
+    if (a >= 0.0 && b < 4294967295.0) {
+      const uint32_t fa = __double2uint_rd(a), fb = __double2uint_rd(b);
+      if (fa == fb) {
+        const long long cnt = (long long)fa + 1ll;
+        return cnt < n_out ? cnt : n_out;
+      }
+    } else if (b < 0.0) {
+      return 0ll;
     }
     return points_below(C);
   }
@@ -501,182 +564,262 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_const
 //                         particle from the fp64 form of M (exact, integer fall-back), write the copies
 // 3S + 16 bytes per particle (max-scaled path: 3S + 24), every tile independent of every other.  Same integers as
 // every other path, so the same indices.
+// Quantised weights of the weight classes of `src` at `scale` (see ModelSrc::NCLASS); returns whether one of them
+// is above the ceiling.  Ends with __syncthreads().
 template <class Src>
-__global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constant__ Src src, long long n,
+__device__ __forceinline__ bool pf_fill_qtab(const Src& src, int scale, unsigned long long* qtab) {
+  bool over = false;
+  for (int c = threadIdx.x; c < Src::NCLASS; c += blockDim.x) {
+    const double w = src.class_weight(c);
+    over = over || pf_over_ceil(w, Src::CEIL_EXP);
+    qtab[c] = pf_quantise(w, scale);
+  }
+  __syncthreads();
+  return over;
+}
+
+template <class Src>
+__global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constant__ Src src, long long n, long long ntiles,
                                                             unsigned long long* __restrict__ q_out,
                                                             unsigned long long* __restrict__ tile_sum, PfCtl* ctl) {
   __shared__ unsigned long long s_sum[PF2_THREADS / 32];
   __shared__ unsigned s_first[PF2_THREADS / 32];
+  __shared__ unsigned long long qtab[Src::NCLASS > 0 ? Src::NCLASS : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int scale = pf_scale_ceil(Src::CEIL_EXP, n);
-  const long long base = (long long)blockIdx.x * PF2_TILE;
-  unsigned long long sum = 0;
-  unsigned first = 0xffffffffu;  // offset inside the tile of the first alive particle this thread met
   bool over = false;
-  // striped over the CTA: every load and store instruction of a warp covers consecutive particles
+  if constexpr (Src::NCLASS > 0) over = pf_fill_qtab(src, scale, qtab);  // once per CTA, which then walks several tiles
+  unsigned long long first_cta = ~0ull;  // thread 0: first alive particle of the tiles of this CTA
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * PF2_TILE;
+    const bool full = base + PF2_TILE <= n;  // uniform
+    unsigned long long sum = 0;
+    unsigned first = 0xffffffffu;  // offset inside the tile of the first alive particle this thread met
+    // striped over the CTA: every load and store instruction of a warp covers consecutive particles
 #pragma unroll
-  for (int k = 0; k < PF2_ITEMS; ++k) {
-    const long long i = base + (long long)k * PF2_THREADS + threadIdx.x;
-    if (i < n) {
-      typename Src::State sp;
-      double wk;
-      const bool alive = src.eval(i, sp, wk);
-      unsigned long long q = 0;
-      if (alive) {
-        first = min(first, (unsigned)(k * PF2_THREADS + (int)threadIdx.x));
-        over = over || pf_over_ceil(wk, Src::CEIL_EXP);
-        q = pf_quantise(wk, scale);
+    for (int k = 0; k < PF2_ITEMS; ++k) {
+      const long long i = base + (long long)k * PF2_THREADS + threadIdx.x;
+      if (full || i < n) {
+        typename Src::State sp;
+        unsigned long long q = 0;
+        bool alive;
+        if constexpr (Src::NCLASS > 0) {
+          const typename Src::State s0 = src.load(i);
+          alive = !Src::M::terminal(src.m, s0);
+          if constexpr (Src::CLASS_IN) {
+            q = alive ? qtab[src.wclass(s0)] : 0ull;
+          } else if (alive) {
+            src.propagate_from(i, s0, sp);
+            q = qtab[src.wclass(sp)];
+          }
+        } else {
+          double wk;
+          alive = src.eval(i, sp, wk);
+          if (alive) {
+            over = over || pf_over_ceil(wk, Src::CEIL_EXP);
+            q = pf_quantise(wk, scale);
+          }
+          q_out[i] = q;
+        }
+        if (alive) first = min(first, (unsigned)(k * PF2_THREADS + (int)threadIdx.x));
+        sum += q;
       }
-      q_out[i] = q;
-      sum += q;
     }
-  }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+    for (int off = 16; off > 0; off >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      first = min(first, __shfl_xor_sync(0xffffffffu, first, off));
+    }
+    if (lane == 0) {
+      s_sum[warp] = sum;
+      s_first[warp] = first;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < PF2_THREADS / 32; ++k) {
+        sum += s_sum[k];
+        first = min(first, s_first[k]);
+      }
+      tile_sum[tile] = sum;
+      if (first != 0xffffffffu && first_cta == ~0ull) first_cta = (unsigned long long)(base + first);  // tiles ascend
+    }
+    __syncthreads();
   }
   over = __any_sync(0xffffffffu, over);
-  if (lane == 0) {
-    s_sum[warp] = sum;
-    s_first[warp] = first;
-    if (over) ctl->over_ceil = 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int k = 1; k < PF2_THREADS / 32; ++k) {
-      sum += s_sum[k];
-      first = min(first, s_first[k]);
-    }
-    tile_sum[blockIdx.x] = sum;
-    if (first != 0xffffffffu) {
-      atomicMax(&ctl->first_alive_inv, ~(unsigned long long)(base + first));
-      ctl->any_alive = 1;
-    }
+  if (lane == 0 && over) ctl->over_ceil = 1;
+  if (threadIdx.x == 0 && first_cta != ~0ull) {
+    atomicMax(&ctl->first_alive_inv, ~first_cta);
+    ctl->any_alive = 1;
   }
 }
 
-// Exclusive prefix of the tile sums in place (one CTA; a thread owns a contiguous chunk), grand total and status.
+// Exclusive prefix of the tile sums in place, grand total and status.  One CTA of 32 warps; a warp owns 1024
+// consecutive tile sums per round and reads them 32 at a time (coalesced): first the segment totals, then - after the
+// 32 totals are scanned - the prefixes.  (A thread per contiguous chunk took 59 us for 32 K tiles: dependent loads.)
 __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* tile_sum, long long ntiles, PfCtl* ctl) {
-  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_seg[32];
+  __shared__ unsigned long long s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long chunk = (ntiles + 1023) / 1024;
-  const long long lo = (long long)threadIdx.x * chunk, hi = lo + chunk < ntiles ? lo + chunk : ntiles;
-  unsigned long long mine = 0;
-  for (long long t = lo; t < hi; ++t) mine += tile_sum[t];
-  unsigned long long x = mine;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
-    if (lane >= off) x += t;
-  }
-  if (lane == 31) s_warp[warp] = x;
+  if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  if (warp == 0) {
-    const unsigned long long v = s_warp[lane];
-    unsigned long long y = v;
+  for (long long round0 = 0; round0 < ntiles; round0 += 32 * 1024) {
+    const long long seg = round0 + (long long)warp * 1024;
+    unsigned long long v[32];
+    unsigned long long mine = 0;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, y, off);
-      if (lane >= off) y += t;
+    for (int j = 0; j < 32; ++j) {
+      const long long t = seg + j * 32 + lane;
+      v[j] = t < ntiles ? tile_sum[t] : 0ull;
+      mine += v[j];
     }
-    s_warp[lane] = y - v;
-    if (lane == 31) {
-      const unsigned long long T = y;
-      ctl->total_ceil = T;
-      ctl->total = T;
-      int st = POMCP_OK;
-      if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
-      else if (ctl->over_ceil || T < PF_MIN_TOTAL_CEIL) st = PF_RETRY_MAX_SCALE;
-      ctl->status = (unsigned)st;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+    if (lane == 0) s_seg[warp] = mine;
+    __syncthreads();
+    const unsigned long long carry_in = s_carry;
+    unsigned long long seg_excl = carry_in;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) seg_excl += (k < warp) ? s_seg[k] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = seg_excl + mine;  // warp 31: everything up to the end of this round
+    unsigned long long run = seg_excl;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      unsigned long long x = v[j];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += t;
+      }
+      const long long t = seg + j * 32 + lane;
+      if (t < ntiles) tile_sum[t] = run + x - v[j];
+      run += __shfl_sync(0xffffffffu, x, 31);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned long long run = s_warp[warp] + (x - mine);
-  for (long long t = lo; t < hi; ++t) {
-    const unsigned long long v = tile_sum[t];
-    tile_sum[t] = run;
-    run += v;
+  if (threadIdx.x == 0) {
+    const unsigned long long T = s_carry;
+    ctl->total_ceil = T;
+    ctl->total = T;
+    int st = POMCP_OK;
+    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+    else if (ctl->over_ceil || T < PF_MIN_TOTAL_CEIL) st = PF_RETRY_MAX_SCALE;
+    ctl->status = (unsigned)st;
   }
 }
 
 template <class Src, class Out>
-__global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_constant__ Src src, long long n,
+__global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_constant__ Src src, long long n, long long ntiles,
                                                                const unsigned long long* __restrict__ q,
                                                                const unsigned long long* __restrict__ tile_off,
                                                                const PfCtl* __restrict__ ctl, uint32_t ru, long long n_out,
                                                                Out* out) {
   __shared__ unsigned long long s_warp[PF2_THREADS / 32];
+  __shared__ unsigned long long qtab[Src::NCLASS > 0 ? Src::NCLASS : 1];
   if (ctl->status != POMCP_OK) return;  // uniform: all terminal, or the max-scaled path takes over
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long T = ctl->total_ceil;
-  const long long base = (long long)blockIdx.x * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
-  unsigned long long qv[PF2_ITEMS];
-  if (base + PF2_ITEMS <= n) {
-    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(q + base);  // 64-byte aligned
-#pragma unroll
-    for (int k = 0; k < PF2_ITEMS / 2; ++k) {
-      const ulonglong2 a = p[k];
-      qv[2 * k] = a.x;
-      qv[2 * k + 1] = a.y;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < PF2_ITEMS; ++k) qv[k] = (base + k < n) ? q[base + k] : 0ull;
-  }
-  // small states are requested now and used after the scan (16-byte states would cost 32 registers)
-  constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;
-  typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];
-  if (PRELOAD) {
-#pragma unroll
-    for (int k = 0; k < PF2_ITEMS; ++k)
-      if (base + k < n) st_in[PRELOAD ? k : 0] = src.load(base + k);
-  }
-  unsigned long long run = 0;
-#pragma unroll
-  for (int k = 0; k < PF2_ITEMS; ++k) {
-    run += qv[k];
-    qv[k] = run;  // inclusive inside the thread
-  }
-  unsigned long long x = run;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
-    if (lane >= off) x += t;
-  }
-  if (lane == 31) s_warp[warp] = x;
-  __syncthreads();
-  unsigned long long warp_excl = 0;
-#pragma unroll
-  for (int k = 0; k < PF2_THREADS / 32; ++k) warp_excl += (k < warp) ? s_warp[k] : 0ull;
-  const unsigned long long off0 = tile_off[blockIdx.x] + warp_excl + (x - run);  // C just before this thread's particles
+  constexpr bool CLASSES = Src::NCLASS > 0;
+  constexpr bool CLASS_IN = CLASSES && Src::CLASS_IN;
+  constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;  // (16-byte states would cost 32 registers)
+  if constexpr (CLASSES) pf_fill_qtab(src, pf_scale_ceil(Src::CEIL_EXP, n), qtab);
   const unsigned long long first_alive = ~ctl->first_alive_inv;
-  // nothing of this thread's is copied (terminal or zero-weight particles only; the first alive particle owns output 0)
-  if (run == 0ull && first_alive - (unsigned long long)base >= (unsigned long long)PF2_ITEMS) return;
   const PfDiv dv(T, ru, n_out);
-  const double ru_frac = (double)ru * 2.3283064365386963e-10;
-  long long lo = dv.points_below_fast(off0, ru_frac);
-  unsigned long long prev = 0;
+  const PfDiv::Fast fs = dv.fast(ru);
+  const bool same = src.identity();  // uniform: copies are the input states themselves
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long base = tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
+    const unsigned long long tile_base_sum = tile_off[tile];  // requested early: used after the scan
+    unsigned long long qv[PF2_ITEMS];
+    typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];  // input states (propagated in place where the class needs it)
+    if constexpr (CLASSES) {
+      static_assert(PRELOAD, "weight classes are for small discrete states");
 #pragma unroll
-  for (int k = 0; k < PF2_ITEMS; ++k) {
-    const long long i = base + k;
-    if (qv[k] != prev || (unsigned long long)i == first_alive) {  // q_i > 0 (or the particle that owns output 0)
-      const long long hi = dv.points_below_fast(off0 + qv[k], ru_frac);
-      if ((unsigned long long)i == first_alive) lo = 0;
-      const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
-      if (copies) {
-        typename Src::State sp;
-        if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
-        else src.propagate(i, sp);
-        Out* o = out + lo;
-        o[0] = (Out)sp;
-        if (copies > 1) {
-          o[1] = (Out)sp;
-          for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
+      for (int k = 0; k < PF2_ITEMS; ++k)
+        if (base + k < n) st_in[k] = src.load(base + k);
+#pragma unroll
+      for (int k = 0; k < PF2_ITEMS; ++k) {
+        qv[k] = 0ull;
+        if (base + k < n) {
+          if (!Src::M::terminal(src.m, st_in[k])) {
+            if constexpr (CLASS_IN) {
+              qv[k] = qtab[src.wclass(st_in[k])];
+            } else {
+              typename Src::State sp;
+              src.propagate_from(base + k, st_in[k], sp);
+              st_in[k] = sp;
+              qv[k] = qtab[src.wclass(sp)];
+            }
+          }
         }
       }
-      lo = hi;
-      prev = qv[k];
+    } else {
+      if (base + PF2_ITEMS <= n) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(q + base);  // 64-byte aligned
+#pragma unroll
+        for (int k = 0; k < PF2_ITEMS / 2; ++k) {
+          const ulonglong2 a = p[k];
+          qv[2 * k] = a.x;
+          qv[2 * k + 1] = a.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < PF2_ITEMS; ++k) qv[k] = (base + k < n) ? q[base + k] : 0ull;
+      }
+      if (PRELOAD) {  // small states are requested now and used after the scan
+#pragma unroll
+        for (int k = 0; k < PF2_ITEMS; ++k)
+          if (base + k < n) st_in[PRELOAD ? k : 0] = src.load(base + k);
+      }
+    }
+    unsigned long long run = 0;
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k) {
+      run += qv[k];
+      qv[k] = run;  // inclusive inside the thread
+    }
+    unsigned long long x = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    unsigned long long warp_excl = 0;
+#pragma unroll
+    for (int k = 0; k < PF2_THREADS / 32; ++k) warp_excl += (k < warp) ? s_warp[k] : 0ull;
+    __syncthreads();  // s_warp is rewritten by the next tile
+    const unsigned long long off0 = tile_base_sum + warp_excl + (x - run);  // C just before this thread's particles
+    // nothing of this thread's is copied: terminal or zero-weight particles only (the first alive particle owns output 0)
+    if (run == 0ull && first_alive - (unsigned long long)base >= (unsigned long long)PF2_ITEMS) continue;
+    long long lo = dv.points_below_fast2(off0, fs);
+    unsigned long long prev = 0;
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k) {
+      const long long i = base + k;
+      if (qv[k] != prev || (unsigned long long)i == first_alive) {  // q_i > 0 (or the particle that owns output 0)
+        const long long hi = dv.points_below_fast2(off0 + qv[k], fs);
+        if ((unsigned long long)i == first_alive) lo = 0;
+        const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
+        if (copies) {
+          typename Src::State sp;
+          if ((CLASSES && !CLASS_IN) || (PRELOAD && same)) sp = st_in[PRELOAD ? k : 0];
+          else if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
+          else src.propagate(i, sp);
+          // up to four copies straight-line (predicated stores): a loop here runs at a handful of active lanes
+          Out* o = out + lo;
+          const Out v = (Out)sp;
+          o[0] = v;
+          if (copies > 1) o[1] = v;
+          if (copies > 2) o[2] = v;
+          if (copies > 3) o[3] = v;
+          if (copies > 4)
+            for (uint32_t j = 4; j < copies; ++j) o[j] = v;
+        }
+        lo = hi;
+        prev = qv[k];
+      }
     }
   }
 }
