@@ -729,18 +729,27 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
   const bool same = src.identity();  // uniform: copies are the input states themselves
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
+    const bool full = (tile + 1) * PF2_TILE <= n;  // uniform: no bounds checks inside a full tile
     const unsigned long long tile_base_sum = tile_off[tile];  // requested early: used after the scan
     unsigned long long qv[PF2_ITEMS];
     typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];  // input states (propagated in place where the class needs it)
     if constexpr (CLASSES) {
       static_assert(PRELOAD, "weight classes are for small discrete states");
+      if (sizeof(typename Src::State) == 4 && PF2_ITEMS == 8 && full) {  // two 16-byte loads (base is a multiple of 8)
+        const uint4* p4 = reinterpret_cast<const uint4*>(src.states + base);
+        const uint4 lo4 = p4[0], hi4 = p4[1];
+        const uint32_t w8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
-      for (int k = 0; k < PF2_ITEMS; ++k)
-        if (base + k < n) st_in[k] = src.load(base + k);
+        for (int k = 0; k < PF2_ITEMS; ++k) memcpy(&st_in[k], &w8[k], 4);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PF2_ITEMS; ++k)
+          if (full || base + k < n) st_in[k] = src.load(base + k);
+      }
 #pragma unroll
       for (int k = 0; k < PF2_ITEMS; ++k) {
         qv[k] = 0ull;
-        if (base + k < n) {
+        if (full || base + k < n) {
           if (!Src::M::terminal(src.m, st_in[k])) {
             if constexpr (CLASS_IN) {
               qv[k] = qtab[src.wclass(st_in[k])];
