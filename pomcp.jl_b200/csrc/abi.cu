@@ -152,6 +152,7 @@ struct pomcp_handle {
   size_t init_cap = 0;
   bool compact_always = false;  // POMCP_COMPACT_ALWAYS=1: compact the pool at every re-root (tests)
   long long compactions = 0;
+  bool inflight_max_auto = true;    // inflight_max was left to the library: it is also capped relative to the budget
   bool force_streaming_pf = false;  // POMCP_PF_STREAMING=1: always use the three-kernel SIR path
   bool pf_legacy_streaming = false;  // POMCP_PF_LEGACY_STREAMING=1: the max-scaled (look-back) kernels even where the tiled ones apply
   bool pf_two_barriers = false;     // POMCP_PF_TWO_BARRIERS=1: never use the one-barrier (a-priori scale) kernel
@@ -331,7 +332,13 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
   cfg.eta_thr = h->d_eta_thr;
   smem += (size_t)h->eta_n * sizeof(uint32_t);
   const int T = std::max(cfg.n_trees, 1);
-  long long workers = std::min<long long>(h->inflight_max, std::max<long long>(Q, 1) * T);
+  // Cap relative to the budget (when the caller left inflight_max to the library): no more than Q / 256 simulations of
+  // a tree in flight (at least 64).  Measured on RockSample(7,8), 96 paired episodes against the sequential oracle at
+  // 1e5 queries: 400 in flight +0.01 +- 0.28, 781 -0.18, 1184 -0.47, 2368 -0.80 +- 0.28 of 16.8; at 1e6 queries the
+  // full 2368 cost nothing measurable (-0.21 +- 0.34).  DESIGN.md 4.1.
+  long long cap = h->inflight_max;
+  if (h->inflight_max_auto) cap = std::min<long long>(cap, std::max<long long>(64, Q / 256) * T);
+  long long workers = std::min<long long>(cap, std::max<long long>(Q, 1) * T);
   int blocks = (int)((workers + nteams - 1) / nteams);
   DISPATCH_PID(h->prob.problem_id, {
     // no more workers than can be co-resident: a worker that is not resident does not search
@@ -341,7 +348,7 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
       if (per_sm > 0 && sms > 0) blocks = std::min(blocks, per_sm * sms);
       // workers are dealt to the trees round-robin: the in-flight cap, the admission floor and the ramp are per tree
-      cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cfg.inflight_max, (long long)blocks * nteams) / T);
+      cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cap, (long long)blocks * nteams) / T);
       // Admission floor relative to the budget: the simulations started while the tree holds fewer than
       // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
       // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
@@ -958,6 +965,7 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->sm_count = prop.multiProcessorCount;
   h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096)
                                          : (p->problem_id == POMCP_ROCKSAMPLE ? 16 : 8) * prop.multiProcessorCount;
+  h->inflight_max_auto = sp->inflight_max <= 0;
   h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
   h->inflight_min_auto = sp->inflight_min <= 0;
   h->inflight_min = std::max(1, std::min(h->inflight_min, h->inflight_max));
