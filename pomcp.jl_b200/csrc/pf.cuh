@@ -1227,6 +1227,10 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   __shared__ unsigned long long s_b[PF_THREADS / 32];
   __shared__ unsigned long long s_c[PF_THREADS / 32];
   __shared__ unsigned long long s_off, s_total;
+  // weight classes (discrete problems, blocked layout): quantised weights by table look-up, see ModelSrc::NCLASS
+  constexpr bool CLASSES = Src::NCLASS > 0 && BLOCKED && sizeof(State) <= 8;
+  constexpr bool CLASS_IN = CLASSES && Src::CLASS_IN;
+  __shared__ unsigned long long qtab[CLASSES ? Src::NCLASS : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // the other control block, for the next launch (nobody uses it now)
   if (blockIdx.x == gridDim.x - 1)
@@ -1254,20 +1258,48 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   unsigned alive_mask = 0;
   unsigned long long first = ~0ull;
   bool over = false;
+  // small sets go without the table: building it costs a round trip to the model's tables (2 us of a 10 us update)
+  const bool cls = CLASSES && n >= 65536;  // uniform
+  if constexpr (CLASSES) {
+    if (cls) over = pf_fill_qtab(src, scale, qtab);  // (the state loads above are in flight meanwhile)
+  }
+  auto eval_direct = [&](int k, long long i) {
+    State sp;
+    double w;
+    const bool alive = KEEP ? src.eval_from(i, st[KEEP ? k : 0], sp, w) : src.eval(i, sp, w);
+    if (KEEP) st[KEEP ? k : 0] = sp;  // the propagated state is what the emit copies
+    if (alive) {
+      alive_mask |= 1u << k;
+      if ((unsigned long long)i < first) first = (unsigned long long)i;
+      over = over || pf_over_ceil(w, Src::CEIL_EXP);
+      q[k] = pf_quantise(w, scale);
+    }
+  };
 #pragma unroll
   for (int k = 0; k < PF_ITEMS; ++k) {
     q[k] = 0ull;
     const long long i = index(k);
     if (k < items && i < n) {
-      State sp;
-      double w;
-      const bool alive = KEEP ? src.eval_from(i, st[KEEP ? k : 0], sp, w) : src.eval(i, sp, w);
-      if (KEEP) st[KEEP ? k : 0] = sp;  // the propagated state is what the emit copies
-      if (alive) {
-        alive_mask |= 1u << k;
-        if ((unsigned long long)i < first) first = (unsigned long long)i;
-        over = over || pf_over_ceil(w, Src::CEIL_EXP);
-        q[k] = pf_quantise(w, scale);
+      if constexpr (CLASSES) {
+        if (cls) {
+          const State s0 = st[KEEP ? k : 0];
+          if (!Src::M::terminal(src.m, s0)) {
+            alive_mask |= 1u << k;
+            if ((unsigned long long)i < first) first = (unsigned long long)i;
+            if constexpr (CLASS_IN) {
+              q[k] = qtab[src.wclass(s0)];  // st keeps the INPUT state: the emit propagates the particles it copies
+            } else {
+              State sp;
+              src.propagate_from(i, s0, sp);
+              st[KEEP ? k : 0] = sp;
+              q[k] = qtab[src.wclass(sp)];
+            }
+          }
+        } else {
+          eval_direct(k, i);
+        }
+      } else {
+        eval_direct(k, i);
       }
     }
   }
@@ -1350,25 +1382,29 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
   const PfDiv dv(T, ru, n_out);
   if (BLOCKED) {
     const unsigned long long off0 = s_off + s_a[warp] + thread_excl;  // C just before this thread's particles
-    const double ru_frac = (double)ru * 2.3283064365386963e-10;  // ru / 2^32, exact
-    long long lo = dv.points_below_fast(off0, ru_frac);
+    const PfDiv::Fast fs = dv.fast(ru);
+    const bool same = src.identity();  // uniform: the action leaves the states as they are
+    long long lo = dv.points_below_fast2(off0, fs);
 #pragma unroll
     for (int k = 0; k < PF_ITEMS; ++k) {
       const long long i = base + k;
-      const long long hi = ((alive_mask >> k) & 1u) ? dv.points_below_fast(off0 + inc[k], ru_frac) : lo;
+      const long long hi = ((alive_mask >> k) & 1u) ? dv.points_below_fast2(off0 + inc[k], fs) : lo;
       if ((alive_mask >> k) & 1u) {
         if ((unsigned long long)i == first_alive) lo = 0;
         const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
         if (copies) {
           State sp;
-          if (KEEP) sp = st[KEEP ? k : 0];
+          if (CLASS_IN && cls && !same) src.propagate_from(i, st[KEEP ? k : 0], sp);
+          else if (KEEP) sp = st[KEEP ? k : 0];
           else src.propagate(i, sp);
           Out* o = out + lo;
-          o[0] = (Out)sp;
-          if (copies > 1) {
-            o[1] = (Out)sp;
-            for (uint32_t j = 2; j < copies; ++j) o[j] = (Out)sp;
-          }
+          const Out v = (Out)sp;
+          o[0] = v;
+          if (copies > 1) o[1] = v;
+          if (copies > 2) o[2] = v;
+          if (copies > 3) o[3] = v;
+          if (copies > 4)
+            for (uint32_t j = 4; j < copies; ++j) o[j] = v;
         }
       }
       lo = hi;
