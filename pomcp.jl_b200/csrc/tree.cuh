@@ -1039,28 +1039,24 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
 // word with ceil(eta * 2^32) - 1, which is the same event as word * 2^-32 < eta.
 __device__ __forceinline__ void rs_tree_step(const DevModel& m, const RsTab* tb, const uint32_t* eta_thr, uint32_t st,
                                              int a, uint32_t w_obs, uint32_t& sp, uint64_t& o, double& r) {
-  const int nmax = m.rs_n - 1;
-  int x = (int)(st & 15u), y = (int)((st >> 4) & 15u);
-  const uint32_t t = shr_clamped(0x3C14u, (uint32_t)a * 4u);
-  y = min(max(y + sbfe2(t, 2), 0), nmax);
-  const int nx = x + sbfe2(t, 0);
-  const bool exits = nx > nmax;
-  x = min(max(nx, 0), nmax);
-  st |= exits ? POMCP_RS_TERMINAL : 0u;
-  const int ri = tb->rock_at[y * 16 + x];
-  const bool hit = (a == 4) & (ri >= 0);
-  const uint32_t sh = 8u + ((uint32_t)ri & 15u);
-  const uint32_t good = (st >> sh) & 1u;
-  st &= ~((hit ? good : 0u) << sh);
-  r = tb->rtab[exits ? 1 : (hit ? 2 + (int)good : 0)];
+  // transition, event and sampled rock from the rollout table (one look-up instead of the move arithmetic, the
+  // clamps and the rock map): entry layout at RsTab::mv
+  const uint32_t e = tb->mv[(st & 0xffu) * 16u + (uint32_t)min(a, 15)];
+  const uint32_t mask = ((e >> RS_ROCK_SHIFT) & 0xffffu) << 8;  // the sampled rock's bit in the state (0: none)
+  const uint32_t good = (st & mask) ? 1u : 0u;
+  r = *(const double*)((const unsigned char*)tb->rtab2 + (e & 0x30u) + good * 8u);
+  uint32_t next = (st & 0xffffff00u & ~mask) | ((e >> 6) & 0xffu);
+  next |= ((e & 0x30u) == 0x10u) ? POMCP_RS_TERMINAL : 0u;  // left the grid at the east edge
+  if ((e & 0x30u) == 0x10u) next = (next & ~0xffu) | (st & 0xf0u) | (uint32_t)(m.rs_n - 1);  // x stays at the edge
   o = 2;  // none
   if (a >= 5) {
     const int rk = a - 5;
+    const int x = (int)(st & 15u), y = (int)((st >> 4) & 15u);
     const uint32_t g = (st >> (8 + rk)) & 1u;
     const uint32_t correct = w_obs <= eta_thr[(y * m.rs_n + x) * m.rs_k + rk] ? 1u : 0u;
     o = (g == correct) ? 0 : 1;
   }
-  sp = (st & ~0xffu) | (uint32_t)x | ((uint32_t)y << 4);
+  sp = next;
 }
 
 // Lane-predicated memory operations: "lane 0 publishes" without splitting the warp (a branch around one
@@ -1684,16 +1680,25 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
     const unsigned long long need =
         (long long)wt < (long long)cfg.inflight_min ? 0ull : ((unsigned long long)wt + 1ull) * (unsigned long long)cfg.ramp_div;
     bool go = true;
-    unsigned spins = 0;
     const uint32_t root = tc->root;
-    while ((unsigned long long)__ldcg(&P.node_N[root]) < need) {
+    unsigned long long t_wait0 = 0;
+    for (;;) {
+      const unsigned long long seen = (unsigned long long)__ldcg(&P.node_N[root]);
+      if (seen >= need) break;
       if (__ldcg((const unsigned long long*)&tc->next_query) >= (unsigned long long)queries) { go = false; break; }
-      if (++spins > (1u << 22)) {  // ~2 s without being admitted: give up instead of hanging the device
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_wait0 == 0) t_wait0 = now;
+      if (now - t_wait0 > 2000000000ull) {  // 2 s without being admitted: give up instead of hanging the device
         c->pool_overflow = 2;
         go = false;
         break;
       }
-      __nanosleep(2000);
+      // Sleep in proportion to the visits still missing: the tree cannot grow faster than about one simulation per
+      // 8 ns, and a polling lane takes the issue slots of a whole warp (a fixed 2 us sleep - which the hardware cuts
+      // short - made the admission loop 5 % of all warp instructions of a 1e6-query search).
+      const unsigned long long gap = need - seen;
+      __nanosleep((unsigned)(gap * 8ull < 1000ull ? 1000ull : (gap * 8ull > 100000ull ? 100000ull : gap * 8ull)));
     }
     if (go) next_q = atomicAdd(&tc->next_query, 1ull);
   }
