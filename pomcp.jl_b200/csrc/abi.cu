@@ -565,7 +565,7 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
   if (ceil_ok && !h->pf_legacy_streaming) {
     // tiled streaming path at the a-priori scale: weigh + quantise + tile sums -> tile prefix -> scan + emit per tile
     const long long ntiles = (n + PF2_TILE - 1) / PF2_TILE;
-    unsigned long long* tile_sum = h->d_scan_status + 9;
+    unsigned long long* tile_sum = h->d_scan_status + 10;  // 16-byte aligned
     // CTAs walk several tiles when the model has a weight-class table (built once per CTA)
     const unsigned grid = (unsigned)std::min<long long>(ntiles, Src::NCLASS > 0 ? (long long)h->sm_count * 8 : ntiles);
     k_pf_weigh_q<Src><<<grid, PF2_THREADS, 0, h->stream>>>(src, n, ntiles, (unsigned long long*)h->d_cum, tile_sum,

@@ -653,9 +653,10 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
   }
 }
 
-// Exclusive prefix of the tile sums in place, grand total and status.  One CTA of 32 warps; a warp owns 1024
-// consecutive tile sums per round and reads them 32 at a time (coalesced): first the segment totals, then - after the
-// 32 totals are scanned - the prefixes.  (A thread per contiguous chunk took 59 us for 32 K tiles: dependent loads.)
+// Exclusive prefix of the tile sums in place, grand total and status.  One CTA of 32 warps; per round a LANE owns 32
+// consecutive tile sums (sixteen 16-byte loads, its own running sum, sixteen 16-byte stores) and a warp 1024: one u64
+// warp scan per 1024 tiles and one CTA scan per 32 K.  (A thread per contiguous chunk of the whole array took 59 us for
+// 32 K tiles - dependent loads; a warp scan per row of 32 took 28 us - 32 scans per warp.)
 __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* tile_sum, long long ntiles, PfCtl* ctl) {
   __shared__ unsigned long long s_seg[32];
   __shared__ unsigned long long s_carry;
@@ -663,37 +664,50 @@ __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* til
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   for (long long round0 = 0; round0 < ntiles; round0 += 32 * 1024) {
-    const long long seg = round0 + (long long)warp * 1024;
+    const long long first = round0 + (long long)warp * 1024 + (long long)lane * 32;  // a multiple of 32: 256-byte aligned
     unsigned long long v[32];
+    if (first + 32 <= ntiles) {
+      const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tile_sum + first);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const ulonglong2 a = p[j];
+        v[2 * j] = a.x;
+        v[2 * j + 1] = a.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = first + j < ntiles ? tile_sum[first + j] : 0ull;
+    }
     unsigned long long mine = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const long long t = seg + j * 32 + lane;
-      v[j] = t < ntiles ? tile_sum[t] : 0ull;
-      mine += v[j];
+    for (int j = 0; j < 32; ++j) mine += v[j];
+    unsigned long long x = mine;  // inclusive over the lanes of the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
+      if (lane >= off) x += t;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
-    if (lane == 0) s_seg[warp] = mine;
+    if (lane == 31) s_seg[warp] = x;
     __syncthreads();
-    const unsigned long long carry_in = s_carry;
-    unsigned long long seg_excl = carry_in;
+    unsigned long long run = s_carry + (x - mine);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) seg_excl += (k < warp) ? s_seg[k] : 0ull;
+    for (int k = 0; k < 32; ++k) run += (k < warp) ? s_seg[k] : 0ull;
     __syncthreads();
-    if (threadIdx.x == 1023) s_carry = seg_excl + mine;  // warp 31: everything up to the end of this round
-    unsigned long long run = seg_excl;
+    if (threadIdx.x == 1023) s_carry = run + mine;  // everything up to the end of this round
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      unsigned long long x = v[j];
+      const unsigned long long t = v[j];
+      v[j] = run;
+      run += t;
+    }
+    if (first + 32 <= ntiles) {
+      ulonglong2* p = reinterpret_cast<ulonglong2*>(tile_sum + first);
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += t;
-      }
-      const long long t = seg + j * 32 + lane;
-      if (t < ntiles) tile_sum[t] = run + x - v[j];
-      run += __shfl_sync(0xffffffffu, x, 31);
+      for (int j = 0; j < 16; ++j) p[j] = make_ulonglong2(v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (first + j < ntiles) tile_sum[first + j] = v[j];
     }
     __syncthreads();
   }
