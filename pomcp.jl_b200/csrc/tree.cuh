@@ -13,6 +13,7 @@
 //   ht[] / node_pslot[] / node_obs[]   continuous observations: open-addressed (slot,obs)->id
 //   log_node[] / log_state[]           append-only particle log = push!(hao.B, sp) (src/solver.jl:146-148)
 #pragma once
+#include <type_traits>
 #include <cstdint>
 #include "models.cuh"
 
@@ -1225,7 +1226,9 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   // will pick): it depends on the state and on this level's draws only, not on the node's
   // statistics, so it runs while those are in flight and is off the critical path.
   State sp_l;
-  uint64_t o_l;
+  // observation label: 32 bits are enough unless observations are continuous (LightDark: the bits of a double)
+  using ObsT = typename std::conditional<M::HASHED, uint64_t, uint32_t>::type;
+  ObsT o_l;
   double r_l;
   // One Philox block feeds several levels (batched mode keeps its own stream map: block = level / LV):
   // RockSample needs one word per level (the sensor draw), the other models two.
@@ -1268,8 +1271,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
       a_new = (int)__umulhi(philox4x32_10((uint32_t)d | 0x80000000u, TAG_TREE | tag_rank, q, tv.epoch, tv.key0, tv.key1).w[0],
                             (uint32_t)nA);
     const int a_l = lane < nA ? lane : nA - 1;
-    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, w0, sp_l, o_l, r_l);
-    else M::template step<true, double>(m, s, a_l, u01(w0), M::T_DRAW ? u01(w1) : u01(w0), u01(w1), sp_l, o_l, r_l);
+    uint64_t o64;
+    if constexpr (PID == POMCP_ROCKSAMPLE) rs_tree_step(m, tb, eta_thr, s, a_l, w0, sp_l, o64, r_l);
+    else M::template step<true, double>(m, s, a_l, u01(w0), M::T_DRAW ? u01(w1) : u01(w0), u01(w1), sp_l, o64, r_l);
+    o_l = (ObsT)o64;
   };
   spec_step(0);
   for (;;) {
@@ -1337,11 +1342,11 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     if (!M::HASHED) {
       mine = st.kid[0];
 #pragma unroll
-      for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o_l == (uint64_t)k) ? st.kid[k] : mine;
+      for (int k = 1; k < ActStats<PID>::K; ++k) mine = (o_l == (ObsT)k) ? st.kid[k] : mine;
     }
     uint32_t raw = __shfl_sync(0xffffffffu, mine, best_a);
     State sp = shfl_state(sp_l, best_a);
-    const uint64_t o = __shfl_sync(0xffffffffu, o_l, best_a);
+    const uint64_t o = (uint64_t)__shfl_sync(0xffffffffu, o_l, best_a);
     const double r = __shfl_sync(0xffffffffu, r_l, best_a);
     // observation progressive widening (src/solver.jl:223-262): re-use an earlier generated (child, state)
     bool reuse = false;
