@@ -168,7 +168,7 @@ typedef struct pomcp_counters {
   int64_t nodes;          /* belief nodes allocated in the pool */
   int64_t log_entries;    /* (node,state) particle-log entries */
   int64_t max_depth_seen;
-  int64_t waves;          /* batched-mode waves launched by the last search */
+  int64_t waves;          /* batched mode: simulations in flight allowed per tree in the last search (the admission cap in effect); 0 in exact mode */
   int64_t kernel_launches;/* kernels launched by this handle since creation */
 } pomcp_counters;
 

@@ -354,6 +354,7 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
       // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
       if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), cfg.inflight_max);
       cfg.inflight_min = std::min(cfg.inflight_min, cfg.inflight_max);
+      h->last_waves = cfg.inflight_max;  // reported as pomcp_counters::waves: the admission cap in effect, per tree
       kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
     };
     if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
@@ -428,7 +429,6 @@ int enqueue_search(pomcp_handle* h, long long Q, const double* d_uni, long long 
     CK(cudaEventRecord(tr.next(), h->stream));
     tr.launches++;
     ts.launches++;
-    h->last_waves = 1;
   }
   h->root_visits += Q;
   k_root_result<<<h->n_trees, 32, 0, h->stream>>>(h->pool, h->nA, h->d_trees, h->exact ? 1 : 0, h->sp.init_V, h->d_res);

@@ -371,6 +371,38 @@ def test_sir_scale_rule_small_weights(oracle, gpu_lib, path, monkeypatch):
     gp.close()
 
 
+@pytest.mark.parametrize("name,n,n_out", [("rs78", 2 * 2048 + 1, 5000), ("rs78", (1 << 21) + 17, (1 << 21) + 17),
+                                          ("lightdark", 1_300_001, 1_000_000), ("baby", 1_250_000, 1_250_000),
+                                          ("tiger", 6 * 2048 - 1, 2048)])
+def test_sir_tiled_path_edges_bit_exact(oracle, gpu_lib, name, n, n_out, monkeypatch):
+    """The tiled kernels (weigh + tile sums, tile prefix, emit) at their edges: ragged last tiles, sets beyond one
+    co-resident grid on the default path, a block of terminal particles in FRONT (the first alive particle owns
+    output 0 and sits in a later tile), every action class of the problem (RockSample: move / sample / sense, i.e. the
+    weight-class table with and without a state change), n_out != n.  Bit-identical to the oracle's sequential walk."""
+    if n < 1_200_000:
+        monkeypatch.setenv("POMCP_PF_STREAMING", "1")  # small sets would take the fused kernel
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=4, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
+    rng = np.random.default_rng(31)
+    states = random_states(pomdp, n, rng)
+    lead = min(n // 3, 3000)
+    if name == "rs78":
+        states[:lead] |= np.uint32(abi.RS_TERMINAL)
+    elif name == "lightdark":
+        states["status"][:lead] = -1
+    script = {"baby": [(0, 1), (1, 0)], "tiger": [(0, 1), (1, 0)], "rs78": [(5, 1), (1, 2), (4, 2), (9, 0)],
+              "lightdark": [(2, 3.0), (0, 2.9)]}[name]
+    for k, (a, o) in enumerate(script):
+        gp.set_belief_particles(states)
+        op.set_belief_particles(states)
+        gp.pf_update_sir(a, o, seed=2000 + k, n_out=n_out)
+        assert op.pf_update_sir(a, o, seed=2000 + k, n_out=n_out, mode=0) == 0
+        pg, po = gp.belief_particles(), op.belief_particles()
+        assert len(pg) == n_out == len(po)
+        assert pg.tobytes() == po.tobytes(), (name, k, a, o)
+    gp.close()
+
+
 def test_sir_baby_posterior_matches_golden_chain(oracle, gpu_lib):
     """D2: exact Baby belief chain 0 -> 0.0240964 -> 0.0298684 (notebooks/Display_Tree.ipynb:385):
     the 10^4-particle... here 2^20-particle SIR posterior mean must approach it within MC error."""
