@@ -1,3 +1,6 @@
+// Microbenchmark: latency of the dependent chain of a rollout step (LOP3 -> shared-memory load -> LOP3 ...), with the
+// bank conflicts of the transition table's layout (mode 1) and without (mode 0 / 2).  DESIGN.md 4.1: 37 cycles per step.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o lds lds.cu && ./lds
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>

@@ -1,3 +1,6 @@
+// Microbenchmark of the RockSample rollout loop as the search kernel compiles it: cycles per step
+// of one warp alone on an SM, and with 4 / 8 / 16 warps per SM, one (NT 1) or two (NT 2) trajectories per lane.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -o roll roll.cu && ./roll
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
@@ -6,8 +9,7 @@
 using namespace pomcp;
 __global__ void k(const __grid_constant__ DevModel m, int steps, int reps, int nt, double* out, long long* cyc, int* ns) {
   __shared__ RsTab tb;
-  extern __shared__ uint2 dbuf[];
-  for (int i = threadIdx.x; i < 16 * 13 * 32; i += blockDim.x) dbuf[i] = make_uint2(0x20100804u * (i % 3), 0x0c1c2c3cu);
+
   rs_tab_init(&tb, m);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0; int nst = 0;
@@ -15,11 +17,7 @@ __global__ void k(const __grid_constant__ DevModel m, int steps, int reps, int n
   for (int r = 0; r < reps; ++r) {
     int n = 0;
     uint32_t s = m.rs_start | (0xA5u << 8);
-    if (nt == 3) {
-      rs_rollout_draws(m, 1u, 2u, TAG_ROLLOUT | ((uint32_t)(lane + 32 * warp) << 16), (uint32_t)(r + 1000 * blockIdx.x), 0u, 12, dbuf + warp * 13 * 32 + lane);
-    } else if (nt == 4) {
-      acc += rollout_rocksample_drawn(m, &tb, s, steps, dbuf + warp * 13 * 32 + lane, n);
-    } else if (nt == 1) {
+    if (nt == 1) {
       acc += rollout_random<POMCP_ROCKSAMPLE, false>(m, &tb, s, steps, 1u, 2u, TAG_ROLLOUT | ((uint32_t)(lane + 32 * warp) << 16), (uint32_t)(r + 1000 * blockIdx.x), 0u, n);
     } else {
       const uint32_t tw[2] = {TAG_ROLLOUT | ((uint32_t)(lane + 64 * warp) << 16), TAG_ROLLOUT | ((uint32_t)(lane + 32 + 64 * warp) << 16)};
@@ -36,7 +34,6 @@ __global__ void k(const __grid_constant__ DevModel m, int steps, int reps, int n
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 int main() {
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 13 * 32 * 8);
   DevModel m; memset(&m, 0, sizeof m);
   m.pid = POMCP_ROCKSAMPLE; m.nA = 13; m.nO = 3; m.state_bytes = 4; m.gamma = 0.95;
   m.rs_n = 7; m.rs_k = 8; m.rs_start = 0 | (3 << 4);
@@ -46,9 +43,9 @@ int main() {
   for (int i = 0; i < 8; ++i) m.rock_at[ry[i] * 16 + rx[i]] = (signed char)i;
   double* out; long long* cyc; int* ns;
   cudaMalloc(&out, 1 << 22); cudaMalloc(&cyc, 8192); cudaMalloc(&ns, 1 << 22);
-  for (int nt : {1, 3, 4}) for (int warps : {1, 4, 8, 16}) {
+  for (int nt : {1, 2}) for (int warps : {1, 4, 8, 16}) {
     const int reps = 200, steps = 85;
-    for (int it = 0; it < 2; ++it) k<<<1, 32 * warps, 16 * 13 * 32 * 8>>>(m, steps, reps, nt, out, cyc, ns);
+    for (int it = 0; it < 2; ++it) k<<<1, 32 * warps>>>(m, steps, reps, nt, out, cyc, ns);
     cudaDeviceSynchronize();
     long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     static int h[512]; cudaMemcpy(h, ns, 4 * 32 * warps, cudaMemcpyDeviceToHost);
