@@ -736,6 +736,11 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
   constexpr bool CLASSES = Src::NCLASS > 0;
   constexpr bool CLASS_IN = CLASSES && Src::CLASS_IN;
   constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;  // (16-byte states would cost 32 registers)
+  // Wider states are staged through shared memory: the tile's states are requested by coalesced loads when the tile
+  // starts (a load per copied particle inside the emit loop made every thread wait for eight round trips in a row);
+  // one entry of padding per eight keeps a warp's reads (lane stride 8 particles) off each other's banks.
+  constexpr bool STAGE = !PRELOAD;
+  __shared__ typename Src::State s_st[STAGE ? PF2_TILE + PF2_TILE / 8 : 1];
   if constexpr (CLASSES) pf_fill_qtab(src, pf_scale_ceil(Src::CEIL_EXP, n), qtab);
   const unsigned long long first_alive = ~ctl->first_alive_inv;
   const PfDiv dv(T, ru, n_out);
@@ -793,6 +798,13 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
 #pragma unroll
         for (int k = 0; k < PF2_ITEMS; ++k)
           if (base + k < n) st_in[PRELOAD ? k : 0] = src.load(base + k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < PF2_ITEMS; ++k) {
+          const int idx = k * PF2_THREADS + (int)threadIdx.x;
+          const long long i = tile * PF2_TILE + idx;
+          if (full || i < n) s_st[STAGE ? idx + idx / 8 : 0] = src.load(i);
+        }
       }
     }
     unsigned long long run = 0;
@@ -829,7 +841,7 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
           typename Src::State sp;
           if ((CLASSES && !CLASS_IN) || (PRELOAD && same)) sp = st_in[PRELOAD ? k : 0];
           else if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
-          else src.propagate(i, sp);
+          else src.propagate_from(i, s_st[STAGE ? (int)threadIdx.x * (PF2_ITEMS + 1) + k : 0], sp);
           // up to four copies straight-line (predicated stores): a loop here runs at a handful of active lanes
           Out* o = out + lo;
           const Out v = (Out)sp;
