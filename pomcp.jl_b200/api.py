@@ -983,11 +983,8 @@ class POMCPDPWSolver(AbstractPOMCPSolver):
             if self.next_action is not None and not isinstance(self.next_action, RandomActionGenerator):
                 raise NotImplementedError("next_action: only RandomActionGenerator runs on device (src/actions.jl:38-41)")
             kw["dpw_action"] = (self.k_action, self.alpha_action)
-        if pomdp.continuous_obs:
+        if pomdp.continuous_obs or pomdp.n_observations > self.k_observation:
             kw["dpw_observation"] = (self.k_observation, self.alpha_observation)
-        elif pomdp.n_observations > self.k_observation:
-            raise NotImplementedError("observation widening on a discrete observation space larger than "
-                                      "k_observation has no device path yet")
         # a discrete observation space of at most k_observation elements never widens (src/solver.jl:223)
         return POMCPSolver(**kw)
 

@@ -844,9 +844,8 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   if (sp->dpw_action && (!(sp->k_action >= 0.0) || !(sp->alpha_action >= 0.0)))
     return fail(nullptr, POMCP_ERR_INVALID_ARG, "k_action / alpha_action < 0");
   if (sp->dpw_observation) {
-    if (nO != 0 || sp->belief_mode != POMCP_BELIEF_EXTERNAL)
-      return fail(nullptr, POMCP_ERR_UNSUPPORTED,
-                  "observation widening runs on continuous-observation problems with an external belief updater");
+    if (sp->belief_mode != POMCP_BELIEF_EXTERNAL)
+      return fail(nullptr, POMCP_ERR_UNSUPPORTED, "observation widening runs with an external belief updater");
     if (!(sp->k_observation >= 0.0) || !(sp->alpha_observation >= 0.0))
       return fail(nullptr, POMCP_ERR_INVALID_ARG, "k_observation / alpha_observation < 0");
   }
@@ -1013,20 +1012,20 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
     CKC(dev_alloc(h, &P.ht, e));
     CKC(dev_alloc(h, &P.node_obs, (size_t)want));
     CKU(cudaMemset(P.ht, 0, e * sizeof(uint32_t)));
-    if (sp->dpw_observation) {
-      // one event per generated tree step: room for 8 per node (POOL_EXHAUSTED beyond)
-      size_t ev = 1;
-      while (ev < (size_t)want * 16) ev <<= 1;
-      h->ev_entries = ev;
-      P.ev_mask = ev - 1;
-      CKC(dev_alloc(h, &P.act_nc, (size_t)want * nA));
-      CKC(dev_alloc(h, &P.act_ng, (size_t)want * nA));
-      CKC(dev_alloc(h, &P.ev_key, ev));
-      CKC(dev_alloc(h, &P.ev_node, ev));
-      CKU(cudaMalloc(&P.ev_state, ev * (size_t)sb));
-    }
   } else {
     CKC(dev_alloc(h, &P.child, (size_t)want * nA * nO));
+  }
+  if (sp->dpw_observation) {  // continuous or discrete observations alike (src/solver.jl:223-262)
+    // one event per generated tree step: room for 8 per node (POOL_EXHAUSTED beyond)
+    size_t ev = 1;
+    while (ev < (size_t)want * 16) ev <<= 1;
+    h->ev_entries = ev;
+    P.ev_mask = ev - 1;
+    CKC(dev_alloc(h, &P.act_nc, (size_t)want * nA));
+    CKC(dev_alloc(h, &P.act_ng, (size_t)want * nA));
+    CKC(dev_alloc(h, &P.ev_key, ev));
+    CKC(dev_alloc(h, &P.ev_node, ev));
+    CKU(cudaMalloc(&P.ev_state, ev * (size_t)sb));
   }
   long long log_want = 0;
   if (h->unweighted) {

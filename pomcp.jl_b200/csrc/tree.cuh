@@ -882,7 +882,7 @@ __device__ __forceinline__ bool simulate_one(const Pool& P, const DevModel& m, c
       pre = __shfl_sync(0xffffffffu, mine, best_a);
     }
     uint32_t hao = 0, ticket = 0;
-    if (M::HASHED && cfg.dpw) {
+    if (cfg.dpw) {
       // POMCPDPWSolver, enable_action_pw = false (exact mode only reaches here sequentially)
       int reuse = 0;
       if (lane == 0) {
@@ -1119,7 +1119,7 @@ struct ActStats {
       n = __ldcg(&P.act_N[sl]);
       w = __ldcg(&P.act_V[sl]);
       mm = __ldcg(&P.act_M[sl]);
-      if (ModelT<PID>::HASHED && dpw) {
+      if (dpw) {
         nc = __ldcg(&P.act_nc[sl]);
         ng = __ldcg(&P.act_ng[sl]);
       }
@@ -1235,7 +1235,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   constexpr int TW = (PID == POMCP_ROCKSAMPLE) ? 1 : 2, LV = 4 / TW;
   Philox4 ptb;
   int a_new = 0;  // action widening: the action this level would add
-  const bool dpw = M::HASHED && cfg.dpw;  // observation widening: one block per level (word 2 draws the event)
+  const bool dpw = cfg.dpw != 0;  // observation widening: one block per level (word 2 draws the event)
   // The tree draws of a whole simulation in one lane-parallel Philox call: lane j holds block j (levels
   // j * LV .. j * LV + LV - 1); a level fetches its words with a shuffle.  Same counters, same words as
   // computing block d / LV at level d (which levels past the 32nd block still do).

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--queries", type=int, required=True)
     ap.add_argument("--episodes", type=int, default=24)
     ap.add_argument("--procs", type=int, default=1)
+    ap.add_argument("--first", type=int, default=0, help="index of the first episode (seeds 300 + e, 4242 + e)")
     ap.add_argument("--inflight-max", type=int, default=0)
     ap.add_argument("--rollouts-per-leaf", type=int, default=0)
     ap.add_argument("--out", default="")
@@ -56,7 +57,7 @@ def main():
         extra["inflight_max"] = a.inflight_max
     if a.rollouts_per_leaf:
         extra["rollouts_per_leaf"] = a.rollouts_per_leaf
-    jobs = [(a.arm, a.queries, ep, extra) for ep in range(a.episodes)]
+    jobs = [(a.arm, a.queries, ep, extra) for ep in range(a.first, a.first + a.episodes)]
     t0 = time.time()
     if a.procs > 1 and a.arm == "oracle":
         with mp.get_context("spawn").Pool(a.procs) as pool:
@@ -64,7 +65,7 @@ def main():
     else:
         res = [one_episode(j) for j in jobs]
     r = np.array([x[1] for x in sorted(res)])
-    out = {"arm": a.arm, "queries": a.queries, "episodes": len(r), "steps": STEPS, "particles": NPART, "extra": extra,
+    out = {"arm": a.arm, "queries": a.queries, "episodes": len(r), "first_episode": a.first, "steps": STEPS, "particles": NPART, "extra": extra,
            "rewards": r.tolist(), "mean": float(r.mean()), "se": float(r.std(ddof=1) / np.sqrt(len(r))),
            "wall_s": time.time() - t0, "episode_s": [x[2] for x in sorted(res)]}
     print(json.dumps({k: v for k, v in out.items() if k not in ("rewards", "episode_s")}), flush=True)

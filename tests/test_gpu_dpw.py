@@ -38,6 +38,65 @@ def test_dpw_exact_bit_exact(oracle, gpu_lib, k, alpha, R):
         gp.close()
 
 
+@pytest.mark.parametrize("name,k,alpha", [("rs44", 1.0, 0.1), ("rs44", 0.5, 0.3), ("rs78", 2.0, 0.0), ("tiger", 1.0, 0.05),
+                                          ("baby", 0.5, 0.2), ("tiger", 0.0, 0.5)])
+def test_dpw_discrete_observations_exact_bit_exact(oracle, gpu_lib, name, k, alpha):
+    """Observation widening on a DISCRETE observation space larger than k_observation (src/solver.jl:223-262): while an
+    action node has more children than k * N^alpha no new observation is generated and the step re-uses one of the
+    earlier (child, state) pairs.  Same code path as for continuous observations (event table), children in the direct
+    table.  Exact mode equals the oracle bit for bit; with k * N^alpha below the size of the observation space the
+    widened tree differs from the plain one."""
+    from helpers import problems, random_states
+    pomdp, c = problems()[name]
+    rng = np.random.default_rng(8)
+    parts = random_states(pomdp, 2000, rng)
+    if name.startswith("rs"):
+        parts &= np.uint32(~np.uint32(abi.RS_TERMINAL))
+    for seed in (1, 2):
+        gp, op = make_pair(oracle, pomdp, c, seed=seed, mode="exact", belief_mode=abi.BELIEF_EXTERNAL, tree_queries=3000,
+                           dpw_observation=(k, alpha))
+        gp.set_belief_particles(parts)
+        op.set_belief_particles(parts)
+        for Q in (3000, 700):  # second search continues on the same tree
+            a_g, N_g, V_g = gp.search(Q)
+            rc, a_o, N_o, V_o = op.search(Q)
+            assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o), (N_g, N_o)
+            assert np.array_equal(_bits(V_g), _bits(V_o)), (V_g, V_o)
+            cg, co = gp.counters(), op.counters()
+            for key in ("simulations", "rollouts", "rollout_steps", "tree_steps", "nodes", "max_depth_seen"):
+                assert cg[key] == co[key], (key, cg[key], co[key])
+        widened = (gp.counters()["tree_steps"], gp.counters()["max_depth_seen"], tuple(N_g))
+        gp.close()
+    # the same search without widening grows a different tree (every generated observation is followed)
+    gp = pj.solve(pj.POMCPSolver(c=c, rng=2, tree_queries=3700, search_mode="exact", dpw_solver=True), pomdp,
+                  belief_mode=abi.BELIEF_EXTERNAL)
+    gp.set_belief_particles(parts)
+    gp.search(3700)
+    plain = (gp.counters()["tree_steps"], gp.counters()["max_depth_seen"])
+    assert plain != widened[:2], (plain, widened)
+    gp.close()
+
+
+def test_dpw_discrete_observations_batched(gpu_lib):
+    """Batched workers with observation widening on RockSample(7,8) (three observations, k = 1): counting invariants
+    hold and the search still finds a useful action."""
+    rs = pj.RockSamplePOMDP(7, 8, seed=7008)
+    Q = 200000
+    gp = pj.solve(pj.POMCPSolver(c=20.0, rng=3, tree_queries=Q, dpw_observation=(1.0, 0.1)), rs,
+                  belief_mode=abi.BELIEF_EXTERNAL)
+    gp.set_belief_initial()
+    a, N, V = gp.search(Q)
+    cs = gp.counters()
+    assert cs["simulations"] == Q and gp.root_stats()[0] == Q and N.sum() == Q - 1
+    assert np.isfinite(V).all() and V[a] > 0.0 and cs["max_depth_seen"] >= 5
+    gp.close()
+    # through the host mirror: POMCPDPWSolver with k_observation below the size of the observation space
+    policy = pj.solve(pj.POMCPDPWSolver(tree_queries=2000, c=20.0, enable_action_pw=False, k_observation=1.0,
+                                        alpha_observation=0.1, rng=2), rs)
+    assert policy._sp.dpw_observation == 1
+    policy.close()
+
+
 def test_dpw_batched_deepens_the_tree(oracle, gpu_lib):
     ld = pj.LightDark1D()
     rng = np.random.default_rng(6)

@@ -114,8 +114,10 @@ def test_tree_navigation_like_the_reference(oracle, gpu_lib):
         b.N  # stale after the re-root, like a dropped Julia reference
     assert pj.convert_estimator(pj.PORollout(pj.RandomSolver(), None), solver, baby) == pj._abi.EST_RANDOM_ROLLOUT
     assert pj.sparse_actions(policy, baby) == [0, 1] and pj.init_V(3, baby) == 3.0 and pj.init_N(2.0, baby) == 2
-    with pytest.raises(NotImplementedError):  # widening would be active on a discrete space larger than k_observation
-        pj.solve(pj.POMCPDPWSolver(tree_queries=100, enable_action_pw=False, k_observation=1.0), baby)
+    # widening is active on a discrete space larger than k_observation (tests/test_gpu_dpw.py has the parity tests)
+    widened = pj.solve(pj.POMCPDPWSolver(tree_queries=100, enable_action_pw=False, k_observation=1.0), baby)
+    assert widened._sp.dpw_observation == 1
+    widened.close()
     policy.close()
     # test/runtests.jl:49-54: DPW without action widening on Baby never widens (2 observations <= k_observation), but it
     # is still POMCPDPWSolver's simulate(): its leaf rollouts get `depth` as their step budget (src/solver.jl:199)
