@@ -135,7 +135,8 @@ typedef struct pomcp_solver_params {
    * (src/solver.jl:161-274, fields src/POMCP.jl:233-253, defaults src/constructor.jl:40-73).  At an action
    * node a new observation is generated while #children <= k_observation * N^alpha_observation
    * (src/solver.jl:223); otherwise one of the earlier generated (child, state) pairs is re-used, chosen with
-   * probability proportional to the child's N (src/solver.jl:249-255).  Device path: continuous observations. */
+   * probability proportional to the child's N (src/solver.jl:249-255).  Device path: continuous and discrete observations, with an
+   * external belief updater. */
   int32_t dpw_observation;   /* 0 = POMCPSolver (default) */
   double k_observation;      /* 10.0 */
   double alpha_observation;  /* 0.5 */
