@@ -332,12 +332,12 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
   cfg.eta_thr = h->d_eta_thr;
   smem += (size_t)h->eta_n * sizeof(uint32_t);
   const int T = std::max(cfg.n_trees, 1);
-  // Cap relative to the budget (when the caller left inflight_max to the library): no more than Q / 128 simulations of
-  // a tree in flight (at least 64).  Measured on RockSample(7,8), 96 paired episodes against the sequential oracle at
-  // 1e5 queries: 400 in flight +0.01 +- 0.28, 781 (this rule) -0.18 +- 0.29, 1184 -0.47 +- 0.30, 2368 -0.80 +- 0.28 of
-  // 16.8; at 1e6 queries the full 2368 cost nothing measurable (-0.21 +- 0.34).  DESIGN.md 4.1.
+  // Cap relative to the budget (when the caller left inflight_max to the library): no more than Q / 256 simulations of
+  // a tree in flight (at least 64).  Measured on RockSample(7,8), 292 paired episodes against the sequential oracle at
+  // 1e5 queries: 195 in flight -0.07 +- 0.14, 390 (this rule) +0.31 +- 0.16, 781 -0.32 +- 0.16, 2368 -0.81 +- 0.18 of
+  // 15.7; at 1e6 queries the full 2368 cost nothing (+0.10 +- 0.14).  DESIGN.md 4.1.
   long long cap = h->inflight_max;
-  if (h->inflight_max_auto) cap = std::min<long long>(cap, std::max<long long>(64, Q / 128) * T);
+  if (h->inflight_max_auto) cap = std::min<long long>(cap, std::max<long long>(64, Q / 256) * T);
   long long workers = std::min<long long>(cap, std::max<long long>(Q, 1) * T);
   int blocks = (int)((workers + nteams - 1) / nteams);
   DISPATCH_PID(h->prob.problem_id, {

@@ -138,13 +138,13 @@ def test_tree_navigation_like_the_reference(oracle, gpu_lib):
 
 
 def test_episode_reward_rocksample_7_8_not_worse_than_oracle(oracle, gpu_lib):
-    """north_star criterion 3 at the headline problem: RockSample(7,8), SIR belief of 2^16 particles, 96 seeded
+    """north_star criterion 3 at the headline problem: RockSample(7,8), SIR belief of 2^16 particles, 292 seeded
     40-step episodes, 10^5 simulations per decision, the batched planner (library defaults) against the sequential
     oracle on the same planner seeds and the same environment draws.  The oracle's rewards are a committed fixture
-    (tests/golden/episodes_rs78_oracle_1e5_96.json, written by scripts/episode_table.py --arm oracle: the oracle is
+    (tests/golden/episodes_rs78_oracle_1e5_292.json, written by scripts/episode_table.py --arm oracle: the oracle is
     deterministic; its first episode is re-run here to make sure the fixture still belongs to this oracle).
-    One-sided paired test: mean(batched - oracle) >= -3 standard errors of the paired difference (0.3 of 16.8; round 2
-    measured +0.01 +- 0.28 with the budget-relative in-flight cap and -0.80 +- 0.28 with 2368 in flight, which this
+    One-sided paired test: mean(batched - oracle) >= -3 standard errors of the paired difference (0.16 of 15.7; round 2
+    measured +0.09 +- 0.16 with the budget-relative in-flight cap and -0.81 +- 0.18 with 2368 in flight, which this
     test rejects)."""
     import json
     import os
@@ -154,13 +154,13 @@ def test_episode_reward_rocksample_7_8_not_worse_than_oracle(oracle, gpu_lib):
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     small = json.load(open(os.path.join(gold, "episodes_rs78_oracle_1e4.json")))
     assert et.one_episode(("oracle", 10000, 0, {}))[1] == small["rewards"][0]  # the fixture is this oracle's
-    ref = json.load(open(os.path.join(gold, "episodes_rs78_oracle_1e5_96.json")))
+    ref = json.load(open(os.path.join(gold, "episodes_rs78_oracle_1e5_292.json")))
     ro = np.array(ref["rewards"])
     rg = np.array([et.one_episode(("gpu", 100000, ep, {}))[1] for ep in range(len(ro))])
     d = rg - ro
     se = d.std(ddof=1) / np.sqrt(len(d))
     print(f"episodes at 1e5: batched {rg.mean():.2f}, oracle {ro.mean():.2f}, paired difference {d.mean():.2f} +- {se:.2f}")
     assert d.mean() >= -3 * se - 1e-9, (rg.mean(), ro.mean(), se)
-    # the 24-episode fixture of round 2's first sessions is the head of the 96-episode one
+    # the 24-episode fixture of round 2's first sessions is the head of the 292-episode one
     assert json.load(open(os.path.join(gold, "episodes_rs78_oracle_1e5.json")))["rewards"] == ref["rewards"][:24]
     assert rg.mean() > 10.0  # a useful policy: samples good rocks and leaves
