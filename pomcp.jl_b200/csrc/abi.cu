@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/pomcp_b200.h"
@@ -357,15 +358,21 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
       h->last_waves = cfg.inflight_max;  // reported as pomcp_counters::waves: the admission cap in effect, per tree
       kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
     };
-    if (cfg.dpa) {  // action progressive widening is a separate instantiation: the POMCP path pays nothing for it
-      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, true>);
-      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, true>);
-      else launch(k_search_workers<PID, 1, 4, true>);
-    } else {
-      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, false>);
-      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, false>);
-      else launch(k_search_workers<PID, 1, 4, false>);
-    }
+    // action widening and (on discrete observations) observation widening are separate instantiations: the POMCP path
+    // pays nothing for them.  Continuous observations always carry the observation-widening code (run-time flag).
+    constexpr bool H = ModelT<PID>::HASHED;
+    const bool dpo = !H && cfg.dpw;
+    auto pick = [&](auto dpa_c, auto dpo_c) {
+      constexpr bool A = decltype(dpa_c)::value, O = decltype(dpo_c)::value;
+      if (cfg.team_warps == 4) launch(k_search_workers<PID, 4, 1, A, O>);
+      else if (cfg.team_warps == 2) launch(k_search_workers<PID, 2, 2, A, O>);
+      else launch(k_search_workers<PID, 1, 4, A, O>);
+    };
+    using T_ = std::true_type;
+    using F_ = std::false_type;
+    using H_ = std::integral_constant<bool, H>;
+    if (cfg.dpa) { if (dpo) pick(T_{}, T_{}); else pick(T_{}, H_{}); }
+    else { if (dpo) pick(F_{}, T_{}); else pick(F_{}, H_{}); }
   });
   return launch_check(h, "k_search_workers");
 }

@@ -1180,7 +1180,7 @@ __device__ __forceinline__ void team_bar(int id, int nthreads) {  // id in 1 .. 
 
 // One simulation by one warp (batched mode).  `next_q` receives the worker's next query id
 // (lane 0; requested early so its latency hides behind the rollouts).
-template <int PID, bool DPA, int NTEAMS>
+template <int PID, bool DPA, int NTEAMS, bool DPO>
 __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m, const RsTab* tb,
                                                const uint32_t* eta_thr, const SearchCfg& cfg, const TreeView& tv,
                                                const PathView<typename ModelT<PID>::State>& pv,
@@ -1199,7 +1199,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   uint32_t h = tv.root;
   uint32_t hN = tv.root_N0 + q;
   ActStats<PID> st;
-  st.load(P, h, nA, lane, cfg.dpw != 0, DPA);
+  st.load(P, h, nA, lane, DPO && cfg.dpw != 0, DPA);
   uint32_t fl = 0;
   if (lane == 0) fl = __ldcg(&P.node_flags[h]);
   __syncwarp();
@@ -1235,7 +1235,10 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
   constexpr int TW = (PID == POMCP_ROCKSAMPLE) ? 1 : 2, LV = 4 / TW;
   Philox4 ptb;
   int a_new = 0;  // action widening: the action this level would add
-  const bool dpw = cfg.dpw != 0;  // observation widening: one block per level (word 2 draws the event)
+  // observation widening: one block per level (word 2 draws the event).  DPO: the kernel instance carries the
+  // widening code at all - always for continuous observations (as before), for discrete ones only when it is asked
+  // for (a run-time flag alone cost the plain RockSample search 14 %: registers and instructions of a path it never takes)
+  const bool dpw = DPO && cfg.dpw != 0;
   // The tree draws of a whole simulation in one lane-parallel Philox call: lane j holds block j (levels
   // j * LV .. j * LV + LV - 1); a level fetches its words with a shuffle.  Same counters, same words as
   // computing block d / LV at level d (which levels past the 32nd block still do).
@@ -1400,7 +1403,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
     red_add_u32_if(l0 && !reuse, &P.node_N[hao]);  // hao.N counts generated arrivals only under widening
     uint32_t seen = 0, nfl = flag_known ? 1u : 0u;
     if (!i_expand_child) {
-      if (!try_claim) st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);
+      if (!try_claim) st.load(P, hao, nA, lane, DPO && cfg.dpw != 0, DPA);
       seen = __ldcg(&P.node_N[hao]);
       if (try_claim) {  // hashed table: bit1 = the claim was attempted here
         if (lane == 0) nfl = atomicOr(&P.node_flags[hao], 1u) | 2u;
@@ -1456,7 +1459,7 @@ __device__ __forceinline__ void simulate_async(const Pool& P, const DevModel& m,
         want_rollout = true;
         break;
       }
-      st.load(P, hao, nA, lane, cfg.dpw != 0, DPA);  // somebody else got there first (rare): descend through it
+      st.load(P, hao, nA, lane, DPO && cfg.dpw != 0, DPA);  // somebody else got there first (rare): descend through it
       fl = 1u;
     }
   }
@@ -1602,7 +1605,7 @@ __device__ __forceinline__ void flush_counters(const Pool& P, const LocalCtr& lc
 // Measured oddity (scripts/cycle_probe.py, same rollout code as a __noinline__ function): the 32
 // rollouts of the tree warp take 18.4 k cycles when it rolls out alone (TEAM = 1) and 12.1 k when a
 // helper warp rolls out next to it (TEAM = 2), so R = 64 is not only free, it is faster per simulation.
-template <int PID, int TEAM, int NTEAMS, bool DPA>
+template <int PID, int TEAM, int NTEAMS, bool DPA, bool DPO = ModelT<PID>::HASHED>
 __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_search_workers(
     const __grid_constant__ Pool P, const __grid_constant__ DevModel m, const __grid_constant__ SearchCfg cfg,
     const __grid_constant__ PathBuf pb, long long queries) {
@@ -1711,7 +1714,7 @@ __global__ void __launch_bounds__(32 * TEAM * NTEAMS, TEAM == 4 ? 7 : 4) k_searc
   for (;;) {
     const unsigned long long q = __shfl_sync(0xffffffffu, next_q, 0);
     if (q >= (unsigned long long)queries) break;
-    simulate_async<PID, DPA, NTEAMS>(P, m, &rs_tab, eta_thr, cfg, tv, pv, job, (uint32_t)q, lc, next_q, spare);
+    simulate_async<PID, DPA, NTEAMS, DPO>(P, m, &rs_tab, eta_thr, cfg, tv, pv, job, (uint32_t)q, lc, next_q, spare);
   }
   if (W > 1) {  // release the helpers
     if (lane == 0) job->cmd = 0;
