@@ -51,9 +51,7 @@ for stage in "$@"; do
                 python scripts/probe.py step > $out/workers_pipes_$tag.log 2>&1
               ncu --set full --clock-control none --import-source on -k regex:k_search_workers -s 1 -c 1 -f \
                 -o $out/prof_workers_$tag python scripts/probe.py step > $out/${tag}_ncu_search.log 2>&1
-              ncu --set full --clock-control none --import-source on -k regex:k_pf_ -s 1 -c 1 -f \
-                -o $out/prof_pf_$tag python scripts/probe.py step > $out/${tag}_ncu_pf.log 2>&1
-              tail -n 2 $out/${tag}_ncu_search.log $out/${tag}_ncu_pf.log ;;
+              tail -n 2 $out/${tag}_ncu_search.log ;;  # the SIR kernel's capture is stage ncupf (gpurun returns <= 64 MiB per call)
     *) echo "unknown stage $stage" ;;
   esac
 done
