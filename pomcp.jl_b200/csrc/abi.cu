@@ -337,8 +337,12 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
   // a tree in flight (at least 64).  Measured on RockSample(7,8), 292 paired episodes against the sequential oracle at
   // 1e5 queries: 195 in flight -0.07 +- 0.14, 390 (this rule) +0.31 +- 0.16, 781 -0.32 +- 0.16, 2368 -0.81 +- 0.18 of
   // 15.7; at 1e6 queries the full 2368 cost nothing (+0.10 +- 0.14).  DESIGN.md 4.1.
+  // The rule is applied where it was measured to matter: on Baby and Tiger 195 / 390 / 1184 simulations in flight give
+  // the same root values and actions at 1e5 queries (12 seeds against the oracle) while the search takes 8.1 / 4.6 / 2.7
+  // ms, and LightDark's plain POMCP tree is one level deep - those problems keep their 8 teams per SM.
   long long cap = h->inflight_max;
-  if (h->inflight_max_auto) cap = std::min<long long>(cap, std::max<long long>(64, Q / 256) * T);
+  if (h->inflight_max_auto && h->prob.problem_id == POMCP_ROCKSAMPLE)
+    cap = std::min<long long>(cap, std::max<long long>(64, Q / 256) * T);
   long long workers = std::min<long long>(cap, std::max<long long>(Q, 1) * T);
   int blocks = (int)((workers + nteams - 1) / nteams);
   DISPATCH_PID(h->prob.problem_id, {
