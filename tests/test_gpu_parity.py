@@ -35,6 +35,35 @@ def test_rollout_batch_bit_exact(oracle, gpu_lib, name):
     gp.close()
 
 
+@pytest.mark.parametrize("n,k", [(11, 11), (10, 12), (13, 14), (15, 16), (2, 1), (1, 0)])
+def test_rollout_and_search_large_rocksample_bit_exact(oracle, gpu_lib, n, k):
+    """The RockSample rollout table at its edges: 16 actions exactly (k = 11: no clamping of the action column), more
+    than 16 actions (k >= 12: actions from 15 on share the sensing column), the largest instance the ABI admits (15 x 15
+    grid, 16 rocks: the rock mask fills bits 14..29 of a table entry), and degenerate grids.  Rollout returns, step
+    counts and an exact-mode search with 64 rollouts per leaf (two trajectories per lane) equal the oracle's."""
+    pomdp = pj.RockSamplePOMDP(n, k, seed=100 * n + k)
+    gp, op = make_pair(oracle, pomdp, 20.0, seed=5, mode="exact", tree_queries=300, rollouts_per_leaf=64)
+    rng = np.random.default_rng(n + k)
+    states = random_states(pomdp, 8000, rng)
+    for steps in (1, 8, 9, 90):
+        ret_g, ns_g = gp.rollout_batch(states, steps, seed=0xABCDEF + steps)
+        ret_o, ns_o = oracle.rollout_batch(pomdp, states, steps, seed=0xABCDEF + steps)
+        assert np.array_equal(ns_g, ns_o), (n, k, steps)
+        assert np.array_equal(_bits(ret_g), _bits(ret_o)), (n, k, steps, np.abs(ret_g - ret_o).max())
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    a_g, N_g, V_g = gp.search(300)
+    rc, a_o, N_o, V_o = op.search(300)
+    assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o))
+    gp.close()
+    # batched workers on the same instance (one-warp workers, the table-driven tree step): counting invariants
+    bp = pj.solve(pj.POMCPSolver(c=20.0, rng=6, tree_queries=20000), pomdp)
+    bp.set_belief_initial()
+    a, N, V = bp.search(20000)
+    assert bp.counters()["simulations"] == 20000 and N.sum() == 20000 - 1 and np.isfinite(V).all()
+    bp.close()
+
+
 # ----------------------------------------------------------------------------- K6 weights
 @pytest.mark.parametrize("name", list(PROBS))
 def test_pf_weights_bit_exact(oracle, gpu_lib, name):
