@@ -665,13 +665,14 @@ int compact_pool(pomcp_handle* h) {
   size_t o_N = 0, o_fl = o_N + al((size_t)kept * 4), o_ps = o_fl + al((size_t)kept * 4),
          o_obs = o_ps + al((size_t)kept * 4), o_aN = o_obs + al((h->hashed || h->exact2) ? (size_t)kept * 8 : 0),
          o_aM = o_aN + al((size_t)kept * nA * 4), o_aV = o_aM + al((size_t)kept * nA * 4),
-         o_ch = o_aV + al((size_t)kept * nA * 8), total = o_ch + al((size_t)kept * nA * nO * 4);
+         o_ch = o_aV + al((size_t)kept * nA * 8), o_am = o_ch + al((size_t)kept * nA * nO * 4),
+         total = o_am + al(P.node_amask ? (size_t)kept * 4 : 0);
   rc = ensure_bytes(h, &h->d_tmp, &h->tmp_cap, total);
   if (rc) return rc;
   char* base = (char*)h->d_tmp;
   PoolScratch T{(uint32_t*)(base + o_N), (uint32_t*)(base + o_fl), (uint32_t*)(base + o_ps),
                 (unsigned long long*)(base + o_obs), (uint32_t*)(base + o_aN), (uint32_t*)(base + o_aM),
-                (double*)(base + o_aV), (uint32_t*)(base + o_ch)};
+                (double*)(base + o_aV), (uint32_t*)(base + o_ch), (uint32_t*)(base + o_am)};
   k_copy_kept<<<(int)((n_nodes + 255) / 256), 256, 0, h->stream>>>(P, T, h->d_newid, h->root, nA, nO, n_nodes);
   rc = launch_check(h, "k_copy_kept");
   if (rc) return rc;
@@ -687,6 +688,7 @@ int compact_pool(pomcp_handle* h) {
   CK(d2d(P.act_M, T.act_M, (size_t)kept * nA * 4));
   CK(d2d(P.act_V, T.act_V, (size_t)kept * nA * 8));
   if (!h->hashed) CK(d2d(P.child, T.child, (size_t)kept * nA * nO * 4));
+  if (P.node_amask) CK(d2d(P.node_amask, T.node_amask, (size_t)kept * 4));
   if (n_nodes > kept) {
     unsigned long long cnt = (unsigned long long)(n_nodes - kept);
     int blocks = (int)std::min<unsigned long long>((cnt * nA * std::max(nO, 1) + 255) / 256, 148ull * 16);
@@ -1296,7 +1298,6 @@ static int gather_child_particles(pomcp_handle* h, uint32_t child, long long cnt
 }
 
 static int maybe_compact(pomcp_handle* h) {
-  if (h->sp.dpw_action) return POMCP_OK;  // the action masks are not compacted yet: the pool (64 x tree_queries) is the limit
   // reclaim the dead part of the pool / particle log once a quarter of either is used
   if (h->compact_always || h->nodes_used * 4 >= h->pool.max_nodes || h->log_used * 4 >= h->pool.log_cap)
     return compact_pool(h);

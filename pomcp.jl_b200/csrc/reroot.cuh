@@ -68,6 +68,7 @@ struct PoolScratch {
   uint32_t* act_M;
   double* act_V;
   uint32_t* child;
+  uint32_t* node_amask;  // action widening only
 };
 
 __global__ void k_copy_kept(const __grid_constant__ Pool P, const __grid_constant__ PoolScratch T,
@@ -81,6 +82,7 @@ __global__ void k_copy_kept(const __grid_constant__ Pool P, const __grid_constan
   uint32_t ps = P.node_pslot[n];
   // parent slot -> (new parent id, same action); the new root has no parent
   T.node_pslot[m] = ((uint32_t)n == new_root) ? 0u : newid[ps / (uint32_t)nA] * (uint32_t)nA + ps % (uint32_t)nA;
+  if (P.node_amask) T.node_amask[m] = P.node_amask[n];
   if (P.node_obs) T.node_obs[m] = P.node_obs[n];
   else if (P.node_bel) T.node_obs[m] = (unsigned long long)__double_as_longlong(P.node_bel[n]);  // same scratch column
   for (int a = 0; a < nA; ++a) {
@@ -154,6 +156,7 @@ __global__ void k_pool_fill_range(const __grid_constant__ Pool P, int nA, int nO
     P.node_flags[first + k] = 0;
     P.node_pslot[first + k] = 0;
     if (P.node_obs) P.node_obs[first + k] = 0;
+    if (P.node_amask) P.node_amask[first + k] = 0;
   }
   if (P.child)
     for (unsigned long long k = i; k < count * nA * nO; k += stride) P.child[first * nA * nO + k] = 0;

@@ -162,3 +162,39 @@ def test_batched_compaction_keeps_the_subtree(gpu_lib, monkeypatch):
     a2, N2, V2 = pl.search(Q)  # and the tree keeps growing from there
     assert pl.root_stats()[0] == rn + Q
     pl.close()
+
+
+@pytest.mark.parametrize("name", ["tiger", "rs44"])
+def test_compaction_with_action_widening_keeps_exact_parity(oracle, gpu_lib, name, monkeypatch):
+    """Action progressive widening keeps a mask of the existing ActNodes per belief node; the compaction moves it with
+    the node (round 2: before, a planner with action widening never compacted).  Exact-mode episodes with a compaction
+    after every re-root stay bit-identical to the never-compacting oracle."""
+    monkeypatch.setenv("POMCP_COMPACT_ALWAYS", "1")
+    pomdp, c = PROBS[name]
+    gp, op = make_pair(oracle, pomdp, c, seed=5, mode="exact", tree_queries=1500, dpw_action=(2.0, 0.3))
+    gp.set_belief_initial()
+    op.set_belief_initial()
+    for step in range(5):
+        rc, a_o, N_o, V_o = op.search(1500)
+        if rc == abi.ERR_ALL_SAMPLES_TERMINAL:
+            with pytest.raises(pj.AllSamplesTerminal):
+                gp.search(1500)
+            break
+        a_g, N_g, V_g = gp.search(1500)
+        assert rc == 0 and a_g == a_o and np.array_equal(N_g, N_o) and np.array_equal(_bits(V_g), _bits(V_o)), step
+        best_o, best_n = None, 0
+        for o in range(pomdp.n_observations):
+            n = op.node_stats([(a_o, o)])[0]
+            if n > best_n:
+                best_o, best_n = o, n
+        if best_o is None:
+            break
+        nodes_before = gp.counters()["nodes"]
+        gp.update_unweighted(a_g, best_o)
+        assert op.update_unweighted(a_o, best_o) == 0
+        assert gp.counters()["nodes"] < nodes_before  # the pool was compacted
+        assert np.array_equal(gp.belief_particles(), op.belief_particles())
+        rn_g, N1_g, V1_g = gp.root_stats()
+        rn_o, N1_o, V1_o = op.root_stats()
+        assert rn_g == rn_o and np.array_equal(N1_g, N1_o) and np.array_equal(_bits(V1_g), _bits(V1_o))
+    gp.close()
