@@ -977,6 +977,9 @@ int32_t pomcp_create(const pomcp_problem* p, const pomcp_solver_params* sp, int3
   h->sm_count = prop.multiProcessorCount;
   h->inflight_max = sp->inflight_max > 0 ? std::min(sp->inflight_max, 4096)
                                          : (p->problem_id == POMCP_ROCKSAMPLE ? 16 : 8) * prop.multiProcessorCount;
+  // every tree needs a worker of its own (workers are dealt to the trees round-robin and stay with their tree): a cap
+  // below n_trees would leave the trees beyond it unsearched and still merge their empty roots
+  h->inflight_max = std::max(h->inflight_max, T);
   h->inflight_max_auto = sp->inflight_max <= 0;
   h->inflight_min = sp->inflight_min > 0 ? sp->inflight_min : 8;
   h->inflight_min_auto = sp->inflight_min <= 0;

@@ -127,3 +127,22 @@ def test_multitree_edge_cases(gpu_lib):
     a, N, V = gp.search(20000)
     assert N.sum() == 4 * 19999 and np.isfinite(V).all()
     gp.close()
+
+
+@pytest.mark.parametrize("kw", [dict(inflight_max=1), dict(inflight_max=3), dict(inflight_max=1, rollouts_per_leaf=32),
+                                dict(inflight_max=1, inflight_ramp_div=1000)])
+def test_multitree_cap_below_tree_count(gpu_lib, kw):
+    """An in-flight cap smaller than n_trees is raised to n_trees: every tree keeps a worker of its own (a tree
+    without one was never searched and its empty root went into the merge)."""
+    T, Q = 5, 2000
+    for pomdp in (pj.RockSamplePOMDP(4, 4, seed=44), pj.BabyPOMDP(-5.0, -10.0)):
+        gp = pj.solve(pj.POMCPSolver(c=10.0, rng=5, tree_queries=Q, n_trees=T, **kw), pomdp,
+                      belief_mode=abi.BELIEF_EXTERNAL)
+        gp.set_belief_initial()
+        a, N, V = gp.search(Q)
+        cs = gp.counters()
+        assert cs["simulations"] + cs["terminal_skips"] == T * Q, (cs, kw)
+        for t in range(T):
+            assert gp.tree_result(t)[1] == Q, (t, kw)
+        assert N.sum() == T * (Q - 1)
+        gp.close()
