@@ -405,6 +405,17 @@ struct PfDiv {
     }
     return points_below(C);
   }
+  // Branch-free form for a batch of independent evaluations: returns the count (32 bits: n_out < 2^32) and clears `ok`
+  // where the fp64 evaluation does not prove it (the caller then asks points_below for that C).
+  __device__ __forceinline__ uint32_t points_below_try(unsigned long long C, const Fast& f, uint32_t n_out32, bool& ok) const {
+    const double y = (double)C * ratio;
+    const double a = y - f.sub_lo, b = y - f.sub_hi;  // x - eps, x + eps
+    const uint32_t fa = __double2uint_rd(a), fb = __double2uint_rd(b);  // saturating conversions
+    const bool neg = b < 0.0;
+    ok = ok && (neg || (a >= 0.0 && b < 4294967295.0 && fa == fb));
+    const uint32_t cnt = neg ? 0u : min(fa, n_out32 - 1u) + 1u;  // n_out >= 1
+    return cnt;
+  }
   // The same count for a run of cumulative sums C, C + q1, C + q1 + q2, ...: (k, rem) is carried and a
   // step adds q * n_out to the remainder, so the quotient grows by the number of copies of that
   // particle (a few subtractions) instead of being divided out again.  Falls back to the closed form
@@ -595,9 +606,38 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
     const bool full = base + PF2_TILE <= n;  // uniform
     unsigned long long sum = 0;
     unsigned first = 0xffffffffu;  // offset inside the tile of the first alive particle this thread met
+    constexpr bool VEC = Src::NCLASS > 0 && sizeof(typename Src::State) == 4 && PF2_ITEMS == 8;
+    if constexpr (VEC) {
+      // Full tile of 4-byte states: both 16-byte loads of a thread are requested before anything looks at a state, and
+      // the look-ups are selects, not branches.  (The general loop below compiles to load -> branch on the terminal bit
+      // -> look-up -> next load: eight memory round trips in a row per thread; 2^26 RockSample particles took 138 us.)
+      if (full) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(src.states + base);  // tiles are 8 KB: 16-byte aligned
+        const uint4 v0 = p4[threadIdx.x], v1 = p4[PF2_THREADS + threadIdx.x];
+        const uint32_t w8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          typename Src::State s0;
+          memcpy(&s0, &w8[k], 4);
+          const unsigned off = (unsigned)(((k >> 2) * PF2_THREADS + (int)threadIdx.x) * 4 + (k & 3));
+          const bool alive = !Src::M::terminal(src.m, s0);
+          unsigned long long q;
+          if constexpr (Src::CLASS_IN) {
+            q = qtab[src.wclass(s0)];  // the class index is in range for any bit pattern
+          } else {
+            typename Src::State sp;
+            src.propagate_from(base + off, s0, sp);
+            q = qtab[src.wclass(sp)];
+          }
+          sum += alive ? q : 0ull;
+          first = alive ? min(first, off) : first;
+        }
+      }
+    }
     // striped over the CTA: every load and store instruction of a warp covers consecutive particles
 #pragma unroll
     for (int k = 0; k < PF2_ITEMS; ++k) {
+      if (VEC && full) break;  // uniform
       const long long i = base + (long long)k * PF2_THREADS + threadIdx.x;
       if (full || i < n) {
         typename Src::State sp;
@@ -746,6 +786,7 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
   const PfDiv dv(T, ru, n_out);
   const PfDiv::Fast fs = dv.fast(ru);
   const bool same = src.identity();  // uniform: copies are the input states themselves
+  const uint32_t n_out32 = (uint32_t)n_out;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long base = tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
     const bool full = (tile + 1) * PF2_TILE <= n;  // uniform: no bounds checks inside a full tile
@@ -828,32 +869,40 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
     const unsigned long long off0 = tile_base_sum + warp_excl + (x - run);  // C just before this thread's particles
     // nothing of this thread's is copied: terminal or zero-weight particles only (the first alive particle owns output 0)
     if (run == 0ull && first_alive - (unsigned long long)base >= (unsigned long long)PF2_ITEMS) continue;
-    long long lo = dv.points_below_fast2(off0, fs);
-    unsigned long long prev = 0;
+    // The nine range ends of this thread as one straight-line batch of independent fp64 evaluations (their conversion
+    // and fp64 latencies overlap; evaluated one after another inside the branches of the copy loop they were a
+    // dependent chain per particle).  A particle of zero weight has hi == lo and copies nothing; an end the fp64 form
+    // does not prove (about 2^-20 of them) is recomputed in integers.
+    uint32_t m[PF2_ITEMS + 1];
+    bool ok = true;
+    m[0] = dv.points_below_try(off0, fs, n_out32, ok);
+#pragma unroll
+    for (int k = 0; k < PF2_ITEMS; ++k) m[k + 1] = dv.points_below_try(off0 + qv[k], fs, n_out32, ok);
+    if (!ok) {
+      m[0] = (uint32_t)dv.points_below_fast2(off0, fs);
+#pragma unroll
+      for (int k = 0; k < PF2_ITEMS; ++k) m[k + 1] = (uint32_t)dv.points_below_fast2(off0 + qv[k], fs);
+    }
+    const unsigned long long fa_rel = first_alive - (unsigned long long)base;  // < PF2_ITEMS: this thread owns output 0
 #pragma unroll
     for (int k = 0; k < PF2_ITEMS; ++k) {
       const long long i = base + k;
-      if (qv[k] != prev || (unsigned long long)i == first_alive) {  // q_i > 0 (or the particle that owns output 0)
-        const long long hi = dv.points_below_fast2(off0 + qv[k], fs);
-        if ((unsigned long long)i == first_alive) lo = 0;
-        const uint32_t copies = (uint32_t)(hi - lo);  // n_out < 2^32
-        if (copies) {
-          typename Src::State sp;
-          if ((CLASSES && !CLASS_IN) || (PRELOAD && same)) sp = st_in[PRELOAD ? k : 0];
-          else if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
-          else src.propagate_from(i, s_st[STAGE ? (int)threadIdx.x * (PF2_ITEMS + 1) + k : 0], sp);
-          // up to four copies straight-line (predicated stores): a loop here runs at a handful of active lanes
-          Out* o = out + lo;
-          const Out v = (Out)sp;
-          o[0] = v;
-          if (copies > 1) o[1] = v;
-          if (copies > 2) o[2] = v;
-          if (copies > 3) o[3] = v;
-          if (copies > 4)
-            for (uint32_t j = 4; j < copies; ++j) o[j] = v;
-        }
-        lo = hi;
-        prev = qv[k];
+      const uint32_t lo = fa_rel == (unsigned long long)k ? 0u : m[k];
+      const uint32_t copies = m[k + 1] - lo;  // n_out < 2^32
+      if (copies) {
+        typename Src::State sp;
+        if ((CLASSES && !CLASS_IN) || (PRELOAD && same)) sp = st_in[PRELOAD ? k : 0];
+        else if (PRELOAD) src.propagate_from(i, st_in[PRELOAD ? k : 0], sp);
+        else src.propagate_from(i, s_st[STAGE ? (int)threadIdx.x * (PF2_ITEMS + 1) + k : 0], sp);
+        // up to four copies straight-line (predicated stores): a loop here runs at a handful of active lanes
+        Out* o = out + lo;
+        const Out v = (Out)sp;
+        o[0] = v;
+        if (copies > 1) o[1] = v;
+        if (copies > 2) o[2] = v;
+        if (copies > 3) o[3] = v;
+        if (copies > 4)
+          for (uint32_t j = 4; j < copies; ++j) o[j] = v;
       }
     }
   }
