@@ -583,14 +583,18 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
                                                            h->d_pfctl);
     rc = launch_check(h, "k_pf_weigh_q");
     if (rc) return rc;
-    k_pf_tile_prefix<<<1, 1024, 0, h->stream>>>(tile_sum, ntiles, h->d_pfctl);
-    rc = launch_check(h, "k_pf_tile_prefix");
-    if (rc) return rc;
+    // weight-class sources: a CTA owns a contiguous chunk of tiles and the emit kernel (same grid) derives offsets,
+    // total and status from the per-CTA sums; the others: one sum per tile and the single-CTA prefix kernel
+    if (Src::NCLASS == 0) {
+      k_pf_tile_prefix<<<1, 1024, 0, h->stream>>>(tile_sum, ntiles, h->d_pfctl);
+      rc = launch_check(h, "k_pf_tile_prefix");
+      if (rc) return rc;
+    }
     k_pf_emit_tiled<Src, Out><<<grid, PF2_THREADS, 0, h->stream>>>(src, n, ntiles, (const unsigned long long*)h->d_cum,
                                                                    tile_sum, h->d_pfctl, ru, n_out, d_out);
     rc = launch_check(h, "k_pf_emit_tiled");
     if (rc) return rc;
-    h->timers[POMCP_PHASE_PF].launches += 3;
+    h->timers[POMCP_PHASE_PF].launches += Src::NCLASS == 0 ? 3 : 2;
     return POMCP_OK;
   }
   // max-scaled streaming path: weigh -> total(s) -> scan + emit (picks the scale by the same rule)

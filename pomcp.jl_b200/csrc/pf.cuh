@@ -601,7 +601,16 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
   bool over = false;
   if constexpr (Src::NCLASS > 0) over = pf_fill_qtab(src, scale, qtab);  // once per CTA, which then walks several tiles
   unsigned long long first_cta = ~0ull;  // thread 0: first alive particle of the tiles of this CTA
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // Sources with a weight-class table: a CTA owns a CONTIGUOUS chunk of tiles and publishes ONE sum, so k_pf_emit_tiled
+  // (same grid, same chunks) gets its offset from the <= 8 * SMs chunk sums and carries it from tile to tile - there is
+  // no prefix kernel between the two passes (one CTA, 25 us for the 32 K tiles of 2^26 particles).
+  constexpr bool CHUNK = Src::NCLASS > 0;
+  const long long per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = CHUNK ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
+  const long long t1 = CHUNK ? (t0 + per_cta < ntiles ? t0 + per_cta : ntiles) : ntiles;
+  const long long tstep = CHUNK ? 1 : (long long)gridDim.x;
+  unsigned long long chunk_sum = 0;  // thread 0
+  for (long long tile = t0; tile < t1; tile += tstep) {
     const long long base = tile * PF2_TILE;
     const bool full = base + PF2_TILE <= n;  // uniform
     unsigned long long sum = 0;
@@ -680,11 +689,13 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
         sum += s_sum[k];
         first = min(first, s_first[k]);
       }
-      tile_sum[tile] = sum;
+      if (CHUNK) chunk_sum += sum;
+      else tile_sum[tile] = sum;
       if (first != 0xffffffffu && first_cta == ~0ull) first_cta = (unsigned long long)(base + first);  // tiles ascend
     }
     __syncthreads();
   }
+  if (CHUNK && threadIdx.x == 0) tile_sum[blockIdx.x] = chunk_sum;  // (also the CTAs beyond the last tile: zero)
   over = __any_sync(0xffffffffu, over);
   if (lane == 0 && over) ctl->over_ceil = 1;
   if (threadIdx.x == 0 && first_cta != ~0ull) {
@@ -693,34 +704,36 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
   }
 }
 
-// Exclusive prefix of the tile sums in place, grand total and status.  One CTA of 32 warps; per round a LANE owns 32
-// consecutive tile sums (sixteen 16-byte loads, its own running sum, sixteen 16-byte stores) and a warp 1024: one u64
-// warp scan per 1024 tiles and one CTA scan per 32 K.  (A thread per contiguous chunk of the whole array took 59 us for
-// 32 K tiles - dependent loads; a warp scan per row of 32 took 28 us - 32 scans per warp.)
+// Exclusive prefix of the tile sums in place, grand total and status.  One CTA of 32 warps; per round a LANE owns 16
+// consecutive tile sums (eight 16-byte loads, its own running sum, eight 16-byte stores) and a warp 512: one u64
+// warp scan per 512 tiles and one CTA scan per 16 K.  (A thread per contiguous chunk of the whole array took 59 us for
+// 32 K tiles - dependent loads; a warp scan per row of 32 took 28 us - 32 scans per warp; 32 sums per lane need 64
+// registers for the values alone, which 1024 threads do not have: the kernel spilled and took 28 us as well.)
+constexpr int PFX_PER = 16;
 __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* tile_sum, long long ntiles, PfCtl* ctl) {
   __shared__ unsigned long long s_seg[32];
   __shared__ unsigned long long s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
-  for (long long round0 = 0; round0 < ntiles; round0 += 32 * 1024) {
-    const long long first = round0 + (long long)warp * 1024 + (long long)lane * 32;  // a multiple of 32: 256-byte aligned
-    unsigned long long v[32];
-    if (first + 32 <= ntiles) {
+  for (long long round0 = 0; round0 < ntiles; round0 += 1024 * PFX_PER) {
+    const long long first = round0 + ((long long)warp * 32 + lane) * PFX_PER;  // a multiple of 16 (tile_sum itself is 16-byte aligned)
+    unsigned long long v[PFX_PER];
+    if (first + PFX_PER <= ntiles) {
       const ulonglong2* p = reinterpret_cast<const ulonglong2*>(tile_sum + first);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < PFX_PER / 2; ++j) {
         const ulonglong2 a = p[j];
         v[2 * j] = a.x;
         v[2 * j + 1] = a.y;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = first + j < ntiles ? tile_sum[first + j] : 0ull;
+      for (int j = 0; j < PFX_PER; ++j) v[j] = first + j < ntiles ? tile_sum[first + j] : 0ull;
     }
     unsigned long long mine = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) mine += v[j];
+    for (int j = 0; j < PFX_PER; ++j) mine += v[j];
     unsigned long long x = mine;  // inclusive over the lanes of the warp
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -735,18 +748,18 @@ __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* til
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = run + mine;  // everything up to the end of this round
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < PFX_PER; ++j) {
       const unsigned long long t = v[j];
       v[j] = run;
       run += t;
     }
-    if (first + 32 <= ntiles) {
+    if (first + PFX_PER <= ntiles) {
       ulonglong2* p = reinterpret_cast<ulonglong2*>(tile_sum + first);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) p[j] = make_ulonglong2(v[2 * j], v[2 * j + 1]);
+      for (int j = 0; j < PFX_PER / 2; ++j) p[j] = make_ulonglong2(v[2 * j], v[2 * j + 1]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < PFX_PER; ++j)
         if (first + j < ntiles) tile_sum[first + j] = v[j];
     }
     __syncthreads();
@@ -762,18 +775,70 @@ __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* til
   }
 }
 
+// Resident CTAs per SM the register allocation must allow: the kernel is bound by the latencies of a few warps per
+// scheduler (ncu: 80 registers -> 3 CTAs, issue-active 50 %, long-scoreboard and fixed-latency stalls on top), and left
+// to itself ptxas takes 126-130 registers.  64 registers (4 CTAs) for the 4-byte states of the weight-class sources -
+// 2^26 RockSample particles: 336 -> 290 us -, 80 (3 CTAs) for wider states.  No spills either way.
+#ifndef PF_EMIT_MIN_CTAS_CLASS
+#define PF_EMIT_MIN_CTAS_CLASS 4
+#endif
+#ifndef PF_EMIT_MIN_CTAS_WIDE
+#define PF_EMIT_MIN_CTAS_WIDE 3
+#endif
 template <class Src, class Out>
-__global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_constant__ Src src, long long n, long long ntiles,
+__global__ void __launch_bounds__(PF2_THREADS, (Src::NCLASS > 0 ? PF_EMIT_MIN_CTAS_CLASS : PF_EMIT_MIN_CTAS_WIDE))
+k_pf_emit_tiled(const __grid_constant__ Src src, long long n, long long ntiles,
                                                                const unsigned long long* __restrict__ q,
                                                                const unsigned long long* __restrict__ tile_off,
-                                                               const PfCtl* __restrict__ ctl, uint32_t ru, long long n_out,
-                                                               Out* out) {
+                                                               PfCtl* ctl, uint32_t ru, long long n_out, Out* out) {
   __shared__ unsigned long long s_warp[PF2_THREADS / 32];
   __shared__ unsigned long long qtab[Src::NCLASS > 0 ? Src::NCLASS : 1];
-  if (ctl->status != POMCP_OK) return;  // uniform: all terminal, or the max-scaled path takes over
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned long long T = ctl->total_ceil;
   constexpr bool CLASSES = Src::NCLASS > 0;
+  constexpr bool CHUNK = CLASSES;  // k_pf_weigh_q left one sum per CTA (chunk of tiles), no prefix kernel ran
+  unsigned long long T, chunk_run = 0;  // chunk_run: C before the next tile of this CTA's chunk
+  if constexpr (CHUNK) {
+    // Every CTA derives the grand total, the status word (the same rule as k_pf_tile_prefix) and its own offset from
+    // the chunk sums: <= 8 * SMs values, a few coalesced loads per thread.
+    __shared__ unsigned long long s_red[2][PF2_THREADS / 32];
+    unsigned long long all = 0, before = 0;
+    for (unsigned c = threadIdx.x; c < gridDim.x; c += PF2_THREADS) {
+      const unsigned long long v = tile_off[c];
+      all += v;
+      before += c < blockIdx.x ? v : 0ull;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      all += __shfl_xor_sync(0xffffffffu, all, off);
+      before += __shfl_xor_sync(0xffffffffu, before, off);
+    }
+    if (lane == 0) {
+      s_red[0][warp] = all;
+      s_red[1][warp] = before;
+    }
+    __syncthreads();
+    all = 0;
+    before = 0;
+#pragma unroll
+    for (int k = 0; k < PF2_THREADS / 32; ++k) {
+      all += s_red[0][k];
+      before += s_red[1][k];
+    }
+    T = all;
+    chunk_run = before;
+    int st = POMCP_OK;
+    if (!ctl->any_alive) st = POMCP_ERR_ALL_SAMPLES_TERMINAL;
+    else if (ctl->over_ceil || T < PF_MIN_TOTAL_CEIL) st = PF_RETRY_MAX_SCALE;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ctl->total_ceil = T;
+      ctl->total = T;
+      ctl->status = (unsigned)st;
+    }
+    if (st != POMCP_OK) return;  // uniform over the grid: all terminal, or the max-scaled path takes over
+  } else {
+    if (ctl->status != POMCP_OK) return;  // uniform: all terminal, or the max-scaled path takes over
+    T = ctl->total_ceil;
+  }
   constexpr bool CLASS_IN = CLASSES && Src::CLASS_IN;
   constexpr bool PRELOAD = sizeof(typename Src::State) <= 8;  // (16-byte states would cost 32 registers)
   // Wider states are staged through shared memory: the tile's states are requested by coalesced loads when the tile
@@ -787,10 +852,15 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
   const PfDiv::Fast fs = dv.fast(ru);
   const bool same = src.identity();  // uniform: copies are the input states themselves
   const uint32_t n_out32 = (uint32_t)n_out;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const long long per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+  const long long t0 = CHUNK ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
+  const long long t1 = CHUNK ? (t0 + per_cta < ntiles ? t0 + per_cta : ntiles) : ntiles;
+  const long long tstep = CHUNK ? 1 : (long long)gridDim.x;
+  for (long long tile = t0; tile < t1; tile += tstep) {
     const long long base = tile * PF2_TILE + (long long)threadIdx.x * PF2_ITEMS;
     const bool full = (tile + 1) * PF2_TILE <= n;  // uniform: no bounds checks inside a full tile
-    const unsigned long long tile_base_sum = tile_off[tile];  // requested early: used after the scan
+    unsigned long long tile_base_sum = chunk_run;
+    if constexpr (!CHUNK) tile_base_sum = tile_off[tile];  // requested early: used after the scan
     unsigned long long qv[PF2_ITEMS];
     typename Src::State st_in[PRELOAD ? PF2_ITEMS : 1];  // input states (propagated in place where the class needs it)
     if constexpr (CLASSES) {
@@ -862,11 +932,16 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_emit_tiled(const __grid_cons
     }
     if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    unsigned long long warp_excl = 0;
+    unsigned long long warp_excl = 0, tile_total = 0;
 #pragma unroll
-    for (int k = 0; k < PF2_THREADS / 32; ++k) warp_excl += (k < warp) ? s_warp[k] : 0ull;
+    for (int k = 0; k < PF2_THREADS / 32; ++k) {
+      const unsigned long long wk = s_warp[k];
+      tile_total += wk;
+      warp_excl += (k < warp) ? wk : 0ull;
+    }
     __syncthreads();  // s_warp is rewritten by the next tile
     const unsigned long long off0 = tile_base_sum + warp_excl + (x - run);  // C just before this thread's particles
+    if constexpr (CHUNK) chunk_run += tile_total;
     // nothing of this thread's is copied: terminal or zero-weight particles only (the first alive particle owns output 0)
     if (run == 0ull && first_alive - (unsigned long long)base >= (unsigned long long)PF2_ITEMS) continue;
     // The nine range ends of this thread as one straight-line batch of independent fp64 evaluations (their conversion
