@@ -1431,19 +1431,20 @@ __global__ void __launch_bounds__(PF_THREADS, 2) k_pf_fused_ceil(const __grid_co
     const long long i = index(k);
     if (k < items && i < n) {
       if constexpr (CLASSES) {
-        if (cls) {
+        if (cls) {  // selects, not branches: the look-ups of a thread's particles overlap
           const State s0 = st[KEEP ? k : 0];
-          if (!Src::M::terminal(src.m, s0)) {
-            alive_mask |= 1u << k;
-            if ((unsigned long long)i < first) first = (unsigned long long)i;
-            if constexpr (CLASS_IN) {
-              q[k] = qtab[src.wclass(s0)];  // st keeps the INPUT state: the emit propagates the particles it copies
-            } else {
-              State sp;
-              src.propagate_from(i, s0, sp);
-              st[KEEP ? k : 0] = sp;
-              q[k] = qtab[src.wclass(sp)];
-            }
+          const bool alive = !Src::M::terminal(src.m, s0);
+          alive_mask |= alive ? 1u << k : 0u;
+          first = alive && (unsigned long long)i < first ? (unsigned long long)i : first;
+          if constexpr (CLASS_IN) {
+            const unsigned long long qk = qtab[src.wclass(s0)];  // (in range for any bit pattern)
+            q[k] = alive ? qk : 0ull;  // st keeps the INPUT state: the emit propagates the particles it copies
+          } else {
+            State sp;
+            src.propagate_from(i, s0, sp);
+            const unsigned long long qk = qtab[src.wclass(sp)];
+            st[KEEP ? k : 0] = alive ? sp : s0;
+            q[k] = alive ? qk : 0ull;
           }
         } else {
           eval_direct(k, i);
