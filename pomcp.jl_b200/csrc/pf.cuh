@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(1024) k_pf_tile_prefix(unsigned long long* til
 // Resident CTAs per SM the register allocation must allow: the kernel is bound by the latencies of a few warps per
 // scheduler (ncu: 80 registers -> 3 CTAs, issue-active 50 %, long-scoreboard and fixed-latency stalls on top), and left
 // to itself ptxas takes 126-130 registers.  64 registers (4 CTAs) for the 4-byte states of the weight-class sources -
-// 2^26 RockSample particles: 336 -> 290 us -, 80 (3 CTAs) for wider states.  No spills either way.
+// 2^26 RockSample particles: 447 -> 395 us per update -, 80 (3 CTAs) for wider states.  No spills either way.
 #ifndef PF_EMIT_MIN_CTAS_CLASS
 #define PF_EMIT_MIN_CTAS_CLASS 4
 #endif
