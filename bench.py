@@ -361,6 +361,25 @@ def config_latencies():
     out["c4_lightdark_sir_alg_GBs"] = 1_000_000 * 48 / us / 1e3
     out["c4_lightdark_1e5_queries_search_us"] = med(c4s, 6)
     pl.close()
+    # SIR at the sizes the HBM roofline is about (tiled streaming path, sets beyond one co-resident grid): RockSample
+    # particles (4-byte states), algorithmic bytes 2 S + 16 per particle over the measured copy bandwidth
+    peak = measured_peaks()[0]
+    rs = make_pomdp("c3")
+    pl = pj.solve(pj.POMCPSolver(tree_queries=100, search_mode="batched"), rs, belief_mode=abi.BELIEF_EXTERNAL)
+    for lg in (24, 26):
+        n = 1 << lg
+        big = (np.uint32(0) | np.uint32(3 << 4) | (np.random.default_rng(lg).integers(0, 256, n).astype(np.uint32) << 8))
+        pl.set_belief_particles(big)
+
+        def tiled(i):
+            pl.flush_l2()
+            pl.pf_update_sir(5, i & 1, seed=i, n_out=n)
+            return pl.phase_ms(abi.PHASE_PF)[0] * 1e3
+        us = med(tiled, 8)
+        gbs = n * 24 / us / 1e3
+        out[f"sir_rocksample_2p{lg}_particles"] = {"us": us, "alg_GBs": gbs, "frac_of_hbm_peak": gbs / peak,
+                                                   "launches": pl.phase_ms(abi.PHASE_PF)[1]}
+    pl.close()
     return out
 
 

@@ -569,8 +569,11 @@ int run_resample(pomcp_handle* h, const Src& src, long long n, uint32_t ru, long
     h->timers[POMCP_PHASE_PF].launches += 1;
     return POMCP_OK;
   }
-  rc = ensure_bytes(h, (void**)&h->d_cum, &h->cum_cap, (size_t)n * sizeof(unsigned long long));
-  if (rc) return rc;
+  // per-particle weights between the passes (the weight-class sources of the tiled path look them up again instead)
+  if (!(ceil_ok && !h->pf_legacy_streaming && Src::NCLASS > 0)) {
+    rc = ensure_bytes(h, (void**)&h->d_cum, &h->cum_cap, (size_t)n * sizeof(unsigned long long));
+    if (rc) return rc;
+  }
   rc = ensure_scan(h, n);
   if (rc) return rc;
   if (ceil_ok && !h->pf_legacy_streaming) {
