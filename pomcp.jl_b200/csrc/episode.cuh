@@ -269,7 +269,7 @@ struct EpisodeSrc {
     return src().eval_from(i, s, sp, w);
   }
   __device__ __forceinline__ void propagate(long long i, State& sp) const { src().propagate(i, sp); }
-  __device__ __forceinline__ State load(long long i) const { return states[i]; }
+  __device__ __forceinline__ State load(long long i) const { return pf_ld_state(states + i); }
   __device__ __forceinline__ void propagate_from(long long i, const State& s, State& sp) const {
     src().propagate_from(i, s, sp);
   }
