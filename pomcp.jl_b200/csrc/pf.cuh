@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
   const long long t0 = CHUNK ? (long long)blockIdx.x * per_cta : (long long)blockIdx.x;
   const long long t1 = CHUNK ? (t0 + per_cta < ntiles ? t0 + per_cta : ntiles) : ntiles;
   const long long tstep = CHUNK ? 1 : (long long)gridDim.x;
-  unsigned long long chunk_sum = 0;  // thread 0
+  unsigned long long acc_sum = 0, acc_first = ~0ull;  // CHUNK: this thread's sum / first alive particle over the chunk
   for (long long tile = t0; tile < t1; tile += tstep) {
     const long long base = tile * PF2_TILE;
     const bool full = base + PF2_TILE <= n;  // uniform
@@ -699,6 +699,13 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
         sum += q;
       }
     }
+    if constexpr (CHUNK) {
+      // one sum per CTA: a thread keeps its own sum (and first alive particle) over the whole chunk and the CTA reduces
+      // once, after the loop - no shuffles and no barrier per tile, the warps stream their tiles independently
+      acc_sum += sum;
+      if (first != 0xffffffffu && acc_first == ~0ull) acc_first = (unsigned long long)(base + first);  // tiles ascend
+      continue;
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       sum += __shfl_xor_sync(0xffffffffu, sum, off);
@@ -714,13 +721,33 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_weigh_q(const __grid_constan
         sum += s_sum[k];
         first = min(first, s_first[k]);
       }
-      if (CHUNK) chunk_sum += sum;
-      else tile_sum[tile] = sum;
+      tile_sum[tile] = sum;
       if (first != 0xffffffffu && first_cta == ~0ull) first_cta = (unsigned long long)(base + first);  // tiles ascend
     }
     __syncthreads();
   }
-  if (CHUNK && threadIdx.x == 0) tile_sum[blockIdx.x] = chunk_sum;  // (also the CTAs beyond the last tile: zero)
+  if constexpr (CHUNK) {
+    __shared__ unsigned long long s_first64[PF2_THREADS / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      acc_sum += __shfl_xor_sync(0xffffffffu, acc_sum, off);
+      const unsigned long long of = __shfl_xor_sync(0xffffffffu, acc_first, off);
+      acc_first = of < acc_first ? of : acc_first;
+    }
+    if (lane == 0) {
+      s_sum[warp] = acc_sum;
+      s_first64[warp] = acc_first;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < PF2_THREADS / 32; ++k) {
+        acc_sum += s_sum[k];
+        acc_first = s_first64[k] < acc_first ? s_first64[k] : acc_first;
+      }
+      tile_sum[blockIdx.x] = acc_sum;  // (also the CTAs beyond the last tile: zero)
+      first_cta = acc_first;
+    }
+  }
   over = __any_sync(0xffffffffu, over);
   if (lane == 0 && over) ctl->over_ceil = 1;
   if (threadIdx.x == 0 && first_cta != ~0ull) {
