@@ -125,7 +125,7 @@ typedef struct pomcp_solver_params {
   int64_t max_nodes;     /* belief-node pool capacity (0 = derive from tree_queries) */
   int64_t max_log;       /* particle-log capacity in entries (0 = derive) */
   int32_t inflight_min;      /* batched: simulations in flight while the tree is empty
-                              * (0 = default: max(8, tree_queries / 1024) of each search) */
+                              * (0 = default: max(8, tree_queries / 512) of each search) */
   int32_t inflight_max;      /* batched: cap on simulations (workers) in flight (0 = default: 16 per SM on RockSample, 8 per SM elsewhere; raised to n_trees when below it: every tree keeps one worker) */
   int32_t inflight_ramp_div; /* batched: in flight = clamp(root visits / div, min, max) (0 = default) */
   int32_t rollouts_per_leaf; /* R rollouts averaged per leaf evaluation (0 = default: 1 exact, 64 batched).  Batched: 1..128, a

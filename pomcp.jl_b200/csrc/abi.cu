@@ -102,7 +102,7 @@ struct pomcp_handle {
   size_t ht_entries = 0, ev_entries = 0;
   PathBuf pb{};
   int n_slots = 0, inflight_min = 8, inflight_max = 1024, ramp_div = 32, rollouts = 32, sm_count = 148;
-  bool inflight_min_auto = true;  // no explicit inflight_min: max(8, tree_queries / 1024) per search
+  bool inflight_min_auto = true;  // no explicit inflight_min: max(8, tree_queries / 512) per search
   void* d_bel[2] = {nullptr, nullptr};
   size_t bel_cap[2] = {0, 0};
   int bel_cur = 0, bel_kind = 0;  // 0 none, 1 initial distribution, 2 particles, 3 exact two-state belief (EXACT2)
@@ -322,6 +322,10 @@ int reset_search_flags(pomcp_handle* h) {
 // One persistent launch of the batched workers: four-warp CTAs, 4 / team_warps workers per CTA, workers dealt to
 // the cfg.n_trees trees round-robin, admission ramped on the device.  The per-tree table (cfg.trees) must be in
 // place on the stream.
+// Admission floor = tree_queries / ADMISSION_FLOOR_DIV simulations in flight from the first query on (see below)
+#ifndef ADMISSION_FLOOR_DIV
+#define ADMISSION_FLOOR_DIV 512
+#endif
 int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
   const int nteams = 4 / cfg.team_warps;
   size_t path_bytes = ((size_t)std::max(h->levels, 1) * (16 + (size_t)h->state_bytes) + 15) & ~(size_t)15;
@@ -355,9 +359,13 @@ int launch_batched_workers(pomcp_handle* h, SearchCfg cfg, long long Q) {
       // workers are dealt to the trees round-robin: the in-flight cap, the admission floor and the ramp are per tree
       cfg.inflight_max = (int)std::max<long long>(1, std::min<long long>(cap, (long long)blocks * nteams) / T);
       // Admission floor relative to the budget: the simulations started while the tree holds fewer than
-      // Q / 1024 visits are a thousandth of the search, so running that many at once costs the final tree
-      // nothing (measured: scripts/probe.py knob --knob inflight_min) and removes most of the ramp from a large search.
-      if (h->inflight_min_auto) cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / 1024), cfg.inflight_max);
+      // Q / 512 visits are two thousandths of the search, so running that many at once costs the final tree
+      // nothing and removes most of the ramp from a large search.  Measured (scripts/probe.py knob --knob inflight_min,
+      // RockSample(7,8), 1e6 queries, 12 seeds): floor 976 / 1953 / 2368: V - V(oracle) -1.63 +- 0.15 / -1.43 +- 0.17 /
+      // -1.78 +- 0.16, the oracle's action 12/12 each, 8.73 / 8.42 / 8.42 ms; at 1e5 queries (floor 97 / 195, cap 390)
+      // 292 paired episodes against the oracle: -0.09 +- 0.15 / +0.24 +- 0.17.  (Q / 1024 until the end of round 2.)
+      if (h->inflight_min_auto)
+        cfg.inflight_min = (int)std::min<long long>(std::max<long long>(8, Q / ADMISSION_FLOOR_DIV), cfg.inflight_max);
       cfg.inflight_min = std::min(cfg.inflight_min, cfg.inflight_max);
       h->last_waves = cfg.inflight_max;  // reported as pomcp_counters::waves: the admission cap in effect, per tree
       kern<<<blocks, 128, smem, h->stream>>>(h->pool, h->dm, cfg, h->pb, Q);
