@@ -402,10 +402,14 @@ def test_sir_scale_rule_small_weights(oracle, gpu_lib, path, monkeypatch):
 
 @pytest.mark.parametrize("name,n,n_out", [("rs78", 2 * 2048 + 1, 5000), ("rs78", (1 << 21) + 17, (1 << 21) + 17),
                                           ("lightdark", 1_300_001, 1_000_000), ("baby", 1_250_000, 1_250_000),
-                                          ("tiger", 6 * 2048 - 1, 2048)])
+                                          ("tiger", 6 * 2048 - 1, 2048),
+                                          # more tiles than CTAs (8 per SM): a CTA's chunk holds several tiles, the last
+                                          # chunks are short or empty, offsets are carried from tile to tile
+                                          ("rs78", 1187 * 2048 + 5, 2_000_003), ("baby", 2_500_001, 2_500_001),
+                                          ("rs78", 5000 * 2048 - 7, 5000 * 2048 - 7)])
 def test_sir_tiled_path_edges_bit_exact(oracle, gpu_lib, name, n, n_out, monkeypatch):
-    """The tiled kernels (weigh + tile sums, tile prefix, emit) at their edges: ragged last tiles, sets beyond one
-    co-resident grid on the default path, a block of terminal particles in FRONT (the first alive particle owns
+    """The tiled kernels (weigh + tile / chunk sums, tile prefix where there is one, emit) at their edges: ragged last
+    tiles, sets beyond one co-resident grid on the default path, chunks of several tiles per CTA, a block of terminal particles in FRONT (the first alive particle owns
     output 0 and sits in a later tile), every action class of the problem (RockSample: move / sample / sense, i.e. the
     weight-class table with and without a state change), n_out != n.  Bit-identical to the oracle's sequential walk."""
     if n < 1_200_000:
