@@ -208,6 +208,28 @@ def test_c4_lightdark_1e6_particles_sir(oracle, gpu_lib, streaming, monkeypatch)
     gp.close()
 
 
+def test_sir_rocksample_2p26_particles_tiled_path(oracle, gpu_lib):
+    """The size bench.py quotes the SIR roofline on: 2^26 RockSample(7,8) particles through the tiled path (28 tiles
+    per CTA).  The resampled set is bit-identical to the oracle's sequential walk, for a sensing action (copies are the
+    input states) and for a move (copies are propagated), with a block of terminal particles in front."""
+    pomdp = pj.RockSamplePOMDP(7, 8, seed=7008)
+    n = 1 << 26
+    gp, op = make_pair(oracle, pomdp, 20.0, seed=4, mode="batched", belief_mode=abi.BELIEF_EXTERNAL, tree_queries=100)
+    rng = np.random.default_rng(26)
+    parts = (rng.integers(0, 7, n).astype(np.uint32) | (rng.integers(0, 7, n).astype(np.uint32) << 4)
+             | (rng.integers(0, 256, n).astype(np.uint32) << 8))
+    parts[:5000] |= np.uint32(abi.RS_TERMINAL)
+    for k, (a, o, n_out) in enumerate([(5, 0, n), (1, 2, n // 2 + 3)]):
+        gp.set_belief_particles(parts)
+        op.set_belief_particles(parts)
+        gp.pf_update_sir(a, o, seed=900 + k, n_out=n_out)
+        assert gp.phase_ms(abi.PHASE_PF)[1] == 2  # two launches: weigh + chunk sums, emit
+        assert op.pf_update_sir(a, o, seed=900 + k, n_out=n_out, mode=0) == 0
+        got, want = gp.belief_particles(), op.belief_particles()
+        assert len(got) == n_out and got.tobytes() == want.tobytes(), (k, a, o)
+    gp.close()
+
+
 # ----------------------------------------------------------------------------- C5 (one rank's share)
 def test_c5_rocksample_11_11_1e7_sims_one_tree(gpu_lib):
     """C5: RockSample(11,11), one tree of 10^7 simulations (the per-GPU share of the 8-tree job; the
