@@ -600,6 +600,9 @@ __global__ void __launch_bounds__(PF2_THREADS) k_pf_scan_emit(const __grid_const
 //                         particle from the fp64 form of M (exact, integer fall-back), write the copies
 // 3S + 16 bytes per particle (max-scaled path: 3S + 24), every tile independent of every other.  Same integers as
 // every other path, so the same indices.
+// Sources with a weight-class table (the discrete problems) run it as TWO launches: nothing is stored per particle (the
+// emit kernel looks the class weight up again: 3S bytes per particle), a CTA owns a contiguous chunk of tiles in both
+// kernels, k_pf_weigh_q publishes one sum per CTA and k_pf_emit_tiled derives total, status and offsets from those.
 // Quantised weights of the weight classes of `src` at `scale` (see ModelSrc::NCLASS); returns whether one of them
 // is above the ceiling.  Ends with __syncthreads().
 template <class Src>
