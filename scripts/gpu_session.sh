@@ -1,6 +1,6 @@
 #!/bin/bash
 # GPU box: one gpurun call's worth of work; stages are picked by name, outputs land in gpurun_out/<tag>_*.
-#   scripts/gpu_session.sh r2a tests bench ref c5 quality episodes ncu
+#   scripts/gpu_session.sh r2a tests bench ref c5 quality episodes ncu ncupf sir multi fuzz
 tag=$1; shift
 out=gpurun_out
 mkdir -p $out
@@ -52,6 +52,7 @@ for stage in "$@"; do
               ncu --set full --clock-control none --import-source on -k regex:k_search_workers -s 1 -c 1 -f \
                 -o $out/prof_workers_$tag python scripts/probe.py step > $out/${tag}_ncu_search.log 2>&1
               tail -n 2 $out/${tag}_ncu_search.log ;;  # the SIR kernel's capture is stage ncupf (gpurun returns <= 64 MiB per call)
+    fuzz)     python scripts/fuzz.py --cases ${FUZZ_CASES:-1000} --seed ${FUZZ_SEED:-0} 2>&1 | grep -v "external belief updater" > $out/${tag}_fuzz.log; tail -n 5 $out/${tag}_fuzz.log ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
