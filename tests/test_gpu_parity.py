@@ -436,6 +436,42 @@ def test_sir_tiled_path_edges_bit_exact(oracle, gpu_lib, name, n, n_out, monkeyp
     gp.close()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_sir_tiled_path_random_cases_bit_exact(oracle, gpu_lib, seed):
+    """Seeded random cases of the tiled path beyond one co-resident grid: set size (one to five tiles per CTA, ragged
+    last tile), output size, problem, action, observation and the share of terminal particles are drawn; the
+    resampled set is bit-identical to the oracle's sequential walk."""
+    rng = np.random.default_rng(7100 + seed)
+    name = ["rs78", "rs78", "baby", "tiger", "lightdark", "rs44"][seed]
+    pomdp, c = PROBS[name]
+    n = int(rng.integers(1_250_000, 11_000_000 if name != "lightdark" else 3_000_000))
+    n_out = int(rng.integers(n // 3, 2 * n if name != "lightdark" else n))
+    gp, op = make_pair(oracle, pomdp, c, seed=5, mode="exact", belief_mode=abi.BELIEF_EXTERNAL)
+    states = random_states(pomdp, n, rng)
+    for k in range(2):
+        a = int(rng.integers(0, pomdp.n_actions))
+        if name == "lightdark":
+            o = float(rng.normal(3.0, 2.0))
+        elif name in ("rs78", "rs44"):
+            o = int(rng.integers(0, 2)) if a >= 5 else 2
+        else:
+            o = int(rng.integers(0, 2))
+        gp.set_belief_particles(states)
+        op.set_belief_particles(states)
+        try:
+            gp.pf_update_sir(a, o, seed=50 + k, n_out=n_out)
+            rc_g = 0
+        except pj.ParticleDepletion:
+            rc_g = abi.ERR_PARTICLE_DEPLETION
+        rc_o = op.pf_update_sir(a, o, seed=50 + k, n_out=n_out, mode=0)
+        assert rc_g == rc_o, (name, n, n_out, a, o, rc_g, rc_o)
+        if rc_o == 0:
+            pg, po = gp.belief_particles(), op.belief_particles()
+            assert len(pg) == n_out == len(po)
+            assert pg.tobytes() == po.tobytes(), (name, n, n_out, a, o)
+    gp.close()
+
+
 def test_sir_baby_posterior_matches_golden_chain(oracle, gpu_lib):
     """D2: exact Baby belief chain 0 -> 0.0240964 -> 0.0298684 (notebooks/Display_Tree.ipynb:385):
     the 10^4-particle... here 2^20-particle SIR posterior mean must approach it within MC error."""
